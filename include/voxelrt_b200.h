@@ -1,0 +1,238 @@
+/*
+ * voxelrt_b200.h — C ABI of the B200-native brickmap traversal path.
+ *
+ * This is the drop-in boundary for the ONE hot path of dubiousconst282/VoxelRT that this
+ * repository accelerates: brickmap residency -> per-ray hierarchical-DDA traversal ->
+ * primary / blue-noise secondary shading -> screen-tile multi-GPU.  Plain pointers and
+ * sizes only; no C++/torch types.  Every entry point names the reference interface it
+ * replaces (paths relative to the reference tree, `src/VoxelRT/...`).
+ *
+ * Threading: a context is externally single-threaded (the reference calls everything from
+ * its one UI/GL thread, Main.cpp:83-127).  All functions return VRT_OK (0) or a negative
+ * VrtStatus; the message is available from vrt_last_error().  There is NO CPU fallback:
+ * if no CUDA device is usable, vrt_create fails with VRT_ERR_CUDA.
+ */
+#ifndef VOXELRT_B200_H
+#define VOXELRT_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(_WIN32)
+#define VRT_API
+#else
+#define VRT_API __attribute__((visibility("default")))
+#endif
+
+/* ------------------------------------------------------------------------------------------
+ * Fixed geometry of the reference brickmap (VoxelMap.h:100-102, CpuRenderer.cpp:14-18)
+ * ------------------------------------------------------------------------------------------ */
+#define VRT_BRICK_DIM 8u          /* BrickIndexer<3,3>: 8x8x8 voxels, 1 byte per voxel            */
+#define VRT_BRICK_BYTES 512u      /* sizeof(Brick)                                                */
+#define VRT_SECTOR_BRICKS 64u     /* MaskIndexer<2,2>: 4x4x4 bricks per sector                    */
+#define VRT_SECTOR_DIM 32u        /* voxels per sector edge                                       */
+#define VRT_CELLS_PER_BRICK 8u    /* 2x2x2 cells of 4x4x4 voxels, one u64 occupancy mask each     */
+#define VRT_PALETTE_SIZE 256u
+#define VRT_MAX_ITERS_DEFAULT 128u /* CpuRenderer.cpp:185                                         */
+#define VRT_BLUE_NOISE_BYTES (128u * 128u * 64u * 2u) /* STBN vec2 128x128x64, (R,G) u8 pairs     */
+
+typedef enum VrtStatus {
+    VRT_OK = 0,
+    VRT_ERR_INVALID = -1,   /* bad argument                                                       */
+    VRT_ERR_CUDA = -2,      /* CUDA runtime/driver error (message holds cudaGetErrorString)       */
+    VRT_ERR_OOM = -3,       /* "Could not allocate brick slots" (BrickSlotAllocator.cpp:15)       */
+    VRT_ERR_STATE = -4,     /* call order violated (e.g. render before any sync)                  */
+    VRT_ERR_UNSUPPORTED = -5
+} VrtStatus;
+
+typedef struct VrtContext VrtContext;
+
+/* View = the window of the world the renderer keeps resident.  The reference hard-codes it:
+ * CPU renderer 64x16x64 sectors (CpuRenderer.cpp:14-16), GPU renderer 128x64x128
+ * (GpuRenderer.cpp:6-8).  Here it is a runtime power-of-two extent, origin at sector (0,0,0). */
+typedef struct VrtConfig {
+    uint32_t struct_size;            /* = sizeof(VrtConfig)                                       */
+    int32_t device;                  /* CUDA ordinal, -1 = current device                         */
+    uint32_t sectors_xz_log2;        /* view extent in sectors along X and Z (6 = reference CPU)  */
+    uint32_t sectors_y_log2;         /* view extent in sectors along Y       (4 = reference CPU)  */
+    uint32_t initial_brick_capacity; /* brick slots to reserve up front; grows on demand (0=auto) */
+    uint32_t flags;                  /* reserved, 0                                               */
+} VrtConfig;
+
+/* One entry of VoxelMap::DirtyLocs (VoxelMap.h:185) as the renderer sees it inside
+ * SyncBuffers (CpuRenderer.cpp:38-59, GpuRenderer.cpp:52-78): the sector position, the
+ * sector's current allocation mask (Sector::GetAllocationMask, VoxelMap.cpp:53-66), which of
+ * its bricks changed, and the voxel bytes of the changed bricks.
+ * `bricks` holds popcount(dirty_mask & alloc_mask) bricks of 512 bytes, ascending bit order,
+ * voxel index = x | z<<3 | y<<6 (BrickIndexer).  A record with VRT_SECTOR_REMOVED means the
+ * sector key is gone from VoxelMap::Sectors (CpuRenderer.cpp:43-46). */
+#define VRT_SECTOR_REMOVED 1u
+typedef struct VrtDirtySector {
+    int32_t sx, sy, sz;  /* sector position (WorldSectorIndexer::GetPos), view-relative       */
+    uint32_t flags;
+    uint64_t alloc_mask; /* bit i = brick i allocated, i = x | z<<2 | y<<4 (MaskIndexer)       */
+    uint64_t dirty_mask;
+    const uint8_t* bricks;
+} VrtDirtySector;
+
+/* Result of one ray — the lane-wise content of VHitResult (CpuRenderer.cpp:88-96,209-223)
+ * plus the hit voxel and bookkeeping the parity tests need.  48 bytes. */
+typedef struct VrtHit {
+    int32_t vx, vy, vz; /* voxel the loop stopped in, world coords (CpuRenderer.cpp:186)      */
+    uint32_t material;  /* low 32 bits of the palette entry: RGB565 | f16 emission << 16      */
+    float dist;         /* min3(sideDist), no bias (CpuRenderer.cpp:204)                      */
+    float px, py, pz;   /* currPos, relative to worldOrigin (CpuRenderer.cpp:212)             */
+    float u, v;         /* face UV (CpuRenderer.cpp:218-221)                                  */
+    uint32_t flags;     /* VRT_HIT_* below                                                    */
+    uint32_t _pad;
+} VrtHit;
+/* flags layout */
+#define VRT_HIT_NORMAL_MASK 0x3Fu   /* (nx+1) | (ny+1)<<2 | (nz+1)<<4  (CpuRenderer.cpp:372-374) */
+#define VRT_HIT_HIT 0x100u          /* VHitResult::Mask: stopped on a solid voxel inside the view */
+#define VRT_HIT_INBOUND 0x200u      /* last voxel was inside the view                             */
+#define VRT_HIT_CAPPED 0x400u       /* ran out of iterations (a miss, CpuRenderer.cpp:222)        */
+#define VRT_HIT_ITERS_SHIFT 16      /* loop iterations executed, bits 16..31                      */
+
+/* Result of the fp64 picking query, VoxelMap::RayCast (VoxelMap.cpp:140-170) / HitResult
+ * (VoxelMap.h:171-178). */
+typedef struct VrtHitD {
+    double dist;        /* tmin at the hit, -1 on miss                                            */
+    float nx, ny, nz;   /* mix(0, -sign(dir), tmin >= sideDist)                                   */
+    float u, v;
+    int32_t vx, vy, vz;
+    uint32_t iters;
+    uint32_t _pad;
+} VrtHitD;
+
+/* Per-frame constants — FrameConstants of the CPU renderer (CpuRenderer.cpp:314-323,444-453).
+ * Matrices are column-major float[16] exactly like glm::mat4 (m[col][row] = a[col*4+row]). */
+#define VRT_FRAME_LINEAR_OUTPUT 1u /* out = 4 planes (albedo, depth, irrRG, irrBX) of w*h u32  */
+#define VRT_FRAME_AUX_HITS 2u      /* also fill the VrtHit of every primary ray (aux_hits)     */
+typedef struct VrtFrame {
+    uint32_t width, height;  /* rounded down to multiples of 4 by the caller (CpuRenderer.cpp:419) */
+    float inv_proj[16];      /* GBuffer::GetInverseProjScreenMat (GBuffer.h:133-139)               */
+    float proj[16];          /* CurrentProj = P * V(rotation only) (GBuffer.h:51)                  */
+    int32_t world_origin[3]; /* floor(camera position)                                             */
+    float origin_frac[3];    /* fract(camera position)                                             */
+    uint32_t frame_no;
+    uint32_t bounces;        /* NumLightBounces (Renderer.h:65)                                    */
+    uint32_t max_iters;      /* 0 = 128                                                            */
+    uint32_t flags;
+    /* screen-tile partition for multi-GPU: this context renders tiles t with
+     * t % part_count == part_index (tile = 32x32 pixels, row-major tile index).  1-GPU: 0/1. */
+    uint32_t part_index, part_count;
+} VrtFrame;
+
+/* Framebuffer::Tile of the reference (CpuRenderer.cpp:299-309) for 16-lane packets: a 4x4
+ * pixel tile stored as four arrays of 16 u32, lane = (x&3) | (y&3)<<2.  Default output of
+ * vrt_render is tiles in row-major tile order, TileStride = width/4. */
+typedef struct VrtTile {
+    uint32_t albedo[16];  /* RGBA8, A = packed normal code << 0 (bits 24..29)                  */
+    float depth[16];      /* proj z/w of pos/16, -1 on miss                                    */
+    uint32_t irr_rg[16];  /* 2 x f16                                                           */
+    uint32_t irr_bx[16];  /* f16 | 0                                                           */
+} VrtTile;
+
+typedef struct VrtStats {
+    uint64_t resident_bricks;   /* FreeList::NumAllocated                                      */
+    uint64_t brick_capacity;    /* slots in the device arena                                   */
+    uint64_t free_ranges;       /* FreeList::FreeRanges.size() (GpuRenderer.cpp:301)           */
+    uint64_t resident_sectors;
+    uint64_t bytes_uploaded;    /* H2D bytes moved by the last vrt_sync                        */
+    uint64_t bricks_uploaded;   /* bricks in the last vrt_sync                                 */
+    uint64_t bricks_relocated;  /* bricks moved device-side by the last vrt_sync               */
+    uint64_t device_bytes;      /* total device memory owned by the context                    */
+    uint64_t last_launches;     /* kernels launched by the last ABI call                       */
+} VrtStats;
+
+/* ---- lifetime ------------------------------------------------------------------------------- */
+/* Replaces CpuRenderer::CpuRenderer / GpuRenderer::GpuRenderer storage setup
+ * (CpuRenderer.cpp:26-31,404-411; GpuRenderer.cpp:41-43,212-236). */
+VRT_API int vrt_create(const VrtConfig* cfg, VrtContext** out);
+VRT_API void vrt_destroy(VrtContext* ctx);
+/* Message of the last failing call on ctx (ctx may be NULL for a failed vrt_create). */
+VRT_API const char* vrt_last_error(const VrtContext* ctx);
+VRT_API int vrt_get_stats(const VrtContext* ctx, VrtStats* out);
+
+/* ---- residency ------------------------------------------------------------------------------ */
+/* Palette[i] = Material::GetEncoded() (VoxelMap.h:27-41); the reference re-encodes it every
+ * frame (CpuRenderer.cpp:34-36, GpuRenderer.cpp:100-102). */
+VRT_API int vrt_set_palette(VrtContext* ctx, const uint64_t palette[256]);
+/* FlatVoxelStorage::SyncBuffers (CpuRenderer.cpp:33-61) / GpuVoxelStorage::SyncBuffers
+ * (GpuRenderer.cpp:45-167): allocate/free brick slots, upload ONLY the dirty bricks, rebuild
+ * their 8 cell masks on the device (UpdateOccupancy, CpuRenderer.cpp:63-83 /
+ * UpdateOccupancy.comp:8-34).  Host data is consumed before return. */
+VRT_API int vrt_sync(VrtContext* ctx, uint32_t n, const VrtDirtySector* sectors);
+/* Test/inspection hook: copy the resident state of one sector back to the host.
+ * out_alloc_mask: allocation mask; out_bricks (64*512 B) / out_cells (64*8 u64) are filled for
+ * allocated bricks in brick-index order (dense, unallocated = 0). Any pointer may be NULL. */
+VRT_API int vrt_read_sector(VrtContext* ctx, int32_t sx, int32_t sy, int32_t sz, uint64_t* out_alloc_mask,
+                            uint32_t* out_base_slot, uint8_t* out_bricks, uint64_t* out_cells);
+
+/* ---- ray cast (explicit rays) ----------------------------------------------------------------- */
+/* RayCast(map, origin, dir, mask, worldOrigin) -> VHitResult (CpuRenderer.cpp:172-224), one
+ * ray per element.  origin3/dir3 are n x 3 floats (origin relative to world_origin).
+ * Host-pointer version copies in and out; the _device version takes device pointers and
+ * runs on `stream` (a cudaStream_t, may be NULL). */
+VRT_API int vrt_trace(VrtContext* ctx, uint64_t n, const float* origin3, const float* dir3, const int32_t world_origin[3],
+                      uint32_t max_iters, VrtHit* out);
+VRT_API int vrt_trace_device(VrtContext* ctx, uint64_t n, const float* d_origin3, const float* d_dir3,
+                             const int32_t world_origin[3], uint32_t max_iters, VrtHit* d_out, void* stream);
+
+/* ---- hit query (picking) ---------------------------------------------------------------------- */
+/* HitResult VoxelMap::RayCast(dvec3 origin, dvec3 dir, maxIters=1024) (VoxelMap.cpp:140-170),
+ * batched.  The reference walks the unbounded sector hash; here sectors outside the resident
+ * view read as "no sector" (step 32). */
+VRT_API int vrt_hit_query(VrtContext* ctx, uint64_t n, const double* origin3, const double* dir3, uint32_t max_iters,
+                          VrtHitD* out);
+
+/* ---- shading inputs --------------------------------------------------------------------------- */
+/* VBlueNoise source image (CpuRenderer.cpp:235-252): 128 x (128*64) texels of (R,G) bytes,
+ * row-major, slice s occupies rows [128 s, 128 s + 128). */
+VRT_API int vrt_set_blue_noise(VrtContext* ctx, const uint8_t* rg, size_t bytes);
+/* Sky cube as swr::HdrTexture2D holds it (Texture.h:401-446): 6 layers of R11G11B10f texels
+ * with a mip chain; texel(layer, mip, x, y) = data[(layer << layer_shift) + mip_offset[mip]
+ * + x + (y << (row_shift - mip))]. */
+typedef struct VrtSkyDesc {
+    uint32_t face_size;   /* power of two                                                      */
+    uint32_t mip_levels;  /* <= 16                                                             */
+    uint32_t layer_shift;
+    uint32_t mip_offset[16];
+    uint64_t texel_count; /* u32 elements in `texels`                                          */
+} VrtSkyDesc;
+VRT_API int vrt_set_sky(VrtContext* ctx, const VrtSkyDesc* desc, const uint32_t* texels);
+
+/* ---- frame ------------------------------------------------------------------------------------ */
+/* Renderer::RenderFrame minus present (Renderer.h:18; CpuRenderer.cpp:415-464 — everything
+ * between SyncBuffers and the blit).  vrt_render writes w*h*16 bytes to HOST memory `out`
+ * (tiles, or planes with VRT_FRAME_LINEAR_OUTPUT); aux_hits (host, w*h VrtHit, row-major
+ * pixel order) is filled when VRT_FRAME_AUX_HITS is set.  vrt_render_device leaves the result
+ * in device memory on `stream` — this is what a CUDA/GL-interop presenter would consume. */
+VRT_API int vrt_render(VrtContext* ctx, const VrtFrame* frame, void* out, VrtHit* aux_hits);
+VRT_API int vrt_render_device(VrtContext* ctx, const VrtFrame* frame, void* d_out, VrtHit* d_aux_hits, void* stream);
+
+/* ---- multi-GPU tile gather over NVLink (no reference counterpart) ------------------ */
+/* One process per GPU.  The presenting rank exports its framebuffer as a CUDA IPC handle;
+ * every other rank opens it and its render kernel stores finished tiles straight into the
+ * owner's memory (peer stores over NVLink).  64-byte opaque handle. */
+VRT_API int vrt_fb_export(VrtContext* ctx, uint64_t bytes, uint8_t handle_out[64], void** d_ptr_out);
+VRT_API int vrt_fb_import(VrtContext* ctx, const uint8_t handle[64], void** d_ptr_out);
+VRT_API int vrt_fb_release(VrtContext* ctx, void* d_ptr);
+
+/* Device-side traversal counters of the last trace/render (TRAVERSAL_METRICS,
+ * VoxelTraversal.glsl:147-151): total loop iterations, sector-mask fetches, cell-mask fetches,
+ * hits.  Enabled with vrt_set_option(ctx, "metrics", 1); costs a few atomics per warp. */
+typedef struct VrtTraversalMetrics {
+    uint64_t rays, iters, sector_fetches, cell_fetches, hits, capped;
+} VrtTraversalMetrics;
+VRT_API int vrt_get_metrics(VrtContext* ctx, VrtTraversalMetrics* out);
+VRT_API int vrt_set_option(VrtContext* ctx, const char* name, int64_t value);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VOXELRT_B200_H */

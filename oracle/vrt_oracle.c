@@ -1,0 +1,744 @@
+/*
+ * vrt_oracle.c — CPU ORACLE (test infrastructure, never linked into the product).
+ *
+ * Scalar lane-wise restatement of the reference CPU renderer.  Every function cites the
+ * reference lines it follows (paths relative to /root/reference/src).  Arithmetic recipe
+ * ("canonical arithmetic"): IEEE-754 binary32, round-to-nearest, FMA exactly
+ * where written as fmaf(), x86 min/cvt semantics spelled out.  Build with
+ *   gcc -O2 -ffp-contract=off -fno-fast-math -mfma  (oracle/Makefile)
+ * so the compiler neither fuses nor splits anything.
+ */
+#include "vrt_oracle.h"
+
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+/* ------------------------------------------------------------------------------------------ */
+/* Storage: FlatVoxelStorage (VoxelRT/CpuRenderer.cpp:20-31) with the dense 2 GiB buffer       */
+/* replaced by per-sector blocks allocated on first use.  Addressing semantics are the dense   */
+/* ones: an unallocated brick reads as zeros, indices wrap by masking.                         */
+/* ------------------------------------------------------------------------------------------ */
+struct OrcMap {
+    uint32_t shift_xz, shift_y; /* ViewSectorIndexer<ShiftXZ,ShiftY> (CpuRenderer.cpp:14-16) */
+    uint32_t n_sectors;
+    uint64_t* sector_masks;  /* SectorMasks[]                                   */
+    uint8_t** sector_voxels; /* StorageBuffer slice of the sector, 64*512 B     */
+    uint64_t** sector_cells; /* OccupancyStorage slice of the sector, 64*8 u64  */
+    uint64_t palette[256];
+    uint8_t* blue_noise; /* 128 x 8192 x (R,G) */
+    VrtSkyDesc sky;
+    uint32_t* sky_texels;
+};
+
+static inline uint32_t sector_index(const OrcMap* m, int32_t sx, int32_t sy, int32_t sz) {
+    /* LinearIndexer3D::GetIndex (VoxelRT/VoxelMap.h:94-97): x | z << sXZ | y << 2 sXZ, masked */
+    uint32_t mxz = (1u << m->shift_xz) - 1, my = (1u << m->shift_y) - 1;
+    return ((uint32_t)sx & mxz) | (((uint32_t)sz & mxz) << m->shift_xz) | (((uint32_t)sy & my) << (2 * m->shift_xz));
+}
+
+OrcMap* orc_map_create(uint32_t sectors_xz_log2, uint32_t sectors_y_log2) {
+    OrcMap* m = (OrcMap*)calloc(1, sizeof(OrcMap));
+    m->shift_xz = sectors_xz_log2;
+    m->shift_y = sectors_y_log2;
+    m->n_sectors = 1u << (2 * sectors_xz_log2 + sectors_y_log2);
+    m->sector_masks = (uint64_t*)calloc(m->n_sectors, sizeof(uint64_t));
+    m->sector_voxels = (uint8_t**)calloc(m->n_sectors, sizeof(uint8_t*));
+    m->sector_cells = (uint64_t**)calloc(m->n_sectors, sizeof(uint64_t*));
+    return m;
+}
+
+void orc_map_destroy(OrcMap* m) {
+    if (!m) return;
+    for (uint32_t i = 0; i < m->n_sectors; i++) {
+        free(m->sector_voxels[i]);
+        free(m->sector_cells[i]);
+    }
+    free(m->sector_masks);
+    free(m->sector_voxels);
+    free(m->sector_cells);
+    free(m->blue_noise);
+    free(m->sky_texels);
+    free(m);
+}
+
+void orc_map_set_palette(OrcMap* m, const uint64_t palette[256]) { memcpy(m->palette, palette, sizeof(m->palette)); }
+
+/* FlatVoxelStorage::UpdateOccupancy, VoxelRT/CpuRenderer.cpp:63-83.
+ * cell (cx,cy,cz) -> BrickMaskIndexer index cx | cz<<1 | cy<<2 (CpuRenderer.cpp:18,80);
+ * bit vx + 4 vz + 16 vy (CpuRenderer.cpp:78); voxel index x | z<<3 | y<<6 (VoxelMap.h:102). */
+void orc_build_occupancy(const uint8_t brick[512], uint64_t cells[8]) {
+    for (uint32_t cy = 0; cy < 8; cy += 4)
+        for (uint32_t cz = 0; cz < 8; cz += 4)
+            for (uint32_t cx = 0; cx < 8; cx += 4) {
+                uint64_t mask = 0;
+                for (uint32_t vy = 0; vy < 4; vy++)
+                    for (uint32_t vz = 0; vz < 4; vz++)
+                        for (uint32_t vx = 0; vx < 4; vx++) {
+                            uint32_t idx = (cx + vx) | ((cz + vz) << 3) | ((cy + vy) << 6);
+                            uint64_t occupied = brick[idx] != 0;
+                            mask |= occupied << (vx + vz * 4 + vy * 16);
+                        }
+                cells[(cx >> 2) | ((cz >> 2) << 1) | ((cy >> 2) << 2)] = mask;
+            }
+}
+
+/* FlatVoxelStorage::SyncBuffers, VoxelRT/CpuRenderer.cpp:38-60 */
+int orc_map_sync(OrcMap* m, uint32_t n, const VrtDirtySector* recs) {
+    for (uint32_t r = 0; r < n; r++) {
+        const VrtDirtySector* d = &recs[r];
+        /* ViewSectorIndexer::CheckInBounds (VoxelMap.h:73-76) */
+        if (((uint32_t)(d->sx | d->sz) >> m->shift_xz) != 0 || ((uint32_t)d->sy >> m->shift_y) != 0) continue;
+        uint32_t si = sector_index(m, d->sx, d->sy, d->sz);
+        if (d->flags & VRT_SECTOR_REMOVED) { /* CpuRenderer.cpp:43-46 */
+            m->sector_masks[si] = 0;
+            /* deviation (documented): the reference leaves stale voxel bytes behind; they are
+             * only observable through the wrapped material fetch of out-of-grid rays (Q4). */
+            if (m->sector_voxels[si]) memset(m->sector_voxels[si], 0, 64 * 512);
+            if (m->sector_cells[si]) memset(m->sector_cells[si], 0, 64 * 8 * sizeof(uint64_t));
+            continue;
+        }
+        uint64_t old_mask = m->sector_masks[si];
+        m->sector_masks[si] = d->alloc_mask; /* CpuRenderer.cpp:49-50 */
+        if (!m->sector_voxels[si]) {
+            m->sector_voxels[si] = (uint8_t*)calloc(64, 512);
+            m->sector_cells[si] = (uint64_t*)calloc(64 * 8, sizeof(uint64_t));
+        }
+        /* bricks that left the allocation mask: zero them (same deviation as above) */
+        uint64_t gone = old_mask & ~d->alloc_mask;
+        for (; gone; gone &= gone - 1) {
+            uint32_t b = (uint32_t)__builtin_ctzll(gone);
+            memset(m->sector_voxels[si] + b * 512, 0, 512);
+            memset(m->sector_cells[si] + b * 8, 0, 64);
+        }
+        const uint8_t* src = d->bricks;
+        uint64_t todo = d->dirty_mask & d->alloc_mask; /* CpuRenderer.cpp:52 */
+        for (; todo; todo &= todo - 1) {
+            uint32_t b = (uint32_t)__builtin_ctzll(todo);
+            memcpy(m->sector_voxels[si] + b * 512, src, 512);            /* :56 */
+            orc_build_occupancy(src, m->sector_cells[si] + b * 8);       /* :57 */
+            src += 512;
+        }
+    }
+    return 0;
+}
+
+int orc_map_read_sector(const OrcMap* m, int32_t sx, int32_t sy, int32_t sz, uint64_t* alloc_mask, uint8_t* bricks,
+                        uint64_t* cells) {
+    if (((uint32_t)(sx | sz) >> m->shift_xz) != 0 || ((uint32_t)sy >> m->shift_y) != 0) return -1;
+    uint32_t si = sector_index(m, sx, sy, sz);
+    if (alloc_mask) *alloc_mask = m->sector_masks[si];
+    if (bricks) {
+        if (m->sector_voxels[si]) memcpy(bricks, m->sector_voxels[si], 64 * 512);
+        else memset(bricks, 0, 64 * 512);
+    }
+    if (cells) {
+        if (m->sector_cells[si]) memcpy(cells, m->sector_cells[si], 64 * 8 * sizeof(uint64_t));
+        else memset(cells, 0, 64 * 8 * sizeof(uint64_t));
+    }
+    return 0;
+}
+
+void orc_set_blue_noise(OrcMap* m, const uint8_t* rg, size_t bytes) {
+    free(m->blue_noise);
+    m->blue_noise = (uint8_t*)malloc(VRT_BLUE_NOISE_BYTES);
+    memset(m->blue_noise, 0, VRT_BLUE_NOISE_BYTES);
+    memcpy(m->blue_noise, rg, bytes < VRT_BLUE_NOISE_BYTES ? bytes : VRT_BLUE_NOISE_BYTES);
+}
+
+void orc_set_sky(OrcMap* m, const VrtSkyDesc* desc, const uint32_t* texels) {
+    free(m->sky_texels);
+    m->sky = *desc;
+    m->sky_texels = (uint32_t*)malloc(desc->texel_count * sizeof(uint32_t));
+    memcpy(m->sky_texels, texels, desc->texel_count * sizeof(uint32_t));
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/* x86 semantics the reference inherits from its intrinsics                                    */
+/* ------------------------------------------------------------------------------------------ */
+/* _mm512_min_ps(a,b): a < b ? a : b — returns b when either is NaN (LibGlimpsw/SwRast/SIMD_AVX512.h:123) */
+static inline float x86_min(float a, float b) { return a < b ? a : b; }
+static inline float x86_max(float a, float b) { return a > b ? a : b; }
+/* _mm512_cvt_roundps_epi32(x, TO_NEG_INF) (SIMD_AVX512.h:110): NaN / out of range -> 0x80000000 */
+static inline int32_t x86_floor2i(float x) {
+    if (!(x >= -2147483648.0f && x < 2147483648.0f)) return INT32_MIN;
+    return (int32_t)floorf(x);
+}
+/* _mm512_cvtps_epi32 (SIMD_AVX512.h:108): round half even, indefinite on NaN / overflow */
+static inline int32_t x86_round2i(float x) {
+    if (!(x >= -2147483648.0f && x < 2147483648.0f)) return INT32_MIN;
+    return (int32_t)nearbyintf(x); /* default rounding mode = RNE */
+}
+static inline int32_t x86_trunc2i(float x) {
+    if (!(x >= -2147483648.0f && x < 2147483648.0f)) return INT32_MIN;
+    return (int32_t)x;
+}
+static inline uint32_t f2u(float f) {
+    uint32_t u;
+    memcpy(&u, &f, 4);
+    return u;
+}
+static inline float u2f(uint32_t u) {
+    float f;
+    memcpy(&f, &u, 4);
+    return f;
+}
+/* canonical replacements of the hardware approximations:
+ * approx_rsqrt = _mm512_rsqrt14_ps, approx_rcp = _mm512_rcp14_ps (SIMD_AVX512.h:140-142) */
+static inline float canon_rsqrt(float x) { return 1.0f / sqrtf(x); }
+static inline float canon_rcp(float x) { return 1.0f / x; }
+
+/* f16 <-> f32, IEEE RNE (Texture.h:101-116 uses vcvtps2ph/vcvtph2ps); NaN canonicalised */
+static uint16_t f32_to_f16(float f) {
+    uint32_t x = f2u(f);
+    uint32_t sign = (x >> 16) & 0x8000u;
+    uint32_t ax = x & 0x7FFFFFFFu;
+    if (ax > 0x7F800000u) return (uint16_t)(sign | 0x7FFFu); /* NaN (CUDA canonical 0x7FFF) */
+    if (ax >= 0x47800000u) {                                /* >= 65536 -> inf unless rounds below */
+        return (uint16_t)(sign | 0x7C00u);
+    }
+    if (ax >= 0x38800000u) { /* normal half */
+        uint32_t mant = ax & 0x7FFFFFu;
+        uint32_t exp = (ax >> 23) - 112;
+        uint32_t h = (exp << 10) | (mant >> 13);
+        uint32_t rem = mant & 0x1FFFu;
+        if (rem > 0x1000u || (rem == 0x1000u && (h & 1))) h++;
+        return (uint16_t)(sign | h); /* carry into exponent (up to inf) is correct */
+    }
+    if (ax < 0x33000000u) return (uint16_t)sign; /* < 2^-25 -> 0 */
+    /* subnormal half */
+    uint32_t mant = (ax & 0x7FFFFFu) | 0x800000u;
+    uint32_t shift = 126 - (ax >> 23); /* 14..24 */
+    uint32_t h = mant >> shift;
+    uint32_t rem = mant & ((1u << shift) - 1);
+    uint32_t half = 1u << (shift - 1);
+    if (rem > half || (rem == half && (h & 1))) h++;
+    return (uint16_t)(sign | h);
+}
+static float f16_to_f32(uint16_t h) {
+    uint32_t sign = (uint32_t)(h & 0x8000u) << 16;
+    uint32_t exp = (h >> 10) & 31, mant = h & 0x3FFu;
+    if (exp == 31) return u2f(sign | 0x7F800000u | (mant << 13));
+    if (exp == 0) {
+        if (mant == 0) return u2f(sign);
+        float v = (float)mant * (1.0f / 16777216.0f); /* mant * 2^-24, exact */
+        return sign ? -v : v;
+    }
+    return u2f(sign | ((exp + 112) << 23) | (mant << 13));
+}
+
+/* Material::GetEncoded, VoxelRT/VoxelMap.h:27-41 */
+uint64_t orc_encode_material(uint8_t r, uint8_t g, uint8_t b, uint8_t fuzz, float emission) {
+    uint64_t packed = 0;
+    packed |= (uint64_t)(r >> 3) << 11;
+    packed |= (uint64_t)(g >> 2) << 5;
+    packed |= (uint64_t)(b >> 3) << 0;
+    packed |= (uint64_t)f32_to_f16(emission) << 16; /* packHalf2x16(vec2(0, Emission)) */
+    packed |= (uint64_t)fuzz << 32;
+    return packed;
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/* Traversal                                                                                   */
+/* ------------------------------------------------------------------------------------------ */
+typedef struct {
+    uint64_t iters, sector_fetches, cell_fetches;
+} CastCounters;
+
+/* GetInboundMask, VoxelRT/CpuRenderer.cpp:114-117 */
+static inline int inbound(const OrcMap* m, int32_t x, int32_t y, int32_t z) {
+    return (uint32_t)(x | z) < (1u << (m->shift_xz + 5)) && (uint32_t)y < (1u << (m->shift_y + 5));
+}
+
+/* GetVoxelMaterial, VoxelRT/CpuRenderer.cpp:120-132 — every index is masked, so any position
+ * reads some in-buffer voxel (the "wrapped address" of quirk Q4). */
+static inline uint32_t voxel_material(const OrcMap* m, int32_t x, int32_t y, int32_t z) {
+    uint32_t si = sector_index(m, x >> 5, y >> 5, z >> 5);
+    uint32_t bi = ((uint32_t)(x >> 3) & 3) | (((uint32_t)(z >> 3) & 3) << 2) | (((uint32_t)(y >> 3) & 3) << 4);
+    uint32_t vi = ((uint32_t)x & 7) | (((uint32_t)z & 7) << 3) | (((uint32_t)y & 7) << 6);
+    uint8_t id = m->sector_voxels[si] ? m->sector_voxels[si][bi * 512 + vi] : 0;
+    return (uint32_t)m->palette[id];
+}
+
+/* GetStepPos, VoxelRT/CpuRenderer.cpp:135-171.  Returns the hit flag; p is advanced to the far
+ * corner of the empty cell it is in (unchanged on hit). */
+static inline int step_pos(const OrcMap* m, int32_t p[3], const float d[3], CastCounters* c) {
+    uint32_t si = sector_index(m, p[0] >> 5, p[1] >> 5, p[2] >> 5); /* :136 */
+    uint64_t mask = m->sector_masks[si];                            /* :138-139 */
+    c->sector_fetches++;
+    uint32_t idx = ((uint32_t)(p[0] >> 3) & 3) | (((uint32_t)(p[2] >> 3) & 3) << 2) | (((uint32_t)(p[1] >> 3) & 3) << 4); /* :141 */
+    int level0 = (int)((mask >> idx) & 1); /* :142-143 */
+    int lod = 3;                           /* :144 */
+    if (level0) {                          /* :146-158 */
+        uint32_t cell = ((uint32_t)(p[0] >> 2) & 1) | (((uint32_t)(p[2] >> 2) & 1) << 1) | (((uint32_t)(p[1] >> 2) & 1) << 2);
+        mask = m->sector_cells[si] ? m->sector_cells[si][idx * 8 + cell] : 0; /* :147-148,153-154 */
+        c->cell_fetches++;
+        idx = ((uint32_t)p[0] & 3) | (((uint32_t)p[2] & 3) << 2) | (((uint32_t)p[1] & 3) << 4); /* :150 */
+        lod = 0;                                                                               /* :151 */
+        level0 = (int)((mask >> idx) & 1);                                                     /* :156-157 */
+    }
+    uint32_t half = idx < 32 ? (uint32_t)mask : (uint32_t)(mask >> 32);
+    int level4 = mask == 0;                                          /* :160 */
+    int level2 = ((half >> (idx & 0xA)) & 0x00330033u) == 0;         /* :161 */
+    lod += level4 ? 2 : (level2 ? 1 : 0);                            /* :162 */
+    int32_t cm = (1 << lod) - 1;                                     /* :164 */
+    for (int a = 0; a < 3; a++) p[a] = d[a] < 0 ? (p[a] & ~cm) : (p[a] | cm); /* :166-168 */
+    return level0;
+}
+
+/* RayCast, VoxelRT/CpuRenderer.cpp:172-224, one lane. */
+static void cast_ray(const OrcMap* m, const float o[3], const float d[3], const int32_t wo[3], uint32_t max_iters,
+                     VrtHit* out, CastCounters* cnt) {
+    float inv[3], ts[3], sd[3] = {0, 0, 0}, cur[3];
+    int32_t p[3] = {0, 0, 0};
+    for (int a = 0; a < 3; a++) {
+        inv[a] = 1.0f / d[a];                               /* :173 */
+        ts[a] = ((d[a] < 0 ? 0.0f : 1.0f) - o[a]) * inv[a]; /* :175-179 */
+        cur[a] = o[a];                                      /* :181 */
+    }
+    int hit = 0, inb = 0, active = 1;
+    uint32_t it = 0;
+    for (; it < max_iters; it++) { /* :185 */
+        for (int a = 0; a < 3; a++) p[a] = (int32_t)((uint32_t)wo[a] + (uint32_t)x86_floor2i(cur[a])); /* :186 */
+        cnt->iters++;
+        inb = inbound(m, p[0], p[1], p[2]); /* :188 */
+        if (!inb) {                         /* :189 */
+            active = 0;
+            break;
+        }
+        hit = step_pos(m, p, d, cnt); /* :190 */
+        if (hit) {                    /* :192-193 */
+            active = 0;
+            break;
+        }
+        for (int a = 0; a < 3; a++) /* :195-198, contracted to FMA by the reference's compilers */
+            sd[a] = fmaf((float)(int32_t)((uint32_t)p[a] - (uint32_t)wo[a]), inv[a], ts[a]);
+        float tmin = x86_min(x86_min(sd[0], sd[1]), sd[2]) + 0.001f; /* :200 */
+        for (int a = 0; a < 3; a++) cur[a] = fmaf(tmin, d[a], o[a]);  /* :201 */
+    }
+    float hd = x86_min(x86_min(sd[0], sd[1]), sd[2]); /* :204 */
+    int mx = sd[0] == hd, my = sd[1] == hd;           /* :205-206 */
+    int mz = !mx && !my;                              /* :207 */
+    /* :214-216  csel(side, (dir & -0.0f) ^ -1.0f, 0): sign BIT of dir set -> +1 else -1 */
+    int nx = mx ? ((f2u(d[0]) >> 31) ? 1 : -1) : 0;
+    int ny = my ? ((f2u(d[1]) >> 31) ? 1 : -1) : 0;
+    int nz = mz ? ((f2u(d[2]) >> 31) ? 1 : -1) : 0;
+    float fu = mx ? cur[1] : cur[0], fv = mz ? cur[1] : cur[2]; /* :218-221 */
+    out->vx = p[0];
+    out->vy = p[1];
+    out->vz = p[2];
+    /* :210  material fetched for every non-active lane; lanes still active (cap) read 0 */
+    out->material = active ? 0u : voxel_material(m, p[0], p[1], p[2]);
+    out->dist = hd;
+    out->px = cur[0];
+    out->py = cur[1];
+    out->pz = cur[2];
+    out->u = fu - floorf(fu); /* fract = _mm512_reduce_ps(x, TO_NEG_INF) (SIMD_AVX512.h:116) */
+    out->v = fv - floorf(fv);
+    uint32_t iters_done = it < max_iters ? it + 1 : max_iters;
+    if (iters_done > 0xFFFF) iters_done = 0xFFFF;
+    out->flags = (uint32_t)((nx + 1) | ((ny + 1) << 2) | ((nz + 1) << 4)) | ((!active && inb) ? VRT_HIT_HIT : 0) | /* :222 */
+                 (inb ? VRT_HIT_INBOUND : 0) | (active ? VRT_HIT_CAPPED : 0) | (iters_done << VRT_HIT_ITERS_SHIFT);
+    out->_pad = 0;
+}
+
+static void stats_add(OrcStats* s, const CastCounters* c, const VrtHit* h) {
+    s->rays++;
+    s->iters += c->iters;
+    s->sector_fetches += c->sector_fetches;
+    s->cell_fetches += c->cell_fetches;
+    if (h->flags & VRT_HIT_HIT) s->hits++;
+    if (h->flags & VRT_HIT_CAPPED) s->capped++;
+    uint32_t it = h->flags >> VRT_HIT_ITERS_SHIFT;
+    int b = it < 4 ? 0 : it < 8 ? 1 : it < 16 ? 2 : it < 32 ? 3 : it < 64 ? 4 : it < 128 ? 5 : it < 256 ? 6 : 7;
+    s->iter_hist[b]++;
+}
+static void stats_merge(OrcStats* dst, const OrcStats* src) {
+    dst->rays += src->rays;
+    dst->iters += src->iters;
+    dst->sector_fetches += src->sector_fetches;
+    dst->cell_fetches += src->cell_fetches;
+    dst->hits += src->hits;
+    dst->capped += src->capped;
+    for (int i = 0; i < 8; i++) dst->iter_hist[i] += src->iter_hist[i];
+}
+
+int orc_num_threads(void) {
+#ifdef _OPENMP
+    return omp_get_max_threads();
+#else
+    return 1;
+#endif
+}
+
+void orc_trace(const OrcMap* m, uint64_t n, const float* origin3, const float* dir3, const int32_t wo[3],
+               uint32_t max_iters, VrtHit* out, OrcStats* stats, int threads) {
+    if (max_iters == 0) max_iters = VRT_MAX_ITERS_DEFAULT;
+    OrcStats total;
+    memset(&total, 0, sizeof(total));
+#ifdef _OPENMP
+    if (threads <= 0) threads = omp_get_max_threads();
+#pragma omp parallel num_threads(threads)
+#endif
+    {
+        OrcStats local;
+        memset(&local, 0, sizeof(local));
+#ifdef _OPENMP
+#pragma omp for schedule(dynamic, 4096)
+#endif
+        for (int64_t i = 0; i < (int64_t)n; i++) {
+            CastCounters c = {0, 0, 0};
+            cast_ray(m, origin3 + 3 * i, dir3 + 3 * i, wo, max_iters, &out[i], &c);
+            stats_add(&local, &c, &out[i]);
+        }
+#ifdef _OPENMP
+#pragma omp critical
+#endif
+        stats_merge(&total, &local);
+    }
+    if (stats) *stats = total;
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/* Hit query: VoxelMap::RayCast + GetStepLevel, VoxelRT/VoxelMap.cpp:125-170 (fp64)            */
+/* ------------------------------------------------------------------------------------------ */
+static inline double glm_min(double x, double y) { return (y < x) ? y : x; } /* glm::min */
+
+/* GetStepLevel, VoxelMap.cpp:125-139.  The reference looks the sector up in the unbounded
+ * hash; the resident view stands in for it (sectors outside the view = absent). */
+static int step_level(const OrcMap* m, int32_t x, int32_t y, int32_t z) {
+    int32_t sx = x >> 5, sy = y >> 5, sz = z >> 5;
+    if (((uint32_t)(sx | sz) >> m->shift_xz) != 0 || ((uint32_t)sy >> m->shift_y) != 0) return 5;
+    uint32_t si = sector_index(m, sx, sy, sz);
+    uint64_t mask = m->sector_masks[si];
+    if (mask == 0 && !m->sector_voxels[si]) return 5; /* sector not in the map            */
+    /* NOTE: a sector present with an all-zero mask also steps 32 here; the reference would
+     * step 8 brick by brick through it.  vrt_sync never reports such a sector as present
+     * (the adapter erases empty sectors like RegionDispatchSIMD does, VoxelMap.h:254-262). */
+    if (mask == 0) return 5;
+    uint32_t bi = ((uint32_t)(x >> 3) & 3) | (((uint32_t)(z >> 3) & 3) << 2) | (((uint32_t)(y >> 3) & 3) << 4);
+    if (!((mask >> bi) & 1)) return 3;
+    uint32_t vi = ((uint32_t)x & 7) | (((uint32_t)z & 7) << 3) | (((uint32_t)y & 7) << 6);
+    return m->sector_voxels[si][bi * 512 + vi] == 0 ? 0 : -1;
+}
+
+static void hit_query_one(const OrcMap* m, const double o[3], const double d[3], uint32_t max_iters, VrtHitD* out) {
+    double inv[3], ts[3];
+    int32_t pos[3];
+    for (int a = 0; a < 3; a++) {
+        inv[a] = 1.0 / d[a];                                   /* :141 */
+        ts[a] = ((d[a] < 0.0 ? 0.0 : 1.0) - o[a]) * inv[a];    /* :142 step(0,dir) */
+        pos[a] = (int32_t)floor(o[a]);                         /* :143 */
+    }
+    memset(out, 0, sizeof(*out));
+    out->dist = -1.0;
+    for (uint32_t i = 0; i < max_iters; i++) {
+        double sd[3], hp[3];
+        for (int a = 0; a < 3; a++) sd[a] = fma((double)pos[a], inv[a], ts[a]); /* :146 */
+        double tmin = glm_min(glm_min(sd[0], sd[1]), sd[2]) + 0.0001;           /* :147 */
+        for (int a = 0; a < 3; a++) {
+            hp[a] = fma(tmin, d[a], o[a]);                                      /* :148 */
+            double f = floor(hp[a]);
+            pos[a] = (f >= -2147483648.0 && f < 2147483648.0) ? (int32_t)f : INT32_MIN; /* :149 */
+        }
+        int k = step_level(m, pos[0], pos[1], pos[2]); /* :151 */
+        if (k < 0) {                                   /* :153-162 */
+            int smx = tmin >= sd[0], smy = tmin >= sd[1], smz = tmin >= sd[2];
+            out->dist = tmin;
+            out->nx = smx ? (float)-((d[0] > 0.0) - (d[0] < 0.0)) : 0.0f;
+            out->ny = smy ? (float)-((d[1] > 0.0) - (d[1] < 0.0)) : 0.0f;
+            out->nz = smz ? (float)-((d[2] > 0.0) - (d[2] < 0.0)) : 0.0f;
+            float fu = smx ? (float)hp[1] : (float)hp[0];
+            float fv = smz ? (float)hp[1] : (float)hp[2];
+            out->u = fu - floorf(fu);
+            out->v = fv - floorf(fv);
+            out->vx = pos[0];
+            out->vy = pos[1];
+            out->vz = pos[2];
+            out->iters = i + 1;
+            return;
+        }
+        int32_t mk = (1 << k) - 1; /* :164-167 */
+        for (int a = 0; a < 3; a++) pos[a] = d[a] < 0.0 ? (pos[a] & ~mk) : (pos[a] | mk);
+    }
+    out->iters = max_iters;
+}
+
+void orc_hit_query(const OrcMap* m, uint64_t n, const double* origin3, const double* dir3, uint32_t max_iters,
+                   VrtHitD* out, int threads) {
+    if (max_iters == 0) max_iters = 1024;
+#ifdef _OPENMP
+    if (threads <= 0) threads = omp_get_max_threads();
+#pragma omp parallel for num_threads(threads) schedule(dynamic, 256)
+#endif
+    for (int64_t i = 0; i < (int64_t)n; i++) hit_query_one(m, origin3 + 3 * i, dir3 + 3 * i, max_iters, &out[i]);
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/* Ray generation and shading                                                                  */
+/* ------------------------------------------------------------------------------------------ */
+/* simd::TransformVector, LibGlimpsw/SwRast/SIMD.h:207-214; m is column-major (glm::mat4) */
+static inline void transform_vec4(const float m[16], const float v[4], float r[4]) {
+    for (int row = 0; row < 4; row++)
+        r[row] = fmaf(m[0 + row], v[0], fmaf(m[4 + row], v[1], fmaf(m[8 + row], v[2], m[12 + row] * v[3])));
+}
+/* simd::normalize, SIMD.h:109-115 (approx_rsqrt -> canonical 1/sqrt) */
+static inline void normalize3(float a[3]) {
+    float len = canon_rsqrt(fmaf(a[0], a[0], fmaf(a[1], a[1], a[2] * a[2])));
+    a[0] *= len;
+    a[1] *= len;
+    a[2] *= len;
+}
+
+/* GetPrimaryRay (CpuRenderer.cpp:226-233) with u = x + 0.5, v = y + 0.5 (:327,330) and
+ * origin += OriginFrac (:334).  The half-pixel offset is applied a second time inside
+ * inv_proj (GBuffer.h:137) — quirk Q9, kept. */
+void orc_primary_ray(const VrtFrame* f, uint32_t x, uint32_t y, float origin[3], float dir[3]) {
+    float uv[4] = {(float)(int32_t)x + 0.5f, (float)(int32_t)y + 0.5f, 0.0f, 1.0f};
+    float nearp[4], farp[4];
+    transform_vec4(f->inv_proj, uv, nearp);                             /* :227 */
+    for (int a = 0; a < 4; a++) farp[a] = nearp[a] + f->inv_proj[8 + a]; /* :228 */
+    float rn = 1.0f / nearp[3], rf = 1.0f / farp[3];
+    for (int a = 0; a < 3; a++) {
+        origin[a] = nearp[a] * rn; /* :229 */
+        dir[a] = farp[a] * rf;     /* :230 */
+    }
+    normalize3(dir); /* :232 */
+    for (int a = 0; a < 3; a++) origin[a] = origin[a] + f->origin_frac[a];
+}
+
+/* simd::sincos_2pi (AVX-512 branch), SIMD.h:175-190 */
+static inline void sincos_2pi(float x, float* s, float* c) {
+    float t = x + 0.25f;
+    float xr = t - nearbyintf(t); /* _mm512_reduce_ps(t, NEAREST) */
+    float x1 = fabsf(xr) - 0.25f;
+    float x2 = x1 * x1;
+    *s = x1 * fmaf(x2, -36.26749369f, 6.23786927f);
+    float cc = fmaf(x2, fmaf(x2, 57.34151006f, -19.56474772f), 0.99940322f);
+    *c = u2f(f2u(cc) | (f2u(xr) & 0x80000000u));
+}
+
+/* SampleDirection, CpuRenderer.cpp:273-291.  approx_sqrt(v) = rsqrt14(v) * v (SIMD_AVX512.h:140);
+ * v = 0 gives inf * 0 = NaN (quirk Q7) in the canonical form too. */
+void orc_sample_direction(float sx, float sy, float out[3]) {
+    float y = fmaf(sy, 2.0f, -1.0f); /* :284 (exact either way) */
+    float x, z;
+    sincos_2pi(sx, &x, &z);          /* :287 */
+    float v = fmaf(-y, y, 1.0f);     /* :288, 1 - y*y contracted */
+    float s = canon_rsqrt(v) * v;
+    out[0] = x * s;
+    out[1] = y;
+    out[2] = z * s;
+}
+
+/* VBlueNoise::Sample, CpuRenderer.cpp:254-270, for the 16-lane (4x4 tile) build: the R2 offset
+ * is applied to the tile origin and snapped to the tile grid; the lane keeps its in-tile
+ * position (quirk Q6). */
+void orc_blue_noise_sample(const OrcMap* m, uint32_t x, uint32_t y, uint32_t frame_no, uint32_t sample_idx, float out[2]) {
+    float fi = (float)sample_idx;
+    float ox = fi * 0.75487766624669276005f + 0.5f, oy = fi * 0.56984029099805326591f + 0.5f; /* :258 */
+    ox = ox - floorf(ox);
+    oy = oy - floorf(oy);
+    uint32_t px = ((x & ~3u) + (uint32_t)(ox * 128.0f)) & 127u; /* :259 */
+    uint32_t py = ((y & ~3u) + (uint32_t)(oy * 128.0f)) & 127u;
+    py += (frame_no & 63u) * 128u;                              /* :260 */
+    uint32_t tx = (px & ~3u) + (x & 3u), ty = (py & ~3u) + (y & 3u); /* :262-263 + ctor :242-250 */
+    const uint8_t* t = m->blue_noise + ((size_t)ty * 128 + tx) * 2;
+    out[0] = (float)t[0] * (float)(1.0 / 255); /* :269 */
+    out[1] = (float)t[1] * (float)(1.0 / 255);
+}
+
+/* R11G11B10f, LibGlimpsw/SwRast/Texture.h:150-205 */
+static inline float unpack_f11(uint32_t x) { return u2f(((x << 17) & 0x0FFE0000u) + 0x38000000u); }
+static inline float unpack_f10(uint32_t x) { return u2f(((x << 18) & 0x0FFC0000u) + 0x38000000u); }
+uint32_t orc_pack_r11g11b10f(float r, float g, float b) {
+    r = x86_min(x86_max(r, 1.0f / (1 << 15)), 130048.0f);
+    g = x86_min(x86_max(g, 1.0f / (1 << 15)), 130048.0f);
+    b = x86_min(x86_max(b, 1.0f / (1 << 15)), 129024.0f);
+    uint32_t pr = (((uint32_t)((int32_t)f2u(r) >> 17)) & 0x3FFFu) - 0x1C00u;
+    uint32_t pg = (((uint32_t)((int32_t)f2u(g) >> 17)) & 0x3FFFu) - 0x1C00u;
+    uint32_t pb = (((uint32_t)((int32_t)f2u(b) >> 18)) & 0x1FFFu) - 0x0E00u;
+    return (pr << 21) | (pg << 10) | pb;
+}
+
+/* texutil::ProjectCubemap (Texture.h:264-288) + Texture2D::Sample<Nearest,…,IsCube>
+ * (Texture.h:487-545) at an integer mip + the x3 of CpuRenderer.cpp:355-356. */
+void orc_sky_sample(const OrcMap* m, const float dir[3], uint32_t mip, float out[3]) {
+    if (!m->sky_texels) {
+        out[0] = out[1] = out[2] = 0.0f;
+        return;
+    }
+    float w = dir[0];
+    int wy = fabsf(dir[1]) > fabsf(w);
+    w = wy ? dir[1] : w;
+    int wz = fabsf(dir[2]) > fabsf(w);
+    w = wz ? dir[2] : w;
+    int wx = wy | wz;
+    wy &= !wz;
+    uint32_t face = wz ? 4u : (wy ? 2u : 0u);
+    face += f2u(w) >> 31;
+    w = canon_rcp(fabsf(w)) * 0.5f; /* approx_rcp -> canonical */
+    float u = fmaf(wx ? dir[0] : dir[2], w, 0.5f);
+    float v = fmaf(wy ? dir[2] : dir[1], w, 0.5f);
+
+    const VrtSkyDesc* s = &m->sky;
+    int32_t mask_lerp = (int32_t)(s->face_size << 8) - 1;
+    float scale_lerp = (float)(mask_lerp + 1);
+    int32_t ix = x86_round2i(u * scale_lerp), iy = x86_round2i(v * scale_lerp);
+    ix = ix < 0 ? 0 : (ix > mask_lerp ? mask_lerp : ix); /* cube sample clamps (Texture.h:493-495) */
+    iy = iy < 0 ? 0 : (iy > mask_lerp ? mask_lerp : iy);
+    uint32_t mlev = mip < s->mip_levels ? mip : s->mip_levels - 1; /* :506 */
+    uint32_t row_shift = (uint32_t)__builtin_ctz(s->face_size);
+    uint32_t stride = row_shift - mlev;
+    uint32_t off = (face << s->layer_shift) + s->mip_offset[mlev];
+    ix = (ix >> mlev) >> 8;
+    iy = (iy >> mlev) >> 8;
+    uint32_t texel = m->sky_texels[off + (uint32_t)ix + ((uint32_t)iy << stride)];
+    out[0] = unpack_f11(texel >> 21) * 3.0f;
+    out[1] = unpack_f11(texel >> 10) * 3.0f;
+    out[2] = unpack_f10(texel) * 3.0f;
+}
+
+/* RGBA8u::Pack, Texture.h:41-62: round2i(v*255), packs (i32->i16 signed sat), packus (->u8) */
+static inline uint32_t pack_unorm8(float v) {
+    int32_t i = x86_round2i(v * 255.0f);
+    if (i < -32768) i = -32768;
+    if (i > 32767) i = 32767;
+    return (uint32_t)(i < 0 ? 0 : (i > 255 ? 255 : i));
+}
+
+/* RenderRow body for one pixel, CpuRenderer.cpp:326-402 (lane-wise: a lane whose mask bit is
+ * off does nothing further — the packet-coupled leftovers are listed in DESIGN.md §3). */
+static void render_pixel(const OrcMap* m, const VrtFrame* f, uint32_t x, uint32_t y, uint32_t* o_albedo, float* o_depth,
+                         uint32_t* o_rg, uint32_t* o_bx, VrtHit* aux, OrcStats* stats) {
+    float origin[3], dir[3];
+    orc_primary_ray(f, x, y, origin, dir); /* :327-334 */
+    uint32_t max_iters = f->max_iters ? f->max_iters : VRT_MAX_ITERS_DEFAULT;
+
+    uint32_t albedo = 0;
+    float depth = 0.0f;
+    float irr[3] = {0, 0, 0}, thr[3] = {1, 1, 1}; /* :338-339 */
+
+    for (uint32_t i = 0; i <= f->bounces; i++) { /* :342 */
+        VrtHit hit;
+        CastCounters c = {0, 0, 0};
+        cast_ray(m, origin, dir, f->world_origin, max_iters, &hit, &c); /* :343 */
+        if (stats) stats_add(stats, &c, &hit);
+        if (i == 0 && aux) *aux = hit;
+
+        uint32_t md = hit.material;
+        /* VHitResult::GetColor / GetEmissionStrength, :97-107 */
+        float col[3] = {(float)((md >> 11) & 31) * (1.0f / 31), (float)((md >> 5) & 63) * (1.0f / 63),
+                        (float)(md & 31) * (1.0f / 31)};
+        for (int a = 0; a < 3; a++) col[a] = col[a] * col[a];
+        float emission = f16_to_f32((uint16_t)(md >> 16));
+
+        int is_hit = (hit.flags & VRT_HIT_HIT) != 0;
+        if (!is_hit) { /* :348-369 */
+            float sky[3];
+            orc_sky_sample(m, dir, i == 0 ? 1 : 3, sky);
+            if (i == 0) {
+                irr[0] = sky[0];
+                irr[1] = sky[1];
+                irr[2] = sky[2];
+            } else {
+                col[0] = sky[0];
+                col[1] = sky[1];
+                col[2] = sky[2];
+                emission = 1.0f;
+            }
+        }
+        int nx = (int)(hit.flags & 3) - 1, ny = (int)((hit.flags >> 2) & 3) - 1, nz = (int)((hit.flags >> 4) & 3) - 1;
+        if (i == 0) { /* :370-382 */
+            albedo = pack_unorm8(col[0]) | (pack_unorm8(col[1]) << 8) | (pack_unorm8(col[2]) << 16) | (pack_unorm8(0.0f) << 24);
+            albedo |= (uint32_t)(nx + 1) << 24;
+            albedo |= (uint32_t)(ny + 1) << 26;
+            albedo |= (uint32_t)(nz + 1) << 28;
+            float pp[4] = {hit.px / 16.0f, hit.py / 16.0f, hit.pz / 16.0f, 1.0f}, pr[4];
+            transform_vec4(f->proj, pp, pr);
+            depth = !is_hit ? -1.0f : pr[2] / pr[3];
+            if (f->bounces == 0) {
+                irr[0] = irr[1] = irr[2] = 1.0f;
+                break;
+            }
+        } else {
+            for (int a = 0; a < 3; a++) thr[a] = thr[a] * col[a]; /* :384 */
+        }
+        for (int a = 0; a < 3; a++) irr[a] = fmaf(thr[a], emission, irr[a]); /* :386 */
+        if (!is_hit) break;                                                /* :387 mask &= hit.Mask */
+
+        float nrm[3] = {(float)nx, (float)ny, (float)nz};
+        origin[0] = fmaf(nrm[0], 0.01f, hit.px); /* :389 */
+        origin[1] = fmaf(nrm[1], 0.01f, hit.py);
+        origin[2] = fmaf(nrm[2], 0.01f, hit.pz);
+        float bn[2], sdv[3];
+        orc_blue_noise_sample(m, x, y, f->frame_no, i, bn); /* :391 */
+        orc_sample_direction(bn[0], bn[1], sdv);
+        for (int a = 0; a < 3; a++) dir[a] = nrm[a] + sdv[a]; /* :392 */
+        normalize3(dir);
+    }
+    *o_albedo = albedo;
+    *o_depth = depth;
+    *o_rg = (uint32_t)f32_to_f16(irr[0]) | ((uint32_t)f32_to_f16(irr[1]) << 16); /* :398 */
+    uint32_t hz = f32_to_f16(irr[2]);
+    *o_bx = hz | (hz << 16); /* :399 Pack({z}) -> VFloat2(v){x=y=v} (SIMD.h:32) */
+}
+
+void orc_render(const OrcMap* m, const VrtFrame* f, void* out, VrtHit* aux_hits, OrcStats* stats, int threads,
+                uint32_t row0, uint32_t row1) {
+    uint32_t w = f->width, h = f->height;
+    if (row1 > h) row1 = h;
+    OrcStats total;
+    memset(&total, 0, sizeof(total));
+    uint32_t part_count = f->part_count ? f->part_count : 1;
+    uint32_t tiles_x = (w + 31) / 32;
+#ifdef _OPENMP
+    if (threads <= 0) threads = omp_get_max_threads();
+#pragma omp parallel num_threads(threads)
+#endif
+    {
+        OrcStats local;
+        memset(&local, 0, sizeof(local));
+#ifdef _OPENMP
+#pragma omp for schedule(dynamic, 1)
+#endif
+        for (int64_t ty = row0 / 4; ty < (int64_t)(row1 / 4); ty++) { /* :455-462 one tile row */
+            for (uint32_t x = 0; x < w; x++) {
+                for (uint32_t yy = 0; yy < 4; yy++) {
+                    uint32_t y = (uint32_t)ty * 4 + yy;
+                    if (part_count > 1) {
+                        uint32_t t = (y / 32) * tiles_x + (x / 32);
+                        if (t % part_count != f->part_index) continue;
+                    }
+                    uint32_t alb, rg, bx;
+                    float dep;
+                    render_pixel(m, f, x, y, &alb, &dep, &rg, &bx, aux_hits ? &aux_hits[(size_t)y * w + x] : NULL,
+                                 stats ? &local : NULL);
+                    if (f->flags & VRT_FRAME_LINEAR_OUTPUT) {
+                        uint32_t* o = (uint32_t*)out;
+                        size_t n = (size_t)w * h, p = (size_t)y * w + x;
+                        o[p] = alb;
+                        memcpy(&o[n + p], &dep, 4);
+                        o[2 * n + p] = rg;
+                        o[3 * n + p] = bx;
+                    } else { /* Framebuffer::Tile, :299-309, tile = (y/4)*TileStride + x/4 (:459) */
+                        VrtTile* t = (VrtTile*)out + ((size_t)(y / 4) * (w / 4) + x / 4);
+                        uint32_t lane = (x & 3) | ((y & 3) << 2);
+                        t->albedo[lane] = alb;
+                        t->depth[lane] = dep;
+                        t->irr_rg[lane] = rg;
+                        t->irr_bx[lane] = bx;
+                    }
+                }
+            }
+        }
+#ifdef _OPENMP
+#pragma omp critical
+#endif
+        stats_merge(&total, &local);
+    }
+    if (stats) *stats = total;
+}

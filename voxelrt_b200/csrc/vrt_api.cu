@@ -1,0 +1,732 @@
+// C ABI of libvoxelrt_b200.so (include/voxelrt_b200.h): context, brickmap residency with
+// sparse brick slots and dirty-brick delta upload, and the launches of the traversal kernels.
+// Host side of the reference this replaces: FlatVoxelStorage / GpuVoxelStorage::SyncBuffers
+// (src/VoxelRT/CpuRenderer.cpp:33-61, GpuRenderer.cpp:45-167) and the body of
+// CpuRenderer::RenderFrame (CpuRenderer.cpp:415-464).
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "slot_allocator.h"
+#include "vrt_kernels.cuh"
+
+using namespace vrt;
+
+namespace {
+
+thread_local std::string g_create_error;
+
+struct DeviceBuffer {
+    void* p = nullptr;
+    size_t bytes = 0;
+};
+
+}  // namespace
+
+struct VrtContext {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev_sync = nullptr;    // end of the last vrt_sync / upload work on `stream`
+    cudaEvent_t ev_render = nullptr;  // end of the last render/trace on a caller stream
+    bool render_pending = false;
+
+    uint32_t sxz = 6, sy = 4, n_sectors = 0;
+    // resident brickmap
+    uint4* d_hdr = nullptr;
+    uint2* d_cells = nullptr;
+    uint8_t* d_voxels = nullptr;
+    uint2* d_palette = nullptr;
+    RangeArena arena;
+    std::vector<SectorSlots> sectors;  // host mirror of d_hdr
+    uint64_t resident_sectors = 0;
+    bool have_palette = false;
+
+    // staging (pinned host + device), grown on demand
+    uint8_t* h_stage = nullptr;
+    size_t h_stage_bytes = 0;
+    DeviceBuffer d_stage;
+    // scratch for the host-pointer entry points
+    DeviceBuffer d_rays_o, d_rays_d, d_hits, d_fb, d_aux, d_q_o, d_q_d, d_q_out;
+
+    // shading inputs
+    uint8_t* d_bn = nullptr;
+    uint32_t* d_sky = nullptr;
+    VrtSkyDesc sky{};
+
+    DevMetrics* d_metrics = nullptr;
+    bool metrics_on = false;
+    int render_variant = 0;
+
+    std::vector<void*> exported, imported;
+    VrtStats stats{};
+    std::string err;
+};
+
+namespace {
+
+int fail(VrtContext* c, int status, const std::string& msg) {
+    if (c) c->err = msg;
+    else g_create_error = msg;
+    return status;
+}
+
+#define CU(call)                                                                                              \
+    do {                                                                                                      \
+        cudaError_t e__ = (call);                                                                             \
+        if (e__ != cudaSuccess)                                                                               \
+            return fail(ctx, VRT_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e__));              \
+    } while (0)
+
+struct DeviceGuard {
+    int prev = -1;
+    explicit DeviceGuard(int dev) {
+        cudaGetDevice(&prev);
+        if (prev != dev) cudaSetDevice(dev);
+        else prev = -1;
+    }
+    ~DeviceGuard() {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+
+int ensure(VrtContext* ctx, DeviceBuffer& b, size_t bytes) {
+    if (b.bytes >= bytes) return VRT_OK;
+    if (b.p) {
+        CU(cudaStreamSynchronize(ctx->stream));
+        CU(cudaFree(b.p));
+        ctx->stats.device_bytes -= b.bytes;
+        b.p = nullptr;
+        b.bytes = 0;
+    }
+    size_t want = std::max(bytes, (size_t)1 << 16);
+    CU(cudaMalloc(&b.p, want));
+    b.bytes = want;
+    ctx->stats.device_bytes += want;
+    return VRT_OK;
+}
+
+int ensure_host_stage(VrtContext* ctx, size_t bytes) {
+    if (ctx->h_stage_bytes >= bytes) return VRT_OK;
+    if (ctx->h_stage) {
+        CU(cudaStreamSynchronize(ctx->stream));
+        CU(cudaFreeHost(ctx->h_stage));
+        ctx->h_stage = nullptr;
+    }
+    size_t want = std::max(bytes + bytes / 2, (size_t)1 << 20);
+    CU(cudaMallocHost((void**)&ctx->h_stage, want));
+    ctx->h_stage_bytes = want;
+    return VRT_OK;
+}
+
+// (Re)allocates the brick arena on the device to `capacity` slots, keeping resident bricks.
+int resize_arena(VrtContext* ctx, uint32_t capacity) {
+    uint32_t old_cap = ctx->arena.capacity();
+    if (capacity <= old_cap && ctx->d_voxels) return VRT_OK;
+    uint8_t* nv = nullptr;
+    uint2* nc = nullptr;
+    cudaError_t e = cudaMalloc((void**)&nv, (size_t)capacity * 512);
+    if (e == cudaSuccess) e = cudaMalloc((void**)&nc, (size_t)capacity * 64);
+    if (e != cudaSuccess) {
+        if (nv) cudaFree(nv);
+        cudaGetLastError();
+        return fail(ctx, VRT_ERR_OOM, "Could not allocate brick slots");  // BrickSlotAllocator.cpp:15
+    }
+    if (ctx->d_voxels) {
+        uint32_t used = ctx->arena.high_water();
+        CU(cudaMemcpyAsync(nv, ctx->d_voxels, (size_t)used * 512, cudaMemcpyDeviceToDevice, ctx->stream));
+        CU(cudaMemcpyAsync(nc, ctx->d_cells, (size_t)used * 64, cudaMemcpyDeviceToDevice, ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));
+        if (ctx->render_pending) CU(cudaEventSynchronize(ctx->ev_render));
+        CU(cudaFree(ctx->d_voxels));
+        CU(cudaFree(ctx->d_cells));
+        ctx->stats.device_bytes -= (size_t)old_cap * 576;
+    }
+    ctx->d_voxels = nv;
+    ctx->d_cells = nc;
+    ctx->stats.device_bytes += (size_t)capacity * 576;
+    if (old_cap == 0) ctx->arena.reset(capacity);
+    else ctx->arena.grow(capacity);
+    return VRT_OK;
+}
+
+DevScene dev_scene(const VrtContext* ctx) {
+    DevScene S;
+    S.hdr = ctx->d_hdr;
+    S.cells = ctx->d_cells;
+    S.voxels = ctx->d_voxels;
+    S.palette = ctx->d_palette;
+    S.sxz = ctx->sxz;
+    S.sy = ctx->sy;
+    S.lim_xz = 1u << (ctx->sxz + 5);
+    S.lim_y = 1u << (ctx->sy + 5);
+    return S;
+}
+
+// Orders work on a caller stream after the context's residency work, and vice versa.
+int begin_on_stream(VrtContext* ctx, cudaStream_t s) {
+    if (s != ctx->stream) CU(cudaStreamWaitEvent(s, ctx->ev_sync, 0));
+    return VRT_OK;
+}
+int end_on_stream(VrtContext* ctx, cudaStream_t s) {
+    if (s != ctx->stream) {
+        CU(cudaEventRecord(ctx->ev_render, s));
+        ctx->render_pending = true;
+    }
+    return VRT_OK;
+}
+
+int launch_trace(VrtContext* ctx, uint64_t n, const float* d_o, const float* d_d, const int32_t wo[3], uint32_t max_iters, VrtHit* d_out,
+                 cudaStream_t s) {
+    if (n == 0) return VRT_OK;
+    if (max_iters == 0) max_iters = VRT_MAX_ITERS_DEFAULT;
+    DevScene S = dev_scene(ctx);
+    uint64_t blocks = (n + 127) / 128;
+    if (blocks > 0x7FFFFFFFull) return fail(ctx, VRT_ERR_INVALID, "too many rays for one launch");
+    if (ctx->metrics_on) {
+        CU(cudaMemsetAsync(ctx->d_metrics, 0, sizeof(DevMetrics), s));
+        k_trace<true><<<(unsigned)blocks, 128, 0, s>>>(S, d_o, d_d, wo[0], wo[1], wo[2], max_iters, n, d_out, ctx->d_metrics);
+    } else {
+        k_trace<false><<<(unsigned)blocks, 128, 0, s>>>(S, d_o, d_d, wo[0], wo[1], wo[2], max_iters, n, d_out, nullptr);
+    }
+    ctx->stats.last_launches = 1;
+    CU(cudaGetLastError());
+    return VRT_OK;
+}
+
+int launch_render(VrtContext* ctx, const VrtFrame* f, void* d_out, VrtHit* d_aux, cudaStream_t s) {
+    if (f->width == 0 || f->height == 0 || (f->width & 3u) || (f->height & 3u))
+        return fail(ctx, VRT_ERR_INVALID, "frame size must be a non-zero multiple of 4 (CpuRenderer.cpp:419)");
+    if (f->bounces > 7) return fail(ctx, VRT_ERR_INVALID, "bounces > 7");
+    if (f->bounces > 0 && ctx->d_bn == nullptr) return fail(ctx, VRT_ERR_STATE, "bounces > 0 needs vrt_set_blue_noise first");
+    uint32_t part_count = f->part_count ? f->part_count : 1;
+    if (f->part_index >= part_count) return fail(ctx, VRT_ERR_INVALID, "part_index >= part_count");
+
+    FrameParams F;
+    memset(&F, 0, sizeof(F));
+    F.width = f->width;
+    F.height = f->height;
+    memcpy(F.inv_proj, f->inv_proj, sizeof(F.inv_proj));
+    memcpy(F.proj, f->proj, sizeof(F.proj));
+    for (int a = 0; a < 3; a++) {
+        F.wo[a] = f->world_origin[a];
+        F.frac[a] = f->origin_frac[a];
+    }
+    F.frame_no = f->frame_no;
+    F.bounces = f->bounces;
+    F.max_iters = f->max_iters ? f->max_iters : VRT_MAX_ITERS_DEFAULT;
+    F.flags = f->flags;
+    F.part_index = f->part_index;
+    F.part_count = part_count;
+    for (uint32_t i = 0; i < 8; i++) {  // CpuRenderer.cpp:258-259, scalar glm on the host there too
+        volatile float fi = (float)i;
+        volatile float ox = fi * 0.75487766624669276005f, oy = fi * 0.56984029099805326591f;
+        float sx = ox + 0.5f, sy = oy + 0.5f;
+        sx -= floorf(sx);
+        sy -= floorf(sy);
+        F.bn_off[i][0] = (uint32_t)(sx * 128.0f);
+        F.bn_off[i][1] = (uint32_t)(sy * 128.0f);
+    }
+    F.bn = ctx->d_bn;
+    F.sky = ctx->d_sky;
+    if (ctx->d_sky) {
+        F.sky_face = ctx->sky.face_size;
+        F.sky_mips = ctx->sky.mip_levels;
+        F.sky_layer_shift = ctx->sky.layer_shift;
+        F.sky_row_shift = (uint32_t)__builtin_ctz(ctx->sky.face_size);
+        for (int i = 0; i < 16; i++) F.sky_mip_offset[i] = ctx->sky.mip_offset[i];
+    }
+    F.out = d_out;
+    F.aux = (f->flags & VRT_FRAME_AUX_HITS) ? d_aux : nullptr;
+    F.metrics = ctx->d_metrics;
+
+    uint32_t macros_x = (f->width + 31) / 32, macros_y = (f->height + 31) / 32;
+    uint32_t macros = macros_x * macros_y;
+    uint32_t my_macros = macros / part_count + ((macros % part_count) > f->part_index ? 1u : 0u);
+    F.n_work = my_macros * 32u;
+    if (F.n_work == 0) return VRT_OK;
+    DevScene S = dev_scene(ctx);
+    unsigned blocks = (F.n_work + 7) / 8;
+    if (ctx->metrics_on) {
+        CU(cudaMemsetAsync(ctx->d_metrics, 0, sizeof(DevMetrics), s));
+        k_render<true><<<blocks, 256, 0, s>>>(S, F);
+    } else {
+        k_render<false><<<blocks, 256, 0, s>>>(S, F);
+    }
+    ctx->stats.last_launches = 1;
+    CU(cudaGetLastError());
+    return VRT_OK;
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------
+// lifetime
+// ------------------------------------------------------------------------------------------------
+extern "C" int vrt_create(const VrtConfig* cfg, VrtContext** out) {
+    VrtContext* ctx = nullptr;  // for the CU macro: errors go to g_create_error
+    if (!cfg || !out) return fail(nullptr, VRT_ERR_INVALID, "null argument");
+    if (cfg->struct_size != sizeof(VrtConfig)) return fail(nullptr, VRT_ERR_INVALID, "VrtConfig.struct_size mismatch");
+    if (cfg->sectors_xz_log2 < 1 || cfg->sectors_xz_log2 > 10 || cfg->sectors_y_log2 < 1 || cfg->sectors_y_log2 > 10 ||
+        2 * cfg->sectors_xz_log2 + cfg->sectors_y_log2 > 26)
+        return fail(nullptr, VRT_ERR_INVALID, "view extent out of range");
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return fail(nullptr, VRT_ERR_CUDA,
+                    std::string("no CUDA device (") + cudaGetErrorString(e) + "); this library has no CPU fallback");
+    int dev = cfg->device;
+    if (dev < 0) CU(cudaGetDevice(&dev));
+    if (dev >= ndev) return fail(nullptr, VRT_ERR_INVALID, "device ordinal out of range");
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, dev));
+    if (prop.major < 10)
+        return fail(nullptr, VRT_ERR_UNSUPPORTED, std::string("device ") + prop.name + " is not sm_100+; built for sm_100a only");
+
+    VrtContext* c = new VrtContext();
+    c->device = dev;
+    c->sxz = cfg->sectors_xz_log2;
+    c->sy = cfg->sectors_y_log2;
+    c->n_sectors = 1u << (2 * c->sxz + c->sy);
+    c->sectors.resize(c->n_sectors);
+    DeviceGuard g(dev);
+    ctx = c;
+    auto bail = [&](int st) {
+        g_create_error = c->err;
+        vrt_destroy(c);
+        return st;
+    };
+#define CUB(call)                                                                         \
+    do {                                                                                  \
+        cudaError_t e__ = (call);                                                         \
+        if (e__ != cudaSuccess) {                                                         \
+            c->err = std::string(#call) + ": " + cudaGetErrorString(e__);                 \
+            return bail(VRT_ERR_CUDA);                                                    \
+        }                                                                                 \
+    } while (0)
+    CUB(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    CUB(cudaEventCreateWithFlags(&c->ev_sync, cudaEventDisableTiming));
+    CUB(cudaEventCreateWithFlags(&c->ev_render, cudaEventDisableTiming));
+    CUB(cudaMalloc((void**)&c->d_hdr, (size_t)c->n_sectors * sizeof(uint4)));
+    CUB(cudaMemsetAsync(c->d_hdr, 0, (size_t)c->n_sectors * sizeof(uint4), c->stream));
+    CUB(cudaMalloc((void**)&c->d_palette, 256 * sizeof(uint2)));
+    CUB(cudaMemsetAsync(c->d_palette, 0, 256 * sizeof(uint2), c->stream));
+    CUB(cudaMalloc((void**)&c->d_metrics, sizeof(DevMetrics)));
+    CUB(cudaMemsetAsync(c->d_metrics, 0, sizeof(DevMetrics), c->stream));
+    c->stats.device_bytes = (size_t)c->n_sectors * sizeof(uint4) + 256 * sizeof(uint2) + sizeof(DevMetrics);
+    uint32_t cap = cfg->initial_brick_capacity ? cfg->initial_brick_capacity : (1u << 16);
+    int st = resize_arena(c, cap);
+    if (st != VRT_OK) return bail(st);
+    CUB(cudaEventRecord(c->ev_sync, c->stream));
+    CUB(cudaStreamSynchronize(c->stream));
+#undef CUB
+    *out = c;
+    return VRT_OK;
+}
+
+extern "C" void vrt_destroy(VrtContext* ctx) {
+    if (!ctx) return;
+    DeviceGuard g(ctx->device);
+    cudaDeviceSynchronize();
+    for (void* p : ctx->imported) cudaIpcCloseMemHandle(p);
+    for (void* p : ctx->exported) cudaFree(p);
+    DeviceBuffer* bufs[] = {&ctx->d_stage, &ctx->d_rays_o, &ctx->d_rays_d, &ctx->d_hits, &ctx->d_fb,
+                            &ctx->d_aux,   &ctx->d_q_o,    &ctx->d_q_d,    &ctx->d_q_out};
+    for (auto* b : bufs)
+        if (b->p) cudaFree(b->p);
+    if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
+    cudaFree(ctx->d_hdr);
+    cudaFree(ctx->d_cells);
+    cudaFree(ctx->d_voxels);
+    cudaFree(ctx->d_palette);
+    cudaFree(ctx->d_bn);
+    cudaFree(ctx->d_sky);
+    cudaFree(ctx->d_metrics);
+    if (ctx->ev_sync) cudaEventDestroy(ctx->ev_sync);
+    if (ctx->ev_render) cudaEventDestroy(ctx->ev_render);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    cudaGetLastError();
+    delete ctx;
+}
+
+extern "C" const char* vrt_last_error(const VrtContext* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+extern "C" int vrt_get_stats(const VrtContext* ctx, VrtStats* out) {
+    if (!ctx || !out) return VRT_ERR_INVALID;
+    *out = ctx->stats;
+    out->resident_bricks = ctx->arena.allocated();
+    out->brick_capacity = ctx->arena.capacity();
+    out->free_ranges = ctx->arena.free_ranges();
+    out->resident_sectors = ctx->resident_sectors;
+    return VRT_OK;
+}
+
+extern "C" int vrt_set_option(VrtContext* ctx, const char* name, int64_t value) {
+    if (!ctx || !name) return VRT_ERR_INVALID;
+    if (!strcmp(name, "metrics")) ctx->metrics_on = value != 0;
+    else if (!strcmp(name, "render_variant")) ctx->render_variant = (int)value;
+    else return fail(ctx, VRT_ERR_INVALID, std::string("unknown option ") + name);
+    return VRT_OK;
+}
+
+extern "C" int vrt_get_metrics(VrtContext* ctx, VrtTraversalMetrics* out) {
+    if (!ctx || !out) return VRT_ERR_INVALID;
+    DeviceGuard g(ctx->device);
+    CU(cudaDeviceSynchronize());
+    DevMetrics m;
+    CU(cudaMemcpy(&m, ctx->d_metrics, sizeof(m), cudaMemcpyDeviceToHost));
+    out->rays = m.rays;
+    out->iters = m.iters;
+    out->sector_fetches = m.sector_fetches;
+    out->cell_fetches = m.cell_fetches;
+    out->hits = m.hits;
+    out->capped = m.capped;
+    return VRT_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// residency
+// ------------------------------------------------------------------------------------------------
+extern "C" int vrt_set_palette(VrtContext* ctx, const uint64_t palette[256]) {
+    if (!ctx || !palette) return VRT_ERR_INVALID;
+    DeviceGuard g(ctx->device);
+    if (ctx->render_pending) CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_render, 0));
+    int st = ensure_host_stage(ctx, 256 * 8);
+    if (st) return st;
+    CU(cudaStreamSynchronize(ctx->stream));  // staging may still feed a previous copy
+    memcpy(ctx->h_stage, palette, 256 * 8);
+    CU(cudaMemcpyAsync(ctx->d_palette, ctx->h_stage, 256 * 8, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaEventRecord(ctx->ev_sync, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    ctx->have_palette = true;
+    return VRT_OK;
+}
+
+extern "C" int vrt_sync(VrtContext* ctx, uint32_t n, const VrtDirtySector* recs) {
+    if (!ctx || (n && !recs)) return VRT_ERR_INVALID;
+    DeviceGuard g(ctx->device);
+    ctx->stats.bytes_uploaded = ctx->stats.bricks_uploaded = ctx->stats.bricks_relocated = 0;
+    ctx->stats.last_launches = 0;
+    if (n == 0) return VRT_OK;
+
+    struct Upload {
+        const uint8_t* src;
+        uint32_t slot;
+    };
+    std::vector<Upload> uploads;
+    std::vector<uint2> moves;
+    std::vector<HeaderUpdate> headers;
+    uploads.reserve(n * 8);
+
+    for (uint32_t r = 0; r < n; r++) {
+        const VrtDirtySector& d = recs[r];
+        // ViewSectorIndexer::CheckInBounds -> continue (CpuRenderer.cpp:40, GpuRenderer.cpp:54-55)
+        if (((uint32_t)(d.sx | d.sz) >> ctx->sxz) != 0 || ((uint32_t)d.sy >> ctx->sy) != 0) continue;
+        uint32_t si = (uint32_t)d.sx | ((uint32_t)d.sz << ctx->sxz) | ((uint32_t)d.sy << (2 * ctx->sxz));
+        SectorSlots old = ctx->sectors[si];
+        uint64_t new_mask = (d.flags & VRT_SECTOR_REMOVED) ? 0ull : d.alloc_mask;  // GpuRenderer.cpp:59-67
+        uint64_t dirty = d.dirty_mask & new_mask;                                   // :62
+        if (dirty && !d.bricks) return fail(ctx, VRT_ERR_INVALID, "dirty bricks without payload");
+
+        SectorSlots cur = old;
+        if (new_mask != old.mask) {
+            uint32_t old_n = popcount64(old.mask), new_n = popcount64(new_mask);
+            // every new brick sorts after every resident one -> resident slots keep their place
+            bool appended = old.mask != 0 && (new_mask & old.mask) == old.mask &&
+                            (uint32_t)__builtin_ctzll(new_mask & ~old.mask) > 63u - (uint32_t)__builtin_clzll(old.mask);
+            if (new_n == 0) {
+                ctx->arena.quarantine(old.base, old_n);
+                cur.base = 0;
+            } else if (appended && ctx->arena.extend(old.base, old_n, new_n)) {
+                // new bricks all sort after the resident ones: the range grows in place, nothing moves
+            } else {
+                uint32_t base = ctx->arena.alloc(new_n);
+                while (base == RangeArena::kNone) {
+                    uint64_t want = std::max<uint64_t>((uint64_t)ctx->arena.capacity() * 2, (uint64_t)ctx->arena.capacity() + new_n);
+                    if (want > 0x7FFFFFFFull) return fail(ctx, VRT_ERR_OOM, "Could not allocate brick slots");
+                    int st = resize_arena(ctx, (uint32_t)want);
+                    if (st) return st;
+                    base = ctx->arena.alloc(new_n);
+                }
+                cur.base = base;
+                // resident bricks that survive and are not re-sent move device-side
+                uint64_t keep = old.mask & new_mask & ~dirty;
+                SectorSlots nw{new_mask, base};
+                for (; keep; keep &= keep - 1) {
+                    uint32_t b = (uint32_t)__builtin_ctzll(keep);
+                    moves.push_back(make_uint2(slot_of(old, b), slot_of(nw, b)));
+                }
+                if (old_n) ctx->arena.quarantine(old.base, old_n);
+            }
+            cur.mask = new_mask;
+            if ((old.mask == 0) != (new_mask == 0)) ctx->resident_sectors += new_mask ? 1 : -1;
+            ctx->sectors[si] = cur;
+            headers.push_back(HeaderUpdate{si, (uint32_t)new_mask, (uint32_t)(new_mask >> 32), cur.base});
+        }
+        const uint8_t* src = d.bricks;
+        // payload order: ascending bit order over dirty_mask & alloc_mask
+        for (uint64_t m = dirty; m; m &= m - 1) {
+            uint32_t b = (uint32_t)__builtin_ctzll(m);
+            uploads.push_back(Upload{src, slot_of(cur, b)});
+            src += 512;
+        }
+    }
+
+    // previous frame may still read the arena from a caller stream
+    if (ctx->render_pending) CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_render, 0));
+
+    size_t nu = uploads.size(), nm = moves.size(), nh = headers.size();
+    size_t off_slots = nu * 512;
+    size_t off_moves = (off_slots + nu * 4 + 15) & ~(size_t)15;
+    size_t off_hdrs = (off_moves + nm * 8 + 15) & ~(size_t)15;
+    size_t total = off_hdrs + nh * sizeof(HeaderUpdate);
+    if (total) {
+        int st = ensure_host_stage(ctx, total);
+        if (st) return st;
+        st = ensure(ctx, ctx->d_stage, total);
+        if (st) return st;
+        CU(cudaStreamSynchronize(ctx->stream));  // the pinned buffer is single-buffered
+        uint32_t* slots = reinterpret_cast<uint32_t*>(ctx->h_stage + off_slots);
+        for (size_t i = 0; i < nu; i++) {
+            memcpy(ctx->h_stage + i * 512, uploads[i].src, 512);
+            slots[i] = uploads[i].slot;
+        }
+        if (nm) memcpy(ctx->h_stage + off_moves, moves.data(), nm * 8);
+        if (nh) memcpy(ctx->h_stage + off_hdrs, headers.data(), nh * sizeof(HeaderUpdate));
+        CU(cudaMemcpyAsync(ctx->d_stage.p, ctx->h_stage, total, cudaMemcpyHostToDevice, ctx->stream));
+        uint8_t* ds = reinterpret_cast<uint8_t*>(ctx->d_stage.p);
+        if (nm) {
+            k_move_bricks<<<(unsigned)((nm + 7) / 8), 256, 0, ctx->stream>>>(reinterpret_cast<const uint2*>(ds + off_moves), (uint32_t)nm,
+                                                                             ctx->d_voxels, ctx->d_cells);
+            ctx->stats.last_launches++;
+        }
+        if (nu) {
+            k_upload_bricks<<<(unsigned)((nu + 7) / 8), 256, 0, ctx->stream>>>(reinterpret_cast<const uint4*>(ds),
+                                                                               reinterpret_cast<const uint32_t*>(ds + off_slots), (uint32_t)nu,
+                                                                               ctx->d_voxels, ctx->d_cells);
+            ctx->stats.last_launches++;
+        }
+        if (nh) {
+            k_write_headers<<<(unsigned)((nh + 255) / 256), 256, 0, ctx->stream>>>(reinterpret_cast<const HeaderUpdate*>(ds + off_hdrs),
+                                                                                  (uint32_t)nh, ctx->d_hdr);
+            ctx->stats.last_launches++;
+        }
+        CU(cudaGetLastError());
+    }
+    ctx->arena.flush_quarantine();
+    CU(cudaEventRecord(ctx->ev_sync, ctx->stream));
+    ctx->stats.bytes_uploaded = total;
+    ctx->stats.bricks_uploaded = nu;
+    ctx->stats.bricks_relocated = nm;
+    return VRT_OK;
+}
+
+extern "C" int vrt_read_sector(VrtContext* ctx, int32_t sx, int32_t sy, int32_t sz, uint64_t* out_alloc_mask, uint32_t* out_base_slot,
+                               uint8_t* out_bricks, uint64_t* out_cells) {
+    if (!ctx) return VRT_ERR_INVALID;
+    if (((uint32_t)(sx | sz) >> ctx->sxz) != 0 || ((uint32_t)sy >> ctx->sy) != 0) return fail(ctx, VRT_ERR_INVALID, "sector outside the view");
+    DeviceGuard g(ctx->device);
+    CU(cudaStreamSynchronize(ctx->stream));
+    uint32_t si = (uint32_t)sx | ((uint32_t)sz << ctx->sxz) | ((uint32_t)sy << (2 * ctx->sxz));
+    uint4 h;
+    CU(cudaMemcpy(&h, ctx->d_hdr + si, sizeof(h), cudaMemcpyDeviceToHost));  // the DEVICE copy is what is inspected
+    uint64_t mask = (uint64_t)h.x | ((uint64_t)h.y << 32);
+    if (out_alloc_mask) *out_alloc_mask = mask;
+    if (out_base_slot) *out_base_slot = h.z;
+    if (out_bricks) memset(out_bricks, 0, 64 * 512);
+    if (out_cells) memset(out_cells, 0, 64 * 8 * sizeof(uint64_t));
+    uint32_t k = 0;
+    for (uint64_t m = mask; m; m &= m - 1, k++) {
+        uint32_t b = (uint32_t)__builtin_ctzll(m);
+        if (out_bricks) CU(cudaMemcpy(out_bricks + b * 512, ctx->d_voxels + (size_t)(h.z + k) * 512, 512, cudaMemcpyDeviceToHost));
+        if (out_cells) CU(cudaMemcpy(out_cells + b * 8, ctx->d_cells + (size_t)(h.z + k) * 8, 64, cudaMemcpyDeviceToHost));
+    }
+    return VRT_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// ray cast / hit query
+// ------------------------------------------------------------------------------------------------
+extern "C" int vrt_trace_device(VrtContext* ctx, uint64_t n, const float* d_origin3, const float* d_dir3, const int32_t wo[3],
+                                uint32_t max_iters, VrtHit* d_out, void* stream) {
+    if (!ctx || !wo || (n && (!d_origin3 || !d_dir3 || !d_out))) return VRT_ERR_INVALID;
+    DeviceGuard g(ctx->device);
+    cudaStream_t s = stream ? (cudaStream_t)stream : ctx->stream;
+    int st = begin_on_stream(ctx, s);
+    if (st) return st;
+    st = launch_trace(ctx, n, d_origin3, d_dir3, wo, max_iters, d_out, s);
+    if (st) return st;
+    return end_on_stream(ctx, s);
+}
+
+extern "C" int vrt_trace(VrtContext* ctx, uint64_t n, const float* origin3, const float* dir3, const int32_t wo[3], uint32_t max_iters,
+                         VrtHit* out) {
+    if (!ctx || !wo || (n && (!origin3 || !dir3 || !out))) return VRT_ERR_INVALID;
+    if (n == 0) return VRT_OK;
+    DeviceGuard g(ctx->device);
+    int st;
+    if ((st = ensure(ctx, ctx->d_rays_o, n * 12))) return st;
+    if ((st = ensure(ctx, ctx->d_rays_d, n * 12))) return st;
+    if ((st = ensure(ctx, ctx->d_hits, n * sizeof(VrtHit)))) return st;
+    CU(cudaMemcpyAsync(ctx->d_rays_o.p, origin3, n * 12, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemcpyAsync(ctx->d_rays_d.p, dir3, n * 12, cudaMemcpyHostToDevice, ctx->stream));
+    st = launch_trace(ctx, n, (const float*)ctx->d_rays_o.p, (const float*)ctx->d_rays_d.p, wo, max_iters, (VrtHit*)ctx->d_hits.p, ctx->stream);
+    if (st) return st;
+    CU(cudaMemcpyAsync(out, ctx->d_hits.p, n * sizeof(VrtHit), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return VRT_OK;
+}
+
+extern "C" int vrt_hit_query(VrtContext* ctx, uint64_t n, const double* origin3, const double* dir3, uint32_t max_iters, VrtHitD* out) {
+    if (!ctx || (n && (!origin3 || !dir3 || !out))) return VRT_ERR_INVALID;
+    if (n == 0) return VRT_OK;
+    if (max_iters == 0) max_iters = 1024;  // VoxelMap.h:214
+    DeviceGuard g(ctx->device);
+    int st;
+    if ((st = ensure(ctx, ctx->d_q_o, n * 24))) return st;
+    if ((st = ensure(ctx, ctx->d_q_d, n * 24))) return st;
+    if ((st = ensure(ctx, ctx->d_q_out, n * sizeof(VrtHitD)))) return st;
+    CU(cudaMemcpyAsync(ctx->d_q_o.p, origin3, n * 24, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemcpyAsync(ctx->d_q_d.p, dir3, n * 24, cudaMemcpyHostToDevice, ctx->stream));
+    k_hit_query<<<(unsigned)((n + 127) / 128), 128, 0, ctx->stream>>>(dev_scene(ctx), (const double*)ctx->d_q_o.p, (const double*)ctx->d_q_d.p,
+                                                                     max_iters, n, (VrtHitD*)ctx->d_q_out.p);
+    ctx->stats.last_launches = 1;
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(out, ctx->d_q_out.p, n * sizeof(VrtHitD), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return VRT_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// shading inputs
+// ------------------------------------------------------------------------------------------------
+extern "C" int vrt_set_blue_noise(VrtContext* ctx, const uint8_t* rg, size_t bytes) {
+    if (!ctx || !rg) return VRT_ERR_INVALID;
+    if (bytes != VRT_BLUE_NOISE_BYTES) return fail(ctx, VRT_ERR_INVALID, "blue noise must be 128x128x64 (R,G) bytes");
+    DeviceGuard g(ctx->device);
+    if (!ctx->d_bn) {
+        CU(cudaMalloc((void**)&ctx->d_bn, VRT_BLUE_NOISE_BYTES));
+        ctx->stats.device_bytes += VRT_BLUE_NOISE_BYTES;
+    }
+    if (ctx->render_pending) CU(cudaEventSynchronize(ctx->ev_render));
+    CU(cudaMemcpyAsync(ctx->d_bn, rg, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaEventRecord(ctx->ev_sync, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return VRT_OK;
+}
+
+extern "C" int vrt_set_sky(VrtContext* ctx, const VrtSkyDesc* desc, const uint32_t* texels) {
+    if (!ctx || !desc || !texels) return VRT_ERR_INVALID;
+    if (desc->face_size < 4 || (desc->face_size & (desc->face_size - 1)) || desc->mip_levels == 0 || desc->mip_levels > 16)
+        return fail(ctx, VRT_ERR_INVALID, "bad sky descriptor");
+    DeviceGuard g(ctx->device);
+    if (ctx->render_pending) CU(cudaEventSynchronize(ctx->ev_render));
+    CU(cudaStreamSynchronize(ctx->stream));
+    if (ctx->d_sky) {
+        CU(cudaFree(ctx->d_sky));
+        ctx->stats.device_bytes -= ctx->sky.texel_count * 4;
+        ctx->d_sky = nullptr;
+    }
+    CU(cudaMalloc((void**)&ctx->d_sky, desc->texel_count * 4));
+    ctx->stats.device_bytes += desc->texel_count * 4;
+    CU(cudaMemcpyAsync(ctx->d_sky, texels, desc->texel_count * 4, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaEventRecord(ctx->ev_sync, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    ctx->sky = *desc;
+    return VRT_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// frame
+// ------------------------------------------------------------------------------------------------
+extern "C" int vrt_render_device(VrtContext* ctx, const VrtFrame* frame, void* d_out, VrtHit* d_aux, void* stream) {
+    if (!ctx || !frame || !d_out) return VRT_ERR_INVALID;
+    if ((frame->flags & VRT_FRAME_AUX_HITS) && !d_aux) return fail(ctx, VRT_ERR_INVALID, "VRT_FRAME_AUX_HITS without aux buffer");
+    DeviceGuard g(ctx->device);
+    cudaStream_t s = stream ? (cudaStream_t)stream : ctx->stream;
+    int st = begin_on_stream(ctx, s);
+    if (st) return st;
+    st = launch_render(ctx, frame, d_out, d_aux, s);
+    if (st) return st;
+    return end_on_stream(ctx, s);
+}
+
+extern "C" int vrt_render(VrtContext* ctx, const VrtFrame* frame, void* out, VrtHit* aux_hits) {
+    if (!ctx || !frame || !out) return VRT_ERR_INVALID;
+    if ((frame->flags & VRT_FRAME_AUX_HITS) && !aux_hits) return fail(ctx, VRT_ERR_INVALID, "VRT_FRAME_AUX_HITS without aux buffer");
+    DeviceGuard g(ctx->device);
+    size_t npx = (size_t)frame->width * frame->height;
+    int st;
+    if ((st = ensure(ctx, ctx->d_fb, npx * 16))) return st;
+    bool aux = (frame->flags & VRT_FRAME_AUX_HITS) != 0;
+    if (aux && (st = ensure(ctx, ctx->d_aux, npx * sizeof(VrtHit)))) return st;
+    uint32_t part_count = frame->part_count ? frame->part_count : 1;
+    if (part_count > 1) {  // pixels of other ranks stay zero in a partial frame
+        CU(cudaMemsetAsync(ctx->d_fb.p, 0, npx * 16, ctx->stream));
+        if (aux) CU(cudaMemsetAsync(ctx->d_aux.p, 0, npx * sizeof(VrtHit), ctx->stream));
+    }
+    st = launch_render(ctx, frame, ctx->d_fb.p, (VrtHit*)ctx->d_aux.p, ctx->stream);
+    if (st) return st;
+    CU(cudaMemcpyAsync(out, ctx->d_fb.p, npx * 16, cudaMemcpyDeviceToHost, ctx->stream));
+    if (aux) CU(cudaMemcpyAsync(aux_hits, ctx->d_aux.p, npx * sizeof(VrtHit), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return VRT_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// multi-GPU framebuffer sharing (CUDA IPC over NVLink peer mappings)
+// ------------------------------------------------------------------------------------------------
+extern "C" int vrt_fb_export(VrtContext* ctx, uint64_t bytes, uint8_t handle_out[64], void** d_ptr_out) {
+    if (!ctx || !handle_out || !d_ptr_out || bytes == 0) return VRT_ERR_INVALID;
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    DeviceGuard g(ctx->device);
+    void* p = nullptr;
+    CU(cudaMalloc(&p, bytes));
+    CU(cudaMemset(p, 0, bytes));
+    cudaIpcMemHandle_t h;
+    cudaError_t e = cudaIpcGetMemHandle(&h, p);
+    if (e != cudaSuccess) {
+        cudaFree(p);
+        return fail(ctx, VRT_ERR_CUDA, std::string("cudaIpcGetMemHandle: ") + cudaGetErrorString(e));
+    }
+    memcpy(handle_out, &h, 64);
+    ctx->exported.push_back(p);
+    ctx->stats.device_bytes += bytes;
+    *d_ptr_out = p;
+    return VRT_OK;
+}
+
+extern "C" int vrt_fb_import(VrtContext* ctx, const uint8_t handle[64], void** d_ptr_out) {
+    if (!ctx || !handle || !d_ptr_out) return VRT_ERR_INVALID;
+    DeviceGuard g(ctx->device);
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, 64);
+    void* p = nullptr;
+    CU(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+    ctx->imported.push_back(p);
+    *d_ptr_out = p;
+    return VRT_OK;
+}
+
+extern "C" int vrt_fb_release(VrtContext* ctx, void* d_ptr) {
+    if (!ctx || !d_ptr) return VRT_ERR_INVALID;
+    DeviceGuard g(ctx->device);
+    auto it = std::find(ctx->imported.begin(), ctx->imported.end(), d_ptr);
+    if (it != ctx->imported.end()) {
+        CU(cudaIpcCloseMemHandle(d_ptr));
+        ctx->imported.erase(it);
+        return VRT_OK;
+    }
+    it = std::find(ctx->exported.begin(), ctx->exported.end(), d_ptr);
+    if (it != ctx->exported.end()) {
+        CU(cudaDeviceSynchronize());
+        CU(cudaFree(d_ptr));
+        ctx->exported.erase(it);
+        return VRT_OK;
+    }
+    return fail(ctx, VRT_ERR_INVALID, "pointer not owned by this context");
+}

@@ -1,0 +1,234 @@
+// Kernels of the traversal path (sm_100a).  See DESIGN.md §5 for the launch shapes and the
+// roofline that bounds each one.
+#pragma once
+#include "vrt_shade.cuh"
+
+namespace vrt {
+
+// ---------------------------------------------------------------------------------------------
+// K_trace: explicit rays, one thread per ray.  Replaces the file-static RayCast
+// (CpuRenderer.cpp:172-224) for callers that bring their own rays.
+// ---------------------------------------------------------------------------------------------
+template <bool METRICS>
+__global__ void __launch_bounds__(128) k_trace(DevScene S, const float* __restrict__ origin3, const float* __restrict__ dir3, int wx,
+                                               int wy, int wz, uint32_t max_iters, uint64_t n, VrtHit* __restrict__ out,
+                                               DevMetrics* metrics) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    bool valid = i < n;
+    HitLane H;
+    CastResult R;
+    R.iters = R.n_sector = R.n_cell = 0;
+    R.capped = false;
+    H.hit = false;
+    if (valid) {
+        float ox = __ldg(origin3 + 3 * i), oy = __ldg(origin3 + 3 * i + 1), oz = __ldg(origin3 + 3 * i + 2);
+        float dx = __ldg(dir3 + 3 * i), dy = __ldg(dir3 + 3 * i + 1), dz = __ldg(dir3 + 3 * i + 2);
+        cast_ray(S, ox, oy, oz, dx, dy, dz, wx, wy, wz, max_iters, H, R);
+        store_hit(out + i, H, R);
+    }
+    if (METRICS) {
+        __syncwarp();
+        metrics_add(metrics, R, valid, valid && H.hit);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// K_render (v1): one warp per 8x4-pixel tile = two of the reference's 4x4 SIMD tiles side by
+// side, so lanes 0-15 / 16-31 fill one Framebuffer::Tile each (CpuRenderer.cpp:299-309) with
+// 64-byte coalesced stores.  Warp tiles are numbered inside 32x32-pixel macro tiles (the unit
+// of the multi-GPU screen split): macro tile t belongs to rank t % part_count.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ bool warp_tile_origin(const FrameParams& F, uint32_t work, uint32_t& x0, uint32_t& y0) {
+    uint32_t macro_local = work >> 5, sub = work & 31u;
+    uint32_t macro = macro_local * F.part_count + F.part_index;
+    uint32_t macros_x = (F.width + 31u) >> 5;
+    uint32_t mx = macro % macros_x, my = macro / macros_x;
+    x0 = (mx << 5) + ((sub & 3u) << 3);
+    y0 = (my << 5) + ((sub >> 2) << 2);
+    return x0 < F.width && y0 < F.height;
+}
+
+__device__ __forceinline__ void store_pixel(const FrameParams& F, uint32_t x, uint32_t y, const PixelOut& P) {
+    if (F.flags & VRT_FRAME_LINEAR_OUTPUT) {
+        uint32_t* o = reinterpret_cast<uint32_t*>(F.out);
+        size_t n = (size_t)F.width * F.height, p = (size_t)y * F.width + x;
+        o[p] = P.albedo;
+        o[n + p] = __float_as_uint(P.depth);
+        o[2 * n + p] = P.irr_rg;
+        o[3 * n + p] = P.irr_bx;
+    } else {
+        VrtTile* t = reinterpret_cast<VrtTile*>(F.out) + ((size_t)(y >> 2) * (F.width >> 2) + (x >> 2));
+        uint32_t lane = (x & 3u) | ((y & 3u) << 2);
+        t->albedo[lane] = P.albedo;
+        t->depth[lane] = P.depth;
+        t->irr_rg[lane] = P.irr_rg;
+        t->irr_bx[lane] = P.irr_bx;
+    }
+}
+
+template <bool METRICS>
+__global__ void __launch_bounds__(256) k_render(DevScene S, const __grid_constant__ FrameParams F) {
+    uint32_t work = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (work >= F.n_work) return;  // warp-uniform
+    uint32_t x0, y0;
+    if (!warp_tile_origin(F, work, x0, y0)) return;
+    uint32_t lane = threadIdx.x & 31u;
+    uint32_t x = x0 + ((lane >> 4) << 2) + (lane & 3u);
+    uint32_t y = y0 + ((lane >> 2) & 3u);
+    bool valid = x < F.width && y < F.height;
+    PixelOut P;
+    shade_pixel<METRICS>(S, F, x, y, valid, P);
+    if (valid) store_pixel(F, x, y, P);
+}
+
+// ---------------------------------------------------------------------------------------------
+// K_upload (K2): one warp per dirty brick.  Copies the 512 voxel bytes from the staging buffer
+// into the brick's slot and rebuilds its eight 4x4x4 occupancy masks
+// (FlatVoxelStorage::UpdateOccupancy, CpuRenderer.cpp:63-83; UpdateOccupancy.comp:8-34).
+// Lane l holds voxels [16 l, 16 l + 16): y = l>>2, z in {2(l&3), 2(l&3)+1}, x = 0..7.
+// Algorithmic bytes per brick: 512 read + 512 + 64 written (HBM-bound).
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_upload_bricks(const uint4* __restrict__ staging, const uint32_t* __restrict__ slots, uint32_t n,
+                                                       uint8_t* __restrict__ voxels, uint2* __restrict__ cells) {
+    uint32_t warp = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (warp >= n) return;
+    uint32_t lane = threadIdx.x & 31u;
+    uint32_t slot = __ldg(slots + warp);
+    uint4 v = __ldg(staging + (size_t)warp * 32u + lane);
+    reinterpret_cast<uint4*>(voxels + (size_t)slot * 512u)[lane] = v;
+
+    // non-zero byte -> 1 bit, 16 voxels -> 16 bits: bits 0-7 row z0 (x=0..7), bits 8-15 row z0+1
+    auto nz4 = [](uint32_t w) -> uint32_t {
+        uint32_t t = (w | (w >> 4)) & 0x0F0F0F0Fu;  // fold nibbles
+        t = (t | (t >> 2)) & 0x03030303u;
+        t = (t | (t >> 1)) & 0x01010101u;            // one bit per byte
+        return (t | (t >> 7) | (t >> 14) | (t >> 21)) & 0xFu;
+    };
+    uint32_t r0 = nz4(v.x) | (nz4(v.y) << 4);  // row z0: x 0..7
+    uint32_t r1 = nz4(v.z) | (nz4(v.w) << 4);  // row z0+1
+    // cell (cx, cz = (l>>1)&1, cy = l>>4); bit = vx + 4 vz + 16 vy, vz0 = 2(l&1), vy = (l>>2)&3
+    uint32_t shift = 8u * (lane & 1u) + 16u * ((lane >> 2) & 1u);  // within a 32-bit half
+    uint32_t c0 = ((r0 & 0xFu) | ((r1 & 0xFu) << 4)) << shift;     // cx = 0
+    uint32_t c1 = ((r0 >> 4) | ((r1 >> 4) << 4)) << shift;         // cx = 1
+    bool upper = (lane >> 3) & 1u;                                 // vy >= 2 -> high word
+    uint32_t c0lo = upper ? 0u : c0, c0hi = upper ? c0 : 0u, c1lo = upper ? 0u : c1, c1hi = upper ? c1 : 0u;
+    // OR over the 8 lanes that share (cz, cy): lane bits 0, 2, 3
+#pragma unroll
+    for (int o = 1; o <= 8; o <<= 1) {
+        if (o == 2) continue;
+        c0lo |= __shfl_xor_sync(0xFFFFFFFFu, c0lo, o);
+        c0hi |= __shfl_xor_sync(0xFFFFFFFFu, c0hi, o);
+        c1lo |= __shfl_xor_sync(0xFFFFFFFFu, c1lo, o);
+        c1hi |= __shfl_xor_sync(0xFFFFFFFFu, c1hi, o);
+    }
+    if ((lane & 0xDu) == 0u) {  // lanes 0, 2, 16, 18: one per (cz, cy)
+        uint32_t cz = (lane >> 1) & 1u, cy = lane >> 4;
+        uint2* c = cells + (size_t)slot * 8u + (cz << 1) + (cy << 2);
+        c[0] = make_uint2(c0lo, c0hi);
+        c[1] = make_uint2(c1lo, c1hi);
+    }
+}
+
+// K_move: device-side relocation of resident bricks when a sector's slot range changes (the
+// reference re-uploads the whole sector instead, BrickSlotAllocator.cpp:19-23).  One warp per
+// brick: 512 + 64 bytes read and written.
+__global__ void __launch_bounds__(256) k_move_bricks(const uint2* __restrict__ pairs, uint32_t n, uint8_t* voxels, uint2* cells) {
+    uint32_t warp = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (warp >= n) return;
+    uint32_t lane = threadIdx.x & 31u;
+    uint2 p = __ldg(pairs + warp);  // {src slot, dst slot}
+    uint4 v = reinterpret_cast<const uint4*>(voxels + (size_t)p.x * 512u)[lane];
+    uint2 c = make_uint2(0, 0);
+    if (lane < 8) c = cells[(size_t)p.x * 8u + lane];
+    reinterpret_cast<uint4*>(voxels + (size_t)p.y * 512u)[lane] = v;
+    if (lane < 8) cells[(size_t)p.y * 8u + lane] = c;
+}
+
+// K_headers: scatter of the per-sector {allocMask, baseSlot} records that changed.
+struct HeaderUpdate {
+    uint32_t sector, mask_lo, mask_hi, base;
+};
+__global__ void k_write_headers(const HeaderUpdate* __restrict__ upd, uint32_t n, uint4* hdr) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    HeaderUpdate u = upd[i];
+    hdr[u.sector] = make_uint4(u.mask_lo, u.mask_hi, u.base, 0u);
+}
+
+// ---------------------------------------------------------------------------------------------
+// K_hit_query: VoxelMap::RayCast + GetStepLevel (VoxelMap.cpp:125-170) in fp64, one thread per
+// query.  Steps 32 (no sector) / 8 (no brick) / 1, bias 1e-4.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ int step_level(const DevScene& S, int x, int y, int z) {
+    int sx = x >> 5, sy = y >> 5, sz = z >> 5;
+    if (((uint32_t)(sx | sz) >> S.sxz) != 0u || ((uint32_t)sy >> S.sy) != 0u) return 5;
+    uint32_t sidx = (uint32_t)sx | ((uint32_t)sz << S.sxz) | ((uint32_t)sy << (2 * S.sxz));
+    uint4 h = ldg_hdr(S.hdr + sidx);
+    if ((h.x | h.y) == 0u) return 5;
+    uint32_t bi = ((uint32_t)(x >> 3) & 3u) | (((uint32_t)(z >> 3) & 3u) << 2) | (((uint32_t)(y >> 3) & 3u) << 4);
+    uint32_t half = (bi & 32u) ? h.y : h.x;
+    if (!((half >> (bi & 31u)) & 1u)) return 3;
+    uint32_t vi = ((uint32_t)x & 7u) | (((uint32_t)z & 7u) << 3) | (((uint32_t)y & 7u) << 6);
+    return __ldg(S.voxels + (size_t)brick_slot(h, bi) * 512u + vi) == 0 ? 0 : -1;
+}
+__device__ __forceinline__ double glm_min(double x, double y) { return (y < x) ? y : x; }
+__device__ __forceinline__ int floor2i_d(double v) {
+    double f = floor(v);
+    return (f >= -2147483648.0 && f < 2147483648.0) ? (int)f : (int)0x80000000;
+}
+
+__global__ void __launch_bounds__(128) k_hit_query(DevScene S, const double* __restrict__ origin3, const double* __restrict__ dir3,
+                                                   uint32_t max_iters, uint64_t n, VrtHitD* __restrict__ out) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double o[3] = {origin3[3 * i], origin3[3 * i + 1], origin3[3 * i + 2]};
+    double d[3] = {dir3[3 * i], dir3[3 * i + 1], dir3[3 * i + 2]};
+    double inv[3], ts[3];
+    int pos[3];
+#pragma unroll
+    for (int a = 0; a < 3; a++) {
+        inv[a] = __ddiv_rn(1.0, d[a]);
+        ts[a] = __dmul_rn(__dsub_rn(d[a] < 0.0 ? 0.0 : 1.0, o[a]), inv[a]);
+        pos[a] = floor2i_d(o[a]);
+    }
+    VrtHitD r;
+    r.dist = -1.0;
+    r.nx = r.ny = r.nz = r.u = r.v = 0.0f;
+    r.vx = r.vy = r.vz = 0;
+    r.iters = max_iters;
+    r._pad = 0;
+    for (uint32_t it = 0; it < max_iters; it++) {
+        double sd[3], hp[3];
+#pragma unroll
+        for (int a = 0; a < 3; a++) sd[a] = __fma_rn((double)pos[a], inv[a], ts[a]);
+        double tmin = __dadd_rn(glm_min(glm_min(sd[0], sd[1]), sd[2]), 0.0001);
+#pragma unroll
+        for (int a = 0; a < 3; a++) {
+            hp[a] = __fma_rn(tmin, d[a], o[a]);
+            pos[a] = floor2i_d(hp[a]);
+        }
+        int k = step_level(S, pos[0], pos[1], pos[2]);
+        if (k < 0) {
+            bool smx = tmin >= sd[0], smy = tmin >= sd[1], smz = tmin >= sd[2];
+            r.dist = tmin;
+            r.nx = smx ? (float)-((d[0] > 0.0) - (d[0] < 0.0)) : 0.0f;
+            r.ny = smy ? (float)-((d[1] > 0.0) - (d[1] < 0.0)) : 0.0f;
+            r.nz = smz ? (float)-((d[2] > 0.0) - (d[2] < 0.0)) : 0.0f;
+            float fu = smx ? (float)hp[1] : (float)hp[0];
+            float fv = smz ? (float)hp[1] : (float)hp[2];
+            r.u = __fsub_rn(fu, floorf(fu));
+            r.v = __fsub_rn(fv, floorf(fv));
+            r.vx = pos[0];
+            r.vy = pos[1];
+            r.vz = pos[2];
+            r.iters = it + 1;
+            break;
+        }
+        int mk = (1 << k) - 1;
+#pragma unroll
+        for (int a = 0; a < 3; a++) pos[a] = d[a] < 0.0 ? (pos[a] & ~mk) : (pos[a] | mk);
+    }
+    out[i] = r;
+}
+
+}  // namespace vrt
