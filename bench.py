@@ -1,0 +1,417 @@
+#!/usr/bin/env python
+"""bench.py — the BASELINE.json metric: Mrays/s of the brickmap traversal path.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+
+Workload at N=1 = BASELINE.json configs[1]: the reference's FastNoise2 terrain (24x7x24 sectors),
+reference camera, 3840x2160 primary rays + normals/material/depth G-buffer.  One step = one frame
+(one launch of the traversal kernel over all 8,294,400 rays).
+
+value   device-resident throughput: CUDA events around each frame's kernel on the launching stream,
+        L2 flushed (256 MiB memset) between frames, max over ranks.
+e2e     the same frame through the host-buffer ABI call (vrt_render): frame constants in, 16 B/px
+        G-buffer copied back into pinned host memory, wall clock around the blocking call.
+roofline  algorithmic bytes (8 I_s + 8 I_c + 9 H + 16 P, counted by the kernel's own traversal
+        counters, which tests check against the oracle) / kernel time, vs the measured HBM peak.
+cpu_baseline  the CPU path (oracle/_ref = the reference's own CpuRenderer.cpp when it was compiled
+        here, else the oracle port) on all host threads, same frame.
+N > 1   screen-tile split of the SAME frame (strong scaling): rank r renders macro tiles t with
+        t % N == r of the replicated brickmap.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+import numpy as np  # noqa: E402
+
+
+def _peaks():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        try:
+            d = json.loads(p.read_text())
+            return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons sampled DURING the timed region."""
+
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index: int):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.index)],
+                stdout=subprocess.PIPE,
+                stderr=subprocess.DEVNULL,
+                text=True,
+            )
+            self.t = threading.Thread(target=self._pump, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {
+            "sm_mhz": float(np.median(sm)) if sm else None,
+            "sm_max_mhz": float(max(mx)) if mx else None,
+            "samples": len(sm),
+            "reasons": sorted(reasons),
+        }
+
+
+def build_scene():
+    from scenes import terrain
+
+    scene = terrain.bench_terrain()
+    return scene, terrain.scene_records(scene), terrain.scene_stats(scene)
+
+
+def bench_frame(width, height, bounces, part_index=0, part_count=1, frame_no=1, flags=0):
+    from scenes import camera
+    from voxelrt_b200 import capi
+
+    cam = camera.Camera()  # Main.cpp:76-78
+    proj, inv, wo, frac = cam.matrices(width, height)
+    return capi.make_frame(width, height, inv, proj, wo, frac, frame_no=frame_no, bounces=bounces, flags=flags, part_index=part_index, part_count=part_count)
+
+
+def cpu_arm(args, scene, recs, want_ref=True):
+    """Times the CPU path on all host threads.  -> (Mrays/s, ms per frame, kind, cores, sample, rays)"""
+    from oracle import pyoracle
+
+    kind, runner = "port", None
+    if want_ref:
+        try:
+            from oracle import refharness
+
+            if refharness.available():
+                runner = refharness.RefRenderer(scene, recs)
+                kind = "reference"
+        except Exception as e:  # pragma: no cover
+            print(f"[bench] oracle/_ref unavailable ({e}); timing the oracle port", file=sys.stderr)
+    cores = pyoracle.num_threads()
+    w, h = args.width, args.height
+    rays = w * h * (1 + args.bounces)
+    if runner is None:
+        orc = pyoracle.OracleMap(6, 4)
+        orc.set_palette(scene["palette"])
+        orc.sync(recs)
+        if args.bounces:
+            from scenes import shading
+
+            orc.set_blue_noise(shading.load_blue_noise()[0])
+            d, t, _ = shading.load_sky()
+            orc.set_sky(d, t)
+        frame = bench_frame(w, h, args.bounces)
+
+        def run():
+            t0 = time.perf_counter()
+            orc.render(frame, want_aux=False)
+            return time.perf_counter() - t0
+
+    else:
+
+        def run():
+            return runner.render_seconds(w, h, args.bounces)
+
+    return run, kind, cores, rays
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    scene, recs, sstats = build_scene()
+    run, kind, cores, rays = cpu_arm(args, scene, recs)
+    for _ in range(min(args.warmup, 2)):
+        run()
+    times = [run() for _ in range(args.steps)]
+    ms = 1000.0 * sum(times) / len(times)
+    val = rays / (ms * 1e-3) / 1e6
+    line = {
+        "impl": "reference",
+        "metric": "Mrays/s primary+secondary, brickmap traversal",
+        "value": val,
+        "unit": "Mrays/s",
+        "n_gpus": args.gpus,
+        "steps": args.steps,
+        "warmup": min(args.warmup, 2),
+        "ms_per_step": ms,
+        "higher_is_better": True,
+        "scaling": "strong",
+        "vs_baseline": None,
+        "dtype": "f32",
+        "data": "synthetic",
+        "config": workload_config(args, scene, sstats),
+        "cpu_baseline": {
+            "value": val,
+            "unit": "Mrays/s",
+            "cores": cores,
+            "kind": kind,
+            "sample": f"{args.steps} full {args.width}x{args.height} frames, {rays} rays each",
+        },
+        "e2e": {"value": val, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+def workload_config(args, scene, sstats):
+    return {
+        "workload": f"BASELINE configs[1]: {scene.get('name', 'terrain')}, reference camera (512,128,512) yaw 1.52 pitch -0.5, "
+        f"{args.width}x{args.height} primary rays + normal/material/depth G-buffer, bounces={args.bounces}",
+        "width": args.width,
+        "height": args.height,
+        "bounces": args.bounces,
+        "bricks": sstats["bricks"],
+        "sectors": sstats["sectors"],
+        "l2": "flushed between timed frames (256 MiB memset outside the event-timed region)",
+        "parallelism": f"screen tiles 32x32 round-robin over {args.gpus} GPU(s), brickmap replicated",
+    }
+
+
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+
+    from voxelrt_b200 import capi
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — the product path has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    n_gpus = world
+
+    scene, recs, sstats = build_scene()
+    ctx = capi.Context(6, 4, device=local, initial_brick_capacity=1 << 18)
+    ctx.set_palette(scene["palette"])
+    ctx.sync(recs)
+    if args.bounces:
+        from scenes import shading
+
+        ctx.set_blue_noise(shading.load_blue_noise()[0])
+        d, t, _ = shading.load_sky()
+        ctx.set_sky(d, t)
+
+    w, h = args.width, args.height
+    npx = w * h
+    rays_frame = npx * (1 + args.bounces)
+    fb = torch.zeros(npx * 4, dtype=torch.int32, device="cuda")  # 16 B/px
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    stream = torch.cuda.current_stream()
+    frame = bench_frame(w, h, args.bounces, part_index=rank, part_count=world)
+
+    def step():
+        ctx.render_device(frame, fb.data_ptr(), None, stream.cuda_stream)
+
+    # traversal counters of this frame (untimed, metrics build of the same kernel)
+    ctx.set_option("metrics", 1)
+    step()
+    torch.cuda.synchronize()
+    m = ctx.metrics()
+    ctx.set_option("metrics", 0)
+    my_primary = 0
+    tiles_x, tiles_y = (w + 31) // 32, (h + 31) // 32
+    for t in range(rank, tiles_x * tiles_y, world):
+        tx, ty = t % tiles_x, t // tiles_x
+        my_primary += min(32, w - tx * 32) * min(32, h - ty * 32)
+    alg_bytes = 8 * m.sector_fetches + 8 * m.cell_fetches + 9 * m.hits + 16 * my_primary
+
+    for _ in range(args.warmup):
+        flush.zero_()
+        step()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    t_wall0 = time.perf_counter()
+    for a, b in evs:
+        flush.zero_()
+        a.record(stream)
+        step()
+        b.record(stream)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t_wall = time.perf_counter() - t_wall0
+    total_ms = sum(a.elapsed_time(b) for a, b in evs)
+    # warm-L2 variant (steady-state renderer: brickmap stays in the 126 MB L2), informational
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record(stream)
+    for _ in range(args.steps):
+        step()
+    b.record(stream)
+    torch.cuda.synchronize()
+    warm_ms = a.elapsed_time(b) / args.steps
+    clocks = sampler.stop() if rank == 0 else None
+
+    tt = torch.tensor([total_ms, warm_ms], dtype=torch.float64, device="cuda")
+    ab = torch.tensor([float(alg_bytes)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    total_ms, warm_ms = float(tt[0]), float(tt[1])
+    ms_per_step = total_ms / args.steps
+    value = rays_frame / (ms_per_step * 1e-3) / 1e6
+
+    # ---- e2e: host-buffer ABI call, pinned output, wall clock (rank-local partition) ----
+    host_out = torch.empty(npx * 4, dtype=torch.int32).pin_memory()
+    e2e_frame = bench_frame(w, h, args.bounces, part_index=rank, part_count=world)
+
+    def e2e_step():
+        st = ctx.lib.vrt_render(ctx.h, C.byref(e2e_frame), host_out.data_ptr(), None)
+        if st != 0:
+            ctx._chk(st)
+
+    for _ in range(max(2, args.warmup // 2)):
+        e2e_step()
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        e2e_step()
+    e2e_s = time.perf_counter() - t0
+    et = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(et, op=dist.ReduceOp.MAX)
+    e2e_ms = float(et[0]) * 1000.0 / args.steps
+    e2e_val = rays_frame / (e2e_ms * 1e-3) / 1e6
+
+    if rank == 0:
+        peak, peak_src = _peaks()
+        kernel_s = ms_per_step * 1e-3
+        achieved = alg_bytes / kernel_s / 1e9
+        line = {
+            "metric": "Mrays/s primary+secondary, brickmap traversal",
+            "value": value,
+            "unit": "Mrays/s",
+            "n_gpus": n_gpus,
+            "steps": args.steps,
+            "warmup": args.warmup,
+            "ms_per_step": ms_per_step,
+            "higher_is_better": True,
+            "scaling": "strong",
+            "vs_baseline": None,
+            "dtype": "f32",
+            "data": "synthetic",
+            "config": workload_config(args, scene, sstats),
+            "value_warm_l2": rays_frame / (warm_ms * 1e-3) / 1e6,
+            "wall_s_timed_region": t_wall,
+            "clocks": clocks,
+            "e2e": {
+                "value": e2e_val,
+                "unit": "Mrays/s",
+                "ms_per_step": e2e_ms,
+                "h2d_bytes_per_step": C.sizeof(capi.VrtFrame),
+                "d2h_bytes_per_step": npx * 16,
+                "api": "vrt_render (host buffers, pinned output)",
+            },
+            "gpu_launches": args.steps,
+            "roofline": {
+                "bound": "hbm",
+                "kernel": "vrt::k_render<false>",
+                "achieved": achieved,
+                "peak": peak,
+                "unit": "GB/s",
+                "frac": achieved / peak,
+                "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": int(alg_bytes),
+                "bytes_per_ray": alg_bytes / max(1, my_primary * (1 + args.bounces)),
+                "traffic": None,
+                "counters": {"rays": m.rays, "iters": m.iters, "sector_fetches": m.sector_fetches, "cell_fetches": m.cell_fetches, "hits": m.hits, "capped": m.capped},
+            },
+        }
+        if not args.no_cpu and n_gpus == 1:
+            run, kind, cores, rays = cpu_arm(args, scene, recs)
+            run()
+            times, t_begin = [], time.perf_counter()
+            while len(times) < 3 or (time.perf_counter() - t_begin < 10.0 and len(times) < 20):
+                times.append(run())
+            best = min(times)
+            line["cpu_baseline"] = {
+                "value": rays / best / 1e6,
+                "unit": "Mrays/s",
+                "cores": cores,
+                "kind": kind,
+                "sample": f"best of {len(times)} full {w}x{h} frames ({rays} rays each) on {cores} host threads",
+            }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    ctx.close()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--width", type=int, default=3840)
+    ap.add_argument("--height", type=int, default=2160)
+    ap.add_argument("--bounces", type=int, default=0)
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_b200(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

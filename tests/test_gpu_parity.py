@@ -1,0 +1,237 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle, bit for bit.
+
+Contract (BASELINE.json north_star): hit voxel coordinates, face normals and material ids are
+bit-exact; here the canonical arithmetic makes distances, positions, UVs and the
+packed G-buffer bit-exact as well, so every comparison below is on raw bytes.
+"""
+from __future__ import annotations
+
+import numpy as np
+import pytest
+
+from conftest import assert_hits_equal, ctx_for, random_rays
+
+pytestmark = pytest.mark.gpu
+
+
+def _frame(cam, w, h, **kw):
+    from voxelrt_b200 import capi
+
+    proj, inv, wo, frac = cam.matrices(w, h)
+    return capi.make_frame(w, h, inv, proj, wo, frac, **kw)
+
+
+# ---------------------------------------------------------------------------------------------
+# explicit rays: vrt_trace == RayCast (CpuRenderer.cpp:172-224)
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("seed", [1, 2, 3])
+def test_trace_random_rays(hash_ctx, hash_oracle, seed):
+    rng = np.random.default_rng(seed)
+    wo = (rng.integers(0, 192), rng.integers(0, 128), rng.integers(0, 192))
+    o, d = random_rays(rng, 200_000, 192, 128, wo)
+    got = hash_ctx.trace(o, d, wo)
+    want, st = hash_oracle.trace(o, d, wo)
+    assert st.hits > 20_000
+    assert_hits_equal(got, want, f"seed {seed}")
+
+
+def test_trace_edge_cases(hash_ctx, hash_oracle):
+    """Zero / negative-zero / denormal / inf / NaN direction components, axis-aligned rays, rays
+    that start inside solid voxels, outside the grid, on integer coordinates, huge origins."""
+    rng = np.random.default_rng(11)
+    n = 60_000
+    wo = (64, 40, 64)
+    o, d = random_rays(rng, n, 192, 128, wo)
+    specials = np.array([0.0, -0.0, 1e-40, -1e-40, np.inf, -np.inf, np.nan, 1.0, -1.0, 1e-30, 3e38], np.float32)
+    for k in range(0, n // 2):
+        axis = rng.integers(0, 3)
+        d[k, axis] = specials[rng.integers(0, specials.size)]
+        if k % 3 == 0:
+            d[k, (axis + 1) % 3] = specials[rng.integers(0, specials.size)]
+        if k % 7 == 0:
+            d[k] = specials[rng.integers(0, specials.size, 3)]
+    o[n // 2 : n // 2 + 5000] = np.round(o[n // 2 : n // 2 + 5000])  # integer coordinates
+    o[n // 2 + 5000 : n // 2 + 6000] *= np.float32(1e6)  # far outside
+    o[n // 2 + 6000 : n // 2 + 6100] = np.float32(np.nan)
+    o[n // 2 + 6100 : n // 2 + 6200] = np.float32(3e9)
+    got = hash_ctx.trace(o, d, wo)
+    want, _ = hash_oracle.trace(o, d, wo)
+    assert_hits_equal(got, want, "edge cases")
+
+
+@pytest.mark.parametrize("max_iters", [1, 2, 7, 128, 1000])
+def test_trace_iteration_cap(hash_ctx, hash_oracle, max_iters):
+    rng = np.random.default_rng(5)
+    wo = (96, 64, 96)
+    o, d = random_rays(rng, 50_000, 192, 128, wo)
+    got = hash_ctx.trace(o, d, wo, max_iters=max_iters)
+    want, _ = hash_oracle.trace(o, d, wo, max_iters=max_iters)
+    assert_hits_equal(got, want, f"max_iters {max_iters}")
+
+
+def test_trace_empty_and_ragged(hash_ctx, hash_oracle):
+    from voxelrt_b200 import capi
+
+    assert hash_ctx.trace(np.zeros((0, 3), np.float32), np.zeros((0, 3), np.float32), (0, 0, 0)).shape == (0,)
+    rng = np.random.default_rng(9)
+    for n in (1, 31, 33, 127, 129, 1000):
+        o, d = random_rays(rng, n, 192, 128, (0, 0, 0))
+        assert_hits_equal(hash_ctx.trace(o, d, (0, 0, 0)), hash_oracle.trace(o, d, (0, 0, 0))[0], f"n={n}")
+    with pytest.raises(capi.VrtError):
+        hash_ctx._chk(hash_ctx.lib.vrt_trace(hash_ctx.h, 4, None, None, None, 0, None))
+
+
+def test_metrics_match_oracle_counters(hash_ctx, hash_oracle):
+    """The device counters behind roofline.achieved are the oracle's I_s / I_c / H."""
+    rng = np.random.default_rng(21)
+    o, d = random_rays(rng, 100_000, 192, 128, (0, 0, 0))
+    hash_ctx.set_option("metrics", 1)
+    try:
+        hash_ctx.trace(o, d, (0, 0, 0))
+        m = hash_ctx.metrics()
+    finally:
+        hash_ctx.set_option("metrics", 0)
+    _, st = hash_oracle.trace(o, d, (0, 0, 0))
+    assert (m.rays, m.sector_fetches, m.cell_fetches, m.hits, m.capped) == (
+        st.rays,
+        st.sector_fetches,
+        st.cell_fetches,
+        st.hits,
+        st.capped,
+    )
+
+
+# ---------------------------------------------------------------------------------------------
+# frames: vrt_render == RenderRow (CpuRenderer.cpp:326-402)
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("size", [(256, 144), (260, 148), (36, 4)])
+@pytest.mark.parametrize("linear", [False, True])
+def test_render_primary_small(hash_ctx, hash_oracle, size, linear):
+    from scenes import camera
+    from voxelrt_b200 import capi
+
+    w, h = size
+    cam = camera.Camera(pos=(96.3, 90.2, 20.7), yaw=0.2, pitch=-0.45)
+    flags = capi.VRT_FRAME_LINEAR_OUTPUT if linear else 0
+    out_g, aux_g = hash_ctx.render(_frame(cam, w, h, flags=flags), want_aux=True)
+    out_c, aux_c, _ = hash_oracle.render(_frame(cam, w, h, flags=flags), want_aux=True)
+    assert_hits_equal(aux_g, aux_c, "primary aux")
+    assert out_g.tobytes() == out_c.tobytes()
+
+
+def test_render_rejects_bad_sizes(hash_ctx):
+    from scenes import camera
+    from voxelrt_b200 import capi
+
+    cam = camera.Camera()
+    for w, h in ((0, 16), (18, 16), (16, 6)):
+        with pytest.raises(capi.VrtError):
+            hash_ctx.render(_frame(cam, w, h))
+
+
+def test_render_config1_720p(bench_ctx, bench_oracle):
+    """BASELINE.json configs[0]: reference camera, 1280x720 primary rays, every hit record bit-exact."""
+    from scenes import camera
+
+    cam = camera.Camera()
+    out_g, aux_g = bench_ctx.render(_frame(cam, 1280, 720), want_aux=True)
+    out_c, aux_c, st = bench_oracle.render(_frame(cam, 1280, 720), want_aux=True)
+    assert st.rays == 1280 * 720
+    assert_hits_equal(aux_g, aux_c, "config 1")
+    assert out_g.tobytes() == out_c.tobytes()
+
+
+def test_render_config2_4k_full(bench_ctx, bench_oracle):
+    """BASELINE.json configs[1] at FULL size: all 8,294,400 primary rays {hit, voxel, normal,
+    material} (in fact the whole record) bit-exact against the oracle."""
+    from scenes import camera
+
+    cam = camera.Camera()
+    out_g, aux_g = bench_ctx.render(_frame(cam, 3840, 2160), want_aux=True)
+    out_c, aux_c, st = bench_oracle.render(_frame(cam, 3840, 2160), want_aux=True)
+    assert st.rays == 3840 * 2160
+    assert_hits_equal(aux_g, aux_c, "config 2")
+    assert out_g.tobytes() == out_c.tobytes()
+
+
+@pytest.mark.parametrize("i", range(4))
+def test_render_orbit_cameras(bench_ctx, bench_oracle, i):
+    from scenes import camera
+
+    cam = camera.orbit_cameras(4, seed=1)[i]
+    out_g, aux_g = bench_ctx.render(_frame(cam, 640, 360), want_aux=True)
+    out_c, aux_c, _ = bench_oracle.render(_frame(cam, 640, 360), want_aux=True)
+    assert_hits_equal(aux_g, aux_c, f"orbit {i}")
+    assert out_g.tobytes() == out_c.tobytes()
+
+
+@pytest.mark.parametrize("bounces", [1, 2, 3])
+def test_render_bounces(hash_scene, hash_oracle, shading_inputs, bounces):
+    """Secondary diffuse rays with the blue-noise table and the sky cube: radiance (f16) bytes equal
+    — tolerance 0 under the canonical arithmetic (stated tolerance of the contract: <= 1 f16 ulp)."""
+    from scenes import camera
+
+    (bn, _), (desc, tex, _) = shading_inputs
+    ctx = ctx_for(hash_scene)
+    ctx.set_blue_noise(bn)
+    ctx.set_sky(desc, tex)
+    hash_oracle.set_blue_noise(bn)
+    hash_oracle.set_sky(desc, tex)
+    cam = camera.Camera(pos=(96.3, 90.2, 20.7), yaw=0.2, pitch=-0.45)
+    for frame_no in (1, 2, 77):
+        out_g, aux_g = ctx.render(_frame(cam, 320, 180, bounces=bounces, frame_no=frame_no), want_aux=True)
+        out_c, aux_c, st = hash_oracle.render(_frame(cam, 320, 180, bounces=bounces, frame_no=frame_no), want_aux=True)
+        assert st.rays > 320 * 180
+        assert_hits_equal(aux_g, aux_c, f"bounces {bounces} primary aux")
+        for k in ("albedo", "depth", "irr_rg", "irr_bx"):
+            a, b = out_g[k].view(np.uint32), out_c[k].view(np.uint32)
+            assert np.array_equal(a, b), f"{k}: {np.count_nonzero(a != b)} texels differ (bounces {bounces}, frame {frame_no})"
+    ctx.close()
+
+
+def test_render_needs_blue_noise_for_bounces(hash_scene):
+    from scenes import camera
+    from voxelrt_b200 import capi
+
+    ctx = ctx_for(hash_scene)
+    with pytest.raises(capi.VrtError):
+        ctx.render(_frame(camera.Camera(), 64, 64, bounces=1))
+    ctx.close()
+
+
+@pytest.mark.parametrize("parts", [2, 4, 8])
+def test_render_tile_partition_union(hash_ctx, parts):
+    """Screen-tile split: the union of the N partial frames is the 1-GPU frame, byte for
+    byte, and the parts are disjoint."""
+    from scenes import camera
+
+    cam = camera.Camera(pos=(96.3, 90.2, 20.7), yaw=0.2, pitch=-0.45)
+    w, h = 416, 260
+    full, _ = hash_ctx.render(_frame(cam, w, h))
+    full = full.view(np.uint32).reshape(-1, 64)
+    acc = np.zeros_like(full)
+    for p in range(parts):
+        part, _ = hash_ctx.render(_frame(cam, w, h, part_index=p, part_count=parts))
+        part = part.view(np.uint32).reshape(-1, 64)
+        assert not np.any((acc != 0) & (part != 0))
+        acc |= part
+    assert np.array_equal(acc, full)
+
+
+# ---------------------------------------------------------------------------------------------
+# hit query: vrt_hit_query == VoxelMap::RayCast (VoxelMap.cpp:140-170), fp64
+# ---------------------------------------------------------------------------------------------
+def test_hit_query(hash_ctx, hash_oracle):
+    rng = np.random.default_rng(3)
+    n = 50_000
+    o = np.stack([rng.uniform(0, 192, n), rng.uniform(0, 128, n), rng.uniform(0, 192, n)], 1)
+    d = rng.normal(size=(n, 3))
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    got = hash_ctx.hit_query(o, d)
+    want = hash_oracle.hit_query(o, d)
+    assert (want["dist"] >= 0).sum() > 5000
+    for name in got.dtype.names:
+        a, b = got[name], want[name]
+        if a.dtype.kind == "f":
+            a, b = a.view(f"u{a.dtype.itemsize}"), b.view(f"u{b.dtype.itemsize}")
+        assert np.array_equal(a, b), name
