@@ -58,6 +58,20 @@ class ClockSampler:
         self.lines = []
 
     def start(self):
+        self.nvml = None
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            self.nvml = pynvml
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            self.samples = []
+            self.stop_flag = False
+            self.t = threading.Thread(target=self._pump_nvml, daemon=True)
+            self.t.start()
+            return
+        except Exception:
+            self.nvml = None
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.index)],
@@ -70,11 +84,55 @@ class ClockSampler:
         except Exception:
             self.proc = None
 
+    def _pump_nvml(self):
+        n = self.nvml
+        while not self.stop_flag:
+            try:
+                sm = n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM)
+                try:
+                    rs = n.nvmlDeviceGetCurrentClocksEventReasons(self.handle)
+                except Exception:
+                    rs = n.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle)
+                self.samples.append((sm, rs))
+            except Exception:
+                break
+            time.sleep(0.002)
+
+    def _stop_nvml(self):
+        n = self.nvml
+        self.stop_flag = True
+        self.t.join(timeout=1)
+        try:
+            mx = n.nvmlDeviceGetMaxClockInfo(self.handle, n.NVML_CLOCK_SM)
+        except Exception:
+            mx = None
+        bits = {
+            "hw_slowdown": getattr(n, "nvmlClocksThrottleReasonHwSlowdown", 0x8),
+            "hw_thermal_slowdown": getattr(n, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40),
+            "sw_thermal_slowdown": getattr(n, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20),
+            "sw_power_cap": getattr(n, "nvmlClocksThrottleReasonSwPowerCap", 0x4),
+        }
+        reasons = set()
+        for _, rs in self.samples:
+            for k, b in bits.items():
+                if rs & b:
+                    reasons.add(k)
+        sm = [x for x, _ in self.samples]
+        return {
+            "sm_mhz": float(np.median(sm)) if sm else None,
+            "sm_max_mhz": float(mx) if mx else None,
+            "samples": len(sm),
+            "reasons": sorted(reasons),
+            "source": "nvml, 2 ms period, during the timed region",
+        }
+
     def _pump(self):
         for line in self.proc.stdout:
             self.lines.append(line.strip())
 
     def stop(self):
+        if getattr(self, "nvml", None):
+            return self._stop_nvml()
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -248,7 +306,11 @@ def run_b200(args):
     rays_frame = npx * (1 + args.bounces)
     fb = torch.zeros(npx * 4, dtype=torch.int32, device="cuda")  # 16 B/px
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
-    stream = torch.cuda.current_stream()
+    # a real (non-legacy) stream: handle 0 would mean "the context's own stream" to the C ABI and
+    # torch events recorded on the legacy stream would not bracket the kernel
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
+    assert stream.cuda_stream != 0
     frame = bench_frame(w, h, args.bounces, part_index=rank, part_count=world)
 
     def step():

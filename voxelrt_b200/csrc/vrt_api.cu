@@ -36,6 +36,7 @@ struct VrtContext {
     bool render_pending = false;
 
     uint32_t sxz = 6, sy = 4, n_sectors = 0;
+    uint32_t sxp = 0, syp = 0, n_hdr = 0;  // bordered header grid (one OUTSIDE sector on every side)
     // resident brickmap
     uint4* d_hdr = nullptr;
     uint2* d_cells = nullptr;
@@ -164,7 +165,34 @@ DevScene dev_scene(const VrtContext* ctx) {
     S.sy = ctx->sy;
     S.lim_xz = 1u << (ctx->sxz + 5);
     S.lim_y = 1u << (ctx->sy + 5);
+    S.sxp = ctx->sxp;
+    S.sxzp = ctx->sxp * ctx->sxp;
+    S.n_hdr = ctx->n_hdr;
     return S;
+}
+
+// Constants of the traversal frame for a world origin (see RayFrame).
+RayFrame ray_frame(const VrtContext* ctx, const int32_t wo[3]) {
+    const int MAGIC_BITS = 0x4B400000;
+    RayFrame W;
+    W.wx = wo[0];
+    W.wy = wo[1];
+    W.wz = wo[2];
+    const int lox = wo[0] & 31, loy = wo[1] & 31, loz = wo[2] & 31;
+    W.cqx = lox - MAGIC_BITS;
+    W.cqy = loy - MAGIC_BITS;
+    W.cqz = loz - MAGIC_BITS;
+    W.hx = wo[0] - lox;
+    W.hy = wo[1] - loy;
+    W.hz = wo[2] - loz;
+    const int lim = 1 << 20;
+    W.fast_ok = (wo[0] >= -lim && wo[0] <= lim && wo[1] >= -lim && wo[1] <= lim && wo[2] >= -lim && wo[2] <= lim) ? 1 : 0;
+    // hdr_index of the (possibly far out-of-view) sector holding the frame origin; int arithmetic wraps harmlessly
+    // because the loop only ever adds offsets that bring the sum back inside [0, n_hdr)
+    W.hoff = W.fast_ok ? (int)((long long)((W.hx >> 5) + 1) + (long long)((W.hz >> 5) + 1) * ctx->sxp +
+                               (long long)((W.hy >> 5) + 1) * ctx->sxp * ctx->sxp)
+                       : 0;
+    return W;
 }
 
 // Orders work on a caller stream after the context's residency work, and vice versa.
@@ -185,13 +213,14 @@ int launch_trace(VrtContext* ctx, uint64_t n, const float* d_o, const float* d_d
     if (n == 0) return VRT_OK;
     if (max_iters == 0) max_iters = VRT_MAX_ITERS_DEFAULT;
     DevScene S = dev_scene(ctx);
+    RayFrame W = ray_frame(ctx, wo);
     uint64_t blocks = (n + 127) / 128;
     if (blocks > 0x7FFFFFFFull) return fail(ctx, VRT_ERR_INVALID, "too many rays for one launch");
     if (ctx->metrics_on) {
         CU(cudaMemsetAsync(ctx->d_metrics, 0, sizeof(DevMetrics), s));
-        k_trace<true><<<(unsigned)blocks, 128, 0, s>>>(S, d_o, d_d, wo[0], wo[1], wo[2], max_iters, n, d_out, ctx->d_metrics);
+        k_trace<true><<<(unsigned)blocks, 128, 0, s>>>(S, W, d_o, d_d, max_iters, n, d_out, ctx->d_metrics);
     } else {
-        k_trace<false><<<(unsigned)blocks, 128, 0, s>>>(S, d_o, d_d, wo[0], wo[1], wo[2], max_iters, n, d_out, nullptr);
+        k_trace<false><<<(unsigned)blocks, 128, 0, s>>>(S, W, d_o, d_d, max_iters, n, d_out, nullptr);
     }
     ctx->stats.last_launches = 1;
     CU(cudaGetLastError());
@@ -212,10 +241,8 @@ int launch_render(VrtContext* ctx, const VrtFrame* f, void* d_out, VrtHit* d_aux
     F.height = f->height;
     memcpy(F.inv_proj, f->inv_proj, sizeof(F.inv_proj));
     memcpy(F.proj, f->proj, sizeof(F.proj));
-    for (int a = 0; a < 3; a++) {
-        F.wo[a] = f->world_origin[a];
-        F.frac[a] = f->origin_frac[a];
-    }
+    F.W = ray_frame(ctx, f->world_origin);
+    for (int a = 0; a < 3; a++) F.frac[a] = f->origin_frac[a];
     F.frame_no = f->frame_no;
     F.bounces = f->bounces;
     F.max_iters = f->max_iters ? f->max_iters : VRT_MAX_ITERS_DEFAULT;
@@ -311,13 +338,17 @@ extern "C" int vrt_create(const VrtConfig* cfg, VrtContext** out) {
     CUB(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     CUB(cudaEventCreateWithFlags(&c->ev_sync, cudaEventDisableTiming));
     CUB(cudaEventCreateWithFlags(&c->ev_render, cudaEventDisableTiming));
-    CUB(cudaMalloc((void**)&c->d_hdr, (size_t)c->n_sectors * sizeof(uint4)));
-    CUB(cudaMemsetAsync(c->d_hdr, 0, (size_t)c->n_sectors * sizeof(uint4), c->stream));
+    c->sxp = (1u << c->sxz) + 2u;
+    c->syp = (1u << c->sy) + 2u;
+    c->n_hdr = c->sxp * c->sxp * c->syp;
+    CUB(cudaMalloc((void**)&c->d_hdr, (size_t)c->n_hdr * sizeof(uint4)));
+    k_init_headers<<<(c->n_hdr + 255) / 256, 256, 0, c->stream>>>(c->d_hdr, c->sxp, c->syp);
+    CUB(cudaGetLastError());
     CUB(cudaMalloc((void**)&c->d_palette, 256 * sizeof(uint2)));
     CUB(cudaMemsetAsync(c->d_palette, 0, 256 * sizeof(uint2), c->stream));
     CUB(cudaMalloc((void**)&c->d_metrics, sizeof(DevMetrics)));
     CUB(cudaMemsetAsync(c->d_metrics, 0, sizeof(DevMetrics), c->stream));
-    c->stats.device_bytes = (size_t)c->n_sectors * sizeof(uint4) + 256 * sizeof(uint2) + sizeof(DevMetrics);
+    c->stats.device_bytes = (size_t)c->n_hdr * sizeof(uint4) + 256 * sizeof(uint2) + sizeof(DevMetrics);
     uint32_t cap = cfg->initial_brick_capacity ? cfg->initial_brick_capacity : (1u << 16);
     int st = resize_arena(c, cap);
     if (st != VRT_OK) return bail(st);
@@ -465,7 +496,8 @@ extern "C" int vrt_sync(VrtContext* ctx, uint32_t n, const VrtDirtySector* recs)
             cur.mask = new_mask;
             if ((old.mask == 0) != (new_mask == 0)) ctx->resident_sectors += new_mask ? 1 : -1;
             ctx->sectors[si] = cur;
-            headers.push_back(HeaderUpdate{si, (uint32_t)new_mask, (uint32_t)(new_mask >> 32), cur.base});
+            headers.push_back(HeaderUpdate{hdr_index(ctx->sxp, ctx->sxp * ctx->sxp, d.sx, d.sy, d.sz), (uint32_t)new_mask,
+                                           (uint32_t)(new_mask >> 32), cur.base});
         }
         const uint8_t* src = d.bricks;
         // payload order: ascending bit order over dirty_mask & alloc_mask
@@ -533,7 +565,9 @@ extern "C" int vrt_read_sector(VrtContext* ctx, int32_t sx, int32_t sy, int32_t 
     CU(cudaStreamSynchronize(ctx->stream));
     uint32_t si = (uint32_t)sx | ((uint32_t)sz << ctx->sxz) | ((uint32_t)sy << (2 * ctx->sxz));
     uint4 h;
-    CU(cudaMemcpy(&h, ctx->d_hdr + si, sizeof(h), cudaMemcpyDeviceToHost));  // the DEVICE copy is what is inspected
+    (void)si;
+    CU(cudaMemcpy(&h, ctx->d_hdr + hdr_index(ctx->sxp, ctx->sxp * ctx->sxp, sx, sy, sz), sizeof(h),
+                  cudaMemcpyDeviceToHost));  // the DEVICE copy is what is inspected
     uint64_t mask = (uint64_t)h.x | ((uint64_t)h.y << 32);
     if (out_alloc_mask) *out_alloc_mask = mask;
     if (out_base_slot) *out_base_slot = h.z;

@@ -10,9 +10,9 @@ namespace vrt {
 // (CpuRenderer.cpp:172-224) for callers that bring their own rays.
 // ---------------------------------------------------------------------------------------------
 template <bool METRICS>
-__global__ void __launch_bounds__(128) k_trace(DevScene S, const float* __restrict__ origin3, const float* __restrict__ dir3, int wx,
-                                               int wy, int wz, uint32_t max_iters, uint64_t n, VrtHit* __restrict__ out,
-                                               DevMetrics* metrics) {
+__global__ void __launch_bounds__(128) k_trace(const __grid_constant__ DevScene S, const __grid_constant__ RayFrame W,
+                                               const float* __restrict__ origin3, const float* __restrict__ dir3, uint32_t max_iters,
+                                               uint64_t n, VrtHit* __restrict__ out, DevMetrics* metrics) {
     uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     bool valid = i < n;
     HitLane H;
@@ -23,7 +23,7 @@ __global__ void __launch_bounds__(128) k_trace(DevScene S, const float* __restri
     if (valid) {
         float ox = __ldg(origin3 + 3 * i), oy = __ldg(origin3 + 3 * i + 1), oz = __ldg(origin3 + 3 * i + 2);
         float dx = __ldg(dir3 + 3 * i), dy = __ldg(dir3 + 3 * i + 1), dz = __ldg(dir3 + 3 * i + 2);
-        cast_ray(S, ox, oy, oz, dx, dy, dz, wx, wy, wz, max_iters, H, R);
+        cast_ray<METRICS>(S, W, ox, oy, oz, dx, dy, dz, max_iters, H, R);
         store_hit(out + i, H, R);
     }
     if (METRICS) {
@@ -67,7 +67,7 @@ __device__ __forceinline__ void store_pixel(const FrameParams& F, uint32_t x, ui
 }
 
 template <bool METRICS>
-__global__ void __launch_bounds__(256) k_render(DevScene S, const __grid_constant__ FrameParams F) {
+__global__ void __launch_bounds__(256, 4) k_render(const __grid_constant__ DevScene S, const __grid_constant__ FrameParams F) {
     uint32_t work = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (work >= F.n_work) return;  // warp-uniform
     uint32_t x0, y0;
@@ -146,13 +146,23 @@ __global__ void __launch_bounds__(256) k_move_bricks(const uint2* __restrict__ p
 
 // K_headers: scatter of the per-sector {allocMask, baseSlot} records that changed.
 struct HeaderUpdate {
-    uint32_t sector, mask_lo, mask_hi, base;
+    uint32_t index, mask_lo, mask_hi, base;  // index = hdr_index() in the bordered grid
 };
 __global__ void k_write_headers(const HeaderUpdate* __restrict__ upd, uint32_t n, uint4* hdr) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     HeaderUpdate u = upd[i];
-    hdr[u.sector] = make_uint4(u.mask_lo, u.mask_hi, u.base, 0u);
+    hdr[u.index] = make_uint4(u.mask_lo, u.mask_hi, u.base, (uint32_t)__popc(u.mask_lo));
+}
+
+// K_init_headers: zero the in-view entries, mark the one-sector border OUTSIDE.
+__global__ void k_init_headers(uint4* hdr, uint32_t sxp, uint32_t syp) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t n = sxp * sxp * syp;
+    if (i >= n) return;
+    uint32_t x = i % sxp, z = (i / sxp) % sxp, y = i / (sxp * sxp);
+    bool border = x == 0 || z == 0 || y == 0 || x == sxp - 1 || z == sxp - 1 || y == syp - 1;
+    hdr[i] = make_uint4(0u, 0u, 0u, border ? VRT_HDR_OUTSIDE : 0u);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -162,8 +172,7 @@ __global__ void k_write_headers(const HeaderUpdate* __restrict__ upd, uint32_t n
 __device__ __forceinline__ int step_level(const DevScene& S, int x, int y, int z) {
     int sx = x >> 5, sy = y >> 5, sz = z >> 5;
     if (((uint32_t)(sx | sz) >> S.sxz) != 0u || ((uint32_t)sy >> S.sy) != 0u) return 5;
-    uint32_t sidx = (uint32_t)sx | ((uint32_t)sz << S.sxz) | ((uint32_t)sy << (2 * S.sxz));
-    uint4 h = ldg_hdr(S.hdr + sidx);
+    uint4 h = ldg_hdr(S.hdr + hdr_index(S.sxp, S.sxzp, sx, sy, sz));
     if ((h.x | h.y) == 0u) return 5;
     uint32_t bi = ((uint32_t)(x >> 3) & 3u) | (((uint32_t)(z >> 3) & 3u) << 2) | (((uint32_t)(y >> 3) & 3u) << 4);
     uint32_t half = (bi & 32u) ? h.y : h.x;
@@ -177,7 +186,7 @@ __device__ __forceinline__ int floor2i_d(double v) {
     return (f >= -2147483648.0 && f < 2147483648.0) ? (int)f : (int)0x80000000;
 }
 
-__global__ void __launch_bounds__(128) k_hit_query(DevScene S, const double* __restrict__ origin3, const double* __restrict__ dir3,
+__global__ void __launch_bounds__(128) k_hit_query(const __grid_constant__ DevScene S, const double* __restrict__ origin3, const double* __restrict__ dir3,
                                                    uint32_t max_iters, uint64_t n, VrtHitD* __restrict__ out) {
     uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
