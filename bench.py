@@ -361,6 +361,17 @@ def run_b200(args):
     torch.cuda.synchronize()
     warm_ms = a.elapsed_time(b) / args.steps
     clocks = sampler.stop() if rank == 0 else None
+    # the step-by-step loop (no empty-box macro steps), informational
+    ctx.set_option("macro_steps", 0)
+    step()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record(stream)
+    for _ in range(args.steps):
+        step()
+    b.record(stream)
+    torch.cuda.synchronize()
+    stepwise_ms = a.elapsed_time(b) / args.steps
+    ctx.set_option("macro_steps", 1)
 
     tt = torch.tensor([total_ms, warm_ms], dtype=torch.float64, device="cuda")
     ab = torch.tensor([float(alg_bytes)], dtype=torch.float64, device="cuda")
@@ -412,6 +423,7 @@ def run_b200(args):
             "data": "synthetic",
             "config": workload_config(args, scene, sstats),
             "value_warm_l2": rays_frame / (warm_ms * 1e-3) / 1e6,
+            "value_stepwise_warm_l2": rays_frame / (stepwise_ms * 1e-3) / 1e6,
             "wall_s_timed_region": t_wall,
             "clocks": clocks,
             "e2e": {

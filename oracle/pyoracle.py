@@ -28,12 +28,14 @@ LIB = HERE / "liboracle.so"
 
 class OrcStats(C.Structure):
     _fields_ = [(n, C.c_uint64) for n in ("rays", "iters", "sector_fetches", "cell_fetches", "hits", "capped")] + [
-        ("iter_hist", C.c_uint64 * 8)
+        ("iter_hist", C.c_uint64 * 8),
+        ("lod_hist", C.c_uint64 * 6),
     ]
 
     def as_dict(self):
         d = {n: int(getattr(self, n)) for n in ("rays", "iters", "sector_fetches", "cell_fetches", "hits", "capped")}
         d["iter_hist"] = [int(v) for v in self.iter_hist]
+        d["lod_hist"] = [int(v) for v in self.lod_hist]
         return d
 
     def algorithmic_bytes(self, primary_rays: int) -> int:
@@ -89,6 +91,8 @@ def load():
     lib.orc_encode_material.argtypes = [C.c_uint8, C.c_uint8, C.c_uint8, C.c_uint8, C.c_float]
     lib.orc_encode_material.restype = u64
     lib.orc_num_threads.restype = C.c_int
+    lib.orc_debug_pixel.argtypes = [vp, C.POINTER(VrtFrame), u32, u32, vp, vp, vp]
+    lib.orc_debug_pixel.restype = u32
     _lib = lib
     return lib
 
@@ -168,6 +172,14 @@ class OracleMap:
             frame.height if row1 is None else row1,
         )
         return out, aux, st
+
+    def debug_pixel(self, frame: VrtFrame, x, y):
+        """-> (rays[n,6], hits[n], out4) of everything pixel (x,y) casts."""
+        rays = np.zeros((8, 6), np.float32)
+        hits = np.zeros(8, HIT_DTYPE)
+        out4 = np.zeros(4, np.uint32)
+        n = self.lib.orc_debug_pixel(self.h, C.byref(frame), x, y, rays.ctypes.data, hits.ctypes.data, out4.ctypes.data)
+        return rays[:n], hits[:n], out4
 
     def primary_rays(self, frame: VrtFrame):
         """(origins, dirs) of every pixel, row-major — GetPrimaryRay through the oracle."""

@@ -196,7 +196,7 @@ static uint16_t f32_to_f16(float f) {
     uint32_t x = f2u(f);
     uint32_t sign = (x >> 16) & 0x8000u;
     uint32_t ax = x & 0x7FFFFFFFu;
-    if (ax > 0x7F800000u) return (uint16_t)(sign | 0x7FFFu); /* NaN (CUDA canonical 0x7FFF) */
+    if (ax > 0x7F800000u) return (uint16_t)(sign | 0x7E00u | ((x >> 13) & 0x1FFu)); /* NaN: vcvtps2ph keeps sign + upper payload, quiets */
     if (ax >= 0x47800000u) {                                /* >= 65536 -> inf unless rounds below */
         return (uint16_t)(sign | 0x7C00u);
     }
@@ -246,6 +246,7 @@ uint64_t orc_encode_material(uint8_t r, uint8_t g, uint8_t b, uint8_t fuzz, floa
 /* ------------------------------------------------------------------------------------------ */
 typedef struct {
     uint64_t iters, sector_fetches, cell_fetches;
+    uint64_t lod[6]; /* steps taken per cell size 1,2,4,8,16,32 */
 } CastCounters;
 
 /* GetInboundMask, VoxelRT/CpuRenderer.cpp:114-117 */
@@ -284,6 +285,7 @@ static inline int step_pos(const OrcMap* m, int32_t p[3], const float d[3], Cast
     int level4 = mask == 0;                                          /* :160 */
     int level2 = ((half >> (idx & 0xA)) & 0x00330033u) == 0;         /* :161 */
     lod += level4 ? 2 : (level2 ? 1 : 0);                            /* :162 */
+    if (!level0) c->lod[lod]++;
     int32_t cm = (1 << lod) - 1;                                     /* :164 */
     for (int a = 0; a < 3; a++) p[a] = d[a] < 0 ? (p[a] & ~cm) : (p[a] | cm); /* :166-168 */
     return level0;
@@ -350,6 +352,7 @@ static void stats_add(OrcStats* s, const CastCounters* c, const VrtHit* h) {
     s->iters += c->iters;
     s->sector_fetches += c->sector_fetches;
     s->cell_fetches += c->cell_fetches;
+    for (int i = 0; i < 6; i++) s->lod_hist[i] += c->lod[i];
     if (h->flags & VRT_HIT_HIT) s->hits++;
     if (h->flags & VRT_HIT_CAPPED) s->capped++;
     uint32_t it = h->flags >> VRT_HIT_ITERS_SHIFT;
@@ -364,6 +367,7 @@ static void stats_merge(OrcStats* dst, const OrcStats* src) {
     dst->hits += src->hits;
     dst->capped += src->capped;
     for (int i = 0; i < 8; i++) dst->iter_hist[i] += src->iter_hist[i];
+    for (int i = 0; i < 6; i++) dst->lod_hist[i] += src->lod_hist[i];
 }
 
 int orc_num_threads(void) {
@@ -390,7 +394,7 @@ void orc_trace(const OrcMap* m, uint64_t n, const float* origin3, const float* d
 #pragma omp for schedule(dynamic, 4096)
 #endif
         for (int64_t i = 0; i < (int64_t)n; i++) {
-            CastCounters c = {0, 0, 0};
+            CastCounters c = {0, 0, 0, {0}};
             cast_ray(m, origin3 + 3 * i, dir3 + 3 * i, wo, max_iters, &out[i], &c);
             stats_add(&local, &c, &out[i]);
         }
@@ -612,8 +616,28 @@ static inline uint32_t pack_unorm8(float v) {
 
 /* RenderRow body for one pixel, CpuRenderer.cpp:326-402 (lane-wise: a lane whose mask bit is
  * off does nothing further — the packet-coupled leftovers are listed in DESIGN.md §3). */
+/* optional capture of every ray a pixel casts (debugging aid for the parity tests) */
+typedef struct {
+    float* rays; /* per bounce: origin xyz, dir xyz */
+    VrtHit* hits;
+    uint32_t n;
+} PixelTrace;
+
+static void render_pixel_ex(const OrcMap* m, const VrtFrame* f, uint32_t x, uint32_t y, uint32_t* o_albedo, float* o_depth,
+                            uint32_t* o_rg, uint32_t* o_bx, VrtHit* aux, OrcStats* stats, PixelTrace* pt);
 static void render_pixel(const OrcMap* m, const VrtFrame* f, uint32_t x, uint32_t y, uint32_t* o_albedo, float* o_depth,
                          uint32_t* o_rg, uint32_t* o_bx, VrtHit* aux, OrcStats* stats) {
+    render_pixel_ex(m, f, x, y, o_albedo, o_depth, o_rg, o_bx, aux, stats, NULL);
+}
+uint32_t orc_debug_pixel(const OrcMap* m, const VrtFrame* f, uint32_t x, uint32_t y, float* rays6, VrtHit* hits, uint32_t out4[4]) {
+    PixelTrace pt = {rays6, hits, 0};
+    float dep;
+    render_pixel_ex(m, f, x, y, &out4[0], &dep, &out4[2], &out4[3], NULL, NULL, &pt);
+    memcpy(&out4[1], &dep, 4);
+    return pt.n;
+}
+static void render_pixel_ex(const OrcMap* m, const VrtFrame* f, uint32_t x, uint32_t y, uint32_t* o_albedo, float* o_depth,
+                            uint32_t* o_rg, uint32_t* o_bx, VrtHit* aux, OrcStats* stats, PixelTrace* pt) {
     float origin[3], dir[3];
     orc_primary_ray(f, x, y, origin, dir); /* :327-334 */
     uint32_t max_iters = f->max_iters ? f->max_iters : VRT_MAX_ITERS_DEFAULT;
@@ -624,8 +648,13 @@ static void render_pixel(const OrcMap* m, const VrtFrame* f, uint32_t x, uint32_
 
     for (uint32_t i = 0; i <= f->bounces; i++) { /* :342 */
         VrtHit hit;
-        CastCounters c = {0, 0, 0};
+        CastCounters c = {0, 0, 0, {0}};
         cast_ray(m, origin, dir, f->world_origin, max_iters, &hit, &c); /* :343 */
+        if (pt) {
+            memcpy(pt->rays + 6 * pt->n, origin, 12);
+            memcpy(pt->rays + 6 * pt->n + 3, dir, 12);
+            pt->hits[pt->n++] = hit;
+        }
         if (stats) stats_add(stats, &c, &hit);
         if (i == 0 && aux) *aux = hit;
 

@@ -36,6 +36,7 @@ typedef struct OrcStats {
     uint64_t hits;           /* H                                                          */
     uint64_t capped;
     uint64_t iter_hist[8];   /* 0-3,4-7,8-15,16-31,32-63,64-127,128-255,256+               */
+    uint64_t lod_hist[6];    /* empty-cell steps by cell edge 1,2,4,8,16,32 voxels         */
 } OrcStats;
 
 OrcMap* orc_map_create(uint32_t sectors_xz_log2, uint32_t sectors_y_log2);
@@ -74,6 +75,9 @@ void orc_sky_sample(const OrcMap* m, const float dir[3], uint32_t mip, float out
 uint32_t orc_pack_r11g11b10f(float r, float g, float b);
 /* Material::GetEncoded, VoxelMap.h:27-41 */
 uint64_t orc_encode_material(uint8_t r, uint8_t g, uint8_t b, uint8_t fuzz, float emission);
+
+/* debugging aid: every ray pixel (x,y) casts (6 floats each) with its hit record; returns the count */
+uint32_t orc_debug_pixel(const OrcMap* m, const VrtFrame* frame, uint32_t x, uint32_t y, float* rays6, VrtHit* hits, uint32_t out4[4]);
 
 int orc_num_threads(void);
 

@@ -14,6 +14,17 @@ from conftest import assert_hits_equal, ctx_for, random_rays
 pytestmark = pytest.mark.gpu
 
 
+@pytest.fixture(params=[0, 1], ids=["stepwise", "macro"])
+def macro(request, hash_ctx, bench_ctx):
+    """Runs a test with the empty-box macro steps off and on.  With macro steps the iteration count in
+    VrtHit.flags is not the reference's (it is an upper bound); everything else must still be bit-exact."""
+    for c in (hash_ctx, bench_ctx):
+        c.set_option("macro_steps", request.param)
+    yield bool(request.param)
+    for c in (hash_ctx, bench_ctx):
+        c.set_option("macro_steps", 1)
+
+
 def _frame(cam, w, h, **kw):
     from voxelrt_b200 import capi
 
@@ -25,17 +36,17 @@ def _frame(cam, w, h, **kw):
 # explicit rays: vrt_trace == RayCast (CpuRenderer.cpp:172-224)
 # ---------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("seed", [1, 2, 3])
-def test_trace_random_rays(hash_ctx, hash_oracle, seed):
+def test_trace_random_rays(hash_ctx, hash_oracle, seed, macro):
     rng = np.random.default_rng(seed)
     wo = (rng.integers(0, 192), rng.integers(0, 128), rng.integers(0, 192))
     o, d = random_rays(rng, 200_000, 192, 128, wo)
     got = hash_ctx.trace(o, d, wo)
     want, st = hash_oracle.trace(o, d, wo)
     assert st.hits > 20_000
-    assert_hits_equal(got, want, f"seed {seed}")
+    assert_hits_equal(got, want, f"seed {seed}", ignore_iters=macro)
 
 
-def test_trace_edge_cases(hash_ctx, hash_oracle):
+def test_trace_edge_cases(hash_ctx, hash_oracle, macro):
     """Zero / negative-zero / denormal / inf / NaN direction components, axis-aligned rays, rays
     that start inside solid voxels, outside the grid, on integer coordinates, huge origins."""
     rng = np.random.default_rng(11)
@@ -56,17 +67,17 @@ def test_trace_edge_cases(hash_ctx, hash_oracle):
     o[n // 2 + 6100 : n // 2 + 6200] = np.float32(3e9)
     got = hash_ctx.trace(o, d, wo)
     want, _ = hash_oracle.trace(o, d, wo)
-    assert_hits_equal(got, want, "edge cases")
+    assert_hits_equal(got, want, "edge cases", ignore_iters=macro)
 
 
 @pytest.mark.parametrize("max_iters", [1, 2, 7, 128, 1000])
-def test_trace_iteration_cap(hash_ctx, hash_oracle, max_iters):
+def test_trace_iteration_cap(hash_ctx, hash_oracle, max_iters, macro):
     rng = np.random.default_rng(5)
     wo = (96, 64, 96)
     o, d = random_rays(rng, 50_000, 192, 128, wo)
     got = hash_ctx.trace(o, d, wo, max_iters=max_iters)
     want, _ = hash_oracle.trace(o, d, wo, max_iters=max_iters)
-    assert_hits_equal(got, want, f"max_iters {max_iters}")
+    assert_hits_equal(got, want, f"max_iters {max_iters}", ignore_iters=macro)
 
 
 def test_trace_empty_and_ragged(hash_ctx, hash_oracle):
@@ -76,7 +87,7 @@ def test_trace_empty_and_ragged(hash_ctx, hash_oracle):
     rng = np.random.default_rng(9)
     for n in (1, 31, 33, 127, 129, 1000):
         o, d = random_rays(rng, n, 192, 128, (0, 0, 0))
-        assert_hits_equal(hash_ctx.trace(o, d, (0, 0, 0)), hash_oracle.trace(o, d, (0, 0, 0))[0], f"n={n}")
+        assert_hits_equal(hash_ctx.trace(o, d, (0, 0, 0)), hash_oracle.trace(o, d, (0, 0, 0))[0], f"n={n}", ignore_iters=True)
     with pytest.raises(capi.VrtError):
         hash_ctx._chk(hash_ctx.lib.vrt_trace(hash_ctx.h, 4, None, None, None, 0, None))
 
@@ -106,7 +117,7 @@ def test_metrics_match_oracle_counters(hash_ctx, hash_oracle):
 # ---------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("size", [(256, 144), (260, 148), (36, 4)])
 @pytest.mark.parametrize("linear", [False, True])
-def test_render_primary_small(hash_ctx, hash_oracle, size, linear):
+def test_render_primary_small(hash_ctx, hash_oracle, size, linear, macro):
     from scenes import camera
     from voxelrt_b200 import capi
 
@@ -115,7 +126,7 @@ def test_render_primary_small(hash_ctx, hash_oracle, size, linear):
     flags = capi.VRT_FRAME_LINEAR_OUTPUT if linear else 0
     out_g, aux_g = hash_ctx.render(_frame(cam, w, h, flags=flags), want_aux=True)
     out_c, aux_c, _ = hash_oracle.render(_frame(cam, w, h, flags=flags), want_aux=True)
-    assert_hits_equal(aux_g, aux_c, "primary aux")
+    assert_hits_equal(aux_g, aux_c, "primary aux", ignore_iters=macro)
     assert out_g.tobytes() == out_c.tobytes()
 
 
@@ -129,7 +140,7 @@ def test_render_rejects_bad_sizes(hash_ctx):
             hash_ctx.render(_frame(cam, w, h))
 
 
-def test_render_config1_720p(bench_ctx, bench_oracle):
+def test_render_config1_720p(bench_ctx, bench_oracle, macro):
     """BASELINE.json configs[0]: reference camera, 1280x720 primary rays, every hit record bit-exact."""
     from scenes import camera
 
@@ -137,11 +148,11 @@ def test_render_config1_720p(bench_ctx, bench_oracle):
     out_g, aux_g = bench_ctx.render(_frame(cam, 1280, 720), want_aux=True)
     out_c, aux_c, st = bench_oracle.render(_frame(cam, 1280, 720), want_aux=True)
     assert st.rays == 1280 * 720
-    assert_hits_equal(aux_g, aux_c, "config 1")
+    assert_hits_equal(aux_g, aux_c, "config 1", ignore_iters=macro)
     assert out_g.tobytes() == out_c.tobytes()
 
 
-def test_render_config2_4k_full(bench_ctx, bench_oracle):
+def test_render_config2_4k_full(bench_ctx, bench_oracle, macro):
     """BASELINE.json configs[1] at FULL size: all 8,294,400 primary rays {hit, voxel, normal,
     material} (in fact the whole record) bit-exact against the oracle."""
     from scenes import camera
@@ -150,18 +161,18 @@ def test_render_config2_4k_full(bench_ctx, bench_oracle):
     out_g, aux_g = bench_ctx.render(_frame(cam, 3840, 2160), want_aux=True)
     out_c, aux_c, st = bench_oracle.render(_frame(cam, 3840, 2160), want_aux=True)
     assert st.rays == 3840 * 2160
-    assert_hits_equal(aux_g, aux_c, "config 2")
+    assert_hits_equal(aux_g, aux_c, "config 2", ignore_iters=macro)
     assert out_g.tobytes() == out_c.tobytes()
 
 
 @pytest.mark.parametrize("i", range(4))
-def test_render_orbit_cameras(bench_ctx, bench_oracle, i):
+def test_render_orbit_cameras(bench_ctx, bench_oracle, i, macro):
     from scenes import camera
 
     cam = camera.orbit_cameras(4, seed=1)[i]
     out_g, aux_g = bench_ctx.render(_frame(cam, 640, 360), want_aux=True)
     out_c, aux_c, _ = bench_oracle.render(_frame(cam, 640, 360), want_aux=True)
-    assert_hits_equal(aux_g, aux_c, f"orbit {i}")
+    assert_hits_equal(aux_g, aux_c, f"orbit {i}", ignore_iters=macro)
     assert out_g.tobytes() == out_c.tobytes()
 
 
@@ -182,7 +193,7 @@ def test_render_bounces(hash_scene, hash_oracle, shading_inputs, bounces):
         out_g, aux_g = ctx.render(_frame(cam, 320, 180, bounces=bounces, frame_no=frame_no), want_aux=True)
         out_c, aux_c, st = hash_oracle.render(_frame(cam, 320, 180, bounces=bounces, frame_no=frame_no), want_aux=True)
         assert st.rays > 320 * 180
-        assert_hits_equal(aux_g, aux_c, f"bounces {bounces} primary aux")
+        assert_hits_equal(aux_g, aux_c, f"bounces {bounces} primary aux", ignore_iters=True)
         for k in ("albedo", "depth", "irr_rg", "irr_bx"):
             a, b = out_g[k].view(np.uint32), out_c[k].view(np.uint32)
             assert np.array_equal(a, b), f"{k}: {np.count_nonzero(a != b)} texels differ (bounces {bounces}, frame {frame_no})"

@@ -93,7 +93,7 @@ def test_random_edit_script(seed):
         if frame % 6 == 5:
             _compare_all(ctx, orc, n_xz, n_y)
             o, d = random_rays(rng, 20_000, 128, 64, (0, 0, 0))
-            assert_hits_equal(ctx.trace(o, d, (0, 0, 0)), orc.trace(o, d, (0, 0, 0))[0], f"frame {frame}")
+            assert_hits_equal(ctx.trace(o, d, (0, 0, 0)), orc.trace(o, d, (0, 0, 0))[0], f"frame {frame}", ignore_iters=True)
     _compare_all(ctx, orc, n_xz, n_y)
     assert ctx.stats().brick_capacity > 64
     ctx.close()

@@ -59,6 +59,9 @@ struct VrtContext {
     uint32_t* d_sky = nullptr;
     VrtSkyDesc sky{};
 
+    uint32_t* d_sat = nullptr;  // summed-volume table of the box builder
+    bool boxes_stale = true;    // some sector's emptiness changed since the boxes were built
+    bool macro_on = true;
     DevMetrics* d_metrics = nullptr;
     bool metrics_on = false;
     int render_variant = 0;
@@ -189,10 +192,33 @@ RayFrame ray_frame(const VrtContext* ctx, const int32_t wo[3]) {
     W.fast_ok = (wo[0] >= -lim && wo[0] <= lim && wo[1] >= -lim && wo[1] <= lim && wo[2] >= -lim && wo[2] <= lim) ? 1 : 0;
     // hdr_index of the (possibly far out-of-view) sector holding the frame origin; int arithmetic wraps harmlessly
     // because the loop only ever adds offsets that bring the sum back inside [0, n_hdr)
+    W.macro = ctx->macro_on ? 1 : 0;
     W.hoff = W.fast_ok ? (int)((long long)((W.hx >> 5) + 1) + (long long)((W.hz >> 5) + 1) * ctx->sxp +
                                (long long)((W.hy >> 5) + 1) * ctx->sxp * ctx->sxp)
                        : 0;
     return W;
+}
+
+// Rebuilds the empty-sector boxes (k_box_*) on the context stream when they are stale.
+int rebuild_boxes(VrtContext* ctx) {
+    if (!ctx->boxes_stale) return VRT_OK;
+    const uint32_t sxp = ctx->sxp, syp = ctx->syp, sxzp = sxp * sxp, n = ctx->n_hdr;
+    if (!ctx->d_sat) {
+        CU(cudaMalloc((void**)&ctx->d_sat, (size_t)n * sizeof(uint32_t)));
+        ctx->stats.device_bytes += (size_t)n * sizeof(uint32_t);
+    }
+    cudaStream_t s = ctx->stream;
+    k_box_occupancy<<<(n + 255) / 256, 256, 0, s>>>(ctx->d_hdr, ctx->d_sat, n);
+    // along x: lines = (z, y); along z: lines = (x, y); along y: lines = (x, z)
+    k_box_scan<<<(sxp * syp + 127) / 128, 128, 0, s>>>(ctx->d_sat, sxp * syp, sxp, 1u, sxp * syp, sxp, 0u);
+    k_box_scan<<<(sxp * syp + 127) / 128, 128, 0, s>>>(ctx->d_sat, sxp * syp, sxp, sxp, sxp, 1u, sxzp);
+    k_box_scan<<<(sxzp + 127) / 128, 128, 0, s>>>(ctx->d_sat, sxzp, syp, sxzp, sxzp, 1u, 0u);
+    const uint32_t n_view = ctx->n_sectors;
+    k_box_grow<<<(n_view + 127) / 128, 128, 0, s>>>(ctx->d_hdr, ctx->d_sat, sxp, sxzp, 1 << ctx->sxz, 1 << ctx->sy);
+    CU(cudaGetLastError());
+    ctx->stats.last_launches += 5;
+    ctx->boxes_stale = false;
+    return VRT_OK;
 }
 
 // Orders work on a caller stream after the context's residency work, and vice versa.
@@ -377,6 +403,7 @@ extern "C" void vrt_destroy(VrtContext* ctx) {
     cudaFree(ctx->d_bn);
     cudaFree(ctx->d_sky);
     cudaFree(ctx->d_metrics);
+    cudaFree(ctx->d_sat);
     if (ctx->ev_sync) cudaEventDestroy(ctx->ev_sync);
     if (ctx->ev_render) cudaEventDestroy(ctx->ev_render);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -400,6 +427,7 @@ extern "C" int vrt_set_option(VrtContext* ctx, const char* name, int64_t value) 
     if (!ctx || !name) return VRT_ERR_INVALID;
     if (!strcmp(name, "metrics")) ctx->metrics_on = value != 0;
     else if (!strcmp(name, "render_variant")) ctx->render_variant = (int)value;
+    else if (!strcmp(name, "macro_steps")) ctx->macro_on = value != 0;
     else return fail(ctx, VRT_ERR_INVALID, std::string("unknown option ") + name);
     return VRT_OK;
 }
@@ -494,7 +522,10 @@ extern "C" int vrt_sync(VrtContext* ctx, uint32_t n, const VrtDirtySector* recs)
                 if (old_n) ctx->arena.quarantine(old.base, old_n);
             }
             cur.mask = new_mask;
-            if ((old.mask == 0) != (new_mask == 0)) ctx->resident_sectors += new_mask ? 1 : -1;
+            if ((old.mask == 0) != (new_mask == 0)) {
+                ctx->resident_sectors += new_mask ? 1 : -1;
+                ctx->boxes_stale = true;
+            }
             ctx->sectors[si] = cur;
             headers.push_back(HeaderUpdate{hdr_index(ctx->sxp, ctx->sxp * ctx->sxp, d.sx, d.sy, d.sz), (uint32_t)new_mask,
                                            (uint32_t)(new_mask >> 32), cur.base});
@@ -550,6 +581,10 @@ extern "C" int vrt_sync(VrtContext* ctx, uint32_t n, const VrtDirtySector* recs)
         CU(cudaGetLastError());
     }
     ctx->arena.flush_quarantine();
+    {
+        int st = rebuild_boxes(ctx);
+        if (st) return st;
+    }
     CU(cudaEventRecord(ctx->ev_sync, ctx->stream));
     ctx->stats.bytes_uploaded = total;
     ctx->stats.bricks_uploaded = nu;

@@ -10,7 +10,7 @@ namespace vrt {
 // (CpuRenderer.cpp:172-224) for callers that bring their own rays.
 // ---------------------------------------------------------------------------------------------
 template <bool METRICS>
-__global__ void __launch_bounds__(128) k_trace(const __grid_constant__ DevScene S, const __grid_constant__ RayFrame W,
+__global__ void __launch_bounds__(128, 8) k_trace(const __grid_constant__ DevScene S, const __grid_constant__ RayFrame W,
                                                const float* __restrict__ origin3, const float* __restrict__ dir3, uint32_t max_iters,
                                                uint64_t n, VrtHit* __restrict__ out, DevMetrics* metrics) {
     uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -163,6 +163,64 @@ __global__ void k_init_headers(uint4* hdr, uint32_t sxp, uint32_t syp) {
     uint32_t x = i % sxp, z = (i / sxp) % sxp, y = i / (sxp * sxp);
     bool border = x == 0 || z == 0 || y == 0 || x == sxp - 1 || z == sxp - 1 || y == syp - 1;
     hdr[i] = make_uint4(0u, 0u, 0u, border ? VRT_HDR_OUTSIDE : 0u);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Empty-box builder.  For every empty in-view sector: a box of empty sectors that
+// contains it, grown greedily one slab at a time; slab emptiness is a 3-D summed-volume-table query
+// over the bordered grid (sat index of sector coordinate c is c + 1; the border counts as empty but
+// boxes never leave [0, extent)).  Rebuilt only when some sector's emptiness changed.
+// ---------------------------------------------------------------------------------------------
+__global__ void k_box_occupancy(const uint4* __restrict__ hdr, uint32_t* __restrict__ sat, uint32_t n) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint4 h = hdr[i];
+    sat[i] = ((h.x | h.y) != 0u) ? 1u : 0u;
+}
+// inclusive prefix sums along one axis: `lines` independent lines of `len` elements, element j of
+// line l at base(l) + j * stride, base(l) = (l / inner) * outer_stride + (l % inner) * inner_stride
+__global__ void k_box_scan(uint32_t* sat, uint32_t lines, uint32_t len, uint32_t stride, uint32_t inner, uint32_t inner_stride,
+                           uint32_t outer_stride) {
+    uint32_t l = blockIdx.x * blockDim.x + threadIdx.x;
+    if (l >= lines) return;
+    uint32_t* p = sat + (size_t)(l / inner) * outer_stride + (size_t)(l % inner) * inner_stride;
+    uint32_t acc = 0;
+    for (uint32_t j = 0; j < len; j++) {
+        acc += p[(size_t)j * stride];
+        p[(size_t)j * stride] = acc;
+    }
+}
+__device__ __forceinline__ uint32_t sat_count(const uint32_t* __restrict__ sat, uint32_t sxp, uint32_t sxzp, int x0, int x1, int y0, int y1,
+                                              int z0, int z1) {
+    // sum over [x0,x1] x [y0,y1] x [z0,z1] (sector coords): indices c + 1 (high) and c (low - 1 + 1)
+    auto at = [&](int X, int Y, int Z) -> uint32_t { return __ldg(sat + (size_t)X + (size_t)Z * sxp + (size_t)Y * sxzp); };
+    int X1 = x1 + 1, Y1 = y1 + 1, Z1 = z1 + 1;
+    return at(X1, Y1, Z1) - at(x0, Y1, Z1) - at(X1, y0, Z1) - at(X1, Y1, z0) + at(x0, y0, Z1) + at(x0, Y1, z0) + at(X1, y0, z0) -
+           at(x0, y0, z0);
+}
+__global__ void __launch_bounds__(128) k_box_grow(uint4* __restrict__ hdr, const uint32_t* __restrict__ sat, uint32_t sxp, uint32_t sxzp,
+                                                  int ext_xz, int ext_y) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t n_view = (uint32_t)ext_xz * (uint32_t)ext_xz * (uint32_t)ext_y;
+    if (i >= n_view) return;
+    int x = (int)(i % (uint32_t)ext_xz), z = (int)((i / (uint32_t)ext_xz) % (uint32_t)ext_xz), y = (int)(i / ((uint32_t)ext_xz * (uint32_t)ext_xz));
+    uint32_t hi = hdr_index(sxp, sxzp, x, y, z);
+    uint4 h = hdr[hi];
+    if ((h.x | h.y) != 0u) return;  // resident sector: z/w hold its slot base and popcount
+    int x0 = x, x1 = x, y0 = y, y1 = y, z0 = z, z1 = z;
+    for (bool grew = true; grew;) {
+        grew = false;
+        if (x1 + 1 < ext_xz && sat_count(sat, sxp, sxzp, x1 + 1, x1 + 1, y0, y1, z0, z1) == 0u) x1++, grew = true;
+        if (x0 > 0 && sat_count(sat, sxp, sxzp, x0 - 1, x0 - 1, y0, y1, z0, z1) == 0u) x0--, grew = true;
+        if (z1 + 1 < ext_xz && sat_count(sat, sxp, sxzp, x0, x1, y0, y1, z1 + 1, z1 + 1) == 0u) z1++, grew = true;
+        if (z0 > 0 && sat_count(sat, sxp, sxzp, x0, x1, y0, y1, z0 - 1, z0 - 1) == 0u) z0--, grew = true;
+        if (y1 + 1 < ext_y && sat_count(sat, sxp, sxzp, x0, x1, y1 + 1, y1 + 1, z0, z1) == 0u) y1++, grew = true;
+        if (y0 > 0 && sat_count(sat, sxp, sxzp, x0, x1, y0 - 1, y0 - 1, z0, z1) == 0u) y0--, grew = true;
+    }
+    bool big = (x1 - x0) >= 2 || (y1 - y0) >= 2 || (z1 - z0) >= 2;  // worth a macro step: >= 3 sectors along some axis
+    h.z = (uint32_t)x0 | ((uint32_t)y0 << 10) | ((uint32_t)z0 << 20);
+    h.w = (uint32_t)x1 | ((uint32_t)y1 << 10) | ((uint32_t)z1 << 20) | (big ? VRT_HDR_HASBOX : 0u);
+    hdr[hi] = h;
 }
 
 // ---------------------------------------------------------------------------------------------
