@@ -61,7 +61,7 @@ struct VrtContext {
 
     uint32_t* d_sat = nullptr;  // summed-volume table of the box builder
     bool boxes_stale = true;    // some sector's emptiness changed since the boxes were built
-    bool macro_on = true;
+    int macro_on = 1;  // 0 off, 1 on, 2 on + "metrics" launches count the macro loop's own trips (diagnostic)
     DevMetrics* d_metrics = nullptr;
     bool metrics_on = false;
     int render_variant = 0;
@@ -192,7 +192,7 @@ RayFrame ray_frame(const VrtContext* ctx, const int32_t wo[3]) {
     W.fast_ok = (wo[0] >= -lim && wo[0] <= lim && wo[1] >= -lim && wo[1] <= lim && wo[2] >= -lim && wo[2] <= lim) ? 1 : 0;
     // hdr_index of the (possibly far out-of-view) sector holding the frame origin; int arithmetic wraps harmlessly
     // because the loop only ever adds offsets that bring the sum back inside [0, n_hdr)
-    W.macro = ctx->macro_on ? 1 : 0;
+    W.macro = ctx->macro_on;
     W.hoff = W.fast_ok ? (int)((long long)((W.hx >> 5) + 1) + (long long)((W.hz >> 5) + 1) * ctx->sxp +
                                (long long)((W.hy >> 5) + 1) * ctx->sxp * ctx->sxp)
                        : 0;
@@ -427,7 +427,7 @@ extern "C" int vrt_set_option(VrtContext* ctx, const char* name, int64_t value) 
     if (!ctx || !name) return VRT_ERR_INVALID;
     if (!strcmp(name, "metrics")) ctx->metrics_on = value != 0;
     else if (!strcmp(name, "render_variant")) ctx->render_variant = (int)value;
-    else if (!strcmp(name, "macro_steps")) ctx->macro_on = value != 0;
+    else if (!strcmp(name, "macro_steps")) ctx->macro_on = (int)value;
     else return fail(ctx, VRT_ERR_INVALID, std::string("unknown option ") + name);
     return VRT_OK;
 }
