@@ -1,0 +1,223 @@
+"""ctypes wrapper of oracle/_ref/libref_cpu.so — the reference's OWN CpuRenderer.cpp / VoxelMap.cpp
+compiled from /root/reference by oracle/Makefile (see oracle/ref_harness.cpp).  TEST INFRASTRUCTURE:
+pins the oracle restatement and serves as the `reference` CPU baseline in bench.py.  The library is
+built with -march=native on an AVX-512 host; `available()` refuses to load it on a CPU without the
+ISA it was built for."""
+from __future__ import annotations
+
+import ctypes as C
+import time
+from pathlib import Path
+
+import numpy as np
+
+from voxelrt_b200.capi import HIT_DTYPE, HITD_DTYPE, TILE_DTYPE, VrtDirtySector, VrtFrame, VrtSkyDesc, make_records
+
+HERE = Path(__file__).resolve().parent
+LIB = HERE / "_ref" / "libref_cpu.so"
+_NEED = ("avx512f", "avx512bw", "avx512dq", "avx512vl", "avx2", "fma", "bmi2")
+_lib = None
+
+
+def _cpu_ok() -> bool:
+    try:
+        flags = set()
+        for line in open("/proc/cpuinfo"):
+            if line.startswith("flags"):
+                flags = set(line.split(":", 1)[1].split())
+                break
+        return all(f in flags for f in _NEED)
+    except OSError:
+        return False
+
+
+def available() -> bool:
+    return LIB.exists() and _cpu_ok()
+
+
+def load():
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not available():
+        raise RuntimeError("oracle/_ref/libref_cpu.so missing or this CPU lacks AVX-512")
+    lib = C.CDLL(str(LIB))
+    vp, u32, u64 = C.c_void_p, C.c_uint32, C.c_uint64
+    lib.ref_create.restype = vp
+    lib.ref_destroy.argtypes = [vp]
+    lib.ref_destroy.restype = None
+    lib.ref_set_palette.argtypes = [vp, vp]
+    lib.ref_set_palette.restype = None
+    lib.ref_encode_material.argtypes = [C.c_uint8] * 4 + [C.c_float]
+    lib.ref_encode_material.restype = u64
+    lib.ref_sync.argtypes = [vp, u32, C.POINTER(VrtDirtySector)]
+    lib.ref_read_sector.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.POINTER(u64), vp, vp]
+    lib.ref_set_blue_noise.argtypes = [vp]
+    lib.ref_set_blue_noise.restype = None
+    lib.ref_set_sky.argtypes = [C.POINTER(VrtSkyDesc), vp]
+    lib.ref_trace.argtypes = [vp, u64, vp, vp, C.POINTER(C.c_int32), vp, C.c_int]
+    lib.ref_trace.restype = None
+    lib.ref_hit_query.argtypes = [vp, u64, vp, vp, u32, vp]
+    lib.ref_hit_query.restype = None
+    lib.ref_primary_rays.argtypes = [C.POINTER(VrtFrame), vp, vp]
+    lib.ref_primary_rays.restype = None
+    lib.ref_render.argtypes = [vp, C.POINTER(VrtFrame), vp, C.c_int]
+    lib.ref_render.restype = C.c_double
+    lib.ref_inverse_proj_screen.argtypes = [vp, C.c_int, C.c_int, vp]
+    lib.ref_inverse_proj_screen.restype = None
+    lib.ref_sincos_2pi.argtypes = [C.c_float, vp, vp]
+    lib.ref_sincos_2pi.restype = None
+    lib.ref_sample_direction.argtypes = [C.c_float, C.c_float, vp]
+    lib.ref_sample_direction.restype = None
+    lib.ref_blue_noise_tile.argtypes = [u32, u32, u32, u32, vp]
+    lib.ref_blue_noise_tile.restype = None
+    lib.ref_sky_sample.argtypes = [vp, C.c_int, vp]
+    lib.ref_sky_sample.restype = None
+    lib.ref_pack_r11g11b10f.argtypes = [C.c_float] * 3
+    lib.ref_pack_r11g11b10f.restype = u32
+    lib.ref_pack_rgba8.argtypes = [C.c_float] * 4
+    lib.ref_pack_rgba8.restype = u32
+    lib.ref_pack_rg16f.argtypes = [C.c_float] * 2
+    lib.ref_pack_rg16f.restype = u32
+    _lib = lib
+    return lib
+
+
+class RefMap:
+    """The reference's VoxelMap + FlatVoxelStorage (a dense 2048x512x2048 view: ~2.3 GB of host memory)."""
+
+    def __init__(self):
+        self.lib = load()
+        self.h = C.c_void_p(self.lib.ref_create())
+
+    def close(self):
+        if getattr(self, "h", None) and self.h.value:
+            self.lib.ref_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_palette(self, palette):
+        p = np.ascontiguousarray(palette, dtype=np.uint64)
+        self.lib.ref_set_palette(self.h, p.ctypes.data)
+
+    def sync(self, sectors):
+        arr, keep, n = make_records(sectors)
+        self.lib.ref_sync(self.h, n, arr)
+        del keep
+
+    def read_sector(self, sx, sy, sz):
+        mask = C.c_uint64()
+        bricks = np.zeros((64, 512), np.uint8)
+        cells = np.zeros((64, 8), np.uint64)
+        st = self.lib.ref_read_sector(self.h, sx, sy, sz, C.byref(mask), bricks.ctypes.data, cells.ctypes.data)
+        assert st == 0
+        return mask.value, bricks, cells
+
+    def set_blue_noise(self, rg):
+        b = np.ascontiguousarray(rg, dtype=np.uint8)
+        self.lib.ref_set_blue_noise(b.ctypes.data)
+
+    def set_sky(self, desc, texels):
+        t = np.ascontiguousarray(texels, dtype=np.uint32)
+        if self.lib.ref_set_sky(C.byref(desc), t.ctypes.data) != 0:
+            raise RuntimeError("sky layout disagrees with swr::Texture2D")
+
+    def trace(self, origin3, dir3, world_origin, lanes_per_packet=16):
+        """lanes_per_packet=1: lane-wise semantics (what the oracle restates); 16: packets as rendered."""
+        o = np.ascontiguousarray(origin3, dtype=np.float32).reshape(-1, 3)
+        d = np.ascontiguousarray(dir3, dtype=np.float32).reshape(-1, 3)
+        out = np.zeros(o.shape[0], HIT_DTYPE)
+        wo = (C.c_int32 * 3)(*[int(v) for v in world_origin])
+        if o.shape[0]:
+            self.lib.ref_trace(self.h, o.shape[0], o.ctypes.data, d.ctypes.data, wo, out.ctypes.data, lanes_per_packet)
+        return out
+
+    def hit_query(self, origin3, dir3, max_iters=1024):
+        o = np.ascontiguousarray(origin3, dtype=np.float64).reshape(-1, 3)
+        d = np.ascontiguousarray(dir3, dtype=np.float64).reshape(-1, 3)
+        out = np.zeros(o.shape[0], HITD_DTYPE)
+        self.lib.ref_hit_query(self.h, o.shape[0], o.ctypes.data, d.ctypes.data, max_iters, out.ctypes.data)
+        return out
+
+    def primary_rays(self, frame: VrtFrame):
+        n = frame.width * frame.height
+        o = np.zeros((n, 3), np.float32)
+        d = np.zeros((n, 3), np.float32)
+        self.lib.ref_primary_rays(C.byref(frame), o.ctypes.data, d.ctypes.data)
+        return o, d
+
+    def render(self, frame: VrtFrame, threads=0):
+        """-> (tiles, seconds inside the row loop)."""
+        nbytes = frame.width * frame.height * 16
+        raw = np.zeros(nbytes + 64, np.uint8)  # Framebuffer::Tile is alignas(64) and stored with aligned moves
+        off = (-raw.ctypes.data) % 64
+        out = raw[off : off + nbytes].view(TILE_DTYPE)
+        secs = self.lib.ref_render(self.h, C.byref(frame), out.ctypes.data, threads)
+        return out, float(secs)
+
+
+def encode_material(r, g, b, fuzz=255, emission=0.0):
+    return int(load().ref_encode_material(r, g, b, fuzz, emission))
+
+
+def inverse_proj_screen(m16, w, h):
+    m = np.ascontiguousarray(m16, np.float32).reshape(16)
+    out = np.zeros(16, np.float32)
+    load().ref_inverse_proj_screen(m.ctypes.data, w, h, out.ctypes.data)
+    return out
+
+
+class RefRenderer:
+    """bench.py helper: the reference renderer holding a scene; render_seconds() times one frame."""
+
+    def __init__(self, scene, recs):
+        self.map = RefMap()
+        self.map.set_palette(scene["palette"])
+        self.map.sync(recs)
+        self._sky = False
+
+    def render_seconds(self, w, h, bounces):
+        from scenes import camera, shading
+        from voxelrt_b200 import capi
+
+        if bounces and not self._sky:
+            self.map.set_blue_noise(shading.load_blue_noise()[0])
+            d, t, _ = shading.load_sky()
+            self.map.set_sky(d, t)
+            self._sky = True
+        cam = camera.Camera()
+        proj, inv, wo, frac = cam.matrices(w, h)
+        frame = capi.make_frame(w, h, inv, proj, wo, frac, frame_no=1, bounces=bounces)
+        _, secs = self.map.render(frame)
+        return secs
+
+
+def sincos_2pi(x):
+    s, c = C.c_float(), C.c_float()
+    load().ref_sincos_2pi(float(x), C.byref(s), C.byref(c))
+    return np.float32(s.value), np.float32(c.value)
+
+
+def sample_direction(sx, sy):
+    out = np.zeros(3, np.float32)
+    load().ref_sample_direction(float(sx), float(sy), out.ctypes.data)
+    return out
+
+
+def blue_noise_tile(x, y, frame_no, sample_idx):
+    """-> float32[4,4,2]: rows = tile y, cols = tile x of the 4x4 tile containing (x, y)."""
+    out = np.zeros(32, np.float32)
+    load().ref_blue_noise_tile(x, y, frame_no, sample_idx, out.ctypes.data)
+    return out.reshape(4, 4, 2)
+
+
+def sky_sample(direction, mip):
+    d = np.ascontiguousarray(direction, np.float32)
+    out = np.zeros(3, np.float32)
+    load().ref_sky_sample(d.ctypes.data, int(mip), out.ctypes.data)
+    return out

@@ -176,6 +176,7 @@ static inline int32_t x86_trunc2i(float x) {
     if (!(x >= -2147483648.0f && x < 2147483648.0f)) return INT32_MIN;
     return (int32_t)x;
 }
+static inline float x86_fract(float x); /* below */
 static inline uint32_t f2u(float f) {
     uint32_t u;
     memcpy(&u, &f, 4);
@@ -185,6 +186,18 @@ static inline float u2f(uint32_t u) {
     float f;
     memcpy(&f, &u, 4);
     return f;
+}
+/* simd::fract = VREDUCEPS imm8=TO_NEG_INF (SIMD_AVX512.h:116): x - floor(x) with the result itself
+ * rounded toward -inf (pinned against oracle/_ref: a negative x whose 1 + x is inexact comes out
+ * one ulp below the round-to-nearest value).  x - floor(x) is exact in binary64. */
+static inline float x86_fract(float x) {
+    if (!(x == x)) return x;     /* NaN propagates */
+    if (isinf(x)) return 0.0f;   /* VREDUCEPS(+-inf) = +0 */
+    double e = (double)x - floor((double)x);
+    if (e == 0.0) return -0.0f; /* an exact zero difference is -0 under round-toward-negative */
+    float r = (float)e;
+    if ((double)r > e) r = nextafterf(r, -INFINITY);
+    return r;
 }
 /* canonical replacements of the hardware approximations:
  * approx_rsqrt = _mm512_rsqrt14_ps, approx_rcp = _mm512_rcp14_ps (SIMD_AVX512.h:140-142) */
@@ -338,8 +351,8 @@ static void cast_ray(const OrcMap* m, const float o[3], const float d[3], const 
     out->px = cur[0];
     out->py = cur[1];
     out->pz = cur[2];
-    out->u = fu - floorf(fu); /* fract = _mm512_reduce_ps(x, TO_NEG_INF) (SIMD_AVX512.h:116) */
-    out->v = fv - floorf(fv);
+    out->u = x86_fract(fu); /* fract = _mm512_reduce_ps(x, TO_NEG_INF) (SIMD_AVX512.h:116) */
+    out->v = x86_fract(fv);
     uint32_t iters_done = it < max_iters ? it + 1 : max_iters;
     if (iters_done > 0xFFFF) iters_done = 0xFFFF;
     out->flags = (uint32_t)((nx + 1) | ((ny + 1) << 2) | ((nz + 1) << 4)) | ((!active && inb) ? VRT_HIT_HIT : 0) | /* :222 */
@@ -613,6 +626,12 @@ static inline uint32_t pack_unorm8(float v) {
     if (i > 32767) i = 32767;
     return (uint32_t)(i < 0 ? 0 : (i > 255 ? 255 : i));
 }
+
+uint32_t orc_pack_unorm8x4(float r, float g, float b, float a) {
+    return pack_unorm8(r) | (pack_unorm8(g) << 8) | (pack_unorm8(b) << 16) | (pack_unorm8(a) << 24);
+}
+uint32_t orc_pack_half2(float x, float y) { return (uint32_t)f32_to_f16(x) | ((uint32_t)f32_to_f16(y) << 16); }
+void orc_sincos_2pi(float x, float* s, float* c) { sincos_2pi(x, s, c); }
 
 /* RenderRow body for one pixel, CpuRenderer.cpp:326-402 (lane-wise: a lane whose mask bit is
  * off does nothing further — the packet-coupled leftovers are listed in DESIGN.md §3). */

@@ -79,6 +79,11 @@ uint64_t orc_encode_material(uint8_t r, uint8_t g, uint8_t b, uint8_t fuzz, floa
 /* debugging aid: every ray pixel (x,y) casts (6 floats each) with its hit record; returns the count */
 uint32_t orc_debug_pixel(const OrcMap* m, const VrtFrame* frame, uint32_t x, uint32_t y, float* rays6, VrtHit* hits, uint32_t out4[4]);
 
+/* RGBA8u::Pack / RG16f::Pack (Texture.h:41-62,101-116), simd::sincos_2pi (SIMD.h:175-190) */
+uint32_t orc_pack_unorm8x4(float r, float g, float b, float a);
+uint32_t orc_pack_half2(float x, float y);
+void orc_sincos_2pi(float x, float* s, float* c);
+
 int orc_num_threads(void);
 
 #ifdef __cplusplus

@@ -246,3 +246,41 @@ def test_hit_query(hash_ctx, hash_oracle):
         if a.dtype.kind == "f":
             a, b = a.view(f"u{a.dtype.itemsize}"), b.view(f"u{b.dtype.itemsize}")
         assert np.array_equal(a, b), name
+
+
+# ---------------------------------------------------------------------------------------------
+# golden vectors computed by the REFERENCE ITSELF (tests/golden, made from oracle/_ref)
+# ---------------------------------------------------------------------------------------------
+def test_gpu_trace_matches_reference_golden(hash_scene, hash_ctx, macro):
+    """vrt_trace against RayCast of the reference's own CpuRenderer.cpp (lane-wise), every field."""
+    from pathlib import Path
+
+    from scenes import terrain
+
+    z = np.load(Path(__file__).resolve().parent / "golden" / "ref_trace_lane.npz")
+    assert str(z["scene_digest"]) == terrain.scene_digest(hash_scene)
+    want = z["hits"]
+    got = hash_ctx.trace(z["origin"], z["dir"], z["world_origin"])
+    hit = (want["flags"] & 0x100) != 0
+    assert np.array_equal(got["flags"] & 0x13F, want["flags"] & 0x13F)
+    assert np.array_equal(got["material"], want["material"])
+    for f in ("dist", "px", "py", "pz", "u", "v"):
+        ok = (got[f].view(np.uint32) == want[f].view(np.uint32)) | (np.isnan(got[f]) & np.isnan(want[f]))
+        assert ok.all(), f
+    for f in ("vx", "vy", "vz"):
+        assert np.array_equal(got[f][hit], want[f][hit]), f
+
+
+def test_gpu_hit_query_matches_reference_golden(hash_scene, hash_ctx):
+    """vrt_hit_query against the reference's VoxelMap::RayCast (fp64), bit-exact."""
+    from pathlib import Path
+
+    z = np.load(Path(__file__).resolve().parent / "golden" / "ref_hit_query.npz")
+    want = z["hits"]
+    got = hash_ctx.hit_query(z["origin"], z["dir"])
+    hit = want["dist"] >= 0
+    assert np.array_equal(got["dist"].view(np.uint64), want["dist"].view(np.uint64))
+    for f in ("nx", "ny", "nz", "u", "v"):
+        assert np.array_equal(got[f][hit].view(np.uint32), want[f][hit].view(np.uint32)), f
+    for f in ("vx", "vy", "vz"):
+        assert np.array_equal(got[f][hit], want[f][hit]), f
