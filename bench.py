@@ -305,6 +305,18 @@ def run_b200(args):
     npx = w * h
     rays_frame = npx * (1 + args.bounces)
     fb = torch.zeros(npx * 4, dtype=torch.int32, device="cuda")  # 16 B/px
+    # N > 1: tile gather over NVLink — rank 0 owns the framebuffer, every other rank maps it through
+    # CUDA IPC and its render kernel stores finished tiles straight into rank 0's memory (peer stores).
+    out_ptr = fb.data_ptr()
+    if world > 1:
+        box = [None]
+        if rank == 0:
+            handle, owner_ptr = ctx.fb_export(npx * 16)
+            box[0] = handle
+            out_ptr = owner_ptr
+        dist.broadcast_object_list(box, src=0)
+        if rank != 0:
+            out_ptr = ctx.fb_import(box[0])
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
     # a real (non-legacy) stream: handle 0 would mean "the context's own stream" to the C ABI and
     # torch events recorded on the legacy stream would not bracket the kernel
@@ -314,7 +326,7 @@ def run_b200(args):
     frame = bench_frame(w, h, args.bounces, part_index=rank, part_count=world)
 
     def step():
-        ctx.render_device(frame, fb.data_ptr(), None, stream.cuda_stream)
+        ctx.render_device(frame, out_ptr, None, stream.cuda_stream)
 
     # traversal counters of this frame (untimed, metrics build of the same kernel)
     ctx.set_option("metrics", 1)
@@ -322,11 +334,9 @@ def run_b200(args):
     torch.cuda.synchronize()
     m = ctx.metrics()
     ctx.set_option("metrics", 0)
-    my_primary = 0
-    tiles_x, tiles_y = (w + 31) // 32, (h + 31) // 32
-    for t in range(rank, tiles_x * tiles_y, world):
-        tx, ty = t % tiles_x, t // tiles_x
-        my_primary += min(32, w - tx * 32) * min(32, h - ty * 32)
+    from voxelrt_b200 import partition
+
+    my_primary = partition.pixels_of_rank(w, h, rank, world)
     alg_bytes = 8 * m.sector_fetches + 8 * m.cell_fetches + 9 * m.hits + 16 * my_primary
 
     for _ in range(args.warmup):
@@ -373,6 +383,22 @@ def run_b200(args):
     stepwise_ms = a.elapsed_time(b) / args.steps
     ctx.set_option("macro_steps", 1)
 
+    gather_ok = None
+    if world > 1:
+        # the gathered frame in rank 0's memory must equal the frame rank 0 renders alone
+        step()
+        torch.cuda.synchronize()
+        dist.barrier()
+        if rank == 0:
+            solo = torch.zeros(npx * 4, dtype=torch.int32, device="cuda")
+            ctx.render_device(bench_frame(w, h, args.bounces), solo.data_ptr(), None, stream.cuda_stream)
+            torch.cuda.synchronize()
+            class _DevPtr:  # view rank 0's exported framebuffer as a tensor
+                __cuda_array_interface__ = {"shape": (npx * 4,), "typestr": "<i4", "data": (int(out_ptr), False), "version": 2}
+
+            gathered = torch.as_tensor(_DevPtr(), device="cuda")
+            gather_ok = bool(torch.equal(solo, gathered))
+        dist.barrier()
     tt = torch.tensor([total_ms, warm_ms], dtype=torch.float64, device="cuda")
     ab = torch.tensor([float(alg_bytes)], dtype=torch.float64, device="cuda")
     if world > 1:
@@ -435,6 +461,7 @@ def run_b200(args):
                 "api": "vrt_render (host buffers, pinned output)",
             },
             "gpu_launches": args.steps,
+            "gather": None if world == 1 else {"how": "peer stores into rank 0's framebuffer (CUDA IPC over NVLink), fused into the render kernel's epilogue", "verified_equal_to_single_gpu_frame": gather_ok},
             "roofline": {
                 "bound": "hbm",
                 "kernel": "vrt::k_render<false>",

@@ -1,0 +1,30 @@
+"""Host-side screen-tile partition: macro tile t (32x32 px, row-major) belongs to rank
+t % part_count — the rule `warp_tile_origin` in csrc/vrt_kernels.cuh applies on the device and
+`orc_render` applies in the oracle.  Used by bench.py (per-rank ray counts) and the multi-rank tests."""
+from __future__ import annotations
+
+TILE = 32
+
+
+def tile_grid(width: int, height: int):
+    return (width + TILE - 1) // TILE, (height + TILE - 1) // TILE
+
+
+def tiles_of_rank(width: int, height: int, part_index: int, part_count: int):
+    tx, ty = tile_grid(width, height)
+    return list(range(part_index, tx * ty, part_count))
+
+
+def tile_rect(width: int, height: int, t: int):
+    """-> (x0, y0, w, h) of macro tile t clipped to the frame."""
+    tx, _ = tile_grid(width, height)
+    x0, y0 = (t % tx) * TILE, (t // tx) * TILE
+    return x0, y0, min(TILE, width - x0), min(TILE, height - y0)
+
+
+def pixels_of_rank(width: int, height: int, part_index: int, part_count: int) -> int:
+    n = 0
+    for t in tiles_of_rank(width, height, part_index, part_count):
+        _, _, w, h = tile_rect(width, height, t)
+        n += w * h
+    return n
