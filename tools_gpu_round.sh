@@ -4,10 +4,15 @@ set -x
 mkdir -p gpurun_out
 nvidia-smi -L > gpurun_out/gpu.txt 2>&1
 nproc >> gpurun_out/gpu.txt
+grep -m1 "model name" /proc/cpuinfo >> gpurun_out/gpu.txt
+grep -m1 -o "avx512f" /proc/cpuinfo >> gpurun_out/gpu.txt
 timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1; echo "pytest exit $?" >> gpurun_out/pytest_gpu.log
-tail -15 gpurun_out/pytest_gpu.log
+tail -6 gpurun_out/pytest_gpu.log
+timeout 120 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1; tail -2 gpurun_out/smoke.log
 timeout 600 python bench.py > gpurun_out/bench.json 2> gpurun_out/bench.err; tail -3 gpurun_out/bench.err; cat gpurun_out/bench.json
 timeout 300 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_ref.json 2>> gpurun_out/bench.err; cat gpurun_out/bench_ref.json
+if [ "$1" != "noprof" ]; then
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches.csv python bench.py --steps 3 --warmup 3 --no-cpu > gpurun_out/bench_under_ncu.log 2>&1
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_render -s 4 -c 2 -o gpurun_out/prof_render python bench.py --steps 3 --warmup 3 --no-cpu > gpurun_out/ncu_full.log 2>&1
+fi
 ls -la gpurun_out

@@ -193,6 +193,8 @@ RayFrame ray_frame(const VrtContext* ctx, const int32_t wo[3]) {
     // hdr_index of the (possibly far out-of-view) sector holding the frame origin; int arithmetic wraps harmlessly
     // because the loop only ever adds offsets that bring the sum back inside [0, n_hdr)
     W.macro = ctx->macro_on;
+    W.hsx = W.hx >> 5, W.hsy = W.hy >> 5, W.hsz = W.hz >> 5;
+    W.klx = -W.hx - W.cqx, W.kly = -W.hy - W.cqy, W.klz = -W.hz - W.cqz;  // int wrap-around is intended (MAGIC_BITS arithmetic)
     W.hoff = W.fast_ok ? (int)((long long)((W.hx >> 5) + 1) + (long long)((W.hz >> 5) + 1) * ctx->sxp +
                                (long long)((W.hy >> 5) + 1) * ctx->sxp * ctx->sxp)
                        : 0;
@@ -301,6 +303,9 @@ int launch_render(VrtContext* ctx, const VrtFrame* f, void* d_out, VrtHit* d_aux
     uint32_t macros = macros_x * macros_y;
     uint32_t my_macros = macros / part_count + ((macros % part_count) > f->part_index ? 1u : 0u);
     F.n_work = my_macros * 32u;
+    F.macros_x = macros_x;
+    F.macros_x_magic = macros_x > 1 ? (uint32_t)((0x100000000ull + macros_x - 1) / macros_x) : 0u;
+    if ((uint64_t)macros * macros_x >= 0xFFFFFFFFull) return fail(ctx, VRT_ERR_INVALID, "frame too large");
     if (F.n_work == 0) return VRT_OK;
     DevScene S = dev_scene(ctx);
     unsigned blocks = (F.n_work + 7) / 8;

@@ -41,8 +41,8 @@ __global__ void __launch_bounds__(128, 8) k_trace(const __grid_constant__ DevSce
 __device__ __forceinline__ bool warp_tile_origin(const FrameParams& F, uint32_t work, uint32_t& x0, uint32_t& y0) {
     uint32_t macro_local = work >> 5, sub = work & 31u;
     uint32_t macro = macro_local * F.part_count + F.part_index;
-    uint32_t macros_x = (F.width + 31u) >> 5;
-    uint32_t mx = macro % macros_x, my = macro / macros_x;
+    // macro / macros_x by multiplication with ceil(2^32 / macros_x): exact while macro * macros_x < 2^32
+    uint32_t my = F.macros_x_magic ? __umulhi(macro, F.macros_x_magic) : macro, mx = macro - my * F.macros_x;
     x0 = (mx << 5) + ((sub & 3u) << 3);
     y0 = (my << 5) + ((sub >> 2) << 2);
     return x0 < F.width && y0 < F.height;
@@ -218,8 +218,9 @@ __global__ void __launch_bounds__(128) k_box_grow(uint4* __restrict__ hdr, const
         if (y0 > 0 && sat_count(sat, sxp, sxzp, x0, x1, y0 - 1, y0 - 1, z0, z1) == 0u) y0--, grew = true;
     }
     bool big = (x1 - x0) >= 2 || (y1 - y0) >= 2 || (z1 - z0) >= 2;  // worth a macro step: >= 3 sectors along some axis
-    h.z = (uint32_t)x0 | ((uint32_t)y0 << 10) | ((uint32_t)z0 << 20);
-    h.w = (uint32_t)x1 | ((uint32_t)y1 << 10) | ((uint32_t)z1 << 20) | (big ? VRT_HDR_HASBOX : 0u);
+    big = big && ext_xz <= 256 && ext_y <= 256;  // corners are stored in 8 bits per axis
+    h.z = ((uint32_t)x0 & 0xFFu) | (((uint32_t)y0 & 0xFFu) << 8) | (((uint32_t)z0 & 0xFFu) << 16);
+    h.w = ((uint32_t)x1 & 0xFFu) | (((uint32_t)y1 & 0xFFu) << 8) | (((uint32_t)z1 & 0xFFu) << 16) | (big ? VRT_HDR_HASBOX : 0u);
     hdr[hi] = h;
 }
 
