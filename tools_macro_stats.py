@@ -17,6 +17,12 @@ for mode in (0, 1, 2):
     ctx.set_option("metrics", 1)
     ctx.render_device(frame, fb.data_ptr(), None, st.cuda_stream); torch.cuda.synchronize()
     m = ctx.metrics()
+    if mode == 2:
+        import ctypes as C
+        arr = (C.c_uint64 * 8)()
+        ctx.lib.vrt_debug_macro_diag(ctx.h, arr)
+        names = ["attempts", "fail_t1<=tcur", "fail_tau", "fail_side", "fail_chord", "jumps", "sum_man", "ambig"]
+        print("   diag", {n: int(v) for n, v in zip(names, arr)})
     print("macro", mode, "rays", m.rays, "iters", m.iters, "sector(or tries)", m.sector_fetches, "cell(or jumps)", m.cell_fetches, "hits", m.hits, "capped", m.capped)
     ctx.set_option("metrics", 0)
     for _ in range(3): ctx.render_device(frame, fb.data_ptr(), None, st.cuda_stream)

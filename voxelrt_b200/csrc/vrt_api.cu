@@ -804,3 +804,15 @@ extern "C" int vrt_fb_release(VrtContext* ctx, void* d_ptr) {
     }
     return fail(ctx, VRT_ERR_INVALID, "pointer not owned by this context");
 }
+
+// Internal diagnostic hook (not part of include/voxelrt_b200.h): reads and clears the macro-loop event
+// counters filled by "metrics" launches while macro_steps = 2.  Used by tools_macro_stats.py only.
+extern "C" __attribute__((visibility("default"))) int vrt_debug_macro_diag(VrtContext* ctx, uint64_t out[8]) {
+    if (!ctx || !out) return VRT_ERR_INVALID;
+    DeviceGuard g(ctx->device);
+    CU(cudaDeviceSynchronize());
+    CU(cudaMemcpyFromSymbol(out, g_macro_diag, 8 * sizeof(uint64_t)));
+    uint64_t zero[8] = {};
+    CU(cudaMemcpyToSymbol(g_macro_diag, zero, sizeof(zero)));
+    return VRT_OK;
+}
