@@ -311,9 +311,11 @@ int launch_render(VrtContext* ctx, const VrtFrame* f, void* d_out, VrtHit* d_aux
     unsigned blocks = (F.n_work + 7) / 8;
     if (ctx->metrics_on) {
         CU(cudaMemsetAsync(ctx->d_metrics, 0, sizeof(DevMetrics), s));
-        k_render<true><<<blocks, 256, 0, s>>>(S, F);
+        if (F.bounces == 0) k_render<true, true><<<blocks, 256, 0, s>>>(S, F);
+        else k_render<true, false><<<blocks, 256, 0, s>>>(S, F);
     } else {
-        k_render<false><<<blocks, 256, 0, s>>>(S, F);
+        if (F.bounces == 0) k_render<false, true><<<blocks, 256, 0, s>>>(S, F);
+        else k_render<false, false><<<blocks, 256, 0, s>>>(S, F);
     }
     ctx->stats.last_launches = 1;
     CU(cudaGetLastError());

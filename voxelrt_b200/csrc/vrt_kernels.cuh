@@ -66,7 +66,7 @@ __device__ __forceinline__ void store_pixel(const FrameParams& F, uint32_t x, ui
     }
 }
 
-template <bool METRICS>
+template <bool METRICS, bool PRIMARY>
 __global__ void __launch_bounds__(256, 4) k_render(const __grid_constant__ DevScene S, const __grid_constant__ FrameParams F) {
     uint32_t work = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (work >= F.n_work) return;  // warp-uniform
@@ -77,7 +77,8 @@ __global__ void __launch_bounds__(256, 4) k_render(const __grid_constant__ DevSc
     uint32_t y = y0 + ((lane >> 2) & 3u);
     bool valid = x < F.width && y < F.height;
     PixelOut P;
-    shade_pixel<METRICS>(S, F, x, y, valid, P);
+    if (PRIMARY) shade_pixel_primary<METRICS>(S, F, x, y, valid, P);
+    else shade_pixel<METRICS>(S, F, x, y, valid, P);
     if (valid) store_pixel(F, x, y, P);
 }
 
