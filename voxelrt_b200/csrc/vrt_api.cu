@@ -308,14 +308,15 @@ int launch_render(VrtContext* ctx, const VrtFrame* f, void* d_out, VrtHit* d_aux
     if ((uint64_t)macros * macros_x >= 0xFFFFFFFFull) return fail(ctx, VRT_ERR_INVALID, "frame too large");
     if (F.n_work == 0) return VRT_OK;
     DevScene S = dev_scene(ctx);
-    unsigned blocks = (F.n_work + 7) / 8;
+    const unsigned wpb = VRT_RENDER_THREADS / 32;
+    unsigned blocks = (F.n_work + wpb - 1) / wpb;
     if (ctx->metrics_on) {
         CU(cudaMemsetAsync(ctx->d_metrics, 0, sizeof(DevMetrics), s));
-        if (F.bounces == 0) k_render<true, true><<<blocks, 256, 0, s>>>(S, F);
-        else k_render<true, false><<<blocks, 256, 0, s>>>(S, F);
+        if (F.bounces == 0) k_render<true, true><<<blocks, VRT_RENDER_THREADS, 0, s>>>(S, F);
+        else k_render<true, false><<<blocks, VRT_RENDER_THREADS, 0, s>>>(S, F);
     } else {
-        if (F.bounces == 0) k_render<false, true><<<blocks, 256, 0, s>>>(S, F);
-        else k_render<false, false><<<blocks, 256, 0, s>>>(S, F);
+        if (F.bounces == 0) k_render<false, true><<<blocks, VRT_RENDER_THREADS, 0, s>>>(S, F);
+        else k_render<false, false><<<blocks, VRT_RENDER_THREADS, 0, s>>>(S, F);
     }
     ctx->stats.last_launches = 1;
     CU(cudaGetLastError());

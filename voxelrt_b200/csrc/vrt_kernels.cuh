@@ -66,8 +66,11 @@ __device__ __forceinline__ void store_pixel(const FrameParams& F, uint32_t x, ui
     }
 }
 
+#ifndef VRT_RENDER_THREADS
+#define VRT_RENDER_THREADS 128  // 4 warp tiles per CTA, 8 CTAs (32 warps, 64 registers each) per SM
+#endif
 template <bool METRICS, bool PRIMARY>
-__global__ void __launch_bounds__(256, 4) k_render(const __grid_constant__ DevScene S, const __grid_constant__ FrameParams F) {
+__global__ void __launch_bounds__(VRT_RENDER_THREADS, 1024 / VRT_RENDER_THREADS) k_render(const __grid_constant__ DevScene S, const __grid_constant__ FrameParams F) {
     uint32_t work = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (work >= F.n_work) return;  // warp-uniform
     uint32_t x0, y0;
