@@ -150,6 +150,10 @@ def test_render_config1_720p(bench_ctx, bench_oracle, macro):
     assert st.rays == 1280 * 720
     assert_hits_equal(aux_g, aux_c, "config 1", ignore_iters=macro)
     assert out_g.tobytes() == out_c.tobytes()
+    # without the aux records the host-buffer call takes the band-pipelined path (8 launches, copies overlapped)
+    out_b, _ = bench_ctx.render(_frame(cam, 1280, 720))
+    assert out_b.tobytes() == out_c.tobytes()
+    assert bench_ctx.stats().last_launches == 8
 
 
 def test_render_config2_4k_full(bench_ctx, bench_oracle, macro):

@@ -31,6 +31,8 @@ struct DeviceBuffer {
 struct VrtContext {
     int device = 0;
     cudaStream_t stream = nullptr;
+    cudaStream_t copy_stream = nullptr;  // D2H copies of finished bands overlap the next band's kernel
+    cudaEvent_t ev_band[16] = {};
     cudaEvent_t ev_sync = nullptr;    // end of the last vrt_sync / upload work on `stream`
     cudaEvent_t ev_render = nullptr;  // end of the last render/trace on a caller stream
     bool render_pending = false;
@@ -255,7 +257,9 @@ int launch_trace(VrtContext* ctx, uint64_t n, const float* d_o, const float* d_d
     return VRT_OK;
 }
 
-int launch_render(VrtContext* ctx, const VrtFrame* f, void* d_out, VrtHit* d_aux, cudaStream_t s) {
+// Launches the frame kernel for macro-tile rows [row0, row1) (32-pixel rows; row1 = 0 means "to the end").
+// Bands are only meaningful for an unpartitioned frame (part_count == 1).
+int launch_render(VrtContext* ctx, const VrtFrame* f, void* d_out, VrtHit* d_aux, cudaStream_t s, uint32_t row0 = 0, uint32_t row1 = 0) {
     if (f->width == 0 || f->height == 0 || (f->width & 3u) || (f->height & 3u))
         return fail(ctx, VRT_ERR_INVALID, "frame size must be a non-zero multiple of 4 (CpuRenderer.cpp:419)");
     if (f->bounces > 7) return fail(ctx, VRT_ERR_INVALID, "bounces > 7");
@@ -303,13 +307,18 @@ int launch_render(VrtContext* ctx, const VrtFrame* f, void* d_out, VrtHit* d_aux
     uint32_t macros = macros_x * macros_y;
     uint32_t my_macros = macros / part_count + ((macros % part_count) > f->part_index ? 1u : 0u);
     F.n_work = my_macros * 32u;
+    F.work_offset = 0;
+    if (row1 != 0 && part_count == 1) {
+        F.work_offset = std::min(row0, macros_y) * macros_x * 32u;
+        F.n_work = std::min(row1, macros_y) * macros_x * 32u;
+    }
     F.macros_x = macros_x;
     F.macros_x_magic = macros_x > 1 ? (uint32_t)((0x100000000ull + macros_x - 1) / macros_x) : 0u;
     if ((uint64_t)macros * macros_x >= 0xFFFFFFFFull) return fail(ctx, VRT_ERR_INVALID, "frame too large");
-    if (F.n_work == 0) return VRT_OK;
+    if (F.n_work <= F.work_offset) return VRT_OK;
     DevScene S = dev_scene(ctx);
     const unsigned wpb = VRT_RENDER_THREADS / 32;
-    unsigned blocks = (F.n_work + wpb - 1) / wpb;
+    unsigned blocks = (F.n_work - F.work_offset + wpb - 1) / wpb;
     if (ctx->metrics_on) {
         CU(cudaMemsetAsync(ctx->d_metrics, 0, sizeof(DevMetrics), s));
         if (F.bounces == 0) k_render<true, true><<<blocks, VRT_RENDER_THREADS, 0, s>>>(S, F);
@@ -318,7 +327,7 @@ int launch_render(VrtContext* ctx, const VrtFrame* f, void* d_out, VrtHit* d_aux
         if (F.bounces == 0) k_render<false, true><<<blocks, VRT_RENDER_THREADS, 0, s>>>(S, F);
         else k_render<false, false><<<blocks, VRT_RENDER_THREADS, 0, s>>>(S, F);
     }
-    ctx->stats.last_launches = 1;
+    ctx->stats.last_launches += 1;
     CU(cudaGetLastError());
     return VRT_OK;
 }
@@ -370,6 +379,8 @@ extern "C" int vrt_create(const VrtConfig* cfg, VrtContext** out) {
         }                                                                                 \
     } while (0)
     CUB(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    CUB(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+    for (auto& e : c->ev_band) CUB(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     CUB(cudaEventCreateWithFlags(&c->ev_sync, cudaEventDisableTiming));
     CUB(cudaEventCreateWithFlags(&c->ev_render, cudaEventDisableTiming));
     c->sxp = (1u << c->sxz) + 2u;
@@ -415,6 +426,9 @@ extern "C" void vrt_destroy(VrtContext* ctx) {
     if (ctx->ev_sync) cudaEventDestroy(ctx->ev_sync);
     if (ctx->ev_render) cudaEventDestroy(ctx->ev_render);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+    for (auto& e : ctx->ev_band)
+        if (e) cudaEventDestroy(e);
     cudaGetLastError();
     delete ctx;
 }
@@ -727,6 +741,7 @@ extern "C" int vrt_render_device(VrtContext* ctx, const VrtFrame* frame, void* d
     cudaStream_t s = stream ? (cudaStream_t)stream : ctx->stream;
     int st = begin_on_stream(ctx, s);
     if (st) return st;
+    ctx->stats.last_launches = 0;
     st = launch_render(ctx, frame, d_out, d_aux, s);
     if (st) return st;
     return end_on_stream(ctx, s);
@@ -745,6 +760,29 @@ extern "C" int vrt_render(VrtContext* ctx, const VrtFrame* frame, void* out, Vrt
     if (part_count > 1) {  // pixels of other ranks stay zero in a partial frame
         CU(cudaMemsetAsync(ctx->d_fb.p, 0, npx * 16, ctx->stream));
         if (aux) CU(cudaMemsetAsync(ctx->d_aux.p, 0, npx * sizeof(VrtHit), ctx->stream));
+    }
+    ctx->stats.last_launches = 0;
+    const bool tiled = (frame->flags & VRT_FRAME_LINEAR_OUTPUT) == 0;
+    const uint32_t macros_y = (frame->height + 31) / 32;
+    if (part_count == 1 && tiled && !aux && macros_y >= 16) {
+        // Band pipeline: the frame is rendered in up to 8 bands of macro-tile rows; a band's 16 B/px
+        // tiles are contiguous in the reference's tile order, so its D2H copy runs on a second stream
+        // while the next band is being traced.  The PCIe copy, not the kernel, bounds this call.
+        const uint32_t n_bands = 8, rows_per = (macros_y + n_bands - 1) / n_bands;
+        const size_t row_bytes = (size_t)32 * frame->width * 16;  // one macro row = 8 tile rows
+        for (uint32_t b = 0; b < n_bands; b++) {
+            uint32_t r0 = b * rows_per, r1 = std::min(macros_y, r0 + rows_per);
+            if (r0 >= r1) break;
+            st = launch_render(ctx, frame, ctx->d_fb.p, nullptr, ctx->stream, r0, r1);
+            if (st) return st;
+            CU(cudaEventRecord(ctx->ev_band[b], ctx->stream));
+            CU(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_band[b], 0));
+            size_t off = (size_t)r0 * row_bytes, end = std::min((size_t)r1 * row_bytes, npx * 16);
+            CU(cudaMemcpyAsync((char*)out + off, (char*)ctx->d_fb.p + off, end - off, cudaMemcpyDeviceToHost, ctx->copy_stream));
+        }
+        CU(cudaStreamSynchronize(ctx->copy_stream));
+        CU(cudaStreamSynchronize(ctx->stream));
+        return VRT_OK;
     }
     st = launch_render(ctx, frame, ctx->d_fb.p, (VrtHit*)ctx->d_aux.p, ctx->stream);
     if (st) return st;

@@ -71,7 +71,7 @@ __device__ __forceinline__ void store_pixel(const FrameParams& F, uint32_t x, ui
 #endif
 template <bool METRICS, bool PRIMARY>
 __global__ void __launch_bounds__(VRT_RENDER_THREADS, 1024 / VRT_RENDER_THREADS) k_render(const __grid_constant__ DevScene S, const __grid_constant__ FrameParams F) {
-    uint32_t work = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    uint32_t work = F.work_offset + blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (work >= F.n_work) return;  // warp-uniform
     uint32_t x0, y0;
     if (!warp_tile_origin(F, work, x0, y0)) return;
