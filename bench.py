@@ -47,6 +47,16 @@ def _peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def _traffic(args):
+    """DRAM bytes per launch of the dominant kernel from the committed ncu capture (null for other shapes)."""
+    try:
+        d = json.loads((ROOT / "profiles" / "traffic.json").read_text())
+        e = d.get(f"k_render<false,true> {args.width}x{args.height} bounces={args.bounces}")
+        return (e["dram_read_bytes"] + e["dram_write_bytes"]) if e and args.gpus == 1 else None
+    except Exception:
+        return None
+
+
 class ClockSampler:
     """nvidia-smi clocks + throttle reasons sampled DURING the timed region."""
 
@@ -383,6 +393,23 @@ def run_b200(args):
     stepwise_ms = a.elapsed_time(b) / args.steps
     ctx.set_option("macro_steps", 1)
 
+    trace_only_ms = None
+    if world > 1:  # the same split without the NVLink gather: every rank stores into its own memory
+        def local_step():
+            ctx.render_device(frame, fb.data_ptr(), None, stream.cuda_stream)
+
+        local_step()
+        torch.cuda.synchronize()
+        dist.barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(stream)
+        for _ in range(args.steps):
+            local_step()
+        b.record(stream)
+        torch.cuda.synchronize()
+        lt = torch.tensor([a.elapsed_time(b) / args.steps], dtype=torch.float64, device="cuda")
+        dist.all_reduce(lt, op=dist.ReduceOp.MAX)
+        trace_only_ms = float(lt[0])
     gather_ok = None
     if world > 1:
         # the gathered frame in rank 0's memory must equal the frame rank 0 renders alone
@@ -461,10 +488,11 @@ def run_b200(args):
                 "api": "vrt_render (host buffers, pinned output)",
             },
             "gpu_launches": args.steps,
-            "gather": None if world == 1 else {"how": "peer stores into rank 0's framebuffer (CUDA IPC over NVLink), fused into the render kernel's epilogue", "verified_equal_to_single_gpu_frame": gather_ok},
+            "gather": None if world == 1 else {"how": "peer stores into rank 0's framebuffer (CUDA IPC over NVLink), fused into the render kernel's epilogue", "verified_equal_to_single_gpu_frame": gather_ok,
+                                                     "value_trace_only_warm_l2": rays_frame / (trace_only_ms * 1e-3) / 1e6},
             "roofline": {
                 "bound": "hbm",
-                "kernel": "vrt::k_render<false>",
+                "kernel": "vrt::k_render<false,%s>" % ("true" if args.bounces == 0 else "false"),
                 "achieved": achieved,
                 "peak": peak,
                 "unit": "GB/s",
@@ -472,7 +500,7 @@ def run_b200(args):
                 "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": int(alg_bytes),
                 "bytes_per_ray": alg_bytes / max(1, my_primary * (1 + args.bounces)),
-                "traffic": None,
+                "traffic": _traffic(args),
                 "counters": {"rays": m.rays, "iters": m.iters, "sector_fetches": m.sector_fetches, "cell_fetches": m.cell_fetches, "hits": m.hits, "capped": m.capped},
             },
         }
