@@ -40,7 +40,9 @@ struct VrtContext {
     uint32_t sxz = 6, sy = 4, n_sectors = 0;
     uint32_t sxp = 0, syp = 0, n_hdr = 0;  // bordered header grid (one OUTSIDE sector on every side)
     // resident brickmap
-    uint4* d_hdr = nullptr;
+    uint4* d_hdr = nullptr;        // entry 0 of the bordered grid, inside d_hdr_alloc
+    uint4* d_hdr_alloc = nullptr;  // grid + a guard shell of OUTSIDE entries on both ends
+    uint32_t hdr_guard = 0;
     uint2* d_cells = nullptr;
     uint8_t* d_voxels = nullptr;
     uint2* d_palette = nullptr;
@@ -178,28 +180,31 @@ DevScene dev_scene(const VrtContext* ctx) {
 
 // Constants of the traversal frame for a world origin (see RayFrame).
 RayFrame ray_frame(const VrtContext* ctx, const int32_t wo[3]) {
-    const int MAGIC_BITS = 0x4B400000;
+    const int MAGIC_BITS = VRT_MAGIC_BITS;
     RayFrame W;
     W.wx = wo[0];
     W.wy = wo[1];
     W.wz = wo[2];
     const int lox = wo[0] & 31, loy = wo[1] & 31, loz = wo[2] & 31;
-    W.cqx = lox - MAGIC_BITS;
-    W.cqy = loy - MAGIC_BITS;
-    W.cqz = loz - MAGIC_BITS;
-    W.hx = wo[0] - lox;
-    W.hy = wo[1] - loy;
-    W.hz = wo[2] - loz;
+    W.mgx = 12582912.0f + (float)lox;  // exact: integers below 2^24
+    W.mgy = 12582912.0f + (float)loy;
+    W.mgz = 12582912.0f + (float)loz;
+    const int bx = wo[0] - lox, by = wo[1] - loy, bz = wo[2] - loz;  // wo & ~31
+    // (unsigned arithmetic: the MAGIC_BITS offsets wrap around by design and cancel in the kernel)
+    W.hx = (int)((uint32_t)bx - (uint32_t)MAGIC_BITS);
+    W.hy = (int)((uint32_t)by - (uint32_t)MAGIC_BITS);
+    W.hz = (int)((uint32_t)bz - (uint32_t)MAGIC_BITS);
     const int lim = 1 << 20;
     W.fast_ok = (wo[0] >= -lim && wo[0] <= lim && wo[1] >= -lim && wo[1] <= lim && wo[2] >= -lim && wo[2] <= lim) ? 1 : 0;
-    // hdr_index of the (possibly far out-of-view) sector holding the frame origin; int arithmetic wraps harmlessly
-    // because the loop only ever adds offsets that bring the sum back inside [0, n_hdr)
     W.macro = ctx->macro_on;
-    W.hsx = W.hx >> 5, W.hsy = W.hy >> 5, W.hsz = W.hz >> 5;
-    W.klx = -W.hx - W.cqx, W.kly = -W.hy - W.cqy, W.klz = -W.hz - W.cqz;  // int wrap-around is intended (MAGIC_BITS arithmetic)
-    W.hoff = W.fast_ok ? (int)((long long)((W.hx >> 5) + 1) + (long long)((W.hz >> 5) + 1) * ctx->sxp +
-                               (long long)((W.hy >> 5) + 1) * ctx->sxp * ctx->sxp)
-                       : 0;
+    W.hsx = (int)((uint32_t)(bx >> 5) - (uint32_t)MAGIC_BITS), W.hsy = (int)((uint32_t)(by >> 5) - (uint32_t)MAGIC_BITS),
+    W.hsz = (int)((uint32_t)(bz >> 5) - (uint32_t)MAGIC_BITS);
+    W.klx = (int)((uint32_t)MAGIC_BITS - (uint32_t)bx), W.kly = (int)((uint32_t)MAGIC_BITS - (uint32_t)by), W.klz = (int)((uint32_t)MAGIC_BITS - (uint32_t)bz);
+    // hdr_index of the (possibly far out-of-view) sector holding the frame origin, minus MAGIC_BITS on every axis: the
+    // loop adds SQ * stride per axis (SQ = MAGIC_BITS + sector coordinate relative to that sector), which brings the
+    // (wrapping) sum back inside the header grid
+    const uint32_t sxp = ctx->sxp, sxzp = ctx->sxp * ctx->sxp, MB = (uint32_t)MAGIC_BITS;
+    W.hoff = W.fast_ok ? (int)(((uint32_t)(bx >> 5) + 1u - MB) + ((uint32_t)(bz >> 5) + 1u - MB) * sxp + ((uint32_t)(by >> 5) + 1u - MB) * sxzp) : 0;
     return W;
 }
 
@@ -386,14 +391,17 @@ extern "C" int vrt_create(const VrtConfig* cfg, VrtContext** out) {
     c->sxp = (1u << c->sxz) + 2u;
     c->syp = (1u << c->sy) + 2u;
     c->n_hdr = c->sxp * c->sxp * c->syp;
-    CUB(cudaMalloc((void**)&c->d_hdr, (size_t)c->n_hdr * sizeof(uint4)));
-    k_init_headers<<<(c->n_hdr + 255) / 256, 256, 0, c->stream>>>(c->d_hdr, c->sxp, c->syp);
+    // guard shell: two y-slabs of OUTSIDE entries before and after the bordered grid
+    c->hdr_guard = 2u * c->sxp * c->sxp;
+    CUB(cudaMalloc((void**)&c->d_hdr_alloc, ((size_t)c->n_hdr + 2u * c->hdr_guard) * sizeof(uint4)));
+    c->d_hdr = c->d_hdr_alloc + c->hdr_guard;
+    k_init_headers<<<(c->n_hdr + 2u * c->hdr_guard + 255) / 256, 256, 0, c->stream>>>(c->d_hdr, c->sxp, c->syp, c->hdr_guard);
     CUB(cudaGetLastError());
     CUB(cudaMalloc((void**)&c->d_palette, 256 * sizeof(uint2)));
     CUB(cudaMemsetAsync(c->d_palette, 0, 256 * sizeof(uint2), c->stream));
     CUB(cudaMalloc((void**)&c->d_metrics, sizeof(DevMetrics)));
     CUB(cudaMemsetAsync(c->d_metrics, 0, sizeof(DevMetrics), c->stream));
-    c->stats.device_bytes = (size_t)c->n_hdr * sizeof(uint4) + 256 * sizeof(uint2) + sizeof(DevMetrics);
+    c->stats.device_bytes = ((size_t)c->n_hdr + 2u * c->hdr_guard) * sizeof(uint4) + 256 * sizeof(uint2) + sizeof(DevMetrics);
     uint32_t cap = cfg->initial_brick_capacity ? cfg->initial_brick_capacity : (1u << 16);
     int st = resize_arena(c, cap);
     if (st != VRT_OK) return bail(st);
@@ -415,7 +423,7 @@ extern "C" void vrt_destroy(VrtContext* ctx) {
     for (auto* b : bufs)
         if (b->p) cudaFree(b->p);
     if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
-    cudaFree(ctx->d_hdr);
+    cudaFree(ctx->d_hdr_alloc);
     cudaFree(ctx->d_cells);
     cudaFree(ctx->d_voxels);
     cudaFree(ctx->d_palette);

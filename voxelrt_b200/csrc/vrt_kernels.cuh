@@ -156,17 +156,25 @@ __global__ void k_write_headers(const HeaderUpdate* __restrict__ upd, uint32_t n
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     HeaderUpdate u = upd[i];
-    hdr[u.index] = make_uint4(u.mask_lo, u.mask_hi, u.base, (uint32_t)__popc(u.mask_lo));
+    // {allocMask, base slot, base slot of the upper 32 bricks}; an empty mask leaves z/w free for the box builder
+    bool any = (u.mask_lo | u.mask_hi) != 0u;
+    hdr[u.index] = make_uint4(u.mask_lo, u.mask_hi, any ? u.base : 0u, any ? u.base + (uint32_t)__popc(u.mask_lo) : 0u);
 }
 
-// K_init_headers: zero the in-view entries, mark the one-sector border OUTSIDE.
-__global__ void k_init_headers(uint4* hdr, uint32_t sxp, uint32_t syp) {
-    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+// K_init_headers: zero the in-view entries, mark the one-sector border OUTSIDE.  `hdr` points at grid
+// entry 0; `guard` further OUTSIDE entries precede and follow the grid (the traversal loop does not clamp
+// its index: DESIGN.md §5).
+__global__ void k_init_headers(uint4* hdr, uint32_t sxp, uint32_t syp, uint32_t guard) {
+    uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
     uint32_t n = sxp * sxp * syp;
-    if (i >= n) return;
-    uint32_t x = i % sxp, z = (i / sxp) % sxp, y = i / (sxp * sxp);
-    bool border = x == 0 || z == 0 || y == 0 || x == sxp - 1 || z == sxp - 1 || y == syp - 1;
-    hdr[i] = make_uint4(0u, 0u, 0u, border ? VRT_HDR_OUTSIDE : 0u);
+    if (j >= n + 2u * guard) return;
+    bool border = true;
+    if (j >= guard && j < guard + n) {
+        uint32_t i = j - guard;
+        uint32_t x = i % sxp, z = (i / sxp) % sxp, y = i / (sxp * sxp);
+        border = x == 0 || z == 0 || y == 0 || x == sxp - 1 || z == sxp - 1 || y == syp - 1;
+    }
+    (hdr - guard)[j] = make_uint4(0u, 0u, 0u, border ? VRT_HDR_OUTSIDE : 0u);
 }
 
 // ---------------------------------------------------------------------------------------------
