@@ -67,10 +67,12 @@ __device__ __forceinline__ void store_pixel(const FrameParams& F, uint32_t x, ui
 }
 
 #ifndef VRT_RENDER_THREADS
-#define VRT_RENDER_THREADS 128  // 4 warp tiles per CTA, 8 CTAs (32 warps, 64 registers each) per SM
+#define VRT_RENDER_THREADS 128  // 4 warp tiles per CTA
 #endif
+// CTAs per SM: the primary-only kernel fits 56 registers (9 CTAs = 36 warps), the bounce kernel needs 64 (8 CTAs)
+#define VRT_RENDER_CTAS(PRIMARY) ((PRIMARY) ? 9 : 8)
 template <bool METRICS, bool PRIMARY>
-__global__ void __launch_bounds__(VRT_RENDER_THREADS, 1024 / VRT_RENDER_THREADS) k_render(const __grid_constant__ DevScene S, const __grid_constant__ FrameParams F) {
+__global__ void __launch_bounds__(VRT_RENDER_THREADS, VRT_RENDER_CTAS(PRIMARY && !METRICS)) k_render(const __grid_constant__ DevScene S, const __grid_constant__ FrameParams F) {
     uint32_t work = F.work_offset + blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (work >= F.n_work) return;  // warp-uniform
     uint32_t x0, y0;
