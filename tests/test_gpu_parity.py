@@ -169,6 +169,61 @@ def test_render_config2_4k_full(bench_ctx, bench_oracle, macro):
     assert out_g.tobytes() == out_c.tobytes()
 
 
+def test_rcp_rn_normal_matches_ieee(hash_ctx):
+    """The fast loop's reciprocal (MUFU.RCP + one FMA Newton step, no range guard) is the correctly rounded 1/x for every
+    operand a fast ray can have: exhaustive over all binary32 patterns with 2^-60 <= |x| <= 16 against rcp.rn on the
+    device (537 M patterns x 2 signs), and a sample against the host's IEEE division."""
+    import ctypes as C
+
+    lo = int(np.float32(2.0**-60).view(np.uint32))
+    hi = int(np.float32(16.0).view(np.uint32))
+    bad = C.c_uint64(123)
+    n = 1 << 20
+    sample = np.zeros(2 * n, np.float32)
+    fn = hash_ctx.lib.vrt_debug_rcp_check
+    fn.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.POINTER(C.c_uint64), C.c_void_p, C.c_uint32]
+    fn.restype = C.c_int
+    assert fn(hash_ctx.h, lo, hi, C.byref(bad), None, 0) == 0
+    assert bad.value == 0
+    # host cross-check on 2^20 patterns around 1.0 (and their negations)
+    lo1 = int(np.float32(0.75).view(np.uint32))
+    assert fn(hash_ctx.h, lo1, lo1 + n - 1, C.byref(bad), sample.ctypes.data, n) == 0
+    x = (np.arange(n, dtype=np.uint32) + np.uint32(lo1)).view(np.float32)
+    want = np.concatenate([np.float32(1.0) / x, np.float32(1.0) / -x])
+    assert np.array_equal(sample.view(np.uint32), want.view(np.uint32))
+
+
+@pytest.mark.parametrize("bounces", [0, 1])
+def test_render_persistent_kernel_equals_grid_kernel(bench_ctx, bench_oracle, shading_inputs, bounces):
+    """The persistent form of the frame kernel (warps pull tiles from a ticket counter) must produce the very bytes of the
+    one-CTA-per-4-tiles form, launch after launch (the counter is never reset), for full frames, tile partitions and
+    the band-pipelined host-buffer path, including grids larger and smaller than the tile count."""
+    from scenes import camera
+
+    (bn, _), (sky_desc, sky_texels, _) = shading_inputs
+    bench_ctx.set_blue_noise(bn)
+    bench_ctx.set_sky(sky_desc, sky_texels)
+    cam = camera.Camera()
+    sizes = [(1280, 720), (36, 4), (260, 148), (1920, 1080)]
+    try:
+        for w, h in sizes:
+            bench_ctx.set_option("persistent", 0)
+            want, _ = bench_ctx.render(_frame(cam, w, h, bounces=bounces, frame_no=3))
+            for mode in (1, 1, 3):
+                bench_ctx.set_option("persistent", mode)
+                got, _ = bench_ctx.render(_frame(cam, w, h, bounces=bounces, frame_no=3))
+                assert got.tobytes() == want.tobytes(), (w, h, mode)
+                got_aux, _ = bench_ctx.render(_frame(cam, w, h, bounces=bounces, frame_no=3), want_aux=True)
+                assert got_aux.tobytes() == want.tobytes(), (w, h, mode, "aux path")
+        if bounces == 0:
+            out_c, _, _ = bench_oracle.render(_frame(cam, 1280, 720), want_aux=False)
+            bench_ctx.set_option("persistent", 1)
+            got, _ = bench_ctx.render(_frame(cam, 1280, 720))
+            assert got.tobytes() == out_c.tobytes()
+    finally:
+        bench_ctx.set_option("persistent", 1)
+
+
 @pytest.mark.parametrize("i", range(4))
 def test_render_orbit_cameras(bench_ctx, bench_oracle, i, macro):
     from scenes import camera

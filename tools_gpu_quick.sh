@@ -1,0 +1,6 @@
+#!/bin/bash
+# Quick GPU session: parity tests + bench (no profiling).  Extra bench args via $BENCH_ARGS.
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1; echo "pytest exit $?" >> gpurun_out/pytest_gpu.log
+tail -4 gpurun_out/pytest_gpu.log
+timeout 600 python bench.py --no-cpu $BENCH_ARGS > gpurun_out/bench.json 2> gpurun_out/bench.err; tail -3 gpurun_out/bench.err; cat gpurun_out/bench.json

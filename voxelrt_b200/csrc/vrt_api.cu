@@ -46,6 +46,7 @@ struct VrtContext {
     uint2* d_cells = nullptr;
     uint8_t* d_voxels = nullptr;
     uint2* d_palette = nullptr;
+    uint32_t* d_albedo = nullptr;  // per palette entry: packed albedo of the primary-only frame kernel (k_palette_albedo)
     RangeArena arena;
     std::vector<SectorSlots> sectors;  // host mirror of d_hdr
     uint64_t resident_sectors = 0;
@@ -69,6 +70,12 @@ struct VrtContext {
     DevMetrics* d_metrics = nullptr;
     bool metrics_on = false;
     int render_variant = 0;
+    // persistent frame kernel: ring of ticket counters (one per launch in flight) and the host's view of each
+    int persist_on = 0;  // measured slower than the grid form on primary frames (tile order loses the L1 locality of 4 adjacent warp tiles per CTA)
+    uint32_t* d_tickets = nullptr;
+    uint32_t ticket_base[16] = {};
+    uint32_t ticket_seq = 0;
+    int sm_count = 0;
 
     std::vector<void*> exported, imported;
     VrtStats stats{};
@@ -168,6 +175,7 @@ DevScene dev_scene(const VrtContext* ctx) {
     S.cells = ctx->d_cells;
     S.voxels = ctx->d_voxels;
     S.palette = ctx->d_palette;
+    S.albedo = ctx->d_albedo;
     S.sxz = ctx->sxz;
     S.sy = ctx->sy;
     S.lim_xz = 1u << (ctx->sxz + 5);
@@ -278,6 +286,10 @@ int launch_render(VrtContext* ctx, const VrtFrame* f, void* d_out, VrtHit* d_aux
     F.height = f->height;
     memcpy(F.inv_proj, f->inv_proj, sizeof(F.inv_proj));
     memcpy(F.proj, f->proj, sizeof(F.proj));
+    for (int k = 0; k < 4; k++) {  // SIMD.h:207-214 with z = 0, w = 1 (IEEE binary32, one rounding per operation as on the device)
+        volatile float t = f->inv_proj[12 + k] * 1.0f;
+        F.ray_c[k] = fmaf(f->inv_proj[8 + k], 0.0f, t);
+    }
     F.W = ray_frame(ctx, f->world_origin);
     for (int a = 0; a < 3; a++) F.frac[a] = f->origin_frac[a];
     F.frame_no = f->frame_no;
@@ -328,6 +340,16 @@ int launch_render(VrtContext* ctx, const VrtFrame* f, void* d_out, VrtHit* d_aux
         CU(cudaMemsetAsync(ctx->d_metrics, 0, sizeof(DevMetrics), s));
         if (F.bounces == 0) k_render<true, true><<<blocks, VRT_RENDER_THREADS, 0, s>>>(S, F);
         else k_render<true, false><<<blocks, VRT_RENDER_THREADS, 0, s>>>(S, F);
+    } else if (ctx->persist_on) {
+        // one resident grid; warps pull tiles from a ticket counter (see k_render_persist)
+        const unsigned resident = (unsigned)ctx->sm_count * (unsigned)VRT_RENDER_CTAS(F.bounces == 0) * (unsigned)ctx->persist_on;
+        const unsigned grid = std::min(blocks, resident);
+        const uint32_t slot = ctx->ticket_seq++ & 15u;
+        uint32_t* ticket = ctx->d_tickets + slot;
+        const uint32_t base = ctx->ticket_base[slot];
+        ctx->ticket_base[slot] += F.n_work - F.work_offset;
+        if (F.bounces == 0) k_render_persist<true><<<grid, VRT_RENDER_THREADS, 0, s>>>(S, F, ticket, base);
+        else k_render_persist<false><<<grid, VRT_RENDER_THREADS, 0, s>>>(S, F, ticket, base);
     } else {
         if (F.bounces == 0) k_render<false, true><<<blocks, VRT_RENDER_THREADS, 0, s>>>(S, F);
         else k_render<false, false><<<blocks, VRT_RENDER_THREADS, 0, s>>>(S, F);
@@ -399,6 +421,11 @@ extern "C" int vrt_create(const VrtConfig* cfg, VrtContext** out) {
     CUB(cudaGetLastError());
     CUB(cudaMalloc((void**)&c->d_palette, 256 * sizeof(uint2)));
     CUB(cudaMemsetAsync(c->d_palette, 0, 256 * sizeof(uint2), c->stream));
+    CUB(cudaMalloc((void**)&c->d_albedo, 256 * sizeof(uint32_t)));
+    CUB(cudaMemsetAsync(c->d_albedo, 0, 256 * sizeof(uint32_t), c->stream));
+    CUB(cudaMalloc((void**)&c->d_tickets, 16 * sizeof(uint32_t)));
+    CUB(cudaMemsetAsync(c->d_tickets, 0, 16 * sizeof(uint32_t), c->stream));
+    CUB(cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, c->device));
     CUB(cudaMalloc((void**)&c->d_metrics, sizeof(DevMetrics)));
     CUB(cudaMemsetAsync(c->d_metrics, 0, sizeof(DevMetrics), c->stream));
     c->stats.device_bytes = ((size_t)c->n_hdr + 2u * c->hdr_guard) * sizeof(uint4) + 256 * sizeof(uint2) + sizeof(DevMetrics);
@@ -427,6 +454,8 @@ extern "C" void vrt_destroy(VrtContext* ctx) {
     cudaFree(ctx->d_cells);
     cudaFree(ctx->d_voxels);
     cudaFree(ctx->d_palette);
+    cudaFree(ctx->d_albedo);
+    cudaFree(ctx->d_tickets);
     cudaFree(ctx->d_bn);
     cudaFree(ctx->d_sky);
     cudaFree(ctx->d_metrics);
@@ -458,6 +487,7 @@ extern "C" int vrt_set_option(VrtContext* ctx, const char* name, int64_t value) 
     if (!strcmp(name, "metrics")) ctx->metrics_on = value != 0;
     else if (!strcmp(name, "render_variant")) ctx->render_variant = (int)value;
     else if (!strcmp(name, "macro_steps")) ctx->macro_on = (int)value;
+    else if (!strcmp(name, "persistent")) ctx->persist_on = (int)value;
     else return fail(ctx, VRT_ERR_INVALID, std::string("unknown option ") + name);
     return VRT_OK;
 }
@@ -489,6 +519,8 @@ extern "C" int vrt_set_palette(VrtContext* ctx, const uint64_t palette[256]) {
     CU(cudaStreamSynchronize(ctx->stream));  // staging may still feed a previous copy
     memcpy(ctx->h_stage, palette, 256 * 8);
     CU(cudaMemcpyAsync(ctx->d_palette, ctx->h_stage, 256 * 8, cudaMemcpyHostToDevice, ctx->stream));
+    k_palette_albedo<<<1, 256, 0, ctx->stream>>>(ctx->d_palette, ctx->d_albedo);
+    CU(cudaGetLastError());
     CU(cudaEventRecord(ctx->ev_sync, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
     ctx->have_palette = true;
@@ -863,5 +895,48 @@ extern "C" __attribute__((visibility("default"))) int vrt_debug_macro_diag(VrtCo
     CU(cudaMemcpyFromSymbol(out, g_macro_diag, 8 * sizeof(uint64_t)));
     uint64_t zero[8] = {};
     CU(cudaMemcpyToSymbol(g_macro_diag, zero, sizeof(zero)));
+    return VRT_OK;
+}
+
+// Internal self-check hook (not part of include/voxelrt_b200.h): compares rcp_rn_normal with rcp.rn for EVERY binary32 bit
+// pattern in [lo_bits, hi_bits] and both signs; *mismatches receives the count.  out_sample (host, 2*n floats, may be null)
+// receives rcp_rn_normal of the first n patterns and of their negations, for a comparison against the host's own 1.0f/x.
+namespace {
+__global__ void k_debug_rcp_check(uint32_t lo_bits, uint64_t count, unsigned long long* mismatches, float* sample, uint32_t n_sample) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    unsigned bad = 0;
+    for (; i < count; i += stride) {
+        float x = __uint_as_float(lo_bits + (uint32_t)i);
+        float a = vrt::rcp_rn_normal(x), b = __frcp_rn(x);
+        float c = vrt::rcp_rn_normal(-x), d = __frcp_rn(-x);
+        bad += (__float_as_uint(a) != __float_as_uint(b)) + (__float_as_uint(c) != __float_as_uint(d));
+        if (sample && i < n_sample) {
+            sample[i] = a;
+            sample[n_sample + i] = c;
+        }
+    }
+    if (bad) atomicAdd(mismatches, (unsigned long long)bad);
+}
+}  // namespace
+extern "C" __attribute__((visibility("default"))) int vrt_debug_rcp_check(VrtContext* ctx, uint32_t lo_bits, uint32_t hi_bits, uint64_t* mismatches,
+                                                                          float* out_sample, uint32_t n_sample) {
+    if (!ctx || !mismatches || hi_bits < lo_bits) return VRT_ERR_INVALID;
+    DeviceGuard g(ctx->device);
+    unsigned long long* d_bad = nullptr;
+    float* d_sample = nullptr;
+    CU(cudaMalloc((void**)&d_bad, sizeof(unsigned long long)));
+    CU(cudaMemset(d_bad, 0, sizeof(unsigned long long)));
+    if (out_sample && n_sample) CU(cudaMalloc((void**)&d_sample, 2ull * n_sample * sizeof(float)));
+    uint64_t count = (uint64_t)hi_bits - lo_bits + 1;
+    k_debug_rcp_check<<<148 * 16, 256, 0, ctx->stream>>>(lo_bits, count, d_bad, d_sample, d_sample ? n_sample : 0u);
+    CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(ctx->stream));
+    unsigned long long bad = 0;
+    CU(cudaMemcpy(&bad, d_bad, sizeof(bad), cudaMemcpyDeviceToHost));
+    if (d_sample) CU(cudaMemcpy(out_sample, d_sample, 2ull * n_sample * sizeof(float), cudaMemcpyDeviceToHost));
+    cudaFree(d_bad);
+    cudaFree(d_sample);
+    *mismatches = bad;
     return VRT_OK;
 }

@@ -69,14 +69,15 @@ __device__ __forceinline__ void store_pixel(const FrameParams& F, uint32_t x, ui
 #ifndef VRT_RENDER_THREADS
 #define VRT_RENDER_THREADS 128  // 4 warp tiles per CTA
 #endif
-// CTAs per SM: the primary-only kernel fits 56 registers (9 CTAs = 36 warps), the bounce kernel needs 64 (8 CTAs)
-#define VRT_RENDER_CTAS(PRIMARY) ((PRIMARY) ? 9 : 8)
+// resident warps per SM: the primary-only kernel fits 56 registers (36 warps), the bounce kernel needs 64 (32 warps)
+#ifndef VRT_RENDER_WARPS_PRIMARY
+#define VRT_RENDER_WARPS_PRIMARY 36
+#endif
+#define VRT_RENDER_CTAS(PRIMARY) (((PRIMARY) ? VRT_RENDER_WARPS_PRIMARY : 32) * 32 / VRT_RENDER_THREADS)
 template <bool METRICS, bool PRIMARY>
-__global__ void __launch_bounds__(VRT_RENDER_THREADS, VRT_RENDER_CTAS(PRIMARY && !METRICS)) k_render(const __grid_constant__ DevScene S, const __grid_constant__ FrameParams F) {
-    uint32_t work = F.work_offset + blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (work >= F.n_work) return;  // warp-uniform
+__device__ __forceinline__ void render_warp_tile(const DevScene& S, const FrameParams& F, uint32_t work) {
     uint32_t x0, y0;
-    if (!warp_tile_origin(F, work, x0, y0)) return;
+    if (!warp_tile_origin(F, work, x0, y0)) return;  // warp-uniform
     uint32_t lane = threadIdx.x & 31u;
     uint32_t x = x0 + ((lane >> 4) << 2) + (lane & 3u);
     uint32_t y = y0 + ((lane >> 2) & 3u);
@@ -85,6 +86,40 @@ __global__ void __launch_bounds__(VRT_RENDER_THREADS, VRT_RENDER_CTAS(PRIMARY &&
     if (PRIMARY) shade_pixel_primary<METRICS>(S, F, x, y, valid, P);
     else shade_pixel<METRICS>(S, F, x, y, valid, P);
     if (valid) store_pixel(F, x, y, P);
+}
+
+template <bool METRICS, bool PRIMARY>
+__global__ void __launch_bounds__(VRT_RENDER_THREADS, VRT_RENDER_CTAS(PRIMARY && !METRICS)) k_render(const __grid_constant__ DevScene S, const __grid_constant__ FrameParams F) {
+    uint32_t work = F.work_offset + blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (work >= F.n_work) return;  // warp-uniform
+    render_warp_tile<METRICS, PRIMARY>(S, F, work);
+}
+
+// K_render, persistent form: the grid is sized to the machine (SMs x resident CTAs) and every WARP pulls warp tiles
+// from a ticket counter until the frame is done, so a warp slot never idles waiting for the slowest warp of its CTA
+// (tile costs differ by an order of magnitude between sky and horizon tiles).  A warp's first tile is its global warp
+// index; every further tile costs one atomicAdd by lane 0.  The counter is never reset: a launch consumes exactly
+// (n_work - work_offset) tickets (each warp that ran ends on exactly one failing fetch), so the host advances
+// `ticket_base` by that amount per launch; the unsigned difference survives the 32-bit wrap.
+template <bool PRIMARY>
+__global__ void __launch_bounds__(VRT_RENDER_THREADS, VRT_RENDER_CTAS(PRIMARY)) k_render_persist(const __grid_constant__ DevScene S, const __grid_constant__ FrameParams F,
+                                                                                                uint32_t* __restrict__ ticket, uint32_t ticket_base) {
+    const uint32_t n_tiles = F.n_work - F.work_offset;
+    const uint32_t n_warps = gridDim.x * (blockDim.x >> 5);
+    uint32_t local = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    while (local < n_tiles) {
+        // the ticket of the NEXT tile is requested before this tile is traced, so its latency is hidden
+        uint32_t t = 0;
+        if ((threadIdx.x & 31u) == 0u) t = atomicAdd(ticket, 1u);
+        render_warp_tile<false, PRIMARY>(S, F, F.work_offset + local);
+        t = __shfl_sync(0xFFFFFFFFu, t, 0);
+        local = n_warps + (t - ticket_base);
+    }
+}
+
+// K_palette_albedo: per palette entry, the albedo bits the primary-only frame kernel would compute from the material.
+__global__ void k_palette_albedo(const uint2* __restrict__ palette, uint32_t* __restrict__ albedo) {
+    albedo[threadIdx.x] = albedo_rgb_bits(palette[threadIdx.x].x);
 }
 
 // ---------------------------------------------------------------------------------------------
