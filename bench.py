@@ -52,7 +52,7 @@ def _traffic(args):
     try:
         d = json.loads((ROOT / "profiles" / "traffic.json").read_text())
         e = d.get(f"k_render<false,true> {args.width}x{args.height} bounces={args.bounces}")
-        return (e["dram_read_bytes"] + e["dram_write_bytes"]) if e and args.gpus == 1 else None
+        return (e["dram_read_bytes"] + e["dram_write_bytes"]) if e and args.gpus == 1 and args.workload == "terrain" else None
     except Exception:
         return None
 
@@ -172,10 +172,38 @@ class ClockSampler:
         }
 
 
-def build_scene():
-    from scenes import terrain
+WORKLOADS = {
+    # name: (BASELINE.json config, default width, height, bounces)
+    "terrain": ("configs[1]", 3840, 2160, 0),
+    "sponza": ("configs[2]", 1920, 1080, 1),
+    "large": ("configs[3]", 3840, 2160, 2),
+    "edits": ("configs[4]", 3840, 2160, 0),
+}
+_WL = {"name": "terrain", "view": (6, 4), "cam": None, "label": None, "reference_ok": True}
 
-    scene = terrain.bench_terrain()
+
+def build_scene(workload="terrain"):
+    """-> (scene, sync records, stats); fills _WL (view extent, camera, label) for the chosen workload."""
+    from scenes import camera, terrain
+
+    _WL["name"] = workload
+    if workload in ("terrain", "edits"):
+        scene = terrain.bench_terrain()
+        _WL.update(view=(6, 4), cam=camera.Camera(), reference_ok=True,
+                   label=f"{scene.get('name', 'terrain')}, reference camera (512,128,512) yaw 1.52 pitch -0.5")
+    elif workload == "sponza":
+        from scenes import models
+
+        scene = models.sponza(2048)  # Main.cpp:42-47: Sponza.gltf voxelised into 2048^3 at the origin
+        # 2048 x 1024 x 2048 view (the model is 860 voxels tall; the reference CPU view of 512 would cut it off)
+        _WL.update(view=(6, 5), cam=camera.Camera(pos=(420.3, 160.2, 1010.7), yaw=1.5, pitch=-0.15), reference_ok=False,
+                   label="bundled assets/models/Sponza voxelised into 2048^3, camera (420,160,1011) yaw 1.5 pitch -0.15")
+    elif workload == "large":
+        scene = terrain.terrain_fastnoise(128, 7, 128) if terrain.fastnoise_available() else terrain.terrain_hash(128, 7, 128, seed=12345, emissive=False)
+        _WL.update(view=(7, 4), cam=camera.Camera(pos=(2048.0, 128.0, 2048.0)), reference_ok=False,
+                   label=f"{scene.get('name', 'terrain')} in a 4096x512x4096 view, camera (2048,128,2048) yaw 1.52 pitch -0.5")
+    else:
+        raise SystemExit(f"unknown workload {workload}")
     return scene, terrain.scene_records(scene), terrain.scene_stats(scene)
 
 
@@ -183,7 +211,7 @@ def bench_frame(width, height, bounces, part_index=0, part_count=1, frame_no=1, 
     from scenes import camera
     from voxelrt_b200 import capi
 
-    cam = camera.Camera()  # Main.cpp:76-78
+    cam = _WL["cam"] or camera.Camera()  # Main.cpp:76-78
     proj, inv, wo, frac = cam.matrices(width, height)
     return capi.make_frame(width, height, inv, proj, wo, frac, frame_no=frame_no, bounces=bounces, flags=flags, part_index=part_index, part_count=part_count)
 
@@ -193,7 +221,7 @@ def cpu_arm(args, scene, recs, want_ref=True):
     from oracle import pyoracle
 
     kind, runner = "port", None
-    if want_ref:
+    if want_ref and _WL["reference_ok"]:
         try:
             from oracle import refharness
 
@@ -206,7 +234,7 @@ def cpu_arm(args, scene, recs, want_ref=True):
     w, h = args.width, args.height
     rays = w * h * (1 + args.bounces)
     if runner is None:
-        orc = pyoracle.OracleMap(6, 4)
+        orc = pyoracle.OracleMap(*_WL["view"])
         orc.set_palette(scene["palette"])
         orc.sync(recs)
         if args.bounces:
@@ -234,7 +262,7 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    scene, recs, sstats = build_scene()
+    scene, recs, sstats = build_scene(args.workload)
     run, kind, cores, rays = cpu_arm(args, scene, recs)
     for _ in range(min(args.warmup, 2)):
         run()
@@ -272,8 +300,9 @@ def run_reference(args):
 
 def workload_config(args, scene, sstats):
     return {
-        "workload": f"BASELINE configs[1]: {scene.get('name', 'terrain')}, reference camera (512,128,512) yaw 1.52 pitch -0.5, "
-        f"{args.width}x{args.height} primary rays + normal/material/depth G-buffer, bounces={args.bounces}",
+        "workload": f"BASELINE {WORKLOADS[args.workload][0]}: {_WL['label']}, "
+        f"{args.width}x{args.height} primary rays + normal/material/depth G-buffer, bounces={args.bounces}"
+        + (f", {args.edits} random voxel edits + vrt_sync before every frame" if args.workload == "edits" else ""),
         "width": args.width,
         "height": args.height,
         "bounces": args.bounces,
@@ -300,8 +329,11 @@ def run_b200(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     n_gpus = world
 
-    scene, recs, sstats = build_scene()
-    ctx = capi.Context(6, 4, device=local, initial_brick_capacity=1 << 18)
+    scene, recs, sstats = build_scene(args.workload)
+    cap = 1 << 18
+    while cap < sstats["bricks"] + 4096:
+        cap <<= 1
+    ctx = capi.Context(*_WL["view"], device=local, initial_brick_capacity=cap)
     ctx.set_palette(scene["palette"])
     ctx.sync(recs)
     if args.bounces:
@@ -335,7 +367,27 @@ def run_b200(args):
     assert stream.cuda_stream != 0
     frame = bench_frame(w, h, args.bounces, part_index=rank, part_count=world)
 
+    # workload "edits" (BASELINE configs[4]): every frame is preceded by a batch of voxel edits whose dirty bricks are
+    # uploaded by vrt_sync (pinned staging + one H2D copy + upload / header / box kernels) inside the timed region; the
+    # host-side world editing (the reference's VoxelMap::Set) is precomputed, one record batch per frame
+    edit_batches, edit_i, edit_stats = None, [0], {"bricks": 0, "bytes": 0, "syncs": 0, "launches": 0}
+    if args.workload == "edits":
+        from scenes import edits as _edits
+
+        n_frames = 3 * args.steps + args.warmup + 8
+        frames_recs, _ = _edits.random_edit_frames(scene, n_frames, args.edits, seed=1)
+        edit_batches = [capi.make_records(r) for r in frames_recs]
+
     def step():
+        if edit_batches is not None:
+            arr, keep, n = edit_batches[edit_i[0] % len(edit_batches)]
+            edit_i[0] += 1
+            ctx.sync_records(arr, n)
+            st_ = ctx.stats()
+            edit_stats["bricks"] += st_.bricks_uploaded
+            edit_stats["bytes"] += st_.bytes_uploaded
+            edit_stats["syncs"] += 1
+            edit_stats["launches"] += st_.last_launches
         ctx.render_device(frame, out_ptr, None, stream.cuda_stream)
 
     # traversal counters of this frame (untimed, metrics build of the same kernel)
@@ -350,19 +402,23 @@ def run_b200(args):
     alg_bytes = 8 * m.sector_fetches + 8 * m.cell_fetches + 9 * m.hits + 16 * my_primary
 
     for _ in range(args.warmup):
-        flush.zero_()
+        if edit_batches is None:
+            flush.zero_()
         step()
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
+    for k in edit_stats:
+        edit_stats[k] = 0
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
     evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     t_wall0 = time.perf_counter()
     for a, b in evs:
-        flush.zero_()
+        if edit_batches is None:
+            flush.zero_()
         a.record(stream)
         step()
         b.record(stream)
@@ -372,6 +428,11 @@ def run_b200(args):
     torch.cuda.synchronize()
     t_wall = time.perf_counter() - t_wall0
     total_ms = sum(a.elapsed_time(b) for a, b in evs)
+    render_only_ms = total_ms / args.steps
+    timed_edit_stats = dict(edit_stats)
+    if edit_batches is not None:
+        # edit -> visible: host-side vrt_sync (staging, H2D, upload kernels) + the frame; the events above see the frame only
+        total_ms = t_wall * 1000.0
     # warm-L2 variant (steady-state renderer: brickmap stays in the 126 MB L2), informational
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     a.record(stream)
@@ -487,7 +548,15 @@ def run_b200(args):
                 "d2h_bytes_per_step": npx * 16,
                 "api": "vrt_render (host buffers, pinned output)",
             },
-            "gpu_launches": args.steps,
+            "gpu_launches": args.steps + timed_edit_stats["launches"],
+            "edits": None if edit_batches is None else {
+                "voxel_edits_per_frame": args.edits,
+                "dirty_bricks_per_frame": timed_edit_stats["bricks"] / max(1, timed_edit_stats["syncs"]),
+                "h2d_bytes_per_frame": timed_edit_stats["bytes"] / max(1, timed_edit_stats["syncs"]),
+                "render_only_ms": render_only_ms,
+                "edit_to_visible_ms": ms_per_step,
+                "timing": "wall clock over the timed loop (vrt_sync is a blocking host call), no L2 flush",
+            },
             "gather": None if world == 1 else {"how": "peer stores into rank 0's framebuffer (CUDA IPC over NVLink), fused into the render kernel's epilogue", "verified_equal_to_single_gpu_frame": gather_ok,
                                                      "value_trace_only_warm_l2": rays_frame / (trace_only_ms * 1e-3) / 1e6},
             "roofline": {
@@ -531,11 +600,17 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--width", type=int, default=3840)
-    ap.add_argument("--height", type=int, default=2160)
-    ap.add_argument("--bounces", type=int, default=0)
+    ap.add_argument("--workload", default="terrain", choices=sorted(WORKLOADS), help="terrain = BASELINE configs[1] (the headline); the others are the remaining configs")
+    ap.add_argument("--width", type=int, default=None)
+    ap.add_argument("--height", type=int, default=None)
+    ap.add_argument("--bounces", type=int, default=None)
+    ap.add_argument("--edits", type=int, default=4096, help="workload 'edits': voxel edits per frame")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()
+    _, dw, dh, db = WORKLOADS[args.workload]
+    args.width = dw if args.width is None else args.width
+    args.height = dh if args.height is None else args.height
+    args.bounces = db if args.bounces is None else args.bounces
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.impl == "reference":
         return run_reference(args)

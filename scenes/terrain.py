@@ -142,12 +142,22 @@ def terrain_fastnoise(nx=24, ny=7, nz=24, cache=True):
     if cache and cp.exists():
         return load_scene(cp)
     sectors = {}
-    for y in range(ny):
-        for z in range(nz):
-            for x in range(nx):
-                mask, bricks = generate_sector_fastnoise(x, y, z)
+    coords = [(x, y, z) for y in range(ny) for z in range(nz) for x in range(nx)]
+    if len(coords) > 8192:
+        # big extents (BASELINE configs[3]): FastNoise2 generation is thread-safe and releases the GIL inside ctypes
+        from concurrent.futures import ThreadPoolExecutor
+
+        _fastnoise()
+        with ThreadPoolExecutor(max_workers=min(32, os.cpu_count() or 1)) as pool:
+            results = pool.map(lambda c: generate_sector_fastnoise(*c), coords, chunksize=64)
+            for c, (mask, bricks) in zip(coords, results):
                 if mask:
-                    sectors[(x, y, z)] = (mask, bricks)
+                    sectors[c] = (mask, bricks)
+    else:
+        for c in coords:
+            mask, bricks = generate_sector_fastnoise(*c)
+            if mask:
+                sectors[c] = (mask, bricks)
     scene = {"sectors": sectors, "palette": reference_palette(), "name": f"FastNoise2 terrain {nx}x{ny}x{nz} sectors"}
     if cache:
         try:

@@ -1,0 +1,104 @@
+"""CPU tests of the scene INPUT generators that feed configs 3-5 (voxeliser, palette quantiser, edit stream)."""
+from __future__ import annotations
+
+import numpy as np
+import pytest
+
+
+def _voxelize(tris, size=32):
+    import ctypes as C
+
+    from scenes import models
+
+    if not models.VOX_LIB.exists():
+        pytest.skip("scenes/_ref/libvoxelizer.so not built")
+    lib = models._voxlib()
+    g = lib.vox_create(size // 8, size // 8, size // 8)
+    vt = np.ascontiguousarray(tris, np.float32)
+    uv = np.zeros((vt.shape[0], 3, 2), np.float32)
+    tex = np.full(vt.shape[0], -1, np.int32)
+    ptrs = (C.c_void_p * 1)()
+    one = np.ones(1, np.int32)
+    lib.vox_triangles(g, vt.shape[0], vt.ctypes.data, uv.ctypes.data, tex.ctypes.data, ptrs, one.ctypes.data, one.ctypes.data, 7)
+    n = lib.vox_brick_count(g)
+    bricks = np.zeros((n, 512), np.uint8)
+    coords = np.zeros((n, 3), np.int32)
+    lib.vox_export(g, bricks.ctypes.data, coords.ctypes.data)
+    lib.vox_destroy(g)
+    vol = np.zeros((size, size, size), np.uint8)  # [y, z, x]
+    for c, b in zip(coords, bricks):
+        vol[c[1] * 8 : c[1] * 8 + 8, c[2] * 8 : c[2] * 8 + 8, c[0] * 8 : c[0] * 8 + 8] = b.reshape(8, 8, 8)
+    return vol
+
+
+def test_voxelizer_axis_aligned_quad():
+    # a quad in the plane z = 3.5 over [2,10] x [4,9] (x, y): exactly the voxels with z = 3 whose cell touches it
+    a, b, c, d = (2.0, 4.0, 3.5), (10.0, 4.0, 3.5), (10.0, 9.0, 3.5), (2.0, 9.0, 3.5)
+    vol = _voxelize([[a, b, c], [a, c, d]])
+    ys, zs, xs = np.nonzero(vol)
+    assert set(zs.tolist()) == {3}
+    assert xs.min() <= 2 and xs.max() >= 9 and ys.min() <= 4 and ys.max() >= 8
+    assert (vol[4:9, 3, 2:10] == 7).all()  # the interior is watertight
+    assert xs.min() >= 1 and xs.max() <= 10 and ys.min() >= 3 and ys.max() <= 9  # conservative by at most one cell
+
+
+def test_voxelizer_covers_every_sampled_surface_point():
+    rng = np.random.default_rng(5)
+    tris = rng.uniform(3, 28, (40, 3, 3)).astype(np.float32)
+    vol = _voxelize(tris)
+    # conservative voxelisation: every voxel that contains a point of a triangle is set ...
+    w = rng.dirichlet((1, 1, 1), 4000).astype(np.float32)
+    for t in tris:
+        p = w @ t
+        cell = np.floor(p).astype(int)
+        assert (vol[cell[:, 1], cell[:, 2], cell[:, 0]] == 7).all()
+    # ... and every set voxel's cube is within reach of some triangle's plane and bounding box
+    ys, zs, xs = np.nonzero(vol)
+    centers = np.stack([xs, ys, zs], 1) + 0.5
+    ok = np.zeros(len(centers), bool)
+    for t in tris:
+        n = np.cross(t[1] - t[0], t[2] - t[0])
+        n /= np.linalg.norm(n)
+        near_plane = np.abs((centers - t[0]) @ n) <= 0.5 * np.abs(n).sum() + 1e-4
+        in_box = ((centers + 0.5 >= t.min(0) - 1e-4) & (centers - 0.5 <= t.max(0) + 1e-4)).all(1)
+        ok |= near_plane & in_box
+    assert ok.all()
+
+
+def test_octree_palette_and_nearest_index():
+    from scenes import models
+
+    rng = np.random.default_rng(2)
+    cols = np.concatenate([rng.integers(0, 256, (5000, 3)), np.tile([[200, 30, 30]], (3000, 1)), np.tile([[10, 10, 240]], (10, 1))]).astype(np.uint8)
+    q = models.OctreePalette()
+    q.add_colors(cols[:4000])
+    q.add_colors(cols[4000:])
+    pal = q.build(240)
+    assert 200 <= pal.shape[0] <= 240
+    idx = models.nearest_palette_index(pal, cols)
+    d = np.abs(cols[:, None, :].astype(int) - pal[None].astype(int)).sum(2)
+    assert np.array_equal(idx, d.argmin(1))
+    assert d[np.arange(len(cols)), idx].mean() < 40  # the palette actually represents the input
+    # a heavily populated colour keeps (nearly) its own entry
+    assert d[5000, idx[5000]] <= 6
+
+
+def test_edit_stream_records_reproduce_the_world(hash_scene):
+    """Feeding the per-frame dirty records to a map incrementally gives the same state as syncing the edited world from
+    scratch (the VrtDirtySector contract: alloc mask + dirty mask + payload of dirty & alloc in ascending brick order)."""
+    from oracle import pyoracle
+    from scenes import edits, terrain
+
+    frames, world = edits.random_edit_frames(hash_scene, 5, 800, seed=9, box=((0, 192), (0, 128), (0, 192)))
+    inc = pyoracle.OracleMap(6, 4)
+    inc.sync(terrain.scene_records(hash_scene))
+    for recs in frames:
+        assert all(r[5].shape[0] == bin(r[3] & r[4]).count("1") for r in recs)
+        inc.sync(recs)
+    fresh = pyoracle.OracleMap(6, 4)
+    final = world.to_scene(hash_scene["palette"])
+    fresh.sync(terrain.scene_records(final))
+    assert terrain.scene_stats(final)["bricks"] > terrain.scene_stats(hash_scene)["bricks"]  # edits allocated bricks
+    for key in sorted(final["sectors"]):
+        a, b = inc.read_sector(*key), fresh.read_sector(*key)
+        assert a[0] == b[0] and np.array_equal(a[1], b[1]) and np.array_equal(a[2], b[2]), key

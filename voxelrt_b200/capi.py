@@ -297,6 +297,10 @@ class Context:
         self._chk(self.lib.vrt_sync(self.h, n, arr))
         del keep
 
+    def sync_records(self, arr, n):
+        """vrt_sync with a record array prepared by make_records() (keeps Python out of a timed loop)."""
+        self._chk(self.lib.vrt_sync(self.h, n, arr))
+
     def read_sector(self, sx, sy, sz):
         mask, base = C.c_uint64(), C.c_uint32()
         bricks = np.zeros((64, 512), np.uint8)

@@ -4,13 +4,24 @@
 
 namespace vrt {
 
+void RangeArena::put_free(uint32_t base, uint32_t count) {
+    free_[base] = count;
+    by_size_.emplace(count, base);
+}
+
+void RangeArena::drop_free(std::map<uint32_t, uint32_t>::iterator it) {
+    by_size_.erase(std::make_pair(it->second, it->first));
+    free_.erase(it);
+}
+
 void RangeArena::reset(uint32_t capacity) {
     free_.clear();
+    by_size_.clear();
     parked_.clear();
     capacity_ = capacity;
     allocated_ = 0;
     high_water_ = 0;
-    if (capacity) free_[0] = capacity;
+    if (capacity) put_free(0, capacity);
 }
 
 void RangeArena::grow(uint32_t new_capacity) {
@@ -25,14 +36,12 @@ uint32_t RangeArena::alloc(uint32_t count) {
     if (count == 0) return 0;
     // best fit = the smallest free range that holds `count` (least fragmentation), lowest
     // address among equals
-    auto best = free_.end();
-    for (auto it = free_.begin(); it != free_.end(); ++it) {
-        if (it->second >= count && (best == free_.end() || it->second < best->second)) best = it;
-    }
-    if (best == free_.end()) return kNone;
-    uint32_t base = best->first, size = best->second;
-    free_.erase(best);
-    if (size > count) free_[base + count] = size - count;
+    // (the size index makes this O(log n); an edit-heavy session leaves thousands of small free ranges behind)
+    auto fit = by_size_.lower_bound(std::make_pair(count, 0u));
+    if (fit == by_size_.end()) return kNone;
+    uint32_t base = fit->second, size = fit->first;
+    drop_free(free_.find(base));
+    if (size > count) put_free(base + count, size - count);
     allocated_ += count;
     high_water_ = std::max(high_water_, base + count);
     return base;
@@ -44,8 +53,8 @@ bool RangeArena::extend(uint32_t base, uint32_t cur, uint32_t want) {
     uint32_t need = want - cur;
     if (it == free_.end() || it->second < need) return false;
     uint32_t fbase = it->first, fsize = it->second;
-    free_.erase(it);
-    if (fsize > need) free_[fbase + need] = fsize - need;
+    drop_free(it);
+    if (fsize > need) put_free(fbase + need, fsize - need);
     allocated_ += need;
     high_water_ = std::max(high_water_, base + want);
     return true;
@@ -61,15 +70,15 @@ void RangeArena::release(uint32_t base, uint32_t count) {
         if (prev->first + prev->second == base) {
             base = prev->first;
             count += prev->second;
-            free_.erase(prev);
+            drop_free(prev);
         }
     }
     // merge with the range that starts at the end
     if (next != free_.end() && base + count == next->first) {
         count += next->second;
-        free_.erase(next);
+        drop_free(next);
     }
-    free_[base] = count;
+    put_free(base, count);
 }
 
 void RangeArena::quarantine(uint32_t base, uint32_t count) {
@@ -98,6 +107,11 @@ bool RangeArena::check_invariants() const {
         prev_end = r.first + r.second;
         free_total += r.second;
         first = false;
+    }
+    if (by_size_.size() != free_.size()) return false;
+    for (auto& r : by_size_) {
+        auto it = free_.find(r.second);
+        if (it == free_.end() || it->second != r.first) return false;
     }
     uint64_t parked = 0;
     for (auto& r : parked_) parked += r.second;

@@ -13,6 +13,8 @@
 #pragma once
 #include <cstdint>
 #include <map>
+#include <set>
+#include <utility>
 #include <vector>
 
 namespace vrt {
@@ -45,7 +47,11 @@ public:
     bool check_invariants() const;                               // ranges sorted, disjoint, coalesced
 
 private:
-    std::map<uint32_t, uint32_t> free_;  // base -> count
+    void put_free(uint32_t base, uint32_t count);
+    void drop_free(std::map<uint32_t, uint32_t>::iterator it);
+
+    std::map<uint32_t, uint32_t> free_;                  // base -> count
+    std::set<std::pair<uint32_t, uint32_t>> by_size_;    // (count, base): best fit = lower_bound({count, 0}), lowest base among equals
     std::vector<std::pair<uint32_t, uint32_t>> parked_;
     uint32_t capacity_ = 0, allocated_ = 0, high_water_ = 0;
 };
