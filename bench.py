@@ -15,8 +15,12 @@ roofline  algorithmic bytes (8 I_s + 8 I_c + 9 H + 16 P, counted by the kernel's
         counters, which tests check against the oracle) / kernel time, vs the measured HBM peak.
 cpu_baseline  the CPU path (oracle/_ref = the reference's own CpuRenderer.cpp when it was compiled
         here, else the oracle port) on all host threads, same frame.
-N > 1   screen-tile split of the SAME frame (strong scaling): rank r renders macro tiles t with
-        t % N == r of the replicated brickmap.
+N > 1   screen split of the SAME frame (strong scaling): rank r renders the 32-pixel bands b with
+        b % N == r of the replicated brickmap into its own buffer, and vrt_render_gather moves them
+        into the presenting GPU's framebuffer with one strided copy over NVLink while the next frame
+        is traced (presenting GPU = frame % N).  value = K frames back to back including the last
+        gather, max over ranks; gather.* carries the non-pipelined frame latency and a trace-only figure.
+--workload  sponza | large | edits: the other BASELINE configs (non-default bench lines).
 """
 from __future__ import annotations
 
@@ -308,8 +312,10 @@ def workload_config(args, scene, sstats):
         "bounces": args.bounces,
         "bricks": sstats["bricks"],
         "sectors": sstats["sectors"],
-        "l2": "flushed between timed frames (256 MiB memset outside the event-timed region)",
-        "parallelism": f"screen tiles 32x32 round-robin over {args.gpus} GPU(s), brickmap replicated",
+        "l2": "flushed between timed frames (256 MiB memset outside the event-timed region)" if args.gpus == 1 else
+              "N>1: frames pipelined back to back, brickmap L2-resident (no flush possible inside the pipelined region; see gather.value_frame_latency_flushed_l2_owner0)",
+        "parallelism": f"screen tiles 32x32 round-robin over {args.gpus} GPU(s), brickmap replicated" if args.gpus == 1 else
+                       f"32-pixel screen bands round-robin over {args.gpus} GPUs, brickmap replicated, bands gathered over NVLink",
     }
 
 
@@ -347,25 +353,39 @@ def run_b200(args):
     npx = w * h
     rays_frame = npx * (1 + args.bounces)
     fb = torch.zeros(npx * 4, dtype=torch.int32, device="cuda")  # 16 B/px
-    # N > 1: tile gather over NVLink — rank 0 owns the framebuffer, every other rank maps it through
-    # CUDA IPC and its render kernel stores finished tiles straight into rank 0's memory (peer stores).
     out_ptr = fb.data_ptr()
+    # N > 1: pipelined tile gather over NVLink (vrt_render_gather).  Every rank renders its 32-pixel bands into its own
+    # buffer; one strided copy per frame then moves them into the presenting GPU's framebuffer while the next frame is
+    # traced.  The presenting GPU rotates with the frame number (frame f is assembled on GPU f % N — one encoder /
+    # display head per GPU), so no single NVLink port has to swallow 7/8 of every frame.
+    owner_ptrs, local_fbs = None, None
     if world > 1:
-        box = [None]
-        if rank == 0:
-            handle, owner_ptr = ctx.fb_export(npx * 16)
-            box[0] = handle
-            out_ptr = owner_ptr
-        dist.broadcast_object_list(box, src=0)
-        if rank != 0:
-            out_ptr = ctx.fb_import(box[0])
+        handle, own_ptr = ctx.fb_export(npx * 16)
+        handles = [None] * world
+        dist.all_gather_object(handles, handle)
+        owner_ptrs = [own_ptr if r == rank else ctx.fb_import(handles[r]) for r in range(world)]
+        local_fbs = [torch.zeros(npx * 4, dtype=torch.int32, device="cuda") for _ in range(capi.VRT_GATHER_DEPTH)]
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
     # a real (non-legacy) stream: handle 0 would mean "the context's own stream" to the C ABI and
     # torch events recorded on the legacy stream would not bracket the kernel
     stream = torch.cuda.Stream()
     torch.cuda.set_stream(stream)
     assert stream.cuda_stream != 0
-    frame = bench_frame(w, h, args.bounces, part_index=rank, part_count=world)
+    # N > 1: consecutive frames alternate between two streams, so the tail of frame f (its last, longest warp tiles) and
+    # the ramp-up of frame f+1 overlap on the SMs instead of adding ~25 us of idle time to every 50-200 us frame
+    stream2 = torch.cuda.Stream() if world > 1 else None
+    join_ev = torch.cuda.Event() if world > 1 else None
+
+    def join_streams():  # `stream` waits for everything issued on stream2 and for the last gather
+        join_ev.record(stream2)
+        stream.wait_event(join_ev)
+        ctx.gather_wait(stream.cuda_stream)
+
+    def fork_streams():  # stream2 starts after everything issued on `stream` so far
+        join_ev.record(stream)
+        stream2.wait_event(join_ev)
+    frame = bench_frame(w, h, args.bounces, part_index=rank, part_count=world, flags=capi.VRT_FRAME_PART_ROWS if world > 1 else 0)
+    frame_i = [0]
 
     # workload "edits" (BASELINE configs[4]): every frame is preceded by a batch of voxel edits whose dirty bricks are
     # uploaded by vrt_sync (pinned staging + one H2D copy + upload / header / box kernels) inside the timed region; the
@@ -388,7 +408,12 @@ def run_b200(args):
             edit_stats["bytes"] += st_.bytes_uploaded
             edit_stats["syncs"] += 1
             edit_stats["launches"] += st_.last_launches
-        ctx.render_device(frame, out_ptr, None, stream.cuda_stream)
+        if world > 1:
+            i = frame_i[0]
+            frame_i[0] += 1
+            ctx.render_gather(frame, local_fbs[i % capi.VRT_GATHER_DEPTH].data_ptr(), owner_ptrs[i % world], (stream2 if i & 1 else stream).cuda_stream)
+        else:
+            ctx.render_device(frame, out_ptr, None, stream.cuda_stream)
 
     # traversal counters of this frame (untimed, metrics build of the same kernel)
     ctx.set_option("metrics", 1)
@@ -398,7 +423,7 @@ def run_b200(args):
     ctx.set_option("metrics", 0)
     from voxelrt_b200 import partition
 
-    my_primary = partition.pixels_of_rank(w, h, rank, world)
+    my_primary = partition.pixels_of_rank(w, h, rank, world, rows=world > 1)
     alg_bytes = 8 * m.sector_fetches + 8 * m.cell_fetches + 9 * m.hits + 16 * my_primary
 
     for _ in range(args.warmup):
@@ -416,18 +441,30 @@ def run_b200(args):
         sampler.start()
     evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     t_wall0 = time.perf_counter()
-    for a, b in evs:
-        if edit_batches is None:
-            flush.zero_()
+    if world == 1:
+        for a, b in evs:
+            if edit_batches is None:
+                flush.zero_()
+            a.record(stream)
+            step()
+            b.record(stream)
+    else:
+        # N > 1: the K frames go back to back (trace of frame f+1 overlaps the gather of frame f); one event pair brackets
+        # all of them INCLUDING the last gather.  No L2 flush is possible inside a pipelined region: the brickmap working
+        # set (9 MB) is L2-resident, which the N=1 line reports separately as value_warm_l2 (+0.5 %).
+        a, b = evs[0]
         a.record(stream)
-        step()
+        fork_streams()
+        for _ in range(args.steps):
+            step()
+        join_streams()
         b.record(stream)
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
     t_wall = time.perf_counter() - t_wall0
-    total_ms = sum(a.elapsed_time(b) for a, b in evs)
+    total_ms = sum(a.elapsed_time(b) for a, b in evs) if world == 1 else evs[0][0].elapsed_time(evs[0][1])
     render_only_ms = total_ms / args.steps
     timed_edit_stats = dict(edit_stats)
     if edit_batches is not None:
@@ -436,8 +473,12 @@ def run_b200(args):
     # warm-L2 variant (steady-state renderer: brickmap stays in the 126 MB L2), informational
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     a.record(stream)
+    if world > 1:
+        fork_streams()
     for _ in range(args.steps):
         step()
+    if world > 1:
+        join_streams()
     b.record(stream)
     torch.cuda.synchronize()
     warm_ms = a.elapsed_time(b) / args.steps
@@ -447,42 +488,57 @@ def run_b200(args):
     step()
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     a.record(stream)
+    if world > 1:
+        fork_streams()
     for _ in range(args.steps):
         step()
+    if world > 1:
+        join_streams()
     b.record(stream)
     torch.cuda.synchronize()
     stepwise_ms = a.elapsed_time(b) / args.steps
     ctx.set_option("macro_steps", 1)
 
-    trace_only_ms = None
-    if world > 1:  # the same split without the NVLink gather: every rank stores into its own memory
-        def local_step():
-            ctx.render_device(frame, fb.data_ptr(), None, stream.cuda_stream)
+    trace_only_ms, latency_ms, gather_ok = None, None, None
+    if world > 1:
+        def local_step(k=0):  # the same split without the NVLink gather: every rank keeps its bands
+            ctx.render_device(frame, (fb if k & 1 == 0 else local_fbs[1]).data_ptr(), None, (stream2 if k & 1 else stream).cuda_stream)
 
         local_step()
         torch.cuda.synchronize()
         dist.barrier()
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record(stream)
-        for _ in range(args.steps):
-            local_step()
+        fork_streams()
+        for k in range(args.steps):
+            local_step(k)
+        join_streams()
         b.record(stream)
         torch.cuda.synchronize()
-        lt = torch.tensor([a.elapsed_time(b) / args.steps], dtype=torch.float64, device="cuda")
+        # frame LATENCY: one frame at a time, L2 flushed, all bands gathered on rank 0 before the next frame starts
+        lat = 0.0
+        for _ in range(args.steps):
+            dist.barrier()
+            flush.zero_()
+            c, d = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            c.record(stream)
+            ctx.render_gather(frame, local_fbs[0].data_ptr(), owner_ptrs[0], stream.cuda_stream)
+            ctx.gather_wait(stream.cuda_stream)
+            d.record(stream)
+            torch.cuda.synchronize()
+            lat += c.elapsed_time(d)
+        lt = torch.tensor([a.elapsed_time(b) / args.steps, lat / args.steps], dtype=torch.float64, device="cuda")
         dist.all_reduce(lt, op=dist.ReduceOp.MAX)
-        trace_only_ms = float(lt[0])
-    gather_ok = None
-    if world > 1:
-        # the gathered frame in rank 0's memory must equal the frame rank 0 renders alone
-        step()
-        torch.cuda.synchronize()
+        trace_only_ms, latency_ms = float(lt[0]), float(lt[1])
+        # the frame assembled in rank 0's memory must equal the frame rank 0 renders alone
         dist.barrier()
-        if rank == 0:
+        if rank == 0 and edit_batches is None:
             solo = torch.zeros(npx * 4, dtype=torch.int32, device="cuda")
             ctx.render_device(bench_frame(w, h, args.bounces), solo.data_ptr(), None, stream.cuda_stream)
             torch.cuda.synchronize()
+
             class _DevPtr:  # view rank 0's exported framebuffer as a tensor
-                __cuda_array_interface__ = {"shape": (npx * 4,), "typestr": "<i4", "data": (int(out_ptr), False), "version": 2}
+                __cuda_array_interface__ = {"shape": (npx * 4,), "typestr": "<i4", "data": (int(owner_ptrs[0]), False), "version": 2}
 
             gathered = torch.as_tensor(_DevPtr(), device="cuda")
             gather_ok = bool(torch.equal(solo, gathered))
@@ -497,7 +553,7 @@ def run_b200(args):
 
     # ---- e2e: host-buffer ABI call, pinned output, wall clock (rank-local partition) ----
     host_out = torch.empty(npx * 4, dtype=torch.int32).pin_memory()
-    e2e_frame = bench_frame(w, h, args.bounces, part_index=rank, part_count=world)
+    e2e_frame = bench_frame(w, h, args.bounces, part_index=rank, part_count=world, flags=capi.VRT_FRAME_PART_ROWS if world > 1 else 0)
 
     def e2e_step():
         st = ctx.lib.vrt_render(ctx.h, C.byref(e2e_frame), host_out.data_ptr(), None)
@@ -546,7 +602,7 @@ def run_b200(args):
                 "ms_per_step": e2e_ms,
                 "h2d_bytes_per_step": C.sizeof(capi.VrtFrame),
                 "d2h_bytes_per_step": npx * 16,
-                "api": "vrt_render (host buffers, pinned output)",
+                "api": "vrt_render (host buffers, pinned output)" + ("" if world == 1 else "; every rank delivers its own bands of the frame into its host buffer"),
             },
             "gpu_launches": args.steps + timed_edit_stats["launches"],
             "edits": None if edit_batches is None else {
@@ -557,8 +613,15 @@ def run_b200(args):
                 "edit_to_visible_ms": ms_per_step,
                 "timing": "wall clock over the timed loop (vrt_sync is a blocking host call), no L2 flush",
             },
-            "gather": None if world == 1 else {"how": "peer stores into rank 0's framebuffer (CUDA IPC over NVLink), fused into the render kernel's epilogue", "verified_equal_to_single_gpu_frame": gather_ok,
-                                                     "value_trace_only_warm_l2": rays_frame / (trace_only_ms * 1e-3) / 1e6},
+            "gather": None if world == 1 else {
+                "how": "vrt_render_gather: 32-pixel bands rendered locally, one strided D2D copy per frame into the presenting GPU's framebuffer "
+                       "(CUDA IPC over NVLink) on the copy stream, overlapped with the next frame; presenting GPU = frame % N",
+                "verified_equal_to_single_gpu_frame": gather_ok,
+                "value_trace_only_warm_l2": rays_frame / (trace_only_ms * 1e-3) / 1e6,
+                "value_frame_latency_flushed_l2_owner0": rays_frame / (latency_ms * 1e-3) / 1e6,
+                "frame_latency_ms": latency_ms,
+                "bytes_over_nvlink_per_frame": npx * 16 * (world - 1) // world,
+            },
             "roofline": {
                 "bound": "hbm",
                 "kernel": "vrt::k_render<false,%s>" % ("true" if args.bounces == 0 else "false"),

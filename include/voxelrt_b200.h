@@ -112,6 +112,10 @@ typedef struct VrtHitD {
  * Matrices are column-major float[16] exactly like glm::mat4 (m[col][row] = a[col*4+row]). */
 #define VRT_FRAME_LINEAR_OUTPUT 1u /* out = 4 planes (albedo, depth, irrRG, irrBX) of w*h u32  */
 #define VRT_FRAME_AUX_HITS 2u      /* also fill the VrtHit of every primary ray (aux_hits)     */
+#define VRT_FRAME_PART_ROWS 8u     /* multi-GPU split by macro-tile ROW: rank r renders the 32-pixel-high
+                                    * bands b with b % part_count == r (each band is one contiguous range
+                                    * of the tile-layout framebuffer, so a rank's result moves with one
+                                    * strided copy); default split is by macro tile, t % part_count       */
 typedef struct VrtFrame {
     uint32_t width, height;  /* rounded down to multiples of 4 by the caller (CpuRenderer.cpp:419) */
     float inv_proj[16];      /* GBuffer::GetInverseProjScreenMat (GBuffer.h:133-139)               */
@@ -222,6 +226,17 @@ VRT_API int vrt_render_device(VrtContext* ctx, const VrtFrame* frame, void* d_ou
 VRT_API int vrt_fb_export(VrtContext* ctx, uint64_t bytes, uint8_t handle_out[64], void** d_ptr_out);
 VRT_API int vrt_fb_import(VrtContext* ctx, const uint8_t handle[64], void** d_ptr_out);
 VRT_API int vrt_fb_release(VrtContext* ctx, void* d_ptr);
+/* Pipelined form of the same exchange: renders this rank's bands (frame->flags must carry
+ * VRT_FRAME_PART_ROWS, tile layout) into its OWN device buffer d_local_fb on `stream`, then copies
+ * exactly those bands to the same offsets of d_owner_fb (the presenting rank's framebuffer opened
+ * with vrt_fb_import, or a local pointer) on the context's copy stream, as one strided
+ * device-to-device copy over NVLink.  The call returns at once; the next frame can be traced while
+ * this one is in flight: a d_local_fb may be reused every VRT_GATHER_DEPTH-th call (the call waits for
+ * the copy issued that many calls ago), and the owner may change from frame to frame.
+ * vrt_gather_wait makes `stream` wait for every gather issued so far. */
+#define VRT_GATHER_DEPTH 4u
+VRT_API int vrt_render_gather(VrtContext* ctx, const VrtFrame* frame, void* d_local_fb, void* d_owner_fb, void* stream);
+VRT_API int vrt_gather_wait(VrtContext* ctx, void* stream);
 
 /* Device-side traversal counters of the last trace/render (TRAVERSAL_METRICS,
  * VoxelTraversal.glsl:147-151): total loop iterations, sector-mask fetches, cell-mask fetches,

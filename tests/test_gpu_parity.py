@@ -288,6 +288,40 @@ def test_render_tile_partition_union(hash_ctx, parts):
     assert np.array_equal(acc, full)
 
 
+@pytest.mark.parametrize("parts", [2, 3, 8])
+def test_render_gather_row_bands(hash_ctx, parts):
+    """vrt_render_gather (the pipelined multi-GPU exchange), exercised on one GPU: every "rank" renders its 32-pixel bands
+    into its own buffer and the strided band copy lands them in the owner's framebuffer; after all ranks the owner holds
+    the single-GPU frame byte for byte, for frame heights with and without a partial last band, with the local buffers
+    alternating as a pipelined caller would."""
+    import torch
+
+    from scenes import camera
+    from voxelrt_b200 import capi
+
+    cam = camera.Camera(pos=(96.3, 90.2, 20.7), yaw=0.2, pitch=-0.45)
+    stream = torch.cuda.Stream()
+    for w, h in ((416, 260), (256, 128), (64, 36)):
+        want, _ = hash_ctx.render(_frame(cam, w, h))
+        owner = torch.zeros(w * h * 4, dtype=torch.int32, device="cuda")
+        local = [torch.full((w * h * 4,), -1, dtype=torch.int32, device="cuda") for _ in range(capi.VRT_GATHER_DEPTH)]
+        torch.cuda.synchronize()
+        for p in range(parts):
+            f = _frame(cam, w, h, part_index=p, part_count=parts, flags=capi.VRT_FRAME_PART_ROWS)
+            hash_ctx.render_gather(f, local[p % capi.VRT_GATHER_DEPTH].data_ptr(), owner.data_ptr(), stream.cuda_stream)
+        hash_ctx.gather_wait(stream.cuda_stream)
+        stream.synchronize()
+        assert owner.cpu().numpy().tobytes() == want.tobytes(), (w, h, parts)
+        # host-buffer form of the band split: every rank's call fills exactly its bands of the caller's frame
+        host = np.zeros_like(want)
+        for p in range(parts):
+            f = _frame(cam, w, h, part_index=p, part_count=parts, flags=capi.VRT_FRAME_PART_ROWS)
+            hash_ctx._chk(hash_ctx.lib.vrt_render(hash_ctx.h, __import__("ctypes").byref(f), host.ctypes.data, None))
+        assert host.tobytes() == want.tobytes(), (w, h, parts, "host bands")
+    with pytest.raises(capi.VrtError):  # the tile split cannot be moved with band copies
+        hash_ctx.render_gather(_frame(cam, 64, 36, part_index=0, part_count=2), local[0].data_ptr(), owner.data_ptr(), stream.cuda_stream)
+
+
 # ---------------------------------------------------------------------------------------------
 # hit query: vrt_hit_query == VoxelMap::RayCast (VoxelMap.cpp:140-170), fp64
 # ---------------------------------------------------------------------------------------------

@@ -20,7 +20,7 @@ def _free_port():
         return s.getsockname()[1]
 
 
-def _worker(rank, world, port, out_dir):
+def _worker(rank, world, port, out_dir, rows=False):
     sys.path.insert(0, str(ROOT))
     sys.path.insert(0, str(ROOT / "tests"))
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
@@ -39,11 +39,11 @@ def _worker(rank, world, port, out_dir):
     w, h = 200, 136  # not a multiple of 32: clipped tiles on both edges
     cam = camera.Camera(pos=(60.2, 70.1, 10.3), yaw=0.3, pitch=-0.5)
     proj, inv, wo, frac = cam.matrices(w, h)
-    flags = capi.VRT_FRAME_LINEAR_OUTPUT
+    flags = capi.VRT_FRAME_LINEAR_OUTPUT | (capi.VRT_FRAME_PART_ROWS if rows else 0)
     part, _, st = orc.render(capi.make_frame(w, h, inv, proj, wo, frac, flags=flags, part_index=rank, part_count=world), threads=2)
     # every rank's ray count is what the host-side partition predicts
-    assert st.rays == partition.pixels_of_rank(w, h, rank, world)
-    mine = torch.tensor(partition.tiles_of_rank(w, h, rank, world), dtype=torch.int64)
+    assert st.rays == partition.pixels_of_rank(w, h, rank, world, rows)
+    mine = torch.tensor(partition.tiles_of_rank(w, h, rank, world, rows), dtype=torch.int64)
     sizes = [torch.zeros(1, dtype=torch.int64) for _ in range(world)]
     dist.all_gather(sizes, torch.tensor([mine.numel()]))
     # gather = sum of the disjoint partial frames (unowned pixels are zero)
@@ -52,7 +52,7 @@ def _worker(rank, world, port, out_dir):
     owned = torch.from_numpy((part != 0).any(axis=0).astype(np.int64))
     dist.all_reduce(owned, op=dist.ReduceOp.SUM)
     if rank == 0:
-        full, _, st_full = orc.render(capi.make_frame(w, h, inv, proj, wo, frac, flags=flags), threads=2)
+        full, _, st_full = orc.render(capi.make_frame(w, h, inv, proj, wo, frac, flags=capi.VRT_FRAME_LINEAR_OUTPUT), threads=2)
         tx, ty = partition.tile_grid(w, h)
         ok = (
             int(sum(int(s) for s in sizes)) == tx * ty
@@ -65,12 +65,12 @@ def _worker(rank, world, port, out_dir):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world", [2, 3])
-def test_tile_split_gather_gloo(tmp_path, world):
+@pytest.mark.parametrize("world,rows", [(2, False), (3, False), (2, True), (3, True)])
+def test_tile_split_gather_gloo(tmp_path, world, rows):
     import torch.multiprocessing as mp
 
     port = _free_port()
-    mp.spawn(_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, port, str(tmp_path), rows), nprocs=world, join=True)
     assert (tmp_path / "result.txt").read_text() == "ok"
 
 
@@ -85,3 +85,12 @@ def test_partition_covers_every_pixel_once():
                 seen[y0 : y0 + th, x0 : x0 + tw] += 1
             assert partition.pixels_of_rank(w, h, r, n) == sum(partition.tile_rect(w, h, t)[2] * partition.tile_rect(w, h, t)[3] for t in partition.tiles_of_rank(w, h, r, n))
         assert (seen == 1).all()
+        # row-band split: bands are disjoint, cover the frame, and each is one contiguous byte range of the tile layout
+        seen[:] = 0
+        for r in range(n):
+            for t in partition.tiles_of_rank(w, h, r, n, rows=True):
+                x0, y0, tw, th = partition.tile_rect(w, h, t)
+                assert (y0 // 32) % n == r
+                seen[y0 : y0 + th, x0 : x0 + tw] += 1
+        assert (seen == 1).all()
+        assert sum(partition.pixels_of_rank(w, h, r, n, rows=True) for r in range(n)) == w * h

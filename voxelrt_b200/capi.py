@@ -23,6 +23,8 @@ VRT_HIT_CAPPED = 0x400
 VRT_HIT_ITERS_SHIFT = 16
 VRT_FRAME_LINEAR_OUTPUT = 1
 VRT_FRAME_AUX_HITS = 2
+VRT_FRAME_PART_ROWS = 8
+VRT_GATHER_DEPTH = 4
 VRT_BLUE_NOISE_BYTES = 128 * 128 * 64 * 2
 
 
@@ -153,6 +155,8 @@ EXPORTS = [
     "vrt_fb_export",
     "vrt_fb_import",
     "vrt_fb_release",
+    "vrt_render_gather",
+    "vrt_gather_wait",
     "vrt_get_metrics",
     "vrt_set_option",
 ]
@@ -192,6 +196,8 @@ def load(path: os.PathLike | None = None) -> C.CDLL:
     lib.vrt_fb_export.argtypes = [vp, u64, vp, C.POINTER(vp)]
     lib.vrt_fb_import.argtypes = [vp, vp, C.POINTER(vp)]
     lib.vrt_fb_release.argtypes = [vp, vp]
+    lib.vrt_render_gather.argtypes = [vp, C.POINTER(VrtFrame), vp, vp, vp]
+    lib.vrt_gather_wait.argtypes = [vp, vp]
     lib.vrt_get_metrics.argtypes = [vp, C.POINTER(VrtTraversalMetrics)]
     lib.vrt_set_option.argtypes = [vp, C.c_char_p, C.c_int64]
     for name in EXPORTS:
@@ -357,6 +363,12 @@ class Context:
 
     def render_device(self, frame: VrtFrame, d_out, d_aux=None, stream=0):
         self._chk(self.lib.vrt_render_device(self.h, C.byref(frame), d_out, d_aux, stream))
+
+    def render_gather(self, frame: VrtFrame, d_local, d_owner, stream=0):
+        self._chk(self.lib.vrt_render_gather(self.h, C.byref(frame), d_local, d_owner, stream))
+
+    def gather_wait(self, stream=0):
+        self._chk(self.lib.vrt_gather_wait(self.h, stream))
 
     def fb_export(self, nbytes):
         handle = (C.c_uint8 * 64)()

@@ -35,6 +35,10 @@ struct VrtContext {
     cudaEvent_t ev_band[16] = {};
     cudaEvent_t ev_sync = nullptr;    // end of the last vrt_sync / upload work on `stream`
     cudaEvent_t ev_render = nullptr;  // end of the last render/trace on a caller stream
+    cudaEvent_t ev_gather_src[8] = {};  // vrt_render_gather: frame kernel done (ring), last gather copy done
+    cudaEvent_t ev_gather_done[8] = {};
+    uint32_t gather_seq = 0;
+    bool gather_pending = false;
     bool render_pending = false;
 
     uint32_t sxz = 6, sy = 4, n_sectors = 0;
@@ -323,6 +327,7 @@ int launch_render(VrtContext* ctx, const VrtFrame* f, void* d_out, VrtHit* d_aux
     uint32_t macros_x = (f->width + 31) / 32, macros_y = (f->height + 31) / 32;
     uint32_t macros = macros_x * macros_y;
     uint32_t my_macros = macros / part_count + ((macros % part_count) > f->part_index ? 1u : 0u);
+    if (f->flags & VRT_FRAME_PART_ROWS) my_macros = (macros_y / part_count + ((macros_y % part_count) > f->part_index ? 1u : 0u)) * macros_x;
     F.n_work = my_macros * 32u;
     F.work_offset = 0;
     if (row1 != 0 && part_count == 1) {
@@ -410,6 +415,8 @@ extern "C" int vrt_create(const VrtConfig* cfg, VrtContext** out) {
     for (auto& e : c->ev_band) CUB(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     CUB(cudaEventCreateWithFlags(&c->ev_sync, cudaEventDisableTiming));
     CUB(cudaEventCreateWithFlags(&c->ev_render, cudaEventDisableTiming));
+    for (auto& e : c->ev_gather_src) CUB(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    for (auto& e : c->ev_gather_done) CUB(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     c->sxp = (1u << c->sxz) + 2u;
     c->syp = (1u << c->sy) + 2u;
     c->n_hdr = c->sxp * c->sxp * c->syp;
@@ -456,6 +463,8 @@ extern "C" void vrt_destroy(VrtContext* ctx) {
     cudaFree(ctx->d_palette);
     cudaFree(ctx->d_albedo);
     cudaFree(ctx->d_tickets);
+    for (auto& e : ctx->ev_gather_src) if (e) cudaEventDestroy(e);
+    for (auto& e : ctx->ev_gather_done) if (e) cudaEventDestroy(e);
     cudaFree(ctx->d_bn);
     cudaFree(ctx->d_sky);
     cudaFree(ctx->d_metrics);
@@ -797,6 +806,24 @@ extern "C" int vrt_render(VrtContext* ctx, const VrtFrame* frame, void* out, Vrt
     bool aux = (frame->flags & VRT_FRAME_AUX_HITS) != 0;
     if (aux && (st = ensure(ctx, ctx->d_aux, npx * sizeof(VrtHit)))) return st;
     uint32_t part_count = frame->part_count ? frame->part_count : 1;
+    if (part_count > 1 && (frame->flags & VRT_FRAME_PART_ROWS) && !(frame->flags & VRT_FRAME_LINEAR_OUTPUT) && !aux) {
+        // Band split: only this rank's 32-pixel bands are traced and only they cross PCIe (one strided D2H copy into the
+        // same offsets of `out`; the other ranks' bands of `out` are left untouched).
+        if (frame->part_index >= part_count) return fail(ctx, VRT_ERR_INVALID, "part_index >= part_count");
+        ctx->stats.last_launches = 0;
+        st = launch_render(ctx, frame, ctx->d_fb.p, nullptr, ctx->stream);
+        if (st) return st;
+        const size_t band = (size_t)(frame->width / 4) * 8u * sizeof(VrtTile);
+        const uint32_t rows_full = frame->height / 32u, rows_all = (frame->height + 31u) / 32u, r = frame->part_index;
+        const uint32_t mine_full = rows_full > r ? (rows_full - r + part_count - 1) / part_count : 0u;
+        if (mine_full) CU(cudaMemcpy2DAsync((char*)out + r * band, part_count * band, (char*)ctx->d_fb.p + r * band, part_count * band, band, mine_full, cudaMemcpyDeviceToHost, ctx->stream));
+        if (rows_all > rows_full && rows_full % part_count == r) {
+            const size_t tail = (size_t)(frame->width / 4) * ((frame->height % 32u) / 4u) * sizeof(VrtTile);
+            CU(cudaMemcpyAsync((char*)out + rows_full * band, (char*)ctx->d_fb.p + rows_full * band, tail, cudaMemcpyDeviceToHost, ctx->stream));
+        }
+        CU(cudaStreamSynchronize(ctx->stream));
+        return VRT_OK;
+    }
     if (part_count > 1) {  // pixels of other ranks stay zero in a partial frame
         CU(cudaMemsetAsync(ctx->d_fb.p, 0, npx * 16, ctx->stream));
         if (aux) CU(cudaMemsetAsync(ctx->d_aux.p, 0, npx * sizeof(VrtHit), ctx->stream));
@@ -884,6 +911,61 @@ extern "C" int vrt_fb_release(VrtContext* ctx, void* d_ptr) {
         return VRT_OK;
     }
     return fail(ctx, VRT_ERR_INVALID, "pointer not owned by this context");
+}
+
+// Pipelined tile gather (include/voxelrt_b200.h): frame kernel into the rank's own buffer on `stream`, then ONE strided
+// device-to-device copy of the rank's 32-pixel bands into the owner's framebuffer on the copy stream.  Band b of a
+// tile-layout framebuffer is the byte range [b * band, (b + 1) * band), band = (width / 4) * 8 tiles * 256 B, and the rank
+// owns bands part_index, part_index + part_count, ... — i.e. a 2-D copy with pitch part_count * band.  A last, shorter
+// band (height % 32 != 0) goes in a second, 1-D copy.
+extern "C" int vrt_render_gather(VrtContext* ctx, const VrtFrame* frame, void* d_local_fb, void* d_owner_fb, void* stream) {
+    if (!ctx || !frame || !d_local_fb || !d_owner_fb) return VRT_ERR_INVALID;
+    uint32_t part_count = frame->part_count ? frame->part_count : 1;
+    if (!(frame->flags & VRT_FRAME_PART_ROWS) && part_count > 1) return fail(ctx, VRT_ERR_INVALID, "vrt_render_gather needs VRT_FRAME_PART_ROWS");
+    if (frame->flags & (VRT_FRAME_LINEAR_OUTPUT | VRT_FRAME_AUX_HITS)) return fail(ctx, VRT_ERR_INVALID, "vrt_render_gather: tile layout, no aux records");
+    DeviceGuard g(ctx->device);
+    cudaStream_t s = stream ? (cudaStream_t)stream : ctx->stream;
+    int st = begin_on_stream(ctx, s);
+    if (st) return st;
+    ctx->stats.last_launches = 0;
+    // a local buffer may be reused every VRT_GATHER_DEPTH-th call: this frame's kernel waits for the copy issued that many calls ago
+    if (ctx->gather_seq >= VRT_GATHER_DEPTH) CU(cudaStreamWaitEvent(s, ctx->ev_gather_done[(ctx->gather_seq - VRT_GATHER_DEPTH) & 7u], 0));
+    st = launch_render(ctx, frame, d_local_fb, nullptr, s);
+    if (st) return st;
+    const uint32_t seq = ctx->gather_seq++;
+    if (d_owner_fb != d_local_fb) {
+        cudaEvent_t ev = ctx->ev_gather_src[seq & 7u];
+        CU(cudaEventRecord(ev, s));
+        CU(cudaStreamWaitEvent(ctx->copy_stream, ev, 0));
+        const size_t band = (size_t)(frame->width / 4) * 8u * sizeof(VrtTile);
+        const uint32_t rows_full = frame->height / 32u, rows_all = (frame->height + 31u) / 32u;
+        const uint32_t r = frame->part_index;
+        const uint32_t mine_full = rows_full > r ? (rows_full - r + part_count - 1) / part_count : 0u;
+        uint8_t* dst = static_cast<uint8_t*>(d_owner_fb);
+        const uint8_t* src = static_cast<const uint8_t*>(d_local_fb);
+        static const int gather_1d = getenv("VRT_GATHER_1D") ? atoi(getenv("VRT_GATHER_1D")) : 0;
+        if (mine_full && gather_1d) {
+            for (uint32_t k = 0; k < mine_full; k++) {
+                size_t off = (size_t)(r + k * part_count) * band;
+                CU(cudaMemcpyAsync(dst + off, src + off, band, cudaMemcpyDeviceToDevice, ctx->copy_stream));
+            }
+        } else if (mine_full) CU(cudaMemcpy2DAsync(dst + r * band, part_count * band, src + r * band, part_count * band, band, mine_full, cudaMemcpyDeviceToDevice, ctx->copy_stream));
+        if (rows_all > rows_full && rows_full % part_count == r) {
+            const size_t tail = (size_t)(frame->width / 4) * ((frame->height % 32u) / 4u) * sizeof(VrtTile);
+            CU(cudaMemcpyAsync(dst + rows_full * band, src + rows_full * band, tail, cudaMemcpyDeviceToDevice, ctx->copy_stream));
+        }
+        ctx->gather_pending = true;
+    }
+    CU(cudaEventRecord(ctx->ev_gather_done[seq & 7u], ctx->copy_stream));  // (copy-stream order also covers the calls without a copy)
+    return end_on_stream(ctx, s);
+}
+
+extern "C" int vrt_gather_wait(VrtContext* ctx, void* stream) {
+    if (!ctx) return VRT_ERR_INVALID;
+    DeviceGuard g(ctx->device);
+    cudaStream_t s = stream ? (cudaStream_t)stream : ctx->stream;
+    if (ctx->gather_pending && ctx->gather_seq) CU(cudaStreamWaitEvent(s, ctx->ev_gather_done[(ctx->gather_seq - 1) & 7u], 0));
+    return VRT_OK;
 }
 
 // Internal diagnostic hook (not part of include/voxelrt_b200.h): reads and clears the macro-loop event

@@ -40,9 +40,12 @@ __global__ void __launch_bounds__(128, 8) k_trace(const __grid_constant__ DevSce
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ bool warp_tile_origin(const FrameParams& F, uint32_t work, uint32_t& x0, uint32_t& y0) {
     uint32_t macro_local = work >> 5, sub = work & 31u;
-    uint32_t macro = macro_local * F.part_count + F.part_index;
+    // split by macro tile (t % part_count) or, with VRT_FRAME_PART_ROWS, by macro-tile row (row % part_count)
+    const bool by_rows = (F.flags & VRT_FRAME_PART_ROWS) != 0u;
+    uint32_t macro = by_rows ? macro_local : macro_local * F.part_count + F.part_index;
     // macro / macros_x by multiplication with ceil(2^32 / macros_x): exact while macro * macros_x < 2^32
     uint32_t my = F.macros_x_magic ? __umulhi(macro, F.macros_x_magic) : macro, mx = macro - my * F.macros_x;
+    if (by_rows) my = my * F.part_count + F.part_index;
     x0 = (mx << 5) + ((sub & 3u) << 3);
     y0 = (my << 5) + ((sub >> 2) << 2);
     return x0 < F.width && y0 < F.height;
