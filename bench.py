@@ -15,7 +15,7 @@ roofline  algorithmic bytes (8 I_s + 8 I_c + 9 H + 16 P, counted by the kernel's
         counters, which tests check against the oracle) / kernel time, vs the measured HBM peak.
 cpu_baseline  the CPU path (oracle/_ref = the reference's own CpuRenderer.cpp when it was compiled
         here, else the oracle port) on all host threads, same frame.
-N > 1   screen split of the SAME frame (strong scaling): rank r renders the 32-pixel bands b with
+N > 1   screen split of the SAME frame (strong scaling): rank r renders the 8-pixel bands b with
         b % N == r of the replicated brickmap into its own buffer, and vrt_render_gather moves them
         into the presenting GPU's framebuffer with one strided copy over NVLink while the next frame
         is traced (presenting GPU = frame % N).  value = K frames back to back including the last
@@ -315,7 +315,7 @@ def workload_config(args, scene, sstats):
         "l2": "flushed between timed frames (256 MiB memset outside the event-timed region)" if args.gpus == 1 else
               "N>1: frames pipelined back to back, brickmap L2-resident (no flush possible inside the pipelined region; see gather.value_frame_latency_flushed_l2_owner0)",
         "parallelism": f"screen tiles 32x32 round-robin over {args.gpus} GPU(s), brickmap replicated" if args.gpus == 1 else
-                       f"32-pixel screen bands round-robin over {args.gpus} GPUs, brickmap replicated, bands gathered over NVLink",
+                       f"8-pixel screen bands round-robin over {args.gpus} GPUs, brickmap replicated, bands gathered over NVLink",
     }
 
 
@@ -354,7 +354,7 @@ def run_b200(args):
     rays_frame = npx * (1 + args.bounces)
     fb = torch.zeros(npx * 4, dtype=torch.int32, device="cuda")  # 16 B/px
     out_ptr = fb.data_ptr()
-    # N > 1: pipelined tile gather over NVLink (vrt_render_gather).  Every rank renders its 32-pixel bands into its own
+    # N > 1: pipelined tile gather over NVLink (vrt_render_gather).  Every rank renders its 8-pixel bands into its own
     # buffer; one strided copy per frame then moves them into the presenting GPU's framebuffer while the next frame is
     # traced.  The presenting GPU rotates with the frame number (frame f is assembled on GPU f % N — one encoder /
     # display head per GPU), so no single NVLink port has to swallow 7/8 of every frame.
@@ -371,19 +371,22 @@ def run_b200(args):
     stream = torch.cuda.Stream()
     torch.cuda.set_stream(stream)
     assert stream.cuda_stream != 0
-    # N > 1: consecutive frames alternate between two streams, so the tail of frame f (its last, longest warp tiles) and
-    # the ramp-up of frame f+1 overlap on the SMs instead of adding ~25 us of idle time to every 50-200 us frame
-    stream2 = torch.cuda.Stream() if world > 1 else None
-    join_ev = torch.cuda.Event() if world > 1 else None
+    # N > 1: consecutive frames rotate over a few streams, so the tail of frame f (its last, longest warp tiles: a capped
+    # ray keeps its warp busy for ~40 us, most of a 50 us frame at 8 GPUs) overlaps the next frames on the SMs
+    n_streams = int(os.environ.get("VRT_BENCH_STREAMS", "4"))
+    streams = [stream] + [torch.cuda.Stream() for _ in range(n_streams - 1)] if world > 1 else [stream]
+    join_evs = [torch.cuda.Event() for _ in streams]
 
-    def join_streams():  # `stream` waits for everything issued on stream2 and for the last gather
-        join_ev.record(stream2)
-        stream.wait_event(join_ev)
+    def join_streams():  # `stream` waits for everything issued on the other streams and for the last gather
+        for s_, e_ in zip(streams[1:], join_evs[1:]):
+            e_.record(s_)
+            stream.wait_event(e_)
         ctx.gather_wait(stream.cuda_stream)
 
-    def fork_streams():  # stream2 starts after everything issued on `stream` so far
-        join_ev.record(stream)
-        stream2.wait_event(join_ev)
+    def fork_streams():  # the other streams start after everything issued on `stream` so far
+        join_evs[0].record(stream)
+        for s_ in streams[1:]:
+            s_.wait_event(join_evs[0])
     frame = bench_frame(w, h, args.bounces, part_index=rank, part_count=world, flags=capi.VRT_FRAME_PART_ROWS if world > 1 else 0)
     frame_i = [0]
 
@@ -411,7 +414,7 @@ def run_b200(args):
         if world > 1:
             i = frame_i[0]
             frame_i[0] += 1
-            ctx.render_gather(frame, local_fbs[i % capi.VRT_GATHER_DEPTH].data_ptr(), owner_ptrs[i % world], (stream2 if i & 1 else stream).cuda_stream)
+            ctx.render_gather(frame, local_fbs[i % capi.VRT_GATHER_DEPTH].data_ptr(), owner_ptrs[i % world], streams[i % len(streams)].cuda_stream)
         else:
             ctx.render_device(frame, out_ptr, None, stream.cuda_stream)
 
@@ -502,7 +505,7 @@ def run_b200(args):
     trace_only_ms, latency_ms, gather_ok = None, None, None
     if world > 1:
         def local_step(k=0):  # the same split without the NVLink gather: every rank keeps its bands
-            ctx.render_device(frame, (fb if k & 1 == 0 else local_fbs[1]).data_ptr(), None, (stream2 if k & 1 else stream).cuda_stream)
+            ctx.render_device(frame, local_fbs[k % len(local_fbs)].data_ptr(), None, streams[k % len(streams)].cuda_stream)
 
         local_step()
         torch.cuda.synchronize()
@@ -614,7 +617,7 @@ def run_b200(args):
                 "timing": "wall clock over the timed loop (vrt_sync is a blocking host call), no L2 flush",
             },
             "gather": None if world == 1 else {
-                "how": "vrt_render_gather: 32-pixel bands rendered locally, one strided D2D copy per frame into the presenting GPU's framebuffer "
+                "how": "vrt_render_gather: 8-pixel bands rendered locally, one strided D2D copy per frame into the presenting GPU's framebuffer "
                        "(CUDA IPC over NVLink) on the copy stream, overlapped with the next frame; presenting GPU = frame % N",
                 "verified_equal_to_single_gpu_frame": gather_ok,
                 "value_trace_only_warm_l2": rays_frame / (trace_only_ms * 1e-3) / 1e6,

@@ -758,7 +758,7 @@ void orc_render(const OrcMap* m, const VrtFrame* f, void* out, VrtHit* aux_hits,
                 for (uint32_t yy = 0; yy < 4; yy++) {
                     uint32_t y = (uint32_t)ty * 4 + yy;
                     if (part_count > 1) {
-                        uint32_t t = (f->flags & VRT_FRAME_PART_ROWS) ? (y / 32) : (y / 32) * tiles_x + (x / 32);
+                        uint32_t t = (f->flags & VRT_FRAME_PART_ROWS) ? (y / VRT_BAND_ROWS) : (y / 32) * tiles_x + (x / 32);
                         if (t % part_count != f->part_index) continue;
                     }
                     uint32_t alb, rg, bx;

@@ -290,7 +290,7 @@ def test_render_tile_partition_union(hash_ctx, parts):
 
 @pytest.mark.parametrize("parts", [2, 3, 8])
 def test_render_gather_row_bands(hash_ctx, parts):
-    """vrt_render_gather (the pipelined multi-GPU exchange), exercised on one GPU: every "rank" renders its 32-pixel bands
+    """vrt_render_gather (the pipelined multi-GPU exchange), exercised on one GPU: every "rank" renders its 8-pixel bands
     into its own buffer and the strided band copy lands them in the owner's framebuffer; after all ranks the owner holds
     the single-GPU frame byte for byte, for frame heights with and without a partial last band, with the local buffers
     alternating as a pipelined caller would."""

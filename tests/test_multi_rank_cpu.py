@@ -43,7 +43,7 @@ def _worker(rank, world, port, out_dir, rows=False):
     part, _, st = orc.render(capi.make_frame(w, h, inv, proj, wo, frac, flags=flags, part_index=rank, part_count=world), threads=2)
     # every rank's ray count is what the host-side partition predicts
     assert st.rays == partition.pixels_of_rank(w, h, rank, world, rows)
-    mine = torch.tensor(partition.tiles_of_rank(w, h, rank, world, rows), dtype=torch.int64)
+    mine = torch.tensor([r[1] * w + r[0] for r in partition.rects_of_rank(w, h, rank, world, rows)], dtype=torch.int64)
     sizes = [torch.zeros(1, dtype=torch.int64) for _ in range(world)]
     dist.all_gather(sizes, torch.tensor([mine.numel()]))
     # gather = sum of the disjoint partial frames (unowned pixels are zero)
@@ -55,7 +55,7 @@ def _worker(rank, world, port, out_dir, rows=False):
         full, _, st_full = orc.render(capi.make_frame(w, h, inv, proj, wo, frac, flags=capi.VRT_FRAME_LINEAR_OUTPUT), threads=2)
         tx, ty = partition.tile_grid(w, h)
         ok = (
-            int(sum(int(s) for s in sizes)) == tx * ty
+            int(sum(int(s) for s in sizes)) == ((h + partition.BAND - 1) // partition.BAND if rows else tx * ty)
             and np.array_equal(t.numpy().astype(np.uint32), full)
             and int(owned.max()) <= 1
             and st_full.rays == w * h
@@ -88,9 +88,8 @@ def test_partition_covers_every_pixel_once():
         # row-band split: bands are disjoint, cover the frame, and each is one contiguous byte range of the tile layout
         seen[:] = 0
         for r in range(n):
-            for t in partition.tiles_of_rank(w, h, r, n, rows=True):
-                x0, y0, tw, th = partition.tile_rect(w, h, t)
-                assert (y0 // 32) % n == r
+            for x0, y0, tw, th in partition.rects_of_rank(w, h, r, n, rows=True):
+                assert (y0 // partition.BAND) % n == r and x0 == 0 and tw == w
                 seen[y0 : y0 + th, x0 : x0 + tw] += 1
         assert (seen == 1).all()
         assert sum(partition.pixels_of_rank(w, h, r, n, rows=True) for r in range(n)) == w * h

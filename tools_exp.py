@@ -22,15 +22,36 @@ from conftest import ctx_for
 from scenes import terrain
 
 N = 40
-scene = terrain.bench_terrain()
-ctx = ctx_for(scene, initial_brick_capacity=1 << 18)
-w, h = 3840, 2160
+workload = "terrain"
+bounces = None
+argv = sys.argv[1:]
+while argv and argv[0].startswith("--"):
+    if argv[0] == "--workload":
+        workload = argv[1]
+    elif argv[0] == "--bounces":
+        bounces = int(argv[1])
+    argv = argv[2:]
+scene, recs, sstats = bench.build_scene(workload)
+cap = 1 << 18
+while cap < sstats["bricks"] + 4096:
+    cap <<= 1
+ctx = capi.Context(*bench._WL["view"], device=0, initial_brick_capacity=cap)
+ctx.set_palette(scene["palette"])
+ctx.sync(recs)
+_, w, h, b0 = bench.WORKLOADS[workload]
+bounces = b0 if bounces is None else bounces
+if bounces:
+    from scenes import shading
+
+    ctx.set_blue_noise(shading.load_blue_noise()[0])
+    d_, t_, _ = shading.load_sky()
+    ctx.set_sky(d_, t_)
 fb = torch.zeros(w * h * 4, dtype=torch.int32, device="cuda")
 flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
 st = torch.cuda.Stream()
 torch.cuda.set_stream(st)
-frame = bench.bench_frame(w, h, 0)
-sets = sys.argv[1:] or ["persistent=1"]
+frame = bench.bench_frame(w, h, bounces)
+sets = argv or ["persistent=0"]
 ref = None
 for rep in range(2):
     for spec in sets:
@@ -52,4 +73,4 @@ for rep in range(2):
         if ref is None:
             ref = digest
         ts = np.array(ts)
-        print(f"{spec:40s} median {np.median(ts):.4f} ms  min {ts.min():.4f} ms  -> {w*h/np.median(ts)/1e6:.2f} Grays/s  same_frame={digest == ref}", flush=True)
+        print(f"{workload} b{bounces} {spec:34s} median {np.median(ts):.4f} ms  min {ts.min():.4f} ms  -> {w*h*(1+bounces)/np.median(ts)/1e6:.2f} Grays/s (nominal rays)  same_frame={digest == ref}", flush=True)

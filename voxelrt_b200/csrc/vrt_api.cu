@@ -35,6 +35,7 @@ struct VrtContext {
     cudaEvent_t ev_band[16] = {};
     cudaEvent_t ev_sync = nullptr;    // end of the last vrt_sync / upload work on `stream`
     cudaEvent_t ev_render = nullptr;  // end of the last render/trace on a caller stream
+    cudaStream_t gather_streams[4] = {};  // a rank's copies to DIFFERENT presenting GPUs run concurrently (several copy engines)
     cudaEvent_t ev_gather_src[8] = {};  // vrt_render_gather: frame kernel done (ring), last gather copy done
     cudaEvent_t ev_gather_done[8] = {};
     uint32_t gather_seq = 0;
@@ -70,6 +71,7 @@ struct VrtContext {
 
     uint32_t* d_sat = nullptr;  // summed-volume table of the box builder
     bool boxes_stale = true;    // some sector's emptiness changed since the boxes were built
+    float macro_gain = 0.0f;  // option "macro_min_gain" (voxels along the ray)
     int macro_on = 1;  // 0 off, 1 on, 2 on + "metrics" launches count the macro loop's own trips (diagnostic)
     DevMetrics* d_metrics = nullptr;
     bool metrics_on = false;
@@ -209,6 +211,7 @@ RayFrame ray_frame(const VrtContext* ctx, const int32_t wo[3]) {
     const int lim = 1 << 20;
     W.fast_ok = (wo[0] >= -lim && wo[0] <= lim && wo[1] >= -lim && wo[1] <= lim && wo[2] >= -lim && wo[2] <= lim) ? 1 : 0;
     W.macro = ctx->macro_on;
+    W.macro_gain = ctx->macro_gain;
     W.hsx = (int)((uint32_t)(bx >> 5) - (uint32_t)MAGIC_BITS), W.hsy = (int)((uint32_t)(by >> 5) - (uint32_t)MAGIC_BITS),
     W.hsz = (int)((uint32_t)(bz >> 5) - (uint32_t)MAGIC_BITS);
     W.klx = (int)((uint32_t)MAGIC_BITS - (uint32_t)bx), W.kly = (int)((uint32_t)MAGIC_BITS - (uint32_t)by), W.klz = (int)((uint32_t)MAGIC_BITS - (uint32_t)bz);
@@ -327,8 +330,12 @@ int launch_render(VrtContext* ctx, const VrtFrame* f, void* d_out, VrtHit* d_aux
     uint32_t macros_x = (f->width + 31) / 32, macros_y = (f->height + 31) / 32;
     uint32_t macros = macros_x * macros_y;
     uint32_t my_macros = macros / part_count + ((macros % part_count) > f->part_index ? 1u : 0u);
-    if (f->flags & VRT_FRAME_PART_ROWS) my_macros = (macros_y / part_count + ((macros_y % part_count) > f->part_index ? 1u : 0u)) * macros_x;
     F.n_work = my_macros * 32u;
+    if (f->flags & VRT_FRAME_PART_ROWS) {  // bands of VRT_BAND_ROWS pixels, 8 warp tiles per 32-pixel group of a band
+        const uint32_t bands = (f->height + VRT_BAND_ROWS - 1) / VRT_BAND_ROWS;
+        const uint32_t mine = bands / part_count + ((bands % part_count) > f->part_index ? 1u : 0u);
+        F.n_work = mine * macros_x * 8u;
+    }
     F.work_offset = 0;
     if (row1 != 0 && part_count == 1) {
         F.work_offset = std::min(row0, macros_y) * macros_x * 32u;
@@ -415,6 +422,7 @@ extern "C" int vrt_create(const VrtConfig* cfg, VrtContext** out) {
     for (auto& e : c->ev_band) CUB(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     CUB(cudaEventCreateWithFlags(&c->ev_sync, cudaEventDisableTiming));
     CUB(cudaEventCreateWithFlags(&c->ev_render, cudaEventDisableTiming));
+    for (auto& gs : c->gather_streams) CUB(cudaStreamCreateWithFlags(&gs, cudaStreamNonBlocking));
     for (auto& e : c->ev_gather_src) CUB(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     for (auto& e : c->ev_gather_done) CUB(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     c->sxp = (1u << c->sxz) + 2u;
@@ -463,6 +471,7 @@ extern "C" void vrt_destroy(VrtContext* ctx) {
     cudaFree(ctx->d_palette);
     cudaFree(ctx->d_albedo);
     cudaFree(ctx->d_tickets);
+    for (auto& gs : ctx->gather_streams) if (gs) cudaStreamDestroy(gs);
     for (auto& e : ctx->ev_gather_src) if (e) cudaEventDestroy(e);
     for (auto& e : ctx->ev_gather_done) if (e) cudaEventDestroy(e);
     cudaFree(ctx->d_bn);
@@ -497,6 +506,7 @@ extern "C" int vrt_set_option(VrtContext* ctx, const char* name, int64_t value) 
     else if (!strcmp(name, "render_variant")) ctx->render_variant = (int)value;
     else if (!strcmp(name, "macro_steps")) ctx->macro_on = (int)value;
     else if (!strcmp(name, "persistent")) ctx->persist_on = (int)value;
+    else if (!strcmp(name, "macro_min_gain")) ctx->macro_gain = (float)value;
     else return fail(ctx, VRT_ERR_INVALID, std::string("unknown option ") + name);
     return VRT_OK;
 }
@@ -807,18 +817,18 @@ extern "C" int vrt_render(VrtContext* ctx, const VrtFrame* frame, void* out, Vrt
     if (aux && (st = ensure(ctx, ctx->d_aux, npx * sizeof(VrtHit)))) return st;
     uint32_t part_count = frame->part_count ? frame->part_count : 1;
     if (part_count > 1 && (frame->flags & VRT_FRAME_PART_ROWS) && !(frame->flags & VRT_FRAME_LINEAR_OUTPUT) && !aux) {
-        // Band split: only this rank's 32-pixel bands are traced and only they cross PCIe (one strided D2H copy into the
+        // Band split: only this rank's 8-pixel bands are traced and only they cross PCIe (one strided D2H copy into the
         // same offsets of `out`; the other ranks' bands of `out` are left untouched).
         if (frame->part_index >= part_count) return fail(ctx, VRT_ERR_INVALID, "part_index >= part_count");
         ctx->stats.last_launches = 0;
         st = launch_render(ctx, frame, ctx->d_fb.p, nullptr, ctx->stream);
         if (st) return st;
-        const size_t band = (size_t)(frame->width / 4) * 8u * sizeof(VrtTile);
-        const uint32_t rows_full = frame->height / 32u, rows_all = (frame->height + 31u) / 32u, r = frame->part_index;
+        const size_t band = (size_t)(frame->width / 4) * (VRT_BAND_ROWS / 4u) * sizeof(VrtTile);
+        const uint32_t rows_full = frame->height / VRT_BAND_ROWS, rows_all = (frame->height + VRT_BAND_ROWS - 1u) / VRT_BAND_ROWS, r = frame->part_index;
         const uint32_t mine_full = rows_full > r ? (rows_full - r + part_count - 1) / part_count : 0u;
         if (mine_full) CU(cudaMemcpy2DAsync((char*)out + r * band, part_count * band, (char*)ctx->d_fb.p + r * band, part_count * band, band, mine_full, cudaMemcpyDeviceToHost, ctx->stream));
         if (rows_all > rows_full && rows_full % part_count == r) {
-            const size_t tail = (size_t)(frame->width / 4) * ((frame->height % 32u) / 4u) * sizeof(VrtTile);
+            const size_t tail = (size_t)(frame->width / 4) * ((frame->height % VRT_BAND_ROWS) / 4u) * sizeof(VrtTile);
             CU(cudaMemcpyAsync((char*)out + rows_full * band, (char*)ctx->d_fb.p + rows_full * band, tail, cudaMemcpyDeviceToHost, ctx->stream));
         }
         CU(cudaStreamSynchronize(ctx->stream));
@@ -914,10 +924,10 @@ extern "C" int vrt_fb_release(VrtContext* ctx, void* d_ptr) {
 }
 
 // Pipelined tile gather (include/voxelrt_b200.h): frame kernel into the rank's own buffer on `stream`, then ONE strided
-// device-to-device copy of the rank's 32-pixel bands into the owner's framebuffer on the copy stream.  Band b of a
-// tile-layout framebuffer is the byte range [b * band, (b + 1) * band), band = (width / 4) * 8 tiles * 256 B, and the rank
+// device-to-device copy of the rank's 8-pixel bands into the owner's framebuffer on the copy stream.  Band b of a
+// tile-layout framebuffer is the byte range [b * band, (b + 1) * band), band = (width / 4) * 2 tile rows * 256 B, and the rank
 // owns bands part_index, part_index + part_count, ... — i.e. a 2-D copy with pitch part_count * band.  A last, shorter
-// band (height % 32 != 0) goes in a second, 1-D copy.
+// band (height % 8 != 0) goes in a second, 1-D copy.
 extern "C" int vrt_render_gather(VrtContext* ctx, const VrtFrame* frame, void* d_local_fb, void* d_owner_fb, void* stream) {
     if (!ctx || !frame || !d_local_fb || !d_owner_fb) return VRT_ERR_INVALID;
     uint32_t part_count = frame->part_count ? frame->part_count : 1;
@@ -933,12 +943,13 @@ extern "C" int vrt_render_gather(VrtContext* ctx, const VrtFrame* frame, void* d
     st = launch_render(ctx, frame, d_local_fb, nullptr, s);
     if (st) return st;
     const uint32_t seq = ctx->gather_seq++;
+    cudaStream_t gs = ctx->gather_streams[seq & 3u];
     if (d_owner_fb != d_local_fb) {
         cudaEvent_t ev = ctx->ev_gather_src[seq & 7u];
         CU(cudaEventRecord(ev, s));
-        CU(cudaStreamWaitEvent(ctx->copy_stream, ev, 0));
-        const size_t band = (size_t)(frame->width / 4) * 8u * sizeof(VrtTile);
-        const uint32_t rows_full = frame->height / 32u, rows_all = (frame->height + 31u) / 32u;
+        CU(cudaStreamWaitEvent(gs, ev, 0));
+        const size_t band = (size_t)(frame->width / 4) * (VRT_BAND_ROWS / 4u) * sizeof(VrtTile);
+        const uint32_t rows_full = frame->height / VRT_BAND_ROWS, rows_all = (frame->height + VRT_BAND_ROWS - 1u) / VRT_BAND_ROWS;
         const uint32_t r = frame->part_index;
         const uint32_t mine_full = rows_full > r ? (rows_full - r + part_count - 1) / part_count : 0u;
         uint8_t* dst = static_cast<uint8_t*>(d_owner_fb);
@@ -947,16 +958,16 @@ extern "C" int vrt_render_gather(VrtContext* ctx, const VrtFrame* frame, void* d
         if (mine_full && gather_1d) {
             for (uint32_t k = 0; k < mine_full; k++) {
                 size_t off = (size_t)(r + k * part_count) * band;
-                CU(cudaMemcpyAsync(dst + off, src + off, band, cudaMemcpyDeviceToDevice, ctx->copy_stream));
+                CU(cudaMemcpyAsync(dst + off, src + off, band, cudaMemcpyDeviceToDevice, gs));
             }
-        } else if (mine_full) CU(cudaMemcpy2DAsync(dst + r * band, part_count * band, src + r * band, part_count * band, band, mine_full, cudaMemcpyDeviceToDevice, ctx->copy_stream));
+        } else if (mine_full) CU(cudaMemcpy2DAsync(dst + r * band, part_count * band, src + r * band, part_count * band, band, mine_full, cudaMemcpyDeviceToDevice, gs));
         if (rows_all > rows_full && rows_full % part_count == r) {
-            const size_t tail = (size_t)(frame->width / 4) * ((frame->height % 32u) / 4u) * sizeof(VrtTile);
-            CU(cudaMemcpyAsync(dst + rows_full * band, src + rows_full * band, tail, cudaMemcpyDeviceToDevice, ctx->copy_stream));
+            const size_t tail = (size_t)(frame->width / 4) * ((frame->height % VRT_BAND_ROWS) / 4u) * sizeof(VrtTile);
+            CU(cudaMemcpyAsync(dst + rows_full * band, src + rows_full * band, tail, cudaMemcpyDeviceToDevice, gs));
         }
         ctx->gather_pending = true;
     }
-    CU(cudaEventRecord(ctx->ev_gather_done[seq & 7u], ctx->copy_stream));  // (copy-stream order also covers the calls without a copy)
+    CU(cudaEventRecord(ctx->ev_gather_done[seq & 7u], gs));  // (copy-stream order also covers the calls without a copy)
     return end_on_stream(ctx, s);
 }
 
@@ -964,7 +975,8 @@ extern "C" int vrt_gather_wait(VrtContext* ctx, void* stream) {
     if (!ctx) return VRT_ERR_INVALID;
     DeviceGuard g(ctx->device);
     cudaStream_t s = stream ? (cudaStream_t)stream : ctx->stream;
-    if (ctx->gather_pending && ctx->gather_seq) CU(cudaStreamWaitEvent(s, ctx->ev_gather_done[(ctx->gather_seq - 1) & 7u], 0));
+    if (ctx->gather_pending)  // the last copy on each of the four gather streams
+        for (uint32_t k = 1; k <= 4u && k <= ctx->gather_seq; k++) CU(cudaStreamWaitEvent(s, ctx->ev_gather_done[(ctx->gather_seq - k) & 7u], 0));
     return VRT_OK;
 }
 

@@ -39,13 +39,20 @@ __global__ void __launch_bounds__(128, 8) k_trace(const __grid_constant__ DevSce
 // of the multi-GPU screen split): macro tile t belongs to rank t % part_count.
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ bool warp_tile_origin(const FrameParams& F, uint32_t work, uint32_t& x0, uint32_t& y0) {
+    if (F.flags & VRT_FRAME_PART_ROWS) {
+        // band split: the unit is a VRT_BAND_ROWS (8) pixel high band; inside a band warp tiles are numbered in 32x8-pixel
+        // groups (4 across, 2 down) so the 4 warps of a CTA still cover one 32x4 strip
+        uint32_t group = work >> 3, sub = work & 7u;
+        uint32_t lb = F.macros_x_magic ? __umulhi(group, F.macros_x_magic) : group, gx = group - lb * F.macros_x;
+        uint32_t band = lb * F.part_count + F.part_index;
+        x0 = (gx << 5) + ((sub & 3u) << 3);
+        y0 = band * VRT_BAND_ROWS + ((sub >> 2) << 2);
+        return x0 < F.width && y0 < F.height;
+    }
     uint32_t macro_local = work >> 5, sub = work & 31u;
-    // split by macro tile (t % part_count) or, with VRT_FRAME_PART_ROWS, by macro-tile row (row % part_count)
-    const bool by_rows = (F.flags & VRT_FRAME_PART_ROWS) != 0u;
-    uint32_t macro = by_rows ? macro_local : macro_local * F.part_count + F.part_index;
+    uint32_t macro = macro_local * F.part_count + F.part_index;
     // macro / macros_x by multiplication with ceil(2^32 / macros_x): exact while macro * macros_x < 2^32
     uint32_t my = F.macros_x_magic ? __umulhi(macro, F.macros_x_magic) : macro, mx = macro - my * F.macros_x;
-    if (by_rows) my = my * F.part_count + F.part_index;
     x0 = (mx << 5) + ((sub & 3u) << 3);
     y0 = (my << 5) + ((sub >> 2) << 2);
     return x0 < F.width && y0 < F.height;
