@@ -373,7 +373,7 @@ def run_b200(args):
     assert stream.cuda_stream != 0
     # N > 1: consecutive frames rotate over a few streams, so the tail of frame f (its last, longest warp tiles: a capped
     # ray keeps its warp busy for ~40 us, most of a 50 us frame at 8 GPUs) overlaps the next frames on the SMs
-    n_streams = int(os.environ.get("VRT_BENCH_STREAMS", "4"))
+    n_streams = int(os.environ.get("VRT_BENCH_STREAMS", "8"))
     streams = [stream] + [torch.cuda.Stream() for _ in range(n_streams - 1)] if world > 1 else [stream]
     join_evs = [torch.cuda.Event() for _ in streams]
 

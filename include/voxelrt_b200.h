@@ -236,7 +236,7 @@ VRT_API int vrt_fb_release(VrtContext* ctx, void* d_ptr);
  * this one is in flight: a d_local_fb may be reused every VRT_GATHER_DEPTH-th call (the call waits for
  * the copy issued that many calls ago), and the owner may change from frame to frame.
  * vrt_gather_wait makes `stream` wait for every gather issued so far. */
-#define VRT_GATHER_DEPTH 4u
+#define VRT_GATHER_DEPTH 8u
 VRT_API int vrt_render_gather(VrtContext* ctx, const VrtFrame* frame, void* d_local_fb, void* d_owner_fb, void* stream);
 VRT_API int vrt_gather_wait(VrtContext* ctx, void* stream);
 

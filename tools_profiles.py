@@ -49,8 +49,14 @@ def main():
             t[key] = {"dram_read_bytes": col["dram__bytes_read.sum#bytes"], "dram_write_bytes": col["dram__bytes_write.sum#bytes"],
                       "capture": f"profiles/{tag}_ncu_k_render_raw_summary.csv launch0"}
             (PROF / "traffic.json").write_text(json.dumps(t, indent=2) + "\n")
+    if (OUT / "prof_render_source.csv").exists():
+        subprocess.run([sys.executable, str(ROOT / "tools_regions.py"), str(OUT / "prof_render_source.csv"), str(PROF / f"{tag}_ncu_k_render_source_regions.txt")],
+                       stdout=subprocess.DEVNULL)
     for src, dst in (("bench.json", f"{tag}_bench_4k_primary.json"), ("bench_ref.json", f"{tag}_bench_reference_arm.json"),
-                     ("launches.csv", f"{tag}_launches_4k_primary.csv")):
+                     ("launches.csv", f"{tag}_launches_4k_primary.csv"), ("bench_sponza.json", f"{tag}_bench_sponza_1080p_1bounce.json"),
+                     ("bench_large.json", f"{tag}_bench_large_4k_2bounces.json"), ("bench_edits.json", f"{tag}_bench_edits_4k.json"),
+                     ("bench_2gpu.json", f"{tag}_bench_4k_primary_2gpu.json"), ("bench_4gpu.json", f"{tag}_bench_4k_primary_4gpu.json"),
+                     ("bench_8gpu.json", f"{tag}_bench_4k_primary_8gpu.json"), ("macro_stats.log", f"{tag}_macro_stats.txt")):
         if (OUT / src).exists() and (OUT / src).stat().st_size:
             shutil.copy(OUT / src, PROF / dst)
 

@@ -35,9 +35,9 @@ struct VrtContext {
     cudaEvent_t ev_band[16] = {};
     cudaEvent_t ev_sync = nullptr;    // end of the last vrt_sync / upload work on `stream`
     cudaEvent_t ev_render = nullptr;  // end of the last render/trace on a caller stream
-    cudaStream_t gather_streams[4] = {};  // a rank's copies to DIFFERENT presenting GPUs run concurrently (several copy engines)
-    cudaEvent_t ev_gather_src[8] = {};  // vrt_render_gather: frame kernel done (ring), last gather copy done
-    cudaEvent_t ev_gather_done[8] = {};
+    cudaStream_t gather_streams[VRT_GATHER_DEPTH] = {};  // a rank's copies to DIFFERENT presenting GPUs run concurrently (several copy engines)
+    cudaEvent_t ev_gather_src[2 * VRT_GATHER_DEPTH] = {};  // vrt_render_gather: frame kernel done (ring), last gather copy done
+    cudaEvent_t ev_gather_done[2 * VRT_GATHER_DEPTH] = {};
     uint32_t gather_seq = 0;
     bool gather_pending = false;
     bool render_pending = false;
@@ -939,13 +939,13 @@ extern "C" int vrt_render_gather(VrtContext* ctx, const VrtFrame* frame, void* d
     if (st) return st;
     ctx->stats.last_launches = 0;
     // a local buffer may be reused every VRT_GATHER_DEPTH-th call: this frame's kernel waits for the copy issued that many calls ago
-    if (ctx->gather_seq >= VRT_GATHER_DEPTH) CU(cudaStreamWaitEvent(s, ctx->ev_gather_done[(ctx->gather_seq - VRT_GATHER_DEPTH) & 7u], 0));
+    if (ctx->gather_seq >= VRT_GATHER_DEPTH) CU(cudaStreamWaitEvent(s, ctx->ev_gather_done[(ctx->gather_seq - VRT_GATHER_DEPTH) % (2u * VRT_GATHER_DEPTH)], 0));
     st = launch_render(ctx, frame, d_local_fb, nullptr, s);
     if (st) return st;
     const uint32_t seq = ctx->gather_seq++;
-    cudaStream_t gs = ctx->gather_streams[seq & 3u];
+    cudaStream_t gs = ctx->gather_streams[seq % VRT_GATHER_DEPTH];
     if (d_owner_fb != d_local_fb) {
-        cudaEvent_t ev = ctx->ev_gather_src[seq & 7u];
+        cudaEvent_t ev = ctx->ev_gather_src[seq % (2u * VRT_GATHER_DEPTH)];
         CU(cudaEventRecord(ev, s));
         CU(cudaStreamWaitEvent(gs, ev, 0));
         const size_t band = (size_t)(frame->width / 4) * (VRT_BAND_ROWS / 4u) * sizeof(VrtTile);
@@ -967,7 +967,7 @@ extern "C" int vrt_render_gather(VrtContext* ctx, const VrtFrame* frame, void* d
         }
         ctx->gather_pending = true;
     }
-    CU(cudaEventRecord(ctx->ev_gather_done[seq & 7u], gs));  // (copy-stream order also covers the calls without a copy)
+    CU(cudaEventRecord(ctx->ev_gather_done[seq % (2u * VRT_GATHER_DEPTH)], gs));  // (copy-stream order also covers the calls without a copy)
     return end_on_stream(ctx, s);
 }
 
@@ -975,8 +975,9 @@ extern "C" int vrt_gather_wait(VrtContext* ctx, void* stream) {
     if (!ctx) return VRT_ERR_INVALID;
     DeviceGuard g(ctx->device);
     cudaStream_t s = stream ? (cudaStream_t)stream : ctx->stream;
-    if (ctx->gather_pending)  // the last copy on each of the four gather streams
-        for (uint32_t k = 1; k <= 4u && k <= ctx->gather_seq; k++) CU(cudaStreamWaitEvent(s, ctx->ev_gather_done[(ctx->gather_seq - k) & 7u], 0));
+    if (ctx->gather_pending)  // the last copy on each of the gather streams
+        for (uint32_t k = 1; k <= VRT_GATHER_DEPTH && k <= ctx->gather_seq; k++)
+            CU(cudaStreamWaitEvent(s, ctx->ev_gather_done[(ctx->gather_seq - k) % (2u * VRT_GATHER_DEPTH)], 0));
     return VRT_OK;
 }
 
