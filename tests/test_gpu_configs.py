@@ -82,6 +82,53 @@ def test_config4_large_view_two_bounces(shading_inputs):
     ctx.close()
 
 
+def test_trace_far_origins_shallow_components(shading_inputs):
+    """Rays that start ~1000 voxels from the frame origin with one shallow component: tStart = (side - o) / d reaches
+    10^4..10^6, its rounding error exceeds the 0.001 step bias and the reference STALLS on cell planes (quirk Q1 on any
+    axis, positive directions included).  Empty-box macro jumps must never skip such a stall — this is the case that
+    slipped through in round 1 until the per-ray tStart bound was added — so every record must equal the
+    oracle's, with macro steps on and off, for explicit rays and for frames whose bounce rays start far from the origin."""
+    from scenes import camera, terrain
+
+    base = terrain.terrain_fastnoise(48, 7, 48) if terrain.fastnoise_available() else terrain.terrain_hash(16, 4, 16, seed=5)
+    ctx, orc = _pair(base, (6, 4), shading_inputs, capacity=1 << 20)
+    rng = np.random.default_rng(21)
+    n = 1_000_000
+    total_capped = 0
+    for wo in ((0, 0, 0), (1500, 200, 1400), (40, 100, 1530)):
+        p = np.stack([rng.uniform(0, 1536, n), rng.uniform(0, 224, n), rng.uniform(0, 1536, n)], 1)
+        o = (p - np.asarray(wo)).astype(np.float32)
+        d = rng.normal(size=(n, 3))
+        shallow = rng.integers(0, 3, n)
+        d[np.arange(n), shallow] *= 10.0 ** rng.uniform(-4, -1, n)  # one component 10..10^4 times smaller
+        d /= np.linalg.norm(d, axis=1, keepdims=True)
+        d = d.astype(np.float32)
+        want, st = orc.trace(o, d, wo)
+        total_capped += int(((want["flags"] & 0xFFFF) & capi_flag("CAPPED")).astype(bool).sum())
+        for macro in (1, 0):
+            ctx.set_option("macro_steps", macro)
+            assert_hits_equal(ctx.trace(o, d, wo), want, f"far origins wo={wo} macro={macro}", ignore_iters=bool(macro))
+    assert total_capped > 1000  # the stalls this test is about do occur
+    ctx.set_option("macro_steps", 1)
+    from voxelrt_b200 import capi
+
+    # frames whose bounce rays start up to ~1500 voxels from the frame origin (camera in a corner of the terrain)
+    for yaw in (0.8, -2.2):
+        cam = camera.Camera(pos=(100.3, 200.2, 90.7), yaw=yaw, pitch=-0.4)
+        proj, inv, wo, frac = cam.matrices(640, 360)
+        out_g, aux_g = ctx.render(capi.make_frame(640, 360, inv, proj, wo, frac, frame_no=2, bounces=2), want_aux=True)
+        out_c, aux_c, _ = orc.render(capi.make_frame(640, 360, inv, proj, wo, frac, frame_no=2, bounces=2), want_aux=True)
+        assert_hits_equal(aux_g, aux_c, f"far frame yaw {yaw}", ignore_iters=True)
+        _assert_frames_equal(out_g, out_c, f"far frame yaw {yaw}")
+    ctx.close()
+
+
+def capi_flag(name):
+    from voxelrt_b200 import capi
+
+    return getattr(capi, f"VRT_HIT_{name}")
+
+
 def test_config5_edit_frames(bench_scene):
     """BASELINE configs[4]: frames of random single-voxel edits (set / clear, bricks allocated on demand), dirty bricks
     uploaded by vrt_sync, then a frame: every frame equals the oracle fed with the same records, and the final

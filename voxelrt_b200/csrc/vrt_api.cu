@@ -71,7 +71,6 @@ struct VrtContext {
 
     uint32_t* d_sat = nullptr;  // summed-volume table of the box builder
     bool boxes_stale = true;    // some sector's emptiness changed since the boxes were built
-    float macro_gain = 0.0f;  // option "macro_min_gain" (voxels along the ray)
     int macro_on = 1;  // 0 off, 1 on, 2 on + "metrics" launches count the macro loop's own trips (diagnostic)
     DevMetrics* d_metrics = nullptr;
     bool metrics_on = false;
@@ -211,7 +210,6 @@ RayFrame ray_frame(const VrtContext* ctx, const int32_t wo[3]) {
     const int lim = 1 << 20;
     W.fast_ok = (wo[0] >= -lim && wo[0] <= lim && wo[1] >= -lim && wo[1] <= lim && wo[2] >= -lim && wo[2] <= lim) ? 1 : 0;
     W.macro = ctx->macro_on;
-    W.macro_gain = ctx->macro_gain;
     W.hsx = (int)((uint32_t)(bx >> 5) - (uint32_t)MAGIC_BITS), W.hsy = (int)((uint32_t)(by >> 5) - (uint32_t)MAGIC_BITS),
     W.hsz = (int)((uint32_t)(bz >> 5) - (uint32_t)MAGIC_BITS);
     W.klx = (int)((uint32_t)MAGIC_BITS - (uint32_t)bx), W.kly = (int)((uint32_t)MAGIC_BITS - (uint32_t)by), W.klz = (int)((uint32_t)MAGIC_BITS - (uint32_t)bz);
@@ -348,23 +346,32 @@ int launch_render(VrtContext* ctx, const VrtFrame* f, void* d_out, VrtHit* d_aux
     DevScene S = dev_scene(ctx);
     const unsigned wpb = VRT_RENDER_THREADS / 32;
     unsigned blocks = (F.n_work - F.work_offset + wpb - 1) / wpb;
-    if (ctx->metrics_on) {
-        CU(cudaMemsetAsync(ctx->d_metrics, 0, sizeof(DevMetrics), s));
-        if (F.bounces == 0) k_render<true, true><<<blocks, VRT_RENDER_THREADS, 0, s>>>(S, F);
-        else k_render<true, false><<<blocks, VRT_RENDER_THREADS, 0, s>>>(S, F);
-    } else if (ctx->persist_on) {
+    const bool rows = (F.flags & VRT_FRAME_PART_ROWS) != 0u, primary = F.bounces == 0;
+    if (ctx->metrics_on) CU(cudaMemsetAsync(ctx->d_metrics, 0, sizeof(DevMetrics), s));
+    if (ctx->persist_on && !ctx->metrics_on && !rows) {
         // one resident grid; warps pull tiles from a ticket counter (see k_render_persist)
-        const unsigned resident = (unsigned)ctx->sm_count * (unsigned)VRT_RENDER_CTAS(F.bounces == 0) * (unsigned)ctx->persist_on;
+        const unsigned resident = (unsigned)ctx->sm_count * (unsigned)VRT_RENDER_CTAS(primary) * (unsigned)ctx->persist_on;
         const unsigned grid = std::min(blocks, resident);
         const uint32_t slot = ctx->ticket_seq++ & 15u;
         uint32_t* ticket = ctx->d_tickets + slot;
         const uint32_t base = ctx->ticket_base[slot];
         ctx->ticket_base[slot] += F.n_work - F.work_offset;
-        if (F.bounces == 0) k_render_persist<true><<<grid, VRT_RENDER_THREADS, 0, s>>>(S, F, ticket, base);
+        if (primary) k_render_persist<true><<<grid, VRT_RENDER_THREADS, 0, s>>>(S, F, ticket, base);
         else k_render_persist<false><<<grid, VRT_RENDER_THREADS, 0, s>>>(S, F, ticket, base);
     } else {
-        if (F.bounces == 0) k_render<false, true><<<blocks, VRT_RENDER_THREADS, 0, s>>>(S, F);
-        else k_render<false, false><<<blocks, VRT_RENDER_THREADS, 0, s>>>(S, F);
+#define VRT_LAUNCH(M, P, R) k_render<M, P, R><<<blocks, VRT_RENDER_THREADS, 0, s>>>(S, F)
+        const int variant = (ctx->metrics_on ? 4 : 0) | (primary ? 2 : 0) | (rows ? 1 : 0);
+        switch (variant) {
+            case 0: VRT_LAUNCH(false, false, false); break;
+            case 1: VRT_LAUNCH(false, false, true); break;
+            case 2: VRT_LAUNCH(false, true, false); break;
+            case 3: VRT_LAUNCH(false, true, true); break;
+            case 4: VRT_LAUNCH(true, false, false); break;
+            case 5: VRT_LAUNCH(true, false, true); break;
+            case 6: VRT_LAUNCH(true, true, false); break;
+            default: VRT_LAUNCH(true, true, true); break;
+        }
+#undef VRT_LAUNCH
     }
     ctx->stats.last_launches += 1;
     CU(cudaGetLastError());
@@ -506,7 +513,6 @@ extern "C" int vrt_set_option(VrtContext* ctx, const char* name, int64_t value) 
     else if (!strcmp(name, "render_variant")) ctx->render_variant = (int)value;
     else if (!strcmp(name, "macro_steps")) ctx->macro_on = (int)value;
     else if (!strcmp(name, "persistent")) ctx->persist_on = (int)value;
-    else if (!strcmp(name, "macro_min_gain")) ctx->macro_gain = (float)value;
     else return fail(ctx, VRT_ERR_INVALID, std::string("unknown option ") + name);
     return VRT_OK;
 }

@@ -38,8 +38,11 @@ __global__ void __launch_bounds__(128, 8) k_trace(const __grid_constant__ DevSce
 // 64-byte coalesced stores.  Warp tiles are numbered inside 32x32-pixel macro tiles (the unit
 // of the multi-GPU screen split): macro tile t belongs to rank t % part_count.
 // ---------------------------------------------------------------------------------------------
+// (ROWS is a template parameter: a run-time test of F.flags here costs the default kernel 4 % — with the extra branch in the
+// prologue ptxas no longer keeps the global-memory descriptor in a uniform register across the traversal loop)
+template <bool ROWS>
 __device__ __forceinline__ bool warp_tile_origin(const FrameParams& F, uint32_t work, uint32_t& x0, uint32_t& y0) {
-    if (F.flags & VRT_FRAME_PART_ROWS) {
+    if (ROWS) {
         // band split: the unit is a VRT_BAND_ROWS (8) pixel high band; inside a band warp tiles are numbered in 32x8-pixel
         // groups (4 across, 2 down) so the 4 warps of a CTA still cover one 32x4 strip
         uint32_t group = work >> 3, sub = work & 7u;
@@ -84,10 +87,10 @@ __device__ __forceinline__ void store_pixel(const FrameParams& F, uint32_t x, ui
 #define VRT_RENDER_WARPS_PRIMARY 36
 #endif
 #define VRT_RENDER_CTAS(PRIMARY) (((PRIMARY) ? VRT_RENDER_WARPS_PRIMARY : 32) * 32 / VRT_RENDER_THREADS)
-template <bool METRICS, bool PRIMARY>
+template <bool METRICS, bool PRIMARY, bool ROWS = false>
 __device__ __forceinline__ void render_warp_tile(const DevScene& S, const FrameParams& F, uint32_t work) {
     uint32_t x0, y0;
-    if (!warp_tile_origin(F, work, x0, y0)) return;  // warp-uniform
+    if (!warp_tile_origin<ROWS>(F, work, x0, y0)) return;  // warp-uniform
     uint32_t lane = threadIdx.x & 31u;
     uint32_t x = x0 + ((lane >> 4) << 2) + (lane & 3u);
     uint32_t y = y0 + ((lane >> 2) & 3u);
@@ -98,11 +101,11 @@ __device__ __forceinline__ void render_warp_tile(const DevScene& S, const FrameP
     if (valid) store_pixel(F, x, y, P);
 }
 
-template <bool METRICS, bool PRIMARY>
+template <bool METRICS, bool PRIMARY, bool ROWS = false>
 __global__ void __launch_bounds__(VRT_RENDER_THREADS, VRT_RENDER_CTAS(PRIMARY && !METRICS)) k_render(const __grid_constant__ DevScene S, const __grid_constant__ FrameParams F) {
     uint32_t work = F.work_offset + blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (work >= F.n_work) return;  // warp-uniform
-    render_warp_tile<METRICS, PRIMARY>(S, F, work);
+    render_warp_tile<METRICS, PRIMARY, ROWS>(S, F, work);
 }
 
 // K_render, persistent form: the grid is sized to the machine (SMs x resident CTAs) and every WARP pulls warp tiles
