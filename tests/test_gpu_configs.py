@@ -123,6 +123,38 @@ def test_trace_far_origins_shallow_components(shading_inputs):
     ctx.close()
 
 
+def _point_source_bursts(ctx, orc, rng, lo, hi, bursts, rays_per_burst, what):
+    """Rays that all qualify for macro steps (origins within one voxel of the frame origin, no tiny direction component),
+    from many frame origins: the macro path is exercised from every part of the scene, not only from a few cameras."""
+    jumps_possible = 0
+    for k in range(bursts):
+        wo = tuple(int(rng.integers(lo[a], hi[a])) for a in range(3))
+        o = rng.uniform(0.0, 1.0, (rays_per_burst, 3)).astype(np.float32)
+        d = rng.normal(size=(rays_per_burst, 3))
+        d /= np.linalg.norm(d, axis=1, keepdims=True)
+        d = np.where(np.abs(d) < 4.0 / 1024, np.sign(d) * 4.0 / 1024 + (d == 0) * 4.0 / 1024, d).astype(np.float32)
+        want, st = orc.trace(o, d, wo)
+        ctx.set_option("macro_steps", 1)
+        assert_hits_equal(ctx.trace(o, d, wo), want, f"{what}: burst {k} wo={wo}", ignore_iters=True)
+        jumps_possible += int(st.rays)
+    return jumps_possible
+
+
+def test_macro_steps_from_everywhere(shading_inputs):
+    from scenes import models, terrain
+
+    rng = np.random.default_rng(33)
+    base = terrain.terrain_fastnoise(48, 7, 48) if terrain.fastnoise_available() else terrain.terrain_hash(16, 4, 16, seed=5)
+    ctx, orc = _pair(base, (6, 4), None, capacity=1 << 20)
+    _point_source_bursts(ctx, orc, rng, (0, 60, 0), (1536, 400, 1536), 120, 16384, "terrain")
+    ctx.close()
+    if models.sponza_available(1024):
+        scene = models.sponza(1024)
+        ctx, orc = _pair(scene, (5, 4), None, capacity=1 << 17)
+        _point_source_bursts(ctx, orc, rng, (0, 0, 250), (1024, 440, 780), 120, 16384, "sponza")
+        ctx.close()
+
+
 def capi_flag(name):
     from voxelrt_b200 import capi
 
