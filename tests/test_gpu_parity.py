@@ -170,13 +170,14 @@ def test_render_config2_4k_full(bench_ctx, bench_oracle, macro):
 
 
 def test_rcp_rn_normal_matches_ieee(hash_ctx):
-    """The fast loop's reciprocal (MUFU.RCP + one FMA Newton step, no range guard) is the correctly rounded 1/x for every
-    operand a fast ray can have: exhaustive over all binary32 patterns with 2^-60 <= |x| <= 16 against rcp.rn on the
-    device (537 M patterns x 2 signs), and a sample against the host's IEEE division."""
+    """The unguarded reciprocal (MUFU.RCP + one FMA Newton step) and square root (MUFU.RSQ + one Newton step) are the
+    correctly rounded 1/x and sqrt(x) wherever the kernels use them: exhaustive over all binary32 patterns with
+    2^-100 <= |x| <= 2^100 against rcp.rn / sqrt.rn on the device (1.68 G patterns, both signs for 1/x), and a sample
+    against the host's IEEE division and square root."""
     import ctypes as C
 
-    lo = int(np.float32(2.0**-60).view(np.uint32))
-    hi = int(np.float32(16.0).view(np.uint32))
+    lo = int(np.float32(2.0**-100).view(np.uint32))
+    hi = int(np.float32(2.0**100).view(np.uint32))
     bad = C.c_uint64(123)
     n = 1 << 20
     sample = np.zeros(2 * n, np.float32)

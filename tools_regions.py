@@ -108,6 +108,10 @@ def main():
     rows = list(csv.reader(open(src_csv)))
     kernel = rows[0][1] if rows and rows[0][0] == "Kernel Name" else "k_render"
     hdr, data = rows[1], rows[2:]
+    for k, r in enumerate(data):  # a capture of several launches repeats the header block: keep the first launch
+        if r and r[0] == "Kernel Name":
+            data = data[:k]
+            break
     ia, ie, it, isamp = hdr.index("Address"), hdr.index("Instructions Executed"), hdr.index("Thread Instructions Executed"), hdr.index("# Samples")
     sub = "k_renderILb0ELb1E" if "(bool)0, (bool)1" in kernel else ("k_renderILb0ELb0E" if "(bool)0, (bool)0" in kernel else "k_render")
     table, regs = line_table(sub), source_regions()

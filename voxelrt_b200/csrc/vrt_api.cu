@@ -291,6 +291,11 @@ int launch_render(VrtContext* ctx, const VrtFrame* f, void* d_out, VrtHit* d_aux
     F.height = f->height;
     memcpy(F.inv_proj, f->inv_proj, sizeof(F.inv_proj));
     memcpy(F.proj, f->proj, sizeof(F.proj));
+    F.ray_finite = 1u;
+    for (int k = 0; k < 16; k++)
+        if (!(fabsf(f->inv_proj[k]) <= 1.0995116e12f)) F.ray_finite = 0u;  // NaN, inf or > 2^40
+    for (int k = 0; k < 3; k++)
+        if (!(fabsf(f->origin_frac[k]) <= 1.0995116e12f)) F.ray_finite = 0u;
     for (int k = 0; k < 4; k++) {  // SIMD.h:207-214 with z = 0, w = 1 (IEEE binary32, one rounding per operation as on the device)
         volatile float t = f->inv_proj[12 + k] * 1.0f;
         F.ray_c[k] = fmaf(f->inv_proj[8 + k], 0.0f, t);
@@ -999,8 +1004,8 @@ extern "C" __attribute__((visibility("default"))) int vrt_debug_macro_diag(VrtCo
     return VRT_OK;
 }
 
-// Internal self-check hook (not part of include/voxelrt_b200.h): compares rcp_rn_normal with rcp.rn for EVERY binary32 bit
-// pattern in [lo_bits, hi_bits] and both signs; *mismatches receives the count.  out_sample (host, 2*n floats, may be null)
+// Internal self-check hook (not part of include/voxelrt_b200.h): compares rcp_rn_normal with rcp.rn (both signs) and sqrt_rn_normal
+// with sqrt.rn for EVERY binary32 bit pattern in [lo_bits, hi_bits]; *mismatches receives the count.  out_sample (host, 2*n floats, may be null)
 // receives rcp_rn_normal of the first n patterns and of their negations, for a comparison against the host's own 1.0f/x.
 namespace {
 __global__ void k_debug_rcp_check(uint32_t lo_bits, uint64_t count, unsigned long long* mismatches, float* sample, uint32_t n_sample) {
@@ -1011,7 +1016,8 @@ __global__ void k_debug_rcp_check(uint32_t lo_bits, uint64_t count, unsigned lon
         float x = __uint_as_float(lo_bits + (uint32_t)i);
         float a = vrt::rcp_rn_normal(x), b = __frcp_rn(x);
         float c = vrt::rcp_rn_normal(-x), d = __frcp_rn(-x);
-        bad += (__float_as_uint(a) != __float_as_uint(b)) + (__float_as_uint(c) != __float_as_uint(d));
+        float e = vrt::sqrt_rn_normal(x), g = __fsqrt_rn(x);
+        bad += (__float_as_uint(a) != __float_as_uint(b)) + (__float_as_uint(c) != __float_as_uint(d)) + (__float_as_uint(e) != __float_as_uint(g));
         if (sample && i < n_sample) {
             sample[i] = a;
             sample[n_sample + i] = c;
