@@ -34,7 +34,8 @@ struct VrtContext {
     cudaStream_t copy_stream = nullptr;  // D2H copies of finished bands overlap the next band's kernel
     cudaEvent_t ev_band[16] = {};
     cudaEvent_t ev_sync = nullptr;    // end of the last vrt_sync / upload work on `stream`
-    cudaEvent_t ev_render = nullptr;  // end of the last render/trace on a caller stream
+    cudaEvent_t ev_render[16] = {};  // ends of the last 16 renders/traces on caller streams (callers may rotate several streams)
+    uint32_t render_seq = 0;
     cudaStream_t gather_streams[VRT_GATHER_DEPTH] = {};  // a rank's copies to DIFFERENT presenting GPUs run concurrently (several copy engines)
     cudaEvent_t ev_gather_src[2 * VRT_GATHER_DEPTH] = {};  // vrt_render_gather: frame kernel done (ring), last gather copy done
     cudaEvent_t ev_gather_done[2 * VRT_GATHER_DEPTH] = {};
@@ -114,6 +115,16 @@ struct DeviceGuard {
     }
 };
 
+// Work issued by the caller on its own streams (up to 16 calls in flight) that residency changes must not overtake.
+int wait_renders(VrtContext* ctx, cudaStream_t s) {
+    for (uint32_t k = 0; k < 16u && k < ctx->render_seq; k++) CU(cudaStreamWaitEvent(s, ctx->ev_render[k], 0));
+    return VRT_OK;
+}
+int sync_renders(VrtContext* ctx) {
+    for (uint32_t k = 0; k < 16u && k < ctx->render_seq; k++) CU(cudaEventSynchronize(ctx->ev_render[k]));
+    return VRT_OK;
+}
+
 int ensure(VrtContext* ctx, DeviceBuffer& b, size_t bytes) {
     if (b.bytes >= bytes) return VRT_OK;
     if (b.p) {
@@ -161,7 +172,7 @@ int resize_arena(VrtContext* ctx, uint32_t capacity) {
         CU(cudaMemcpyAsync(nv, ctx->d_voxels, (size_t)used * 512, cudaMemcpyDeviceToDevice, ctx->stream));
         CU(cudaMemcpyAsync(nc, ctx->d_cells, (size_t)used * 64, cudaMemcpyDeviceToDevice, ctx->stream));
         CU(cudaStreamSynchronize(ctx->stream));
-        if (ctx->render_pending) CU(cudaEventSynchronize(ctx->ev_render));
+        if (ctx->render_pending) { int st_ = sync_renders(ctx); if (st_) return st_; }
         CU(cudaFree(ctx->d_voxels));
         CU(cudaFree(ctx->d_cells));
         ctx->stats.device_bytes -= (size_t)old_cap * 576;
@@ -250,7 +261,7 @@ int begin_on_stream(VrtContext* ctx, cudaStream_t s) {
 }
 int end_on_stream(VrtContext* ctx, cudaStream_t s) {
     if (s != ctx->stream) {
-        CU(cudaEventRecord(ctx->ev_render, s));
+        CU(cudaEventRecord(ctx->ev_render[ctx->render_seq++ & 15u], s));
         ctx->render_pending = true;
     }
     return VRT_OK;
@@ -433,7 +444,7 @@ extern "C" int vrt_create(const VrtConfig* cfg, VrtContext** out) {
     CUB(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
     for (auto& e : c->ev_band) CUB(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     CUB(cudaEventCreateWithFlags(&c->ev_sync, cudaEventDisableTiming));
-    CUB(cudaEventCreateWithFlags(&c->ev_render, cudaEventDisableTiming));
+    for (auto& e : c->ev_render) CUB(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     for (auto& gs : c->gather_streams) CUB(cudaStreamCreateWithFlags(&gs, cudaStreamNonBlocking));
     for (auto& e : c->ev_gather_src) CUB(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     for (auto& e : c->ev_gather_done) CUB(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
@@ -491,7 +502,7 @@ extern "C" void vrt_destroy(VrtContext* ctx) {
     cudaFree(ctx->d_metrics);
     cudaFree(ctx->d_sat);
     if (ctx->ev_sync) cudaEventDestroy(ctx->ev_sync);
-    if (ctx->ev_render) cudaEventDestroy(ctx->ev_render);
+    for (auto& e : ctx->ev_render) if (e) cudaEventDestroy(e);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     for (auto& e : ctx->ev_band)
@@ -543,7 +554,7 @@ extern "C" int vrt_get_metrics(VrtContext* ctx, VrtTraversalMetrics* out) {
 extern "C" int vrt_set_palette(VrtContext* ctx, const uint64_t palette[256]) {
     if (!ctx || !palette) return VRT_ERR_INVALID;
     DeviceGuard g(ctx->device);
-    if (ctx->render_pending) CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_render, 0));
+    if (ctx->render_pending) { int st_ = wait_renders(ctx, ctx->stream); if (st_) return st_; }
     int st = ensure_host_stage(ctx, 256 * 8);
     if (st) return st;
     CU(cudaStreamSynchronize(ctx->stream));  // staging may still feed a previous copy
@@ -632,7 +643,7 @@ extern "C" int vrt_sync(VrtContext* ctx, uint32_t n, const VrtDirtySector* recs)
     }
 
     // previous frame may still read the arena from a caller stream
-    if (ctx->render_pending) CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_render, 0));
+    if (ctx->render_pending) { int st_ = wait_renders(ctx, ctx->stream); if (st_) return st_; }
 
     size_t nu = uploads.size(), nm = moves.size(), nh = headers.size();
     size_t off_slots = nu * 512;
@@ -773,7 +784,7 @@ extern "C" int vrt_set_blue_noise(VrtContext* ctx, const uint8_t* rg, size_t byt
         CU(cudaMalloc((void**)&ctx->d_bn, VRT_BLUE_NOISE_BYTES));
         ctx->stats.device_bytes += VRT_BLUE_NOISE_BYTES;
     }
-    if (ctx->render_pending) CU(cudaEventSynchronize(ctx->ev_render));
+    if (ctx->render_pending) { int st_ = sync_renders(ctx); if (st_) return st_; }
     CU(cudaMemcpyAsync(ctx->d_bn, rg, bytes, cudaMemcpyHostToDevice, ctx->stream));
     CU(cudaEventRecord(ctx->ev_sync, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
@@ -785,7 +796,7 @@ extern "C" int vrt_set_sky(VrtContext* ctx, const VrtSkyDesc* desc, const uint32
     if (desc->face_size < 4 || (desc->face_size & (desc->face_size - 1)) || desc->mip_levels == 0 || desc->mip_levels > 16)
         return fail(ctx, VRT_ERR_INVALID, "bad sky descriptor");
     DeviceGuard g(ctx->device);
-    if (ctx->render_pending) CU(cudaEventSynchronize(ctx->ev_render));
+    if (ctx->render_pending) { int st_ = sync_renders(ctx); if (st_) return st_; }
     CU(cudaStreamSynchronize(ctx->stream));
     if (ctx->d_sky) {
         CU(cudaFree(ctx->d_sky));
