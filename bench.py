@@ -341,7 +341,17 @@ def run_b200(args):
         cap <<= 1
     ctx = capi.Context(*_WL["view"], device=local, initial_brick_capacity=cap)
     ctx.set_palette(scene["palette"])
-    ctx.sync(recs)
+    # whole-scene upload through vrt_sync (pinned staging, one H2D copy, upload / header / box kernels), timed once
+    rec_arr, rec_keep, rec_n = capi.make_records(recs)
+    torch.cuda.synchronize()
+    t_up = time.perf_counter()
+    ctx.sync_records(rec_arr, rec_n)
+    torch.cuda.synchronize()
+    t_up = time.perf_counter() - t_up
+    up_stats = ctx.stats()
+    residency = {"scene_upload_ms": t_up * 1e3, "bricks": int(up_stats.bricks_uploaded), "h2d_bytes": int(up_stats.bytes_uploaded),
+                 "upload_GB_per_s": up_stats.bytes_uploaded / t_up / 1e9, "device_bytes": int(up_stats.device_bytes)}
+    del rec_keep
     if args.bounces:
         from scenes import shading
 
@@ -608,6 +618,7 @@ def run_b200(args):
                 "api": "vrt_render (host buffers, pinned output)" + ("" if world == 1 else "; every rank delivers its own bands of the frame into its host buffer"),
             },
             "gpu_launches": args.steps + timed_edit_stats["launches"],
+            "residency": residency,
             "edits": None if edit_batches is None else {
                 "voxel_edits_per_frame": args.edits,
                 "dirty_bricks_per_frame": timed_edit_stats["bricks"] / max(1, timed_edit_stats["syncs"]),

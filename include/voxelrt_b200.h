@@ -247,6 +247,9 @@ typedef struct VrtTraversalMetrics {
     uint64_t rays, iters, sector_fetches, cell_fetches, hits, capped;
 } VrtTraversalMetrics;
 VRT_API int vrt_get_metrics(VrtContext* ctx, VrtTraversalMetrics* out);
+/* Settings (the role of Renderer::DrawSettings, Renderer.h:19): "metrics" 0/1 (above); "macro_steps" 0/1 — exact
+ * empty-box space skipping for camera rays, default 1 (2 = diagnostic counters); "persistent" 0/n — the resident-grid
+ * form of the frame kernel with n x (SMs x CTAs/SM) CTAs, default 0.  Unknown names return VRT_ERR_INVALID. */
 VRT_API int vrt_set_option(VrtContext* ctx, const char* name, int64_t value);
 
 #ifdef __cplusplus

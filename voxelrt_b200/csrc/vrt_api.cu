@@ -10,6 +10,7 @@
 #include <cstdio>
 #include <cstring>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "slot_allocator.h"
@@ -33,6 +34,7 @@ struct VrtContext {
     cudaStream_t stream = nullptr;
     cudaStream_t copy_stream = nullptr;  // D2H copies of finished bands overlap the next band's kernel
     cudaEvent_t ev_band[16] = {};
+    cudaEvent_t ev_stage[2] = {};  // vrt_sync: a half of the staging buffers has been consumed
     cudaEvent_t ev_sync = nullptr;    // end of the last vrt_sync / upload work on `stream`
     cudaEvent_t ev_render[16] = {};  // ends of the last 16 renders/traces on caller streams (callers may rotate several streams)
     uint32_t render_seq = 0;
@@ -75,7 +77,6 @@ struct VrtContext {
     int macro_on = 1;  // 0 off, 1 on, 2 on + "metrics" launches count the macro loop's own trips (diagnostic)
     DevMetrics* d_metrics = nullptr;
     bool metrics_on = false;
-    int render_variant = 0;
     // persistent frame kernel: ring of ticket counters (one per launch in flight) and the host's view of each
     int persist_on = 0;  // measured slower than the grid form on primary frames (tile order loses the L1 locality of 4 adjacent warp tiles per CTA)
     uint32_t* d_tickets = nullptr;
@@ -443,6 +444,7 @@ extern "C" int vrt_create(const VrtConfig* cfg, VrtContext** out) {
     CUB(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     CUB(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
     for (auto& e : c->ev_band) CUB(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    for (auto& e : c->ev_stage) CUB(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     CUB(cudaEventCreateWithFlags(&c->ev_sync, cudaEventDisableTiming));
     for (auto& e : c->ev_render) CUB(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     for (auto& gs : c->gather_streams) CUB(cudaStreamCreateWithFlags(&gs, cudaStreamNonBlocking));
@@ -507,6 +509,8 @@ extern "C" void vrt_destroy(VrtContext* ctx) {
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     for (auto& e : ctx->ev_band)
         if (e) cudaEventDestroy(e);
+    for (auto& e : ctx->ev_stage)
+        if (e) cudaEventDestroy(e);
     cudaGetLastError();
     delete ctx;
 }
@@ -526,7 +530,6 @@ extern "C" int vrt_get_stats(const VrtContext* ctx, VrtStats* out) {
 extern "C" int vrt_set_option(VrtContext* ctx, const char* name, int64_t value) {
     if (!ctx || !name) return VRT_ERR_INVALID;
     if (!strcmp(name, "metrics")) ctx->metrics_on = value != 0;
-    else if (!strcmp(name, "render_variant")) ctx->render_variant = (int)value;
     else if (!strcmp(name, "macro_steps")) ctx->macro_on = (int)value;
     else if (!strcmp(name, "persistent")) ctx->persist_on = (int)value;
     else return fail(ctx, VRT_ERR_INVALID, std::string("unknown option ") + name);
@@ -645,43 +648,70 @@ extern "C" int vrt_sync(VrtContext* ctx, uint32_t n, const VrtDirtySector* recs)
     // previous frame may still read the arena from a caller stream
     if (ctx->render_pending) { int st_ = wait_renders(ctx, ctx->stream); if (st_) return st_; }
 
-    size_t nu = uploads.size(), nm = moves.size(), nh = headers.size();
-    size_t off_slots = nu * 512;
-    size_t off_moves = (off_slots + nu * 4 + 15) & ~(size_t)15;
-    size_t off_hdrs = (off_moves + nm * 8 + 15) & ~(size_t)15;
-    size_t total = off_hdrs + nh * sizeof(HeaderUpdate);
-    if (total) {
-        int st = ensure_host_stage(ctx, total);
+    // Staging is chunked and double-buffered: a chunk of at most kChunkBricks bricks (64 MiB) is gathered into one half of the
+    // pinned buffer (several host threads for big chunks) while the previous chunk's H2D copy and upload kernel run from the
+    // other half — a multi-GB scene never needs a multi-GB pinned allocation, and the host gather overlaps the PCIe copy.
+    // Chunk 0 also carries the relocation pairs and header records ("meta").
+    const size_t nu = uploads.size(), nm = moves.size(), nh = headers.size();
+    const size_t kChunkBricks = (size_t)1 << 17;
+    const size_t meta_moves = (nm * 8 + 15) & ~(size_t)15, meta_bytes = meta_moves + nh * sizeof(HeaderUpdate);
+    const size_t chunk0 = std::min(nu, kChunkBricks);
+    const size_t half = ((chunk0 * 516 + 15) & ~(size_t)15) + meta_bytes + 16;  // bricks, slots, meta
+    const size_t n_chunks = nu ? (nu + kChunkBricks - 1) / kChunkBricks : (meta_bytes ? 1 : 0);
+    size_t total = 0;
+    if (n_chunks) {
+        int st = ensure_host_stage(ctx, 2 * half);
         if (st) return st;
-        st = ensure(ctx, ctx->d_stage, total);
+        st = ensure(ctx, ctx->d_stage, 2 * half);
         if (st) return st;
-        CU(cudaStreamSynchronize(ctx->stream));  // the pinned buffer is single-buffered
-        uint32_t* slots = reinterpret_cast<uint32_t*>(ctx->h_stage + off_slots);
-        for (size_t i = 0; i < nu; i++) {
-            memcpy(ctx->h_stage + i * 512, uploads[i].src, 512);
-            slots[i] = uploads[i].slot;
+        CU(cudaStreamSynchronize(ctx->stream));  // both halves are free again
+        for (size_t c = 0; c < n_chunks; c++) {
+            const size_t i0 = c * kChunkBricks, nb = std::min(kChunkBricks, nu - std::min(nu, i0));
+            uint8_t* hs = ctx->h_stage + (c & 1) * half;
+            uint8_t* ds = reinterpret_cast<uint8_t*>(ctx->d_stage.p) + (c & 1) * half;
+            if (c >= 2) CU(cudaEventSynchronize(ctx->ev_stage[c & 1]));  // the chunk that used this half has been consumed
+            const size_t off_slots = nb * 512, off_meta = (off_slots + nb * 4 + 15) & ~(size_t)15;
+            uint32_t* slots = reinterpret_cast<uint32_t*>(hs + off_slots);
+            auto gather = [&](size_t lo, size_t hi) {
+                for (size_t i = lo; i < hi; i++) {
+                    memcpy(hs + i * 512, uploads[i0 + i].src, 512);
+                    slots[i] = uploads[i0 + i].slot;
+                }
+            };
+            const unsigned hw = std::max(1u, std::min(8u, std::thread::hardware_concurrency()));
+            if (nb >= 16384 && hw > 1) {
+                std::vector<std::thread> pool;
+                for (unsigned t = 1; t < hw; t++) pool.emplace_back(gather, nb * t / hw, nb * (t + 1) / hw);
+                gather(0, nb / hw);
+                for (auto& th : pool) th.join();
+            } else gather(0, nb);
+            size_t bytes = off_meta;
+            if (c == 0) {
+                if (nm) memcpy(hs + off_meta, moves.data(), nm * 8);
+                if (nh) memcpy(hs + off_meta + meta_moves, headers.data(), nh * sizeof(HeaderUpdate));
+                bytes += meta_bytes;
+            }
+            CU(cudaMemcpyAsync(ds, hs, bytes, cudaMemcpyHostToDevice, ctx->stream));
+            total += bytes;
+            if (c == 0 && nm) {
+                k_move_bricks<<<(unsigned)((nm + 7) / 8), 256, 0, ctx->stream>>>(reinterpret_cast<const uint2*>(ds + off_meta), (uint32_t)nm,
+                                                                                 ctx->d_voxels, ctx->d_cells);
+                ctx->stats.last_launches++;
+            }
+            if (nb) {
+                k_upload_bricks<<<(unsigned)((nb + 7) / 8), 256, 0, ctx->stream>>>(reinterpret_cast<const uint4*>(ds),
+                                                                                   reinterpret_cast<const uint32_t*>(ds + off_slots), (uint32_t)nb,
+                                                                                   ctx->d_voxels, ctx->d_cells);
+                ctx->stats.last_launches++;
+            }
+            if (c == 0 && nh) {
+                k_write_headers<<<(unsigned)((nh + 255) / 256), 256, 0, ctx->stream>>>(reinterpret_cast<const HeaderUpdate*>(ds + off_meta + meta_moves),
+                                                                                      (uint32_t)nh, ctx->d_hdr);
+                ctx->stats.last_launches++;
+            }
+            CU(cudaGetLastError());
+            CU(cudaEventRecord(ctx->ev_stage[c & 1], ctx->stream));
         }
-        if (nm) memcpy(ctx->h_stage + off_moves, moves.data(), nm * 8);
-        if (nh) memcpy(ctx->h_stage + off_hdrs, headers.data(), nh * sizeof(HeaderUpdate));
-        CU(cudaMemcpyAsync(ctx->d_stage.p, ctx->h_stage, total, cudaMemcpyHostToDevice, ctx->stream));
-        uint8_t* ds = reinterpret_cast<uint8_t*>(ctx->d_stage.p);
-        if (nm) {
-            k_move_bricks<<<(unsigned)((nm + 7) / 8), 256, 0, ctx->stream>>>(reinterpret_cast<const uint2*>(ds + off_moves), (uint32_t)nm,
-                                                                             ctx->d_voxels, ctx->d_cells);
-            ctx->stats.last_launches++;
-        }
-        if (nu) {
-            k_upload_bricks<<<(unsigned)((nu + 7) / 8), 256, 0, ctx->stream>>>(reinterpret_cast<const uint4*>(ds),
-                                                                               reinterpret_cast<const uint32_t*>(ds + off_slots), (uint32_t)nu,
-                                                                               ctx->d_voxels, ctx->d_cells);
-            ctx->stats.last_launches++;
-        }
-        if (nh) {
-            k_write_headers<<<(unsigned)((nh + 255) / 256), 256, 0, ctx->stream>>>(reinterpret_cast<const HeaderUpdate*>(ds + off_hdrs),
-                                                                                  (uint32_t)nh, ctx->d_hdr);
-            ctx->stats.last_launches++;
-        }
-        CU(cudaGetLastError());
     }
     ctx->arena.flush_quarantine();
     {

@@ -82,11 +82,15 @@ __device__ __forceinline__ void store_pixel(const FrameParams& F, uint32_t x, ui
 #ifndef VRT_RENDER_THREADS
 #define VRT_RENDER_THREADS 128  // 4 warp tiles per CTA
 #endif
-// resident warps per SM: the primary-only kernel fits 56 registers (36 warps), the bounce kernel needs 64 (32 warps)
+// resident warps per SM: the primary-only kernel fits 56 registers (36 warps); the bounce kernel would take 71, runs best capped
+// at 48 (40 warps, a few spills outside the loop: +3 % over 32 warps at 64 registers; 44/48 warps at 40 registers lose it again)
 #ifndef VRT_RENDER_WARPS_PRIMARY
 #define VRT_RENDER_WARPS_PRIMARY 36
 #endif
-#define VRT_RENDER_CTAS(PRIMARY) (((PRIMARY) ? VRT_RENDER_WARPS_PRIMARY : 32) * 32 / VRT_RENDER_THREADS)
+#ifndef VRT_RENDER_WARPS_BOUNCE
+#define VRT_RENDER_WARPS_BOUNCE 40
+#endif
+#define VRT_RENDER_CTAS(PRIMARY) (((PRIMARY) ? VRT_RENDER_WARPS_PRIMARY : VRT_RENDER_WARPS_BOUNCE) * 32 / VRT_RENDER_THREADS)
 template <bool METRICS, bool PRIMARY, bool ROWS = false>
 __device__ __forceinline__ void render_warp_tile(const DevScene& S, const FrameParams& F, uint32_t work) {
     uint32_t x0, y0;
