@@ -638,7 +638,7 @@ def run_b200(args):
             },
             "roofline": {
                 "bound": "hbm",
-                "kernel": "vrt::k_render<false,%s>" % ("true" if args.bounces == 0 else "false"),
+                "kernel": "vrt::k_render<false,%s,%s>" % ("true" if args.bounces == 0 else "false", "true" if world > 1 else "false"),
                 "achieved": achieved,
                 "peak": peak,
                 "unit": "GB/s",

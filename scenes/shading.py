@@ -115,5 +115,11 @@ def load_sky(face_size=None):
         tex = np.fromfile(p, np.uint32)
         if tex.size == desc.texel_count:
             return desc, tex, f"reference panorama cube {fs}^2 ({p.name})"
+        if tex.size % 6 == 0 and tex.size // 6 <= (1 << desc.layer_shift):  # compact file: used texels of each layer
+            full = np.zeros(desc.texel_count, np.uint32)
+            per = tex.size // 6
+            for layer in range(6):
+                full[layer << desc.layer_shift : (layer << desc.layer_shift) + per] = tex[layer * per : (layer + 1) * per]
+            return desc, full, f"reference panorama cube {fs}^2 ({p.name}: evening_road_01_puresky_4k.hdr)"
     desc, tex = procedural_sky(face_size or 64)
     return desc, tex, "procedural gradient sky (reference HDR not converted)"

@@ -192,3 +192,32 @@ int64_t vox_triangles(VoxGrid* g, int64_t T, const float* tris, const float* uvs
     }
     return degenerate;
 }
+
+/* Radiance RGBE (.hdr) scanline decoder for scenes/convert_assets.py (new-style RLE, the only form the bundled skyboxes use).
+ * data: the bytes after the resolution line; out: h * w * 4 bytes (R, G, B, E).  Returns 0, or -1 on malformed input. */
+int rgbe_decode(const uint8_t* data, int64_t n, int32_t w, int32_t h, uint8_t* out) {
+    int64_t p = 0;
+    for (int32_t y = 0; y < h; y++) {
+        uint8_t* row = out + (size_t)y * w * 4;
+        if (p + 4 > n) return -1;
+        if (data[p] != 2 || data[p + 1] != 2 || ((data[p + 2] << 8) | data[p + 3]) != w) return -1; /* flat / old RLE not needed */
+        p += 4;
+        for (int c = 0; c < 4; c++) {
+            int32_t x = 0;
+            while (x < w) {
+                if (p >= n) return -1;
+                int count = data[p++];
+                if (count > 128) { /* run */
+                    count -= 128;
+                    if (p >= n || x + count > w) return -1;
+                    uint8_t v = data[p++];
+                    for (int i = 0; i < count; i++) row[(size_t)(x++) * 4 + c] = v;
+                } else { /* literal */
+                    if (count == 0 || p + count > n || x + count > w) return -1;
+                    for (int i = 0; i < count; i++) row[(size_t)(x++) * 4 + c] = data[p++];
+                }
+            }
+        }
+    }
+    return 0;
+}
