@@ -260,6 +260,37 @@ def test_render_bounces(hash_scene, hash_oracle, shading_inputs, bounces):
     ctx.close()
 
 
+@pytest.mark.parametrize("size", [(320, 180), (36, 4), (260, 148)])
+def test_bounce_compaction_equals_per_pixel_path(bench_ctx, bench_oracle, shading_inputs, size):
+    """Frames with bounces: the CTA-compacted kernel (live bounce rays re-dealt to full warps through shared memory) gives the
+    bytes of the one-thread-per-pixel kernel and of the oracle, incl. aux records, partitions and odd frame sizes."""
+    from scenes import camera
+    from voxelrt_b200 import capi
+
+    (bn, _), (desc, tex, _) = shading_inputs
+    bench_ctx.set_blue_noise(bn)
+    bench_ctx.set_sky(desc, tex)
+    bench_oracle.set_blue_noise(bn)
+    bench_oracle.set_sky(desc, tex)
+    w, h = size
+    cam = camera.orbit_cameras(4, seed=2)[1]
+    try:
+        for bounces in (1, 3):
+            want, aux_c, _ = bench_oracle.render(_frame(cam, w, h, bounces=bounces, frame_no=7), want_aux=True)
+            for mode in (0, 1):
+                bench_ctx.set_option("compact_bounces", mode)
+                got, aux_g = bench_ctx.render(_frame(cam, w, h, bounces=bounces, frame_no=7), want_aux=True)
+                assert got.tobytes() == want.tobytes(), (size, bounces, mode)
+                assert_hits_equal(aux_g, aux_c, f"compact={mode}", ignore_iters=True)
+                part = np.zeros_like(want)
+                for p in range(3):
+                    f = _frame(cam, w, h, bounces=bounces, frame_no=7, part_index=p, part_count=3, flags=capi.VRT_FRAME_PART_ROWS)
+                    bench_ctx._chk(bench_ctx.lib.vrt_render(bench_ctx.h, __import__("ctypes").byref(f), part.ctypes.data, None))
+                assert part.tobytes() == want.tobytes(), (size, bounces, mode, "band split")
+    finally:
+        bench_ctx.set_option("compact_bounces", 0)
+
+
 def test_render_needs_blue_noise_for_bounces(hash_scene):
     from scenes import camera
     from voxelrt_b200 import capi

@@ -78,6 +78,8 @@ struct VrtContext {
     DevMetrics* d_metrics = nullptr;
     bool metrics_on = false;
     // persistent frame kernel: ring of ticket counters (one per launch in flight) and the host's view of each
+    int compact_on = 0;  // frames with bounces: pack the live bounce rays of a CTA between bounces (k_render_cta); measured 10 % SLOWER
+                         // (the bounce phase is latency-bound: fewer tracing warps hide less latency than idle lanes cost)
     int persist_on = 0;  // measured slower than the grid form on primary frames (tile order loses the L1 locality of 4 adjacent warp tiles per CTA)
     uint32_t* d_tickets = nullptr;
     uint32_t ticket_base[16] = {};
@@ -365,7 +367,14 @@ int launch_render(VrtContext* ctx, const VrtFrame* f, void* d_out, VrtHit* d_aux
     unsigned blocks = (F.n_work - F.work_offset + wpb - 1) / wpb;
     const bool rows = (F.flags & VRT_FRAME_PART_ROWS) != 0u, primary = F.bounces == 0;
     if (ctx->metrics_on) CU(cudaMemsetAsync(ctx->d_metrics, 0, sizeof(DevMetrics), s));
-    if (ctx->persist_on && !ctx->metrics_on && !rows) {
+    if (!primary && ctx->compact_on && !ctx->persist_on) {
+        // frames with bounces: CTA-compacted bounce rays (k_render_cta)
+        const int v = (ctx->metrics_on ? 2 : 0) | (rows ? 1 : 0);
+        if (v == 0) k_render_cta<false, false><<<blocks, VRT_RENDER_THREADS, 0, s>>>(S, F);
+        else if (v == 1) k_render_cta<false, true><<<blocks, VRT_RENDER_THREADS, 0, s>>>(S, F);
+        else if (v == 2) k_render_cta<true, false><<<blocks, VRT_RENDER_THREADS, 0, s>>>(S, F);
+        else k_render_cta<true, true><<<blocks, VRT_RENDER_THREADS, 0, s>>>(S, F);
+    } else if (ctx->persist_on && !ctx->metrics_on && !rows) {
         // one resident grid; warps pull tiles from a ticket counter (see k_render_persist)
         const unsigned resident = (unsigned)ctx->sm_count * (unsigned)VRT_RENDER_CTAS(primary) * (unsigned)ctx->persist_on;
         const unsigned grid = std::min(blocks, resident);
@@ -532,6 +541,7 @@ extern "C" int vrt_set_option(VrtContext* ctx, const char* name, int64_t value) 
     if (!strcmp(name, "metrics")) ctx->metrics_on = value != 0;
     else if (!strcmp(name, "macro_steps")) ctx->macro_on = (int)value;
     else if (!strcmp(name, "persistent")) ctx->persist_on = (int)value;
+    else if (!strcmp(name, "compact_bounces")) ctx->compact_on = (int)value;
     else return fail(ctx, VRT_ERR_INVALID, std::string("unknown option ") + name);
     return VRT_OK;
 }

@@ -112,6 +112,24 @@ __global__ void __launch_bounds__(VRT_RENDER_THREADS, VRT_RENDER_CTAS(PRIMARY &&
     render_warp_tile<METRICS, PRIMARY, ROWS>(S, F, work);
 }
 
+// K_render for frames with bounces, CTA-compacted (shade_pixel_cta): same tiles, same pixels, but between bounces the CTA's
+// live rays are packed through shared memory so that its warps trace full batches.  No thread may leave before the last
+// barrier, so out-of-frame warps stay in the kernel with all lanes invalid.
+template <bool METRICS, bool ROWS>
+__global__ void __launch_bounds__(VRT_RENDER_THREADS, VRT_RENDER_CTAS(false)) k_render_cta(const __grid_constant__ DevScene S, const __grid_constant__ FrameParams F) {
+    __shared__ BounceExchange X;
+    const uint32_t work = F.work_offset + blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    uint32_t x0 = 0, y0 = 0;
+    const bool in_frame = work < F.n_work && warp_tile_origin<ROWS>(F, work, x0, y0);  // warp-uniform
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t x = x0 + ((lane >> 4) << 2) + (lane & 3u);
+    const uint32_t y = y0 + ((lane >> 2) & 3u);
+    const bool valid = in_frame && x < F.width && y < F.height;
+    PixelOut P;
+    shade_pixel_cta<METRICS>(S, F, x, y, valid, P, X);
+    if (valid) store_pixel(F, x, y, P);
+}
+
 // K_render, persistent form: the grid is sized to the machine (SMs x resident CTAs) and every WARP pulls warp tiles
 // from a ticket counter until the frame is done, so a warp slot never idles waiting for the slowest warp of its CTA
 // (tile costs differ by an order of magnitude between sky and horizon tiles).  A warp's first tile is its global warp
