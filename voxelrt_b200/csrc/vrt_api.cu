@@ -35,6 +35,7 @@ struct VrtContext {
     cudaStream_t copy_stream = nullptr;  // D2H copies of finished bands overlap the next band's kernel
     cudaEvent_t ev_band[16] = {};
     cudaEvent_t ev_stage[2] = {};  // vrt_sync: a half of the staging buffers has been consumed
+    bool stage_used[2] = {false, false};
     cudaEvent_t ev_sync = nullptr;    // end of the last vrt_sync / upload work on `stream`
     cudaEvent_t ev_render[16] = {};  // ends of the last 16 renders/traces on caller streams (callers may rotate several streams)
     uint32_t render_seq = 0;
@@ -655,9 +656,6 @@ extern "C" int vrt_sync(VrtContext* ctx, uint32_t n, const VrtDirtySector* recs)
         }
     }
 
-    // previous frame may still read the arena from a caller stream
-    if (ctx->render_pending) { int st_ = wait_renders(ctx, ctx->stream); if (st_) return st_; }
-
     // Staging is chunked and double-buffered: a chunk of at most kChunkBricks bricks (64 MiB) is gathered into one half of the
     // pinned buffer (several host threads for big chunks) while the previous chunk's H2D copy and upload kernel run from the
     // other half — a multi-GB scene never needs a multi-GB pinned allocation, and the host gather overlaps the PCIe copy.
@@ -674,7 +672,18 @@ extern "C" int vrt_sync(VrtContext* ctx, uint32_t n, const VrtDirtySector* recs)
         if (st) return st;
         st = ensure(ctx, ctx->d_stage, 2 * half);
         if (st) return st;
-        CU(cudaStreamSynchronize(ctx->stream));  // both halves are free again
+        // The previous frame may still read the arena from a caller stream: the kernels below wait for it on the device, but
+        // the host gather and the H2D copies do not — they overlap the frame that is still being traced.
+        // (the halves' offsets depend on this call's sizes, so both halves of the PREVIOUS call must have been consumed first;
+        // their events follow that call's upload kernels, which never wait for the frame traced after them)
+        for (int h2 = 0; h2 < 2; h2++)
+            if (ctx->stage_used[h2]) CU(cudaEventSynchronize(ctx->ev_stage[h2]));
+        bool waited = false;
+        auto wait_once = [&]() -> int {
+            if (waited || !ctx->render_pending) return VRT_OK;
+            waited = true;
+            return wait_renders(ctx, ctx->stream);
+        };
         for (size_t c = 0; c < n_chunks; c++) {
             const size_t i0 = c * kChunkBricks, nb = std::min(kChunkBricks, nu - std::min(nu, i0));
             uint8_t* hs = ctx->h_stage + (c & 1) * half;
@@ -703,6 +712,7 @@ extern "C" int vrt_sync(VrtContext* ctx, uint32_t n, const VrtDirtySector* recs)
             }
             CU(cudaMemcpyAsync(ds, hs, bytes, cudaMemcpyHostToDevice, ctx->stream));
             total += bytes;
+            if ((st = wait_once())) return st;
             if (c == 0 && nm) {
                 k_move_bricks<<<(unsigned)((nm + 7) / 8), 256, 0, ctx->stream>>>(reinterpret_cast<const uint2*>(ds + off_meta), (uint32_t)nm,
                                                                                  ctx->d_voxels, ctx->d_cells);
@@ -721,8 +731,10 @@ extern "C" int vrt_sync(VrtContext* ctx, uint32_t n, const VrtDirtySector* recs)
             }
             CU(cudaGetLastError());
             CU(cudaEventRecord(ctx->ev_stage[c & 1], ctx->stream));
+            ctx->stage_used[c & 1] = true;
         }
     }
+    if (ctx->render_pending) { int st_ = wait_renders(ctx, ctx->stream); if (st_) return st_; }  // (box rebuild / callers that sync nothing)
     ctx->arena.flush_quarantine();
     {
         int st = rebuild_boxes(ctx);
