@@ -182,7 +182,9 @@ WORKLOADS = {
     "sponza": ("configs[2]", 1920, 1080, 1),
     "large": ("configs[3]", 3840, 2160, 2),
     "edits": ("configs[4]", 3840, 2160, 0),
+    "file": ("(a voxel-map cache file of the reference, --scene-file)", 1920, 1080, 1),
 }
+_SCENE_FILE = [None]
 _WL = {"name": "terrain", "view": (6, 4), "cam": None, "label": None, "reference_ok": True}
 
 
@@ -206,6 +208,19 @@ def build_scene(workload="terrain"):
         scene = terrain.terrain_fastnoise(128, 7, 128) if terrain.fastnoise_available() else terrain.terrain_hash(128, 7, 128, seed=12345, emissive=False)
         _WL.update(view=(7, 4), cam=camera.Camera(pos=(2048.0, 128.0, 2048.0)), reference_ok=False,
                    label=f"{scene.get('name', 'terrain')} in a 4096x512x4096 view, camera (2048,128,2048) yaw 1.52 pitch -0.5")
+    elif workload == "file":
+        # any "cvox 0004" file the reference wrote (e.g. its logs/voxels_2k_sponza.dat, Main.cpp:38-49), read by scenes/cvox.py
+        from scenes import cvox
+
+        if not _SCENE_FILE[0]:
+            raise SystemExit("--workload file needs --scene-file <cvox file>")
+        scene = cvox.load_cvox(_SCENE_FILE[0])
+        keys = np.array(list(scene["sectors"].keys()) or [(0, 0, 0)])
+        lo, hi = keys.min(0), keys.max(0)
+        scene["sectors"] = {k: v for k, v in scene["sectors"].items() if min(k) >= 0 and k[0] < 128 and k[2] < 128 and k[1] < 64}
+        cx, cy, cz = (float((lo[a] + hi[a] + 1) * 16) for a in range(3))
+        _WL.update(view=(7, 6), cam=camera.Camera(pos=(cx + 0.3, cy + 0.2, cz + 0.7), yaw=1.5, pitch=-0.15), reference_ok=False,
+                   label=f"{scene['name']} in the reference GPU renderer's 4096x2048x4096 view, camera at the centre of the populated box")
     else:
         raise SystemExit(f"unknown workload {workload}")
     return scene, terrain.scene_records(scene), terrain.scene_stats(scene)
@@ -682,8 +697,10 @@ def main():
     ap.add_argument("--height", type=int, default=None)
     ap.add_argument("--bounces", type=int, default=None)
     ap.add_argument("--edits", type=int, default=4096, help="workload 'edits': voxel edits per frame")
+    ap.add_argument("--scene-file", default=None, help="workload 'file': a cvox 0004 voxel-map file written by the reference (or by scenes/cvox.py)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()
+    _SCENE_FILE[0] = args.scene_file
     _, dw, dh, db = WORKLOADS[args.workload]
     args.width = dw if args.width is None else args.width
     args.height = dh if args.height is None else args.height

@@ -41,10 +41,9 @@ namespace texutil {
 HdrTexture2D LoadCubemapFromPanoramaHDR(std::string_view, uint32_t mipLevels) { return HdrTexture2D(8, 8, mipLevels, 6); }
 }  // namespace texutil
 }  // namespace swr
-namespace glim::io {  // Common/BinaryIO.cpp (zstd) — the serialiser is out of scope
-void WriteCompressed(std::ostream&, const void*, size_t) { throw std::runtime_error("zstd unavailable"); }
-void ReadCompressed(std::istream&, void*, size_t) { throw std::runtime_error("zstd unavailable"); }
-}  // namespace glim::io
+// The "cvox 0004" (de)serialiser (VoxelMap.cpp:205-274) sits on the reference's Common/BinaryIO.cpp, which oracle/Makefile
+// compiles as a second translation unit straight from /root/reference (its header has no include guard): <zstd.h> resolves to
+// oracle/shim/zstd.h (declarations only) and the system libzstd.so.1 is linked.
 void VoxelMap::VoxelizeModel(const glim::Model&, glm::uvec3, glm::uvec3) {}
 
 // ---- C API -----------------------------------------------------------------------------------------
@@ -106,6 +105,56 @@ REF_API int ref_sync(RefCtx* c, uint32_t n, const VrtDirtySector* recs) {
     }
     c->storage->SyncBuffers(c->map);
     std::memcpy(c->storage->Palette, c->palette, sizeof(c->palette));  // SyncBuffers re-encodes map.Palette (unused here)
+    return 0;
+}
+
+// ---- cvox files: the reference's own VoxelMap::Serialize / Deserialize (VoxelMap.cpp:205-274) ----
+REF_API int ref_serialize(RefCtx* c, const char* path) {
+    try {
+        c->map.Serialize(path);
+        return 0;
+    } catch (const std::exception&) { return -1; }
+}
+REF_API int ref_deserialize(RefCtx* c, const char* path) {
+    try {
+        c->map.Sectors.clear();
+        c->map.Deserialize(path);
+        return 0;
+    } catch (const std::exception&) { return -1; }
+}
+REF_API void ref_set_material(RefCtx* c, int i, uint8_t r, uint8_t g, uint8_t b, uint8_t fuzz, float emission) {
+    Material& m = c->map.Palette[i & 255];
+    m.Color[0] = r, m.Color[1] = g, m.Color[2] = b;
+    m.MetalFuzziness = fuzz;
+    m.Emission = emission;
+}
+REF_API void ref_get_material(RefCtx* c, int i, uint8_t* rgbf4, float* emission) {
+    const Material& m = c->map.Palette[i & 255];
+    rgbf4[0] = m.Color[0], rgbf4[1] = m.Color[1], rgbf4[2] = m.Color[2], rgbf4[3] = m.MetalFuzziness;
+    *emission = m.Emission;
+}
+REF_API uint32_t ref_map_sector_count(RefCtx* c) { return (uint32_t)c->map.Sectors.size(); }
+// sectors of the VoxelMap itself (not the renderer's view), in hash-map order: world sector coordinates + allocation mask
+REF_API uint32_t ref_map_list_sectors(RefCtx* c, int32_t* xyz, uint64_t* masks, uint32_t cap) {
+    uint32_t n = 0;
+    for (auto& [idx, sector] : c->map.Sectors) {
+        if (n >= cap) break;
+        glm::ivec3 p = WorldSectorIndexer::GetPos(idx);
+        xyz[3 * n] = p.x, xyz[3 * n + 1] = p.y, xyz[3 * n + 2] = p.z;
+        masks[n++] = sector.GetAllocationMask();
+    }
+    return n;
+}
+REF_API int ref_map_read_sector(RefCtx* c, int sx, int sy, int sz, uint64_t* mask, uint8_t* bricks /* popcount(mask) x 512, ascending */) {
+    auto it = c->map.Sectors.find(WorldSectorIndexer::GetIndex(glm::ivec3(sx, sy, sz)));
+    if (it == c->map.Sectors.end()) return -1;
+    uint64_t m = it->second.GetAllocationMask();
+    *mask = m;
+    for (uint32_t b = 0; b < 64; b++)
+        if ((m >> b) & 1) {
+            std::memcpy(bricks, it->second.GetBrick(b)->Data, 512);
+            bricks += 512;
+        }
     return 0;
 }
 

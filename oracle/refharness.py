@@ -54,6 +54,17 @@ def load():
     lib.ref_read_sector.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.POINTER(u64), vp, vp]
     lib.ref_set_blue_noise.argtypes = [vp]
     lib.ref_set_blue_noise.restype = None
+    lib.ref_serialize.argtypes = [vp, C.c_char_p]
+    lib.ref_deserialize.argtypes = [vp, C.c_char_p]
+    lib.ref_set_material.argtypes = [vp, C.c_int] + [C.c_uint8] * 4 + [C.c_float]
+    lib.ref_set_material.restype = None
+    lib.ref_get_material.argtypes = [vp, C.c_int, vp, vp]
+    lib.ref_get_material.restype = None
+    lib.ref_map_sector_count.argtypes = [vp]
+    lib.ref_map_sector_count.restype = u32
+    lib.ref_map_list_sectors.argtypes = [vp, vp, vp, u32]
+    lib.ref_map_list_sectors.restype = u32
+    lib.ref_map_read_sector.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.POINTER(u64), vp]
     lib.ref_set_sky.argtypes = [C.POINTER(VrtSkyDesc), vp]
     lib.ref_trace.argtypes = [vp, u64, vp, vp, C.POINTER(C.c_int32), vp, C.c_int]
     lib.ref_trace.restype = None
@@ -121,6 +132,43 @@ class RefMap:
     def set_blue_noise(self, rg):
         b = np.ascontiguousarray(rg, dtype=np.uint8)
         self.lib.ref_set_blue_noise(b.ctypes.data)
+
+    # ---- the reference's own cvox (de)serialiser, VoxelMap.cpp:205-274 ----
+    def serialize(self, path):
+        if self.lib.ref_serialize(self.h, str(path).encode()) != 0:
+            raise IOError("VoxelMap::Serialize failed")
+
+    def deserialize(self, path):
+        if self.lib.ref_deserialize(self.h, str(path).encode()) != 0:
+            raise IOError("VoxelMap::Deserialize failed")
+
+    def set_materials(self, mats):
+        for i, (r, g, b, f, e) in enumerate(mats):
+            self.lib.ref_set_material(self.h, i, int(r), int(g), int(b), int(f), float(e))
+
+    def materials(self):
+        out = []
+        for i in range(256):
+            rgbf = (C.c_uint8 * 4)()
+            em = C.c_float()
+            self.lib.ref_get_material(self.h, i, rgbf, C.byref(em))
+            out.append((rgbf[0], rgbf[1], rgbf[2], rgbf[3], em.value))
+        return out
+
+    def map_sectors(self):
+        """-> {(sx, sy, sz): (alloc_mask, bricks[k, 512])} read from the VoxelMap itself (not the renderer's dense view)."""
+        n = self.lib.ref_map_sector_count(self.h)
+        xyz = np.zeros((max(n, 1), 3), np.int32)
+        masks = np.zeros(max(n, 1), np.uint64)
+        n = self.lib.ref_map_list_sectors(self.h, xyz.ctypes.data, masks.ctypes.data, n)
+        out = {}
+        for i in range(n):
+            k = bin(int(masks[i])).count("1")
+            bricks = np.zeros((max(k, 1), 512), np.uint8)
+            m = C.c_uint64()
+            assert self.lib.ref_map_read_sector(self.h, int(xyz[i, 0]), int(xyz[i, 1]), int(xyz[i, 2]), C.byref(m), bricks.ctypes.data) == 0
+            out[(int(xyz[i, 0]), int(xyz[i, 1]), int(xyz[i, 2]))] = (int(m.value), bricks[:k])
+        return out
 
     def set_sky(self, desc, texels):
         t = np.ascontiguousarray(texels, dtype=np.uint32)

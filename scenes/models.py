@@ -17,8 +17,9 @@ images through PIL instead of stb_image; neither is pinned against the reference
 libraries absent here), so the result is "the reference's scene by the reference's recipe", not a bit-copy.
 Parity of the TRAVERSAL does not depend on it: oracle and GPU consume the same bricks.
 
-The voxelised scene is cached as scenes/_ref/sponza_<size>.npz (git-ignored, travels to the GPU box, where
-/root/reference does not exist).
+The voxelised scene is cached as scenes/_ref/sponza_<size>.dat in the reference's own "cvox 0004" cache format
+(scenes/cvox.py — the file the reference app itself would load as logs/voxels_2k_sponza.dat, Main.cpp:38-49); git-ignored,
+travels to the GPU box, where /root/reference does not exist.
 """
 from __future__ import annotations
 
@@ -334,7 +335,7 @@ def voxelize_model(gltf: Path, size: int):
 
 
 def _cache_path(size):
-    return HERE / "_ref" / f"sponza_{size}.npz"
+    return HERE / "_ref" / f"sponza_{size}.dat"
 
 
 def sponza_available(size=2048):
@@ -343,27 +344,19 @@ def sponza_available(size=2048):
 
 def sponza(size=2048):
     """The reference app's model scene (Main.cpp:42-47).  Cached; the cache file is what the GPU box sees."""
+    from . import cvox
+
     cp = _cache_path(size)
     if cp.exists():
-        return terrain.load_scene(cp)
+        scene = cvox.load_cvox(cp)
+        scene["name"] = f"Sponza/Sponza.gltf voxelised into {size}^3 ({cp.name})"
+        return scene
     if not (REF_MODEL.exists() and VOX_LIB.exists()):
         raise FileNotFoundError("Sponza scene: neither the cache (scenes/_ref) nor the reference assets + voxeliser are present")
     scene = voxelize_model(REF_MODEL, size)
-    save_scene_compressed(scene, cp)
+    cp.parent.mkdir(parents=True, exist_ok=True)
+    cvox.save_cvox(scene, cp)
     return scene
-
-
-def save_scene_compressed(scene, path):
-    import os
-
-    keys = sorted(scene["sectors"].keys())
-    pos = np.array(keys, np.int32).reshape(-1, 3)
-    masks = np.array([scene["sectors"][k][0] for k in keys], np.uint64)
-    bricks = np.concatenate([scene["sectors"][k][1] for k in keys], axis=0) if keys else np.zeros((0, 512), np.uint8)
-    path.parent.mkdir(parents=True, exist_ok=True)
-    tmp = path.with_name(f".{path.stem}.{os.getpid()}.tmp.npz")
-    np.savez_compressed(tmp, pos=pos, masks=masks, bricks=bricks, palette=scene["palette"], name=scene.get("name", ""))
-    os.replace(tmp, path)
 
 
 if __name__ == "__main__":

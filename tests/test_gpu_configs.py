@@ -48,7 +48,7 @@ def test_config3_sponza_1080p_one_bounce(shading_inputs):
     from scenes import camera, models
 
     if not models.sponza_available(1024):
-        pytest.skip("scenes/_ref/sponza_1024.npz absent (built by __graft_entry__.build() where the reference assets exist)")
+        pytest.skip("scenes/_ref/sponza_1024.dat absent (built by __graft_entry__.build() where the reference assets exist)")
     scene = models.sponza(1024)
     ctx, orc = _pair(scene, (5, 4), shading_inputs, capacity=1 << 17)
     cams = [camera.Camera(pos=(210.3, 80.2, 505.7), yaw=1.5, pitch=-0.15), camera.Camera(pos=(700.1, 300.4, 520.2), yaw=-1.2, pitch=-0.6)]

@@ -135,3 +135,55 @@ def test_sample_direction_and_sky_within_approximation(ref_map, hash_oracle):
             lib.orc_sky_sample(hash_oracle.h, dvec.ctypes.data, mip, out)
             same += np.array_equal(np.array(out[:], np.float32), refharness.sky_sample(dvec, mip))
     assert same / (2 * len(dirs)) > 0.99  # nearest-texel fetch: rcp14 moves < 1 % of samples to a neighbour
+
+
+def test_cvox_files_are_wire_compatible_with_the_reference(ref_map, hash_scene, tmp_path):
+    """scenes/cvox.py against the reference's own VoxelMap::Serialize / Deserialize (compiled into oracle/_ref together with its
+    Common/BinaryIO.cpp): a file the reference writes is read into the very sectors and materials, and a file we write is
+    accepted by the reference and gives it the very same map — negative sector coordinates and a multi-pack file included."""
+    from oracle import refharness
+    from scenes import cvox, terrain
+
+    scene = {"sectors": dict(hash_scene["sectors"]), "palette": hash_scene["palette"]}
+    rng = np.random.default_rng(4)
+    for key in [(-3, -2, -7), (2047, 127, -2048), (-1, 0, 5)]:  # the signed world range of WorldSectorIndexer (VoxelMap.h:100)
+        mask = int(rng.integers(1, 1 << 62))
+        scene["sectors"][key] = (mask, rng.integers(0, 256, (bin(mask).count("1"), 512), dtype=np.uint8))
+    big = terrain.terrain_hash(10, 4, 10, seed=8)  # > 16 MiB of bricks: several packs
+    for (x, y, z), v in big["sectors"].items():
+        scene["sectors"][(x + 100, y, z + 100)] = v
+    mats = cvox.decode_palette(scene["palette"])
+    mats[7] = (12, 200, 99, 31, 2.5)  # a raw Material that is not an RGB565 multiple
+
+    ref = refharness.RefMap()
+    ref.sync(terrain.scene_records(scene))
+    ref.set_materials(mats)
+    theirs = tmp_path / "reference.dat"
+    ref.serialize(theirs)
+    got = cvox.load_cvox(theirs)
+    assert got["materials"] == [tuple(m) for m in mats] or all(a[:4] == tuple(b)[:4] and abs(a[4] - b[4]) < 1e-7 for a, b in zip(got["materials"], mats))
+    assert set(got["sectors"]) == set(scene["sectors"])
+    for k, (m, b) in scene["sectors"].items():
+        assert got["sectors"][k][0] == m and np.array_equal(got["sectors"][k][1], b), k
+
+    ours = tmp_path / "ours.dat"
+    scene["materials"] = mats
+    cvox.save_cvox(scene, ours)
+    back = refharness.RefMap()
+    back.deserialize(ours)
+    their_view = back.map_sectors()
+    assert set(their_view) == set(scene["sectors"])
+    for k, (m, b) in scene["sectors"].items():
+        assert their_view[k][0] == m and np.array_equal(their_view[k][1], b), k
+    assert [m[:4] for m in back.materials()] == [tuple(m)[:4] for m in mats]
+    assert abs(back.materials()[7][4] - 2.5) < 1e-7
+    assert ours.stat().st_size > (16 << 20) // 8  # (several packs were written)
+    # error behaviour of Deserialize (VoxelMap.cpp:214-220)
+    bad = tmp_path / "bad.dat"
+    bad.write_bytes(b"nope" + bytes(20))
+    with pytest.raises(IOError):
+        cvox.load_cvox(bad)
+    with pytest.raises(IOError):
+        back.deserialize(bad)
+    ref.close()
+    back.close()

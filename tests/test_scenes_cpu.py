@@ -102,3 +102,30 @@ def test_edit_stream_records_reproduce_the_world(hash_scene):
     for key in sorted(final["sectors"]):
         a, b = inc.read_sector(*key), fresh.read_sector(*key)
         assert a[0] == b[0] and np.array_equal(a[1], b[1]) and np.array_equal(a[2], b[2]), key
+
+
+def test_cvox_reads_the_reference_written_golden_file_and_round_trips(tmp_path):
+    """tests/golden/ref_cvox_small.dat was written by the reference's own VoxelMap::Serialize (make_golden_cvox.py):
+    scenes/cvox.py reads it back to the content that went in, and what it writes it reads again (the live, both-direction
+    pin against the reference is tests/test_ref_pin.py::test_cvox_files_are_wire_compatible_with_the_reference)."""
+    from pathlib import Path
+
+    from scenes import cvox, terrain
+
+    g = Path(__file__).parent / "golden"
+    want = np.load(g / "ref_cvox_small.npz")
+    got = cvox.load_cvox(g / "ref_cvox_small.dat")
+    keys = [tuple(int(v) for v in k) for k in want["keys"]]
+    assert sorted(got["sectors"]) == keys
+    off = 0
+    for k, m in zip(keys, want["masks"].tolist()):
+        n = bin(m).count("1")
+        assert got["sectors"][k][0] == m and np.array_equal(got["sectors"][k][1], want["bricks"][off : off + n]), k
+        off += n
+    for a, b in zip(got["materials"], want["materials"]):
+        assert a[:4] == tuple(int(v) for v in b[:4]) and a[4] == np.float32(b[4])
+    out = tmp_path / "again.dat"
+    cvox.save_cvox(got, out)
+    again = cvox.load_cvox(out)
+    assert terrain.scene_digest(again) == terrain.scene_digest(got) and again["materials"] == got["materials"]
+    assert cvox.sector_pos(cvox.sector_index(-5, -1, 7)) == (-5, -1, 7) and cvox.sector_pos(cvox.sector_index(2047, 127, -2048)) == (2047, 127, -2048)
