@@ -52,6 +52,7 @@ struct VrtContext {
     uint4* d_hdr = nullptr;        // entry 0 of the bordered grid, inside d_hdr_alloc
     uint4* d_hdr_alloc = nullptr;  // grid + a guard shell of OUTSIDE entries on both ends
     uint32_t hdr_guard = 0;
+    uint32_t* d_occ = nullptr;     // 1 bit per header entry incl. the guards (k_build_occ)
     uint2* d_cells = nullptr;
     uint8_t* d_voxels = nullptr;
     uint2* d_palette = nullptr;
@@ -196,6 +197,8 @@ DevScene dev_scene(const VrtContext* ctx) {
     S.voxels = ctx->d_voxels;
     S.palette = ctx->d_palette;
     S.albedo = ctx->d_albedo;
+    S.occ = ctx->d_occ;
+    S.occ_bias = ctx->hdr_guard;
     S.sxz = ctx->sxz;
     S.sy = ctx->sy;
     S.lim_xz = 1u << (ctx->sxz + 5);
@@ -388,9 +391,17 @@ int launch_render(VrtContext* ctx, const VrtFrame* f, void* d_out, VrtHit* d_aux
     } else {
 #define VRT_LAUNCH(M, P, R) k_render<M, P, R><<<blocks, VRT_RENDER_THREADS, 0, s>>>(S, F)
         const int variant = (ctx->metrics_on ? 4 : 0) | (primary ? 2 : 0) | (rows ? 1 : 0);
+        // big views (header table >= 4 MB): bounce rays consult the one-bit sector table first (OCC kernels, see cast_loop_fast)
+        const bool occ = (size_t)ctx->n_hdr * sizeof(uint4) >= ((size_t)4 << 20);
         switch (variant) {
-            case 0: VRT_LAUNCH(false, false, false); break;
-            case 1: VRT_LAUNCH(false, false, true); break;
+            case 0:
+                if (occ) k_render<false, false, false, true><<<blocks, VRT_RENDER_THREADS, 0, s>>>(S, F);
+                else VRT_LAUNCH(false, false, false);
+                break;
+            case 1:
+                if (occ) k_render<false, false, true, true><<<blocks, VRT_RENDER_THREADS, 0, s>>>(S, F);
+                else VRT_LAUNCH(false, false, true);
+                break;
             case 2: VRT_LAUNCH(false, true, false); break;
             case 3: VRT_LAUNCH(false, true, true); break;
             case 4: VRT_LAUNCH(true, false, false); break;
@@ -468,6 +479,8 @@ extern "C" int vrt_create(const VrtConfig* cfg, VrtContext** out) {
     CUB(cudaMalloc((void**)&c->d_hdr_alloc, ((size_t)c->n_hdr + 2u * c->hdr_guard) * sizeof(uint4)));
     c->d_hdr = c->d_hdr_alloc + c->hdr_guard;
     k_init_headers<<<(c->n_hdr + 2u * c->hdr_guard + 255) / 256, 256, 0, c->stream>>>(c->d_hdr, c->sxp, c->syp, c->hdr_guard);
+    CUB(cudaMalloc((void**)&c->d_occ, (((size_t)c->n_hdr + 2u * c->hdr_guard + 31) / 32 + 1) * sizeof(uint32_t)));
+    k_build_occ<<<(c->n_hdr + 2u * c->hdr_guard + 255) / 256, 256, 0, c->stream>>>(c->d_hdr_alloc, c->n_hdr + 2u * c->hdr_guard, c->d_occ);
     CUB(cudaGetLastError());
     CUB(cudaMalloc((void**)&c->d_palette, 256 * sizeof(uint2)));
     CUB(cudaMemsetAsync(c->d_palette, 0, 256 * sizeof(uint2), c->stream));
@@ -501,6 +514,7 @@ extern "C" void vrt_destroy(VrtContext* ctx) {
         if (b->p) cudaFree(b->p);
     if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
     cudaFree(ctx->d_hdr_alloc);
+    cudaFree(ctx->d_occ);
     cudaFree(ctx->d_cells);
     cudaFree(ctx->d_voxels);
     cudaFree(ctx->d_palette);
@@ -735,6 +749,11 @@ extern "C" int vrt_sync(VrtContext* ctx, uint32_t n, const VrtDirtySector* recs)
         }
     }
     if (ctx->render_pending) { int st_ = wait_renders(ctx, ctx->stream); if (st_) return st_; }  // (box rebuild / callers that sync nothing)
+    if (nh) {  // some sector's allocation mask changed: refresh the one-bit view (78 k entries for the 2048x512x2048 view)
+        const uint32_t n_all = ctx->n_hdr + 2u * ctx->hdr_guard;
+        k_build_occ<<<(n_all + 255) / 256, 256, 0, ctx->stream>>>(ctx->d_hdr_alloc, n_all, ctx->d_occ);
+        ctx->stats.last_launches++;
+    }
     ctx->arena.flush_quarantine();
     {
         int st = rebuild_boxes(ctx);

@@ -91,7 +91,7 @@ __device__ __forceinline__ void store_pixel(const FrameParams& F, uint32_t x, ui
 #define VRT_RENDER_WARPS_BOUNCE 40
 #endif
 #define VRT_RENDER_CTAS(PRIMARY) (((PRIMARY) ? VRT_RENDER_WARPS_PRIMARY : VRT_RENDER_WARPS_BOUNCE) * 32 / VRT_RENDER_THREADS)
-template <bool METRICS, bool PRIMARY, bool ROWS = false>
+template <bool METRICS, bool PRIMARY, bool ROWS = false, bool OCC = false>
 __device__ __forceinline__ void render_warp_tile(const DevScene& S, const FrameParams& F, uint32_t work) {
     uint32_t x0, y0;
     if (!warp_tile_origin<ROWS>(F, work, x0, y0)) return;  // warp-uniform
@@ -101,15 +101,15 @@ __device__ __forceinline__ void render_warp_tile(const DevScene& S, const FrameP
     bool valid = x < F.width && y < F.height;
     PixelOut P;
     if (PRIMARY) shade_pixel_primary<METRICS>(S, F, x, y, valid, P);
-    else shade_pixel<METRICS>(S, F, x, y, valid, P);
+    else shade_pixel<METRICS, OCC>(S, F, x, y, valid, P);
     if (valid) store_pixel(F, x, y, P);
 }
 
-template <bool METRICS, bool PRIMARY, bool ROWS = false>
+template <bool METRICS, bool PRIMARY, bool ROWS = false, bool OCC = false>
 __global__ void __launch_bounds__(VRT_RENDER_THREADS, VRT_RENDER_CTAS(PRIMARY && !METRICS)) k_render(const __grid_constant__ DevScene S, const __grid_constant__ FrameParams F) {
     uint32_t work = F.work_offset + blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (work >= F.n_work) return;  // warp-uniform
-    render_warp_tile<METRICS, PRIMARY, ROWS>(S, F, work);
+    render_warp_tile<METRICS, PRIMARY, ROWS, OCC>(S, F, work);
 }
 
 // K_render for frames with bounces, CTA-compacted (shade_pixel_cta): same tiles, same pixels, but between bounces the CTA's
@@ -247,6 +247,19 @@ __global__ void k_init_headers(uint4* hdr, uint32_t sxp, uint32_t syp, uint32_t 
         border = x == 0 || z == 0 || y == 0 || x == sxp - 1 || z == sxp - 1 || y == syp - 1;
     }
     (hdr - guard)[j] = make_uint4(0u, 0u, 0u, border ? VRT_HDR_OUTSIDE : 0u);
+}
+
+// K_occ: the one-bit-per-entry view of the header table that the step-by-step loop consults first (DevScene::occ).  One warp
+// per 32 entries; bit set = resident sector, border or guard entry.  `hdr_all` points at the first guard entry.
+__global__ void __launch_bounds__(256) k_build_occ(const uint4* __restrict__ hdr_all, uint32_t n_all, uint32_t* __restrict__ occ) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    bool bit = false;
+    if (i < n_all) {
+        const uint4 h = hdr_all[i];
+        bit = (h.x | h.y) != 0u || (int)h.w < 0;
+    }
+    const unsigned word = __ballot_sync(0xFFFFFFFFu, bit);
+    if ((threadIdx.x & 31u) == 0u && i < n_all) occ[i >> 5] = word;
 }
 
 // ---------------------------------------------------------------------------------------------
