@@ -321,7 +321,7 @@ def workload_config(args, scene, sstats):
     return {
         "workload": f"BASELINE {WORKLOADS[args.workload][0]}: {_WL['label']}, "
         f"{args.width}x{args.height} primary rays + normal/material/depth G-buffer, bounces={args.bounces}"
-        + (f", {args.edits} random voxel edits + vrt_sync before every frame" if args.workload == "edits" else ""),
+        + ((f", {args.edits} random voxel edits" if args.edit_mode == "random" else ", one brush stroke (capsule r=30, fill/erase/replace)") + " + vrt_sync before every frame" if args.workload == "edits" else ""),
         "width": args.width,
         "height": args.height,
         "bounces": args.bounces,
@@ -423,7 +423,10 @@ def run_b200(args):
         from scenes import edits as _edits
 
         n_frames = 3 * args.steps + args.warmup + 8
-        frames_recs, _ = _edits.random_edit_frames(scene, n_frames, args.edits, seed=1)
+        if args.edit_mode == "brush":  # the reference's brush: capsule strokes of radius 30 (Brush.cpp), fill / erase / replace
+            frames_recs, _ = _edits.brush_stroke_frames(scene, n_frames, seed=1)
+        else:
+            frames_recs, _ = _edits.random_edit_frames(scene, n_frames, args.edits, seed=1)
         edit_batches = [capi.make_records(r) for r in frames_recs]
 
     def step():
@@ -635,7 +638,8 @@ def run_b200(args):
             "gpu_launches": args.steps + timed_edit_stats["launches"],
             "residency": residency,
             "edits": None if edit_batches is None else {
-                "voxel_edits_per_frame": args.edits,
+                "mode": args.edit_mode,
+                "voxel_edits_per_frame": args.edits if args.edit_mode == "random" else None,
                 "dirty_bricks_per_frame": timed_edit_stats["bricks"] / max(1, timed_edit_stats["syncs"]),
                 "h2d_bytes_per_frame": timed_edit_stats["bytes"] / max(1, timed_edit_stats["syncs"]),
                 "render_only_ms": render_only_ms,
@@ -697,6 +701,7 @@ def main():
     ap.add_argument("--height", type=int, default=None)
     ap.add_argument("--bounces", type=int, default=None)
     ap.add_argument("--edits", type=int, default=4096, help="workload 'edits': voxel edits per frame")
+    ap.add_argument("--edit-mode", default="random", choices=["random", "brush"], help="workload 'edits': uniform single-voxel edits, or the reference's brush strokes")
     ap.add_argument("--scene-file", default=None, help="workload 'file': a cvox 0004 voxel-map file written by the reference (or by scenes/cvox.py)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()

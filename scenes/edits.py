@@ -84,3 +84,88 @@ def random_edit_frames(scene, n_frames, edits_per_frame, seed=1, box=((0, 768), 
         val = np.where(rng.random(edits_per_frame) < 0.5, ids[rng.integers(0, ids.size, edits_per_frame)], 0).astype(np.uint8)
         frames.append(world.apply(pos, val))
     return frames, world
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# the reference's brush (VoxelRT/Brush.cpp:3-37, Brush.h:9-17): a capsule of radius 30 from the previous to the current
+# brush position; Fill writes the material into every voxel whose CENTRE is inside, Replace only into non-empty voxels,
+# material 0 erases.  (VoxelMap::RegionDispatchSIMD creates bricks only when filling, VoxelMap.h:216-264.)
+# ---------------------------------------------------------------------------------------------------------------------
+def _capsule_inside(px, py, pz, a, b, r):
+    """sdCapsule(p, a, b, r) < 0 (Brush.cpp:4-8) for voxel centres p; float32 like the reference."""
+    f = np.float32
+    pa = [px - f(a[0]), py - f(a[1]), pz - f(a[2])]
+    ba = [f(b[0] - a[0]), f(b[1] - a[1]), f(b[2] - a[2])]
+    bb = f(ba[0] * ba[0] + ba[1] * ba[1] + ba[2] * ba[2])
+    if bb > 0:
+        h = np.clip((pa[0] * ba[0] + pa[1] * ba[1] + pa[2] * ba[2]) / bb, f(0), f(1))
+    else:
+        h = np.zeros_like(px)
+    d = [pa[i] - ba[i] * h for i in range(3)]
+    return np.sqrt(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]) - f(r) < 0
+
+
+def brush_dispatch(world: EditableWorld, point_a, point_b, radius=30.0, material=255, action="fill"):
+    """BrushSession::Dispatch on an EditableWorld -> sync records of the bricks it changed."""
+    a, b = np.asarray(point_a, np.int64), np.asarray(point_b, np.int64)
+    pad = int(radius + 0.5)
+    lo, hi = np.minimum(a, b) - pad, np.maximum(a, b) + pad  # Brush.cpp:11-12
+    erasing = material == 0
+    dirty = {}
+    ax = np.arange(8, dtype=np.float32) + np.float32(0.5)
+    for by in range(int(lo[1]) >> 3, (int(hi[1]) >> 3) + 1):
+        for bz in range(int(lo[2]) >> 3, (int(hi[2]) >> 3) + 1):
+            for bx in range(int(lo[0]) >> 3, (int(hi[0]) >> 3) + 1):
+                # voxel index x | z << 3 | y << 6  ->  arrays shaped [y, z, x]
+                py, pz, px = np.meshgrid(ax + np.float32(by * 8), ax + np.float32(bz * 8), ax + np.float32(bx * 8), indexing="ij")
+                inside = _capsule_inside(px, py, pz, a, b, radius)
+                ix, iy, iz = px.astype(np.int64), py.astype(np.int64), pz.astype(np.int64)
+                inside &= (ix >= lo[0]) & (ix <= hi[0]) & (iy >= lo[1]) & (iy <= hi[1]) & (iz >= lo[2]) & (iz <= hi[2])
+                if not inside.any():
+                    continue
+                key = (bx >> 2, by >> 2, bz >> 2)
+                if min(key) < 0:
+                    continue
+                bi = (bx & 3) | ((bz & 3) << 2) | ((by & 3) << 4)
+                d = world.sectors.get(key)
+                have = d is not None and bi in d
+                if not have and (erasing or action == "replace"):
+                    continue  # nothing to erase / replace in a missing brick (createEmpty = false)
+                if not have:
+                    if d is None:
+                        d = world.sectors[key] = {}
+                    d[bi] = np.zeros(512, np.uint8)
+                    world._owned.add((key, bi))
+                elif (key, bi) not in world._owned:
+                    d[bi] = d[bi].copy()
+                    world._owned.add((key, bi))
+                vox = d[bi].reshape(8, 8, 8)
+                m = inside & (vox != 0) if (action == "replace" or erasing) else inside
+                if not m.any():
+                    continue
+                vox[m] = material
+                dirty[key] = dirty.get(key, 0) | (1 << bi)
+    recs = []
+    for key in sorted(dirty):
+        d = world.sectors[key]
+        dm = dirty[key]
+        recs.append((key[0], key[1], key[2], world.alloc_mask(key), dm, np.stack([d[bb] for bb in sorted(d) if (dm >> bb) & 1])))
+    return recs
+
+
+def brush_stroke_frames(scene, n_frames, seed=1, radius=30.0, box=((120, 640), (100, 170), (120, 640)), step=24):
+    """A seeded brush session: the brush position random-walks through `box`, `step` voxels per frame; strokes alternate between
+    filling with an emissive material, erasing, and replacing (eight frames each).  -> (per-frame record lists, world)."""
+    rng = np.random.default_rng(seed)
+    world = EditableWorld(scene)
+    pos = np.array([rng.integers(lo, hi) for lo, hi in box], np.int64)
+    frames = []
+    for f in range(n_frames):
+        delta = rng.normal(size=3)
+        delta = (delta / np.linalg.norm(delta) * step).astype(np.int64)
+        nxt = np.array([int(np.clip(pos[a] + delta[a], box[a][0], box[a][1])) for a in range(3)], np.int64)
+        phase = (f // 8) % 3
+        material, action = ((254, "fill"), (0, "replace"), (252, "replace"))[phase]
+        frames.append(brush_dispatch(world, pos, nxt, radius, material, action))
+        pos = nxt
+    return frames, world

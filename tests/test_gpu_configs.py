@@ -161,6 +161,26 @@ def capi_flag(name):
     return getattr(capi, f"VRT_HIT_{name}")
 
 
+def test_config5_brush_strokes(bench_scene):
+    """The reference's brush (capsule r=30: fill, erase, replace strokes) as the edit stream: every frame equals the oracle
+    fed with the same records; bricks are allocated by fills and whole sectors change emptiness (empty boxes rebuilt)."""
+    from scenes import camera, edits
+
+    frames, world = edits.brush_stroke_frames(bench_scene, 20, seed=5, box=((400, 640), (110, 170), (420, 640)))
+    ctx, orc = _pair(bench_scene, (6, 4), capacity=1 << 18)
+    cam = camera.Camera()
+    for i, recs in enumerate(frames):
+        ctx.sync(recs)
+        orc.sync(recs)
+        if i % 3 == 2 or i == len(frames) - 1:
+            out_g, aux_g = ctx.render(_frame(cam, 1280, 720, frame_no=i + 1), want_aux=True)
+            out_c, aux_c, _ = orc.render(_frame(cam, 1280, 720, frame_no=i + 1), want_aux=True)
+            assert_hits_equal(aux_g, aux_c, f"brush frame {i}", ignore_iters=True)
+            assert out_g.tobytes() == out_c.tobytes()
+    assert sum(len(r) for r in frames) > 100
+    ctx.close()
+
+
 def test_config5_edit_frames(bench_scene):
     """BASELINE configs[4]: frames of random single-voxel edits (set / clear, bricks allocated on demand), dirty bricks
     uploaded by vrt_sync, then a frame: every frame equals the oracle fed with the same records, and the final

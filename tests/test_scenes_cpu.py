@@ -129,3 +129,54 @@ def test_cvox_reads_the_reference_written_golden_file_and_round_trips(tmp_path):
     again = cvox.load_cvox(out)
     assert terrain.scene_digest(again) == terrain.scene_digest(got) and again["materials"] == got["materials"]
     assert cvox.sector_pos(cvox.sector_index(-5, -1, 7)) == (-5, -1, 7) and cvox.sector_pos(cvox.sector_index(2047, 127, -2048)) == (2047, 127, -2048)
+
+
+def test_brush_capsule_matches_the_distance_function(hash_scene):
+    """scenes/edits.brush_dispatch against a direct evaluation of the brush's capsule distance function (Brush.cpp:4-8,19-30)
+    over the whole bounding box: fill sets exactly the voxels whose centre is inside, replace only the non-empty ones,
+    erase clears them, and the records rebuild the world."""
+    from oracle import pyoracle
+    from scenes import edits, terrain
+
+    world = edits.EditableWorld(hash_scene)
+    a, b, r = (40, 70, 50), (75, 82, 61), 12.0
+
+    def dense(w, lo, hi):
+        out = np.zeros((hi[1] - lo[1], hi[2] - lo[2], hi[0] - lo[0]), np.uint8)
+        for (sx, sy, sz), d in w.sectors.items():
+            for bi, vox in d.items():
+                x0, y0, z0 = sx * 32 + (bi & 3) * 8, sy * 32 + (bi >> 4) * 8, sz * 32 + ((bi >> 2) & 3) * 8
+                if x0 + 8 <= lo[0] or x0 >= hi[0] or y0 + 8 <= lo[1] or y0 >= hi[1] or z0 + 8 <= lo[2] or z0 >= hi[2]:
+                    continue
+                for y in range(8):
+                    for z in range(8):
+                        for x in range(8):
+                            X, Y, Z = x0 + x, y0 + y, z0 + z
+                            if lo[0] <= X < hi[0] and lo[1] <= Y < hi[1] and lo[2] <= Z < hi[2]:
+                                out[Y - lo[1], Z - lo[2], X - lo[0]] = vox[x | (z << 3) | (y << 6)]
+        return out
+
+    lo, hi = (24, 56, 32), (96, 96, 80)
+    before = dense(world, lo, hi)
+    ys, zs, xs = np.meshgrid(np.arange(lo[1], hi[1]), np.arange(lo[2], hi[2]), np.arange(lo[0], hi[0]), indexing="ij")
+    inside = edits._capsule_inside(xs.astype(np.float32) + np.float32(0.5), ys.astype(np.float32) + np.float32(0.5), zs.astype(np.float32) + np.float32(0.5), np.array(a), np.array(b), r)
+    recs_all = []
+    recs_all.append(edits.brush_dispatch(world, a, b, r, 253, "fill"))
+    after_fill = dense(world, lo, hi)
+    assert np.array_equal(after_fill, np.where(inside, 253, before))
+    recs_all.append(edits.brush_dispatch(world, a, b, r, 0, "replace"))
+    assert np.array_equal(dense(world, lo, hi), np.where(inside, 0, before))
+    world2 = edits.EditableWorld(hash_scene)
+    edits.brush_dispatch(world2, a, b, r, 7, "replace")
+    assert np.array_equal(dense(world2, lo, hi), np.where(inside & (before != 0), 7, before))
+    # the records rebuild the edited world
+    inc = pyoracle.OracleMap(6, 4)
+    inc.sync(terrain.scene_records(hash_scene))
+    for recs in recs_all:
+        inc.sync(recs)
+    fresh = pyoracle.OracleMap(6, 4)
+    final = world.to_scene(hash_scene["palette"])
+    fresh.sync(terrain.scene_records(final))
+    for key in sorted(final["sectors"]):
+        x, y = inc.read_sector(*key), fresh.read_sector(*key)
+        assert x[0] == y[0] and np.array_equal(x[1], y[1]) and np.array_equal(x[2], y[2]), key
