@@ -22,8 +22,31 @@ smsp__thread_inst_executed_per_inst_executed.ratio lts__throughput.avg.pct_of_pe
 l1tex__throughput.avg.pct_of_peak_sustained_elapsed lts__t_sectors.sum""".split()
 
 
+def summarise(rep, name):
+    """ncu report -> profiles/<name>_details.txt + <name>_raw_summary.csv (the metrics listed above, one column per launch)."""
+    det = subprocess.run(["ncu", "-i", str(rep), "--page", "details"], capture_output=True, text=True).stdout
+    (PROF / f"{name}_details.txt").write_text(det)
+    raw = subprocess.run(["ncu", "-i", str(rep), "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(raw.splitlines()))
+    head, units, launches = rows[0], rows[1], rows[2:]
+    extra = ["smsp__average_warp_latency_issue_stalled_long_scoreboard.ratio", "smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio",
+             "smsp__average_warps_issue_stalled_wait_per_issue_active.ratio", "smsp__average_warps_issue_stalled_math_pipe_throttle_per_issue_active.ratio",
+             "smsp__average_warps_issue_stalled_not_selected_per_issue_active.ratio", "smsp__average_warps_issue_stalled_branch_resolving_per_issue_active.ratio"]
+    with open(PROF / f"{name}_raw_summary.csv", "w") as f:
+        f.write("metric,unit," + ",".join(f"launch{i}" for i in range(len(launches))) + "\n")
+        for m in METRICS + extra:
+            i = next((j for j, h in enumerate(head) if h == m), None)
+            if i is not None:
+                f.write(f"{m},{units[i]}," + ",".join(r[i].replace(",", "") for r in launches) + "\n")
+
+
 def main():
     tag = sys.argv[1] if len(sys.argv) > 1 else "r01"
+    if (OUT / "prof_bounce.ncu-rep").exists():
+        summarise(OUT / "prof_bounce.ncu-rep", f"{tag}_ncu_k_render_bounce1")
+        if (OUT / "prof_bounce_source.csv").exists():
+            subprocess.run([sys.executable, str(ROOT / "tools_regions.py"), str(OUT / "prof_bounce_source.csv"), str(PROF / f"{tag}_ncu_k_render_bounce1_source_regions.txt")],
+                           stdout=subprocess.DEVNULL)
     rep = OUT / "prof_render.ncu-rep"
     if rep.exists():
         det = subprocess.run(["ncu", "-i", str(rep), "--page", "details"], capture_output=True, text=True).stdout
@@ -54,7 +77,7 @@ def main():
                        stdout=subprocess.DEVNULL)
     for src, dst in (("bench.json", f"{tag}_bench_4k_primary.json"), ("bench_ref.json", f"{tag}_bench_reference_arm.json"),
                      ("launches.csv", f"{tag}_launches_4k_primary.csv"), ("bench_sponza.json", f"{tag}_bench_sponza_1080p_1bounce.json"),
-                     ("bench_large.json", f"{tag}_bench_large_4k_2bounces.json"), ("bench_edits.json", f"{tag}_bench_edits_4k.json"),
+                     ("bench_large.json", f"{tag}_bench_large_4k_2bounces.json"), ("bench_edits.json", f"{tag}_bench_edits_4k.json"), ("bench_edits_brush.json", f"{tag}_bench_edits_brush_4k.json"),
                      ("bench_2gpu.json", f"{tag}_bench_4k_primary_2gpu.json"), ("bench_4gpu.json", f"{tag}_bench_4k_primary_4gpu.json"),
                      ("bench_8gpu.json", f"{tag}_bench_4k_primary_8gpu.json"), ("macro_stats.log", f"{tag}_macro_stats.txt")):
         if (OUT / src).exists() and (OUT / src).stat().st_size:

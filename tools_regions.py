@@ -113,7 +113,9 @@ def main():
             data = data[:k]
             break
     ia, ie, it, isamp = hdr.index("Address"), hdr.index("Instructions Executed"), hdr.index("Thread Instructions Executed"), hdr.index("# Samples")
-    sub = "k_renderILb0ELb1E" if "(bool)0, (bool)1" in kernel else ("k_renderILb0ELb0E" if "(bool)0, (bool)0" in kernel else "k_render")
+    flags = re.findall(r"\(bool\)([01])", kernel.split("(vrt::")[0])
+    base = "k_render_cta" if "k_render_cta" in kernel else ("k_render_persist" if "k_render_persist" in kernel else "k_render")
+    sub = f"{len(base)}{base}I" + "".join(f"Lb{f}E" for f in flags) if flags else base
     table, regs = line_table(sub), source_regions()
     base = int(data[0][ia], 16)
     agg, tot_e, tot_s = {}, 0, 0
