@@ -262,8 +262,8 @@ def test_render_bounces(hash_scene, hash_oracle, shading_inputs, bounces):
 
 @pytest.mark.parametrize("size", [(320, 180), (36, 4), (260, 148)])
 def test_bounce_compaction_equals_per_pixel_path(bench_ctx, bench_oracle, shading_inputs, size):
-    """Frames with bounces: the CTA-compacted kernel (live bounce rays re-dealt to full warps through shared memory) gives the
-    bytes of the one-thread-per-pixel kernel and of the oracle, incl. aux records, partitions and odd frame sizes."""
+    """Frames with bounces: the wavefront passes (queues + trip budgets) and the CTA-compacted kernel give the bytes of the
+    one-thread-per-pixel kernel and of the oracle, incl. aux records, partitions and odd frame sizes."""
     from scenes import camera
     from voxelrt_b200 import capi
 
@@ -277,11 +277,12 @@ def test_bounce_compaction_equals_per_pixel_path(bench_ctx, bench_oracle, shadin
     try:
         for bounces in (1, 3):
             want, aux_c, _ = bench_oracle.render(_frame(cam, w, h, bounces=bounces, frame_no=7), want_aux=True)
-            for mode in (0, 1):
-                bench_ctx.set_option("compact_bounces", mode)
+            for mode in ("per-pixel", "compact", "wavefront"):
+                bench_ctx.set_option("compact_bounces", int(mode == "compact"))
+                bench_ctx.set_option("wavefront", int(mode == "wavefront"))
                 got, aux_g = bench_ctx.render(_frame(cam, w, h, bounces=bounces, frame_no=7), want_aux=True)
                 assert got.tobytes() == want.tobytes(), (size, bounces, mode)
-                assert_hits_equal(aux_g, aux_c, f"compact={mode}", ignore_iters=True)
+                assert_hits_equal(aux_g, aux_c, f"bounce mode {mode}", ignore_iters=True)
                 part = np.zeros_like(want)
                 for p in range(3):
                     f = _frame(cam, w, h, bounces=bounces, frame_no=7, part_index=p, part_count=3, flags=capi.VRT_FRAME_PART_ROWS)
@@ -289,6 +290,42 @@ def test_bounce_compaction_equals_per_pixel_path(bench_ctx, bench_oracle, shadin
                 assert part.tobytes() == want.tobytes(), (size, bounces, mode, "band split")
     finally:
         bench_ctx.set_option("compact_bounces", 0)
+        bench_ctx.set_option("wavefront", 2)
+
+
+def test_wavefront_self_tuning_keeps_frames_identical(bench_ctx, bench_oracle, shading_inputs):
+    """Default setting: the first bounce frames after a scene change are timed in both forms and one is kept — every frame of
+    the sequence, whichever form traced it, equals the oracle's, also across a sync that changes sector emptiness."""
+    import torch
+
+    from scenes import camera
+
+    (bn, _), (desc, tex, _) = shading_inputs
+    for m in (bench_ctx, bench_oracle):
+        m.set_blue_noise(bn)
+        m.set_sky(desc, tex)
+    bench_ctx.set_option("wavefront", 2)
+    cam = camera.orbit_cameras(4, seed=3)[2]
+    w, h = 640, 360
+    want, _, _ = bench_oracle.render(_frame(cam, w, h, bounces=2, frame_no=4), want_aux=False)
+    fb = torch.zeros(w * h * 4, dtype=torch.int32, device="cuda")
+    stream = torch.cuda.Stream()
+    for k in range(6):
+        bench_ctx.render_device(_frame(cam, w, h, bounces=2, frame_no=4), fb.data_ptr(), None, stream.cuda_stream)
+        stream.synchronize()
+        assert fb.cpu().numpy().tobytes() == want.tobytes(), f"frame {k}"
+    # a new resident sector (emptiness changes) restarts the tuning
+    brick = np.zeros((1, 512), np.uint8)
+    brick[0, 7] = 250
+    for m in (bench_ctx, bench_oracle):
+        m.sync([(30, 9, 30, 1, 1, brick)])
+    want2, _, _ = bench_oracle.render(_frame(cam, w, h, bounces=2, frame_no=4), want_aux=False)
+    for k in range(4):
+        bench_ctx.render_device(_frame(cam, w, h, bounces=2, frame_no=4), fb.data_ptr(), None, stream.cuda_stream)
+        stream.synchronize()
+        assert fb.cpu().numpy().tobytes() == want2.tobytes(), f"frame {k} after the edit"
+    for m in (bench_ctx, bench_oracle):  # put the shared scene back
+        m.sync([(30, 9, 30, 0, 1, None, True)])
 
 
 def test_render_needs_blue_noise_for_bounces(hash_scene):

@@ -80,6 +80,19 @@ struct VrtContext {
     DevMetrics* d_metrics = nullptr;
     bool metrics_on = false;
     // persistent frame kernel: ring of ticket counters (one per launch in flight) and the host's view of each
+    // frames with bounces: wavefront passes with trip budgets (k_wave_*, vrt_shade.cuh) against the one-thread-per-pixel kernel.
+    // Bit-identical, but which is faster depends on the scene (open terrain, 2 bounces: +10..15 %; inside Sponza: -8..12 %), so
+    // the default (2) measures: after every change of scene emptiness / bounce count / frame size the next two bounce frames
+    // run one form each between CUDA events, and the faster one is kept.  0 / 1 force a form.
+    int wave_on = 2;
+    int wave_choice = -1;         // -1 undecided, 0 per-pixel, 1 wavefront
+    int wave_phase = 0;           // 0: time per-pixel next, 1: time wavefront next, 2: waiting for the events
+    uint64_t wave_key = 0;        // (bounces, width, height, scene epoch) the decision was taken for
+    uint64_t scene_epoch = 0;     // bumped when a sync changes some sector's emptiness
+    cudaEvent_t ev_tune[4] = {};
+    DeviceBuffer d_wave_q[2], d_wave_c[2], d_wave_n;
+    cudaEvent_t ev_wave = nullptr;  // the queues are shared: a wave frame on another stream waits for the previous one
+    bool wave_used = false;
     int compact_on = 0;  // frames with bounces: pack the live bounce rays of a CTA between bounces (k_render_cta); measured 10 % SLOWER
                          // (the bounce phase is latency-bound: fewer tracing warps hide less latency than idle lanes cost)
     int persist_on = 0;  // measured slower than the grid form on primary frames (tile order loses the L1 locality of 4 adjacent warp tiles per CTA)
@@ -371,6 +384,102 @@ int launch_render(VrtContext* ctx, const VrtFrame* f, void* d_out, VrtHit* d_aux
     unsigned blocks = (F.n_work - F.work_offset + wpb - 1) / wpb;
     const bool rows = (F.flags & VRT_FRAME_PART_ROWS) != 0u, primary = F.bounces == 0;
     if (ctx->metrics_on) CU(cudaMemsetAsync(ctx->d_metrics, 0, sizeof(DevMetrics), s));
+    // which form traces a frame with bounces (see wave_on)
+    bool use_wave = false;
+    int tune_slot = -1;  // >= 0: this frame is one of the two timed ones (events tune_slot, tune_slot + 1)
+    if (!primary && !ctx->metrics_on && !ctx->compact_on && !ctx->persist_on && ctx->wave_on) {
+        if (ctx->wave_on == 1) use_wave = true;
+        else if (row0 != 0 || row1 != 0 || part_count > 1) use_wave = ctx->wave_choice == 1;  // band / partial launches never tune
+        else {
+            const uint64_t key = ((uint64_t)F.bounces << 56) ^ ((uint64_t)F.width << 40) ^ ((uint64_t)F.height << 24) ^ (ctx->scene_epoch & 0xFFFFFFu);
+            if (key != ctx->wave_key) ctx->wave_key = key, ctx->wave_choice = -1, ctx->wave_phase = 0;
+            if (ctx->wave_choice < 0 && ctx->wave_phase == 2 && cudaEventQuery(ctx->ev_tune[3]) == cudaSuccess) {
+                float t_pixel = 0.0f, t_wave = 0.0f;
+                if (cudaEventElapsedTime(&t_pixel, ctx->ev_tune[0], ctx->ev_tune[1]) == cudaSuccess &&
+                    cudaEventElapsedTime(&t_wave, ctx->ev_tune[2], ctx->ev_tune[3]) == cudaSuccess)
+                    ctx->wave_choice = t_wave < t_pixel ? 1 : 0;
+                else ctx->wave_phase = 0;
+                cudaGetLastError();
+            }
+            if (ctx->wave_choice >= 0) use_wave = ctx->wave_choice == 1;
+            else if (ctx->wave_phase == 0) use_wave = false, tune_slot = 0, ctx->wave_phase = 1;
+            else if (ctx->wave_phase == 1) use_wave = true, tune_slot = 2, ctx->wave_phase = 2;
+            else use_wave = true;  // both timed frames are still in flight
+        }
+    }
+    // (the timed region starts right before the first launch — after any one-time buffer allocation of the form)
+    auto tune_begin = [&]() {
+        if (tune_slot >= 0) cudaEventRecord(ctx->ev_tune[tune_slot], s);
+    };
+    struct TuneEnd {  // closes the timed region on every return path below
+        VrtContext* c;
+        int slot;
+        cudaStream_t st;
+        ~TuneEnd() {
+            if (slot >= 0) cudaEventRecord(c->ev_tune[slot + 1], st);
+        }
+    } tune_end{ctx, tune_slot, s};
+    if (use_wave) {
+        // Wavefront: camera pass, then for each bounce level passes with trip budgets 16 / 32 / the rest (vrt_shade.cuh).
+        const size_t cap = (size_t)(F.n_work - F.work_offset) * 32u;  // at most one path per pixel of this launch
+        int st2;
+        for (int k = 0; k < 2; k++) {
+            if ((st2 = ensure(ctx, ctx->d_wave_q[k], cap * sizeof(PathRec)))) return st2;
+            if ((st2 = ensure(ctx, ctx->d_wave_c[k], cap * sizeof(ContRec)))) return st2;
+        }
+        const uint32_t n_counters = 2u + 8u * 3u;
+        if ((st2 = ensure(ctx, ctx->d_wave_n, n_counters * sizeof(uint32_t)))) return st2;
+        if (ctx->wave_used) CU(cudaStreamWaitEvent(s, ctx->ev_wave, 0));
+        tune_begin();
+        uint32_t* cnt = static_cast<uint32_t*>(ctx->d_wave_n.p);
+        CU(cudaMemsetAsync(cnt, 0, n_counters * sizeof(uint32_t), s));
+        PathRec* q[2] = {static_cast<PathRec*>(ctx->d_wave_q[0].p), static_cast<PathRec*>(ctx->d_wave_q[1].p)};
+        ContRec* c[2] = {static_cast<ContRec*>(ctx->d_wave_c[0].p), static_cast<ContRec*>(ctx->d_wave_c[1].p)};
+        // counters: [level] for the level queues (level 1 = cnt[1] ...), then 2 per level for the continuation queues
+        if (rows) k_wave_primary<true><<<blocks, VRT_RENDER_THREADS, 0, s>>>(S, F, q[1], cnt + 1);
+        else k_wave_primary<false><<<blocks, VRT_RENDER_THREADS, 0, s>>>(S, F, q[1], cnt + 1);
+        ctx->stats.last_launches += 1;
+        const bool occ = (size_t)ctx->n_hdr * sizeof(uint4) >= ((size_t)4 << 20);
+        const unsigned grid = (unsigned)std::min<size_t>((cap + VRT_RENDER_THREADS - 1) / VRT_RENDER_THREADS,
+                                                         (size_t)ctx->sm_count * VRT_RENDER_CTAS(false) * 4u);
+        for (uint32_t level = 1; level <= F.bounces; level++) {
+            uint32_t* n_level = cnt + level;                     // rays of this level (filled by the previous level / camera pass)
+            uint32_t* n_next = level < 8 ? cnt + level + 1 : cnt;  // (never written at the last level)
+            uint32_t* n_c = cnt + 9 + (level - 1) * 2;           // two continuation counters per level
+            WaveArgs A;
+            A.q_in = q[level & 1];
+            A.c_in = nullptr;
+            A.n_in = n_level;
+            A.q_out = q[(level + 1) & 1];
+            A.n_q_out = n_next;
+            A.c_out = c[0];
+            A.n_c_out = n_c;
+            A.budget = 16u;
+            if (occ) k_wave_trace<false, true><<<grid, VRT_RENDER_THREADS, 0, s>>>(S, F, A);
+            else k_wave_trace<false, false><<<grid, VRT_RENDER_THREADS, 0, s>>>(S, F, A);
+            A.q_in = nullptr;
+            A.c_in = c[0];
+            A.n_in = n_c;
+            A.c_out = c[1];
+            A.n_c_out = n_c + 1;
+            A.budget = 32u;
+            if (occ) k_wave_trace<true, true><<<grid, VRT_RENDER_THREADS, 0, s>>>(S, F, A);
+            else k_wave_trace<true, false><<<grid, VRT_RENDER_THREADS, 0, s>>>(S, F, A);
+            A.c_in = c[1];
+            A.n_in = n_c + 1;
+            A.c_out = nullptr;
+            A.n_c_out = nullptr;
+            A.budget = 0xFFFFFFFFu;
+            if (occ) k_wave_trace<true, true><<<grid, VRT_RENDER_THREADS, 0, s>>>(S, F, A);
+            else k_wave_trace<true, false><<<grid, VRT_RENDER_THREADS, 0, s>>>(S, F, A);
+            ctx->stats.last_launches += 3;
+        }
+        CU(cudaEventRecord(ctx->ev_wave, s));
+        ctx->wave_used = true;
+        CU(cudaGetLastError());
+        return VRT_OK;
+    }
+    tune_begin();
     if (!primary && ctx->compact_on && !ctx->persist_on) {
         // frames with bounces: CTA-compacted bounce rays (k_render_cta)
         const int v = (ctx->metrics_on ? 2 : 0) | (rows ? 1 : 0);
@@ -468,6 +577,8 @@ extern "C" int vrt_create(const VrtConfig* cfg, VrtContext** out) {
     for (auto& e : c->ev_stage) CUB(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     CUB(cudaEventCreateWithFlags(&c->ev_sync, cudaEventDisableTiming));
     for (auto& e : c->ev_render) CUB(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    CUB(cudaEventCreateWithFlags(&c->ev_wave, cudaEventDisableTiming));
+    for (auto& e : c->ev_tune) CUB(cudaEventCreate(&e));
     for (auto& gs : c->gather_streams) CUB(cudaStreamCreateWithFlags(&gs, cudaStreamNonBlocking));
     for (auto& e : c->ev_gather_src) CUB(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     for (auto& e : c->ev_gather_done) CUB(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
@@ -508,7 +619,9 @@ extern "C" void vrt_destroy(VrtContext* ctx) {
     cudaDeviceSynchronize();
     for (void* p : ctx->imported) cudaIpcCloseMemHandle(p);
     for (void* p : ctx->exported) cudaFree(p);
-    DeviceBuffer* bufs[] = {&ctx->d_stage, &ctx->d_rays_o, &ctx->d_rays_d, &ctx->d_hits, &ctx->d_fb,
+    if (ctx->ev_wave) cudaEventDestroy(ctx->ev_wave);
+    for (auto& e : ctx->ev_tune) if (e) cudaEventDestroy(e);
+    DeviceBuffer* bufs[] = {&ctx->d_wave_q[0], &ctx->d_wave_q[1], &ctx->d_wave_c[0], &ctx->d_wave_c[1], &ctx->d_wave_n, &ctx->d_stage, &ctx->d_rays_o, &ctx->d_rays_d, &ctx->d_hits, &ctx->d_fb,
                             &ctx->d_aux,   &ctx->d_q_o,    &ctx->d_q_d,    &ctx->d_q_out};
     for (auto* b : bufs)
         if (b->p) cudaFree(b->p);
@@ -557,6 +670,7 @@ extern "C" int vrt_set_option(VrtContext* ctx, const char* name, int64_t value) 
     else if (!strcmp(name, "macro_steps")) ctx->macro_on = (int)value;
     else if (!strcmp(name, "persistent")) ctx->persist_on = (int)value;
     else if (!strcmp(name, "compact_bounces")) ctx->compact_on = (int)value;
+    else if (!strcmp(name, "wavefront")) ctx->wave_on = (int)value;
     else return fail(ctx, VRT_ERR_INVALID, std::string("unknown option ") + name);
     return VRT_OK;
 }
@@ -656,6 +770,7 @@ extern "C" int vrt_sync(VrtContext* ctx, uint32_t n, const VrtDirtySector* recs)
             if ((old.mask == 0) != (new_mask == 0)) {
                 ctx->resident_sectors += new_mask ? 1 : -1;
                 ctx->boxes_stale = true;
+                ctx->scene_epoch++;
             }
             ctx->sectors[si] = cur;
             headers.push_back(HeaderUpdate{hdr_index(ctx->sxp, ctx->sxp * ctx->sxp, d.sx, d.sy, d.sz), (uint32_t)new_mask,

@@ -130,6 +130,34 @@ __global__ void __launch_bounds__(VRT_RENDER_THREADS, VRT_RENDER_CTAS(false)) k_
     if (valid) store_pixel(F, x, y, P);
 }
 
+// Wavefront form of a frame with bounces (vrt_shade.cuh): the camera pass, then per bounce level three budgeted passes.
+template <bool ROWS>
+__global__ void __launch_bounds__(VRT_RENDER_THREADS, VRT_RENDER_CTAS(false)) k_wave_primary(const __grid_constant__ DevScene S, const __grid_constant__ FrameParams F,
+                                                                                             PathRec* __restrict__ q, uint32_t* __restrict__ n_q) {
+    const uint32_t work = F.work_offset + blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (work >= F.n_work) return;  // warp-uniform
+    uint32_t x0, y0;
+    if (!warp_tile_origin<ROWS>(F, work, x0, y0)) return;
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t x = x0 + ((lane >> 4) << 2) + (lane & 3u);
+    const uint32_t y = y0 + ((lane >> 2) & 3u);
+    wave_primary_pixel(S, F, x, y, x < F.width && y < F.height, q, n_q);
+}
+#ifndef VRT_WAVE_WARPS
+#define VRT_WAVE_WARPS 40
+#endif
+template <bool CONT, bool OCC>
+__global__ void __launch_bounds__(VRT_RENDER_THREADS, VRT_WAVE_WARPS * 32 / VRT_RENDER_THREADS) k_wave_trace(const __grid_constant__ DevScene S, const __grid_constant__ FrameParams F,
+                                                                                           const __grid_constant__ WaveArgs A) {
+    const uint32_t n = *A.n_in;
+    const uint32_t stride = gridDim.x * blockDim.x;
+    // whole warps iterate together (queue_push is a warp collective)
+    for (uint32_t base = (blockIdx.x * blockDim.x + threadIdx.x) & ~31u; base < n; base += stride) {
+        const uint32_t idx = base + (threadIdx.x & 31u);
+        wave_trace_one<CONT, OCC>(S, F, A, idx, idx < n);
+    }
+}
+
 // K_render, persistent form: the grid is sized to the machine (SMs x resident CTAs) and every WARP pulls warp tiles
 // from a ticket counter until the frame is done, so a warp slot never idles waiting for the slowest warp of its CTA
 // (tile costs differ by an order of magnitude between sky and horizon tiles).  A warp's first tile is its global warp
