@@ -15,8 +15,8 @@ if [ "$1" != "noprof" ]; then
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches.csv python bench.py --steps 3 --warmup 3 --no-cpu > gpurun_out/bench_under_ncu.log 2>&1
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_render -s 4 -c 2 -f -o gpurun_out/prof_render python bench.py --steps 3 --warmup 3 --no-cpu > gpurun_out/ncu_full.log 2>&1
 ncu -i gpurun_out/prof_render.ncu-rep --page source --csv > gpurun_out/prof_render_source.csv 2>/dev/null
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_render -s 4 -c 1 -f -o gpurun_out/prof_bounce python bench.py --bounces 1 --steps 3 --warmup 3 --no-cpu > gpurun_out/ncu_bounce.log 2>&1
-ncu -i gpurun_out/prof_bounce.ncu-rep --page source --csv > gpurun_out/prof_bounce_source.csv 2>/dev/null
+# wavefront passes of a 2-bounce frame (level 1: budgets 16 / 32 / rest); the per-pixel bounce kernel's capture is r01_ncu_k_render_bounce1_*
+timeout 600 ncu --set full --clock-control none -k regex:k_wave_trace -s 6 -c 3 -f -o gpurun_out/prof_wave python tools_exp.py --workload terrain --bounces 2 wavefront=1 > gpurun_out/ncu_wave.log 2>&1
 timeout 300 python bench.py --workload edits --edit-mode brush --steps 20 --warmup 3 --no-cpu > gpurun_out/bench_edits_brush.json 2>/dev/null
 for wl in sponza large edits; do
   timeout 900 python bench.py --workload $wl --steps 10 --warmup 3 > gpurun_out/bench_$wl.json 2> gpurun_out/bench_$wl.err; tail -1 gpurun_out/bench_$wl.json | cut -c1-300

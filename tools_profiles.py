@@ -47,6 +47,8 @@ def main():
         if (OUT / "prof_bounce_source.csv").exists():
             subprocess.run([sys.executable, str(ROOT / "tools_regions.py"), str(OUT / "prof_bounce_source.csv"), str(PROF / f"{tag}_ncu_k_render_bounce1_source_regions.txt")],
                            stdout=subprocess.DEVNULL)
+    if (OUT / "prof_wave.ncu-rep").exists():
+        summarise(OUT / "prof_wave.ncu-rep", f"{tag}_ncu_k_wave_trace_2bounces")
     rep = OUT / "prof_render.ncu-rep"
     if rep.exists():
         det = subprocess.run(["ncu", "-i", str(rep), "--page", "details"], capture_output=True, text=True).stdout
