@@ -69,3 +69,31 @@ def test_product_never_imports_the_oracle():
         if p.suffix in (".py", ".cu", ".cuh", ".cpp", ".h", ".hpp") or p.name == "Makefile":
             t = p.read_text(errors="ignore")
             assert "pyoracle" not in t and "liboracle" not in t and "vrt_oracle" not in t and "refharness" not in t, p
+
+
+def test_post_header_symbols_all_exported():
+    """include/voxelrt_b200_post.h (the GBuffer step) lives in the same shared library."""
+    from voxelrt_b200 import post
+
+    text = (ROOT / "include" / "voxelrt_b200_post.h").read_text()
+    declared = sorted(set(re.findall(r"VRT_API\s+[\w\s\*]+?\b(vrt_gbuffer_\w+)\s*\(", text)))
+    assert len(declared) == 11 and sorted(post.EXPORTS) == declared
+    lib = post.load()
+    for name in declared:
+        assert hasattr(lib, name), f"libvoxelrt_b200.so does not export {name}"
+    assert C.sizeof(post.VrtGBufferCamera) == 8 + 64 + 64 + 24 + 8 and post.RECORD_DTYPE.itemsize == 16
+
+
+def test_gbuffer_has_no_cpu_fallback_and_validates_arguments():
+    import torch
+
+    from voxelrt_b200 import capi, post
+
+    lib = post.load()
+    assert lib.vrt_gbuffer_create(0, None) == -1
+    assert lib.vrt_gbuffer_set_passes(None, 5) == -1 and lib.vrt_gbuffer_set_camera(None, None) == -1
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    with pytest.raises(capi.VrtError) as e:
+        post.GBuffer(0)
+    assert e.value.status == -2 and "no CPU fallback" in str(e.value)

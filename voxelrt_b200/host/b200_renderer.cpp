@@ -97,11 +97,15 @@ B200Renderer::B200Renderer(std::shared_ptr<VoxelMap> map, int device, uint32_t x
     cfg.device = device;
     cfg.sectors_xz_log2 = xz;
     cfg.sectors_y_log2 = y;
+    _device = device;
     int st = vrt_create(&cfg, &_ctx);
     if (st != VRT_OK) throw std::runtime_error(std::string("vrt_create: ") + vrt_last_error(nullptr));
     _map->MarkAllDirty();  // CpuRenderer.cpp:410
 }
-B200Renderer::~B200Renderer() { vrt_destroy(_ctx); }
+B200Renderer::~B200Renderer() {
+    vrt_gbuffer_destroy(_gbuffer);
+    vrt_destroy(_ctx);
+}
 
 void B200Renderer::SyncBuffers(VoxelMap& map) {
     // palette: the reference re-encodes it every frame (CpuRenderer.cpp:34-36); upload only on change
@@ -150,6 +154,7 @@ void B200Renderer::SyncBuffers(VoxelMap& map) {
 void B200Renderer::RenderFrame(Camera& cam, uvec2 viewSize) {
     viewSize.x &= ~3u;  // round down to 4x4 steps (CpuRenderer.cpp:419)
     viewSize.y &= ~3u;
+    const bool worldChanged = !_map->DirtyLocs.empty();  // CpuRenderer.cpp:421
     SyncBuffers(*_map);
     FrameNo++;  // GBuffer::SetCamera (GBuffer.h:57)
 
@@ -171,7 +176,26 @@ void B200Renderer::RenderFrame(Camera& cam, uvec2 viewSize) {
     _tiles.resize((size_t)viewSize.x * viewSize.y / 16);
     _size = viewSize;
     auto t0 = std::chrono::steady_clock::now();
-    Check(vrt_render(_ctx, &f, _tiles.data(), nullptr), "vrt_render");
+    if (DenoiseAndPresent) {
+        if (!_gbuffer && vrt_gbuffer_create(_device, &_gbuffer) != VRT_OK)
+            throw std::runtime_error(std::string("vrt_gbuffer_create: ") + vrt_gbuffer_last_error(nullptr));
+        auto gcheck = [&](int st, const char* what) {
+            if (st != VRT_OK) throw std::runtime_error(std::string(what) + ": " + vrt_gbuffer_last_error(_gbuffer));
+        };
+        VrtGBufferCamera gc{};
+        gc.width = viewSize.x, gc.height = viewSize.y;
+        std::memcpy(gc.proj, proj.m, sizeof(proj.m));
+        std::memcpy(gc.inv_proj, inv.m, sizeof(inv.m));
+        for (int a = 0; a < 3; a++) gc.position[a] = p[a];
+        gc.reset_history = worldChanged ? 1u : 0u;  // GBuffer::SetCamera(cam, viewSize, worldChanged), CpuRenderer.cpp:423
+        gcheck(vrt_gbuffer_set_passes(_gbuffer, NumDenoiserPasses), "vrt_gbuffer_set_passes");
+        gcheck(vrt_gbuffer_set_debug_channel(_gbuffer, DebugChannelView), "vrt_gbuffer_set_debug_channel");
+        gcheck(vrt_gbuffer_set_camera(_gbuffer, &gc), "vrt_gbuffer_set_camera");
+        _rgba.resize((size_t)viewSize.x * viewSize.y);
+        gcheck(vrt_gbuffer_render_present(_gbuffer, _ctx, &f, _rgba.data()), "vrt_gbuffer_render_present");
+    } else {
+        Check(vrt_render(_ctx, &f, _tiles.data(), nullptr), "vrt_render");
+    }
     double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
     _raysPerSec = (double)viewSize.x * viewSize.y * (NumLightBounces + 1) * (1000.0 / ms);  // CpuRenderer.cpp:490-492
 }

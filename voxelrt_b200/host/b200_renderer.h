@@ -12,7 +12,7 @@
 #include <string>
 #include <vector>
 
-#include "../../include/voxelrt_b200.h"
+#include "../../include/voxelrt_b200_post.h"
 #include "voxel_map.h"
 
 namespace vrt_host {
@@ -57,7 +57,10 @@ public:
     B200Renderer(std::shared_ptr<VoxelMap> map, int device = -1, uint32_t viewSectorsXZLog2 = 6, uint32_t viewSectorsYLog2 = 4);
     ~B200Renderer() override;
 
-    void RenderFrame(Camera& cam, uvec2 viewSize) override;  // CpuRenderer.cpp:415-464 minus present
+    // CpuRenderer.cpp:415-474.  With DenoiseAndPresent == false (default) it stops before the blit and leaves the 16 B/px
+    // tiles in Tiles(); with true the frame stays on the device through GBuffer::DenoiseAndPresent (GBuffer.h:86-130) and
+    // only the presented RGBA8 image comes back (Presented()).
+    void RenderFrame(Camera& cam, uvec2 viewSize) override;
     void SyncBuffers(VoxelMap& map);                         // CpuRenderer.cpp:33-61
     // VoxelMap::RayCast (VoxelMap.cpp:140-170) on the device, batched
     std::vector<HitResult> RayCast(const std::vector<dvec3>& origins, const std::vector<dvec3>& dirs, uint32_t maxIters = 1024);
@@ -66,6 +69,10 @@ public:
     void SetSky(const VrtSkyDesc& desc, const uint32_t* texels);   // swr::HdrTexture2D cube
 
     uint32_t NumLightBounces = 1;  // Renderer.h:65
+    bool DenoiseAndPresent = false;
+    uint32_t NumDenoiserPasses = 5;  // GBuffer.h:23
+    uint32_t DebugChannelView = 0;   // GBuffer::DebugChannel (GBuffer.h:8,22)
+    const std::vector<uint32_t>& Presented() const { return _rgba; }  // w*h RGBA8, what GBufferBlit.frag draws
     uint32_t FrameNo = 0;          // GBuffer::FrameNo
     // The last frame, 16 B/px in Framebuffer::Tile order (CpuRenderer.cpp:299-309); host copy for a presenter.
     const std::vector<VrtTile>& Tiles() const { return _tiles; }
@@ -77,6 +84,9 @@ private:
     void Check(int status, const char* what);
     std::shared_ptr<VoxelMap> _map;
     VrtContext* _ctx = nullptr;
+    VrtGBuffer* _gbuffer = nullptr;  // created on first use
+    std::vector<uint32_t> _rgba;
+    int _device = -1;
     std::vector<VrtTile> _tiles;
     std::vector<uint8_t> _payload;
     uint64_t _paletteEncoded[256] = {};
