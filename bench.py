@@ -334,6 +334,62 @@ def workload_config(args, scene, sstats):
     }
 
 
+def present_block(args, ctx, frame, stream, fb, w, h, peak):
+    """--present: the step after the path — the reference's GBuffer (tile blit + reprojection + SVGF + tone-mapped present,
+    include/voxelrt_b200_post.h) on the frames the bench just traced.  Device-timed with CUDA events on the launching
+    stream (camera panning a little every frame so the reprojection does real work), plus the trace-to-window time
+    through vrt_gbuffer_render_present with a host RGBA8 buffer.  Algorithmic bytes: DESIGN.md §10."""
+    import torch
+
+    from scenes import camera as _camera
+    from voxelrt_b200 import post
+
+    gb = post.GBuffer(torch.cuda.current_device())
+    gb.set_passes(args.present_passes)
+    d_rgba = torch.zeros(w * h, dtype=torch.int32, device="cuda")
+    cams = []
+    base = _WL["cam"] or _camera.Camera()  # Main.cpp:76-78
+    for f in range(args.warmup + args.steps):
+        cam = _camera.Camera(pos=(base.pos[0] + 0.25 * f, base.pos[1], base.pos[2] + 0.125 * f), yaw=base.yaw, pitch=base.pitch)
+        proj, inv, wo, frac = cam.matrices(w, h)
+        cams.append((capi.make_frame(w, h, inv, proj, wo, frac, frame_no=f + 1, bounces=args.bounces), post.make_camera(w, h, proj, inv, cam.pos)))
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    for f, (fr, gc) in enumerate(cams):
+        ctx.render_device(fr, fb.data_ptr(), None, stream.cuda_stream)
+        gb.set_camera(gc)
+        k = f - args.warmup
+        if k >= 0:
+            evs[k][0].record(stream)
+        gb.denoise_present_device(fb.data_ptr(), d_rgba.data_ptr(), stream.cuda_stream)
+        if k >= 0:
+            evs[k][1].record(stream)
+    torch.cuda.synchronize()
+    ms = sum(a.elapsed_time(b) for a, b in evs) / args.steps
+    launches = gb.last_launches()
+    npx = w * h
+    n = args.present_passes
+    alg = npx * (58 + (49 + 32 * n if n else 0) + 28)
+    # trace -> window through the one-call entry point, host RGBA8 buffer (4 B/px D2H instead of 16)
+    t0 = time.perf_counter()
+    for fr, gc in cams[: args.steps]:
+        gb.set_camera(gc)
+        gb.render_present(ctx, fr)
+    e2e_ms = (time.perf_counter() - t0) * 1e3 / args.steps
+    gb.close()
+    return {
+        "what": "CopyTiledFramebuffer + Reproject + Filter(-1, 0..%d) + GBufferBlit as CUDA kernels on the traced frame" % (n - 1),
+        "passes": n,
+        "ms_per_frame": ms,
+        "launches_per_frame": launches,
+        "algorithmic_bytes_per_frame": alg,
+        "achieved_GB_per_s": alg / (ms * 1e-3) / 1e9,
+        "frac_of_hbm_peak": alg / (ms * 1e-3) / 1e9 / peak,
+        "trace_to_window_ms": e2e_ms,
+        "trace_to_window_d2h_bytes": npx * 4,
+        "timing": "CUDA events on the launching stream around the %d launches of each frame, warm L2" % launches,
+    }
+
+
 def run_b200(args):
     import torch
     import torch.distributed as dist
@@ -675,6 +731,8 @@ def run_b200(args):
                 "counters": {"rays": m.rays, "iters": m.iters, "sector_fetches": m.sector_fetches, "cell_fetches": m.cell_fetches, "hits": m.hits, "capped": m.capped},
             },
         }
+        if args.present and n_gpus == 1:
+            line["present"] = present_block(args, ctx, frame, stream, fb, w, h, peak)
         if not args.no_cpu and n_gpus == 1:
             run, kind, cores, rays = cpu_arm(args, scene, recs)
             run()
@@ -708,6 +766,8 @@ def main():
     ap.add_argument("--bounces", type=int, default=None)
     ap.add_argument("--edits", type=int, default=4096, help="workload 'edits': voxel edits per frame")
     ap.add_argument("--edit-mode", default="random", choices=["random", "brush"], help="workload 'edits': uniform single-voxel edits, or the reference's brush strokes")
+    ap.add_argument("--present", action="store_true", help="also time the step after the path (the reference's GBuffer: denoise + present) and add a 'present' block")
+    ap.add_argument("--present-passes", type=int, default=5, help="GBuffer::NumDenoiserPasses for --present (0..5)")
     ap.add_argument("--scene-file", default=None, help="workload 'file': a cvox 0004 voxel-map file written by the reference (or by scenes/cvox.py)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()

@@ -169,11 +169,66 @@ static void test_gpu() {
     std::printf("gpu: %.1f Mrays/s (host-buffer frame), %llu bricks resident\n", r.RaysPerSecondOfLastFrame() / 1e6, (unsigned long long)st.resident_bricks);
 }
 
+// ---- GPU: RenderFrame through GBuffer::DenoiseAndPresent vs the two oracles chained ----------------------------
+extern "C" {
+struct PostOracle;
+PostOracle* post_oracle_create(int w, int h);
+void post_oracle_destroy(PostOracle*);
+void post_oracle_set_camera(PostOracle*, const float proj[16], const float inv_proj[16], const double pos[3]);
+void post_oracle_frame(PostOracle*, const uint32_t* tiles, int reset_history, int num_passes, int debug_channel, uint32_t* out_rgba8);
+}
+static void test_gpu_present() {
+    auto map = std::make_shared<VoxelMap>();
+    fill_scene(*map);
+    B200Renderer r(map, 0);
+    r.NumLightBounces = 0;
+    r.DenoiseAndPresent = true;
+    r.NumDenoiserPasses = 3;
+    Camera cam;
+    cam.Euler[0] = 0.1f, cam.Euler[1] = -0.5f;
+    uvec2 size{320, 180};
+    cam.AspectRatio = 320.0f / 180.0f;
+    PostOracle* po = post_oracle_create(320, 180);
+    OrcMap* orc = orc_map_create(6, 4);
+    oracle_sync_all(orc, *map);
+    for (int frame = 0; frame < 4; frame++) {
+        cam.ViewPosition = {80.3 + 0.4 * frame, 60.7, 12.2 + 0.3 * frame};
+        const bool worldChanged = !map->DirtyLocs.empty();  // frame 0: MarkAllDirty in the constructor
+        r.RenderFrame(cam, size);
+        mat4 proj = cam.GetProjMatrix() * cam.GetViewMatrix(false);
+        mat4 inv = GetInverseProjScreenMat(proj, size.x, size.y);
+        VrtFrame f{};
+        f.width = size.x, f.height = size.y;
+        std::memcpy(f.inv_proj, inv.m, 64);
+        std::memcpy(f.proj, proj.m, 64);
+        const double p[3] = {cam.ViewPosition.x, cam.ViewPosition.y, cam.ViewPosition.z};
+        for (int a = 0; a < 3; a++) f.world_origin[a] = (int32_t)std::floor(p[a]), f.origin_frac[a] = (float)(p[a] - std::floor(p[a]));
+        f.frame_no = r.FrameNo, f.bounces = 0, f.part_count = 1;
+        std::vector<VrtTile> tiles((size_t)size.x * size.y / 16);
+        orc_render(orc, &f, tiles.data(), nullptr, nullptr, 0, 0, size.y);
+        std::vector<uint32_t> want((size_t)size.x * size.y);
+        post_oracle_set_camera(po, proj.m, inv.m, p);
+        post_oracle_frame(po, (const uint32_t*)tiles.data(), worldChanged ? 1 : 0, 3, 0, want.data());
+        CHECK(r.Presented().size() == want.size());
+        CHECK(std::memcmp(want.data(), r.Presented().data(), want.size() * 4) == 0);
+    }
+    orc_map_destroy(orc);
+    post_oracle_destroy(po);
+    std::printf("gpu-present: 4 frames through RenderFrame + DenoiseAndPresent equal the oracles\n");
+}
+
 int main(int argc, char** argv) {
     test_indexers();
     test_voxel_map();
     test_arena();
-    if (argc > 1 && !std::strcmp(argv[1], "--gpu")) {
+    if (argc > 1 && !std::strcmp(argv[1], "--gpu-present")) {
+        try {
+            test_gpu_present();
+        } catch (const std::exception& e) {
+            std::printf("FAIL exception: %s\n", e.what());
+            g_fail++;
+        }
+    } else if (argc > 1 && !std::strcmp(argv[1], "--gpu")) {
         try {
             test_gpu();
         } catch (const std::exception& e) {

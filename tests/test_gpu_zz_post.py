@@ -169,3 +169,15 @@ def test_size_change_drops_history_and_errors_are_loud():
         gb.set_passes(6)
     with pytest.raises(capi.VrtError):
         gb.set_camera(post.make_camera(30, 20, proj, inv, pos))
+
+
+def test_native_adapter_denoise_and_present():
+    """vrt_host::B200Renderer with DenoiseAndPresent = true (C++ host, tests/native/test_host.cpp --gpu-present): four
+    frames from a moving camera, presented image == traversal oracle + image-space oracle chained."""
+    import subprocess
+
+    exe = Path(__file__).resolve().parent / "native" / "test_host"
+    if not exe.exists():
+        subprocess.run(["make", "-s", "-C", str(exe.parent)], check=True)
+    r = subprocess.run([str(exe), "--gpu-present"], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "native tests: ok" in r.stdout and "gpu-present:" in r.stdout, r.stdout + r.stderr
