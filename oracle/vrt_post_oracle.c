@@ -22,9 +22,12 @@
  * vec dot / mat*vec accumulate left to right; mix(a,b,t) = a*(1-t) + b*t (GLSL definition);
  * max(a,b) = a<b ? b : a, min(a,b) = b<a ? b : a (NaN keeps the first operand); rgba16f / rg16f image
  * stores round to nearest even; unorm8 stores are (int)(clamp(c,0,1)*255 + 0.5); exp() and log() are
- * the polynomial forms post_exp / post_log below (relative error < 2e-7, bit-reproducible on any IEEE
+ * the polynomial forms post_exp / post_log below (relative error < 3e-7, bit-reproducible on any IEEE
  * machine); pow(x,128) is seven squarings; pow(c,0.45) = post_exp(0.45 * post_log(c)), 0 for c below the
- * smallest normal.  Out-of-range image loads return 0 (robust buffer access).
+ * smallest normal.  The two per-tap quotients of the filters (w_luma = |dl| / lumaPhi, w_depth = |dd| / (length + 0.001),
+ * Filter.comp:51,57,117,123) are evaluated as a * (1/b) with a correctly rounded reciprocal — what GPU GLSL compilers emit
+ * for `/` (the spec allows 2.5 ulp), and the divisor is per pixel / per tap, so the reciprocal is shared by all taps.
+ * Out-of-range image loads return 0 (robust buffer access).
  *
  * One documented deviation: Reproject.comp reads u_HistoryLenTex at NEIGHBOUR positions (:78) while
  * other invocations of the same dispatch store to it (:100,106) — a data race whose outcome depends
@@ -315,10 +318,10 @@ static void variance_pass(PostOracle* o) {
                     float v[4], n[3];
                     load_h4(o->irr, j, v);
                     float l = luminance(v);
-                    float w_luma = fabsf(l - cl) / luma_phi;
+                    float w_luma = fabsf(l - cl) * (1.0f / luma_phi);
                     unpack_normal(o->albedo[j], n);
                     float w_normal = pow128(fmin_g(fmax_g(dot3(n, cn), 0.001f), 1.0f));
-                    float w_depth = fabsf(cd - o->depth[j]) / (sqrtf((float)kx * (float)kx + (float)ky * (float)ky) + 0.001f);
+                    float w_depth = fabsf(cd - o->depth[j]) * (1.0f / (sqrtf((float)kx * (float)kx + (float)ky * (float)ky) + 0.001f));
                     float w = post_exp(-(w_luma + w_depth)) * w_normal;
                     for (int k = 0; k < 3; k++) si[k] = si[k] + v[k] * w;
                     sm[0] = sm[0] + l * w; sm[1] = sm[1] + (l * l) * w;
@@ -366,10 +369,10 @@ static void atrous_pass(PostOracle* o, const Half4* in, Half4* out, int pass_no)
                     size_t j = (size_t)sy * o->w + sx;
                     float v[4], n[3];
                     load_h4(in, j, v);
-                    float w_luma = fabsf(luminance(v) - cl) / luma_phi;
+                    float w_luma = fabsf(luminance(v) - cl) * (1.0f / luma_phi);
                     unpack_normal(o->albedo[j], n);
                     float w_normal = pow128(fmin_g(fmax_g(dot3(n, cn), 0.001f), 1.0f));
-                    float w_depth = fabsf(cd - o->depth[j]) / (sqrtf((float)ox * (float)ox + (float)oy * (float)oy) + 0.001f);
+                    float w_depth = fabsf(cd - o->depth[j]) * (1.0f / (sqrtf((float)ox * (float)ox + (float)oy * (float)oy) + 0.001f));
                     float w = kern[abs(kx)] * kern[abs(ky)];
                     w = w * (post_exp(-(w_luma + w_depth)) * w_normal);
                     for (int k = 0; k < 3; k++) sum[k] = sum[k] + v[k] * w;

@@ -49,6 +49,46 @@ for passes, frames, moving in ((5, 5, True), (0, 4, True), (2, 4, True), (1, 3, 
             worst[k] = max(worst.get(k, 0), v)
     res[f"passes{passes}"] = worst
     gb.close()
+# real traced frames (1 bounce, blue noise, sky) from a moving camera; then the one-call trace->window entry point
+from scenes import camera, shading, terrain  # noqa: E402
+from voxelrt_b200 import capi  # noqa: E402
+
+scene = terrain.terrain_hash(6, 4, 6, seed=77)
+ctx = capi.Context(6, 4, device=0)
+ctx.set_palette(scene["palette"])
+ctx.sync(terrain.scene_records(scene))
+ctx.set_blue_noise(shading.load_blue_noise()[0])
+sd, st, _ = shading.load_sky()
+ctx.set_sky(sd, st)
+w, h = 256, 144
+gb, gb2, orc = post.GBuffer(0), post.GBuffer(0), pp.PostOracle(w, h)
+worst = {"rgba": 0, "irr": 0, "hist": 0, "render_present": 0}
+for f in range(5):
+    cam = camera.Camera(pos=(96.3 + 0.6 * f, 90.2 + 0.1 * f, 20.7 + 0.4 * f), yaw=0.2 + 0.01 * f, pitch=-0.45)
+    proj, inv, wo, frac = cam.matrices(w, h)
+    fr = capi.make_frame(w, h, inv, proj, wo, frac, frame_no=f + 1, bounces=1)
+    out, _ = ctx.render(fr)
+    tiles = np.frombuffer(out.tobytes(), dtype=capi.TILE_DTYPE).copy()
+    gc = post.make_camera(w, h, proj, inv, cam.pos)
+    gb.set_camera(gc)
+    orc.set_camera(proj, inv, cam.pos)
+    ig, io = gb.denoise_present(tiles), orc.denoise_present(tiles)
+    gb2.set_camera(gc)
+    ip = gb2.render_present(ctx, capi.make_frame(w, h, inv, proj, wo, frac, frame_no=f + 1, bounces=1))
+    d = {"rgba": int((ig != io).sum()), "irr": int((gb.read(0)["irr"] != orc.read(orc.IRR)).any(axis=1).sum()),
+         "hist": int((gb.read(4) != orc.read(orc.HIST)).sum()), "render_present": int((ip != io).sum())}
+    say(f"traced frame={f} mismatching pixels: {d}; history>0: {float((orc.read(orc.HIST) > 0).mean()):.3f}")
+    for k, v in d.items():
+        worst[k] = max(worst[k], v)
+res["traced"] = worst
+gb.close()
+gb2.close()
+ctx.close()
+import subprocess  # noqa: E402
+
+r = subprocess.run([str(ROOT / "tests" / "native" / "test_host"), "--gpu-present"], capture_output=True, text=True, timeout=120)
+say("native:", r.stdout.strip().replace("\n", " | "), r.stderr.strip()[:300])
+res["native_present_ok"] = (r.returncode == 0)
 say("parity seconds", round(time.time() - t0, 2))
 
 # timing at 3840x2160 on device buffers (wall clock around K frames with a device synchronise on both sides)

@@ -12,6 +12,7 @@
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
 
+#include <cmath>
 #include <cstdio>
 #include <cstring>
 #include <string>
@@ -229,15 +230,55 @@ __global__ void __launch_bounds__(256) k_reproject(const uint32_t* __restrict__ 
     }
 }
 
-// Filter tap weight shared by both filter kernels: exp(-(w_luma + w_depth)) * pow(clamp(dot(n, cn), .001, 1), 128)
-__device__ __forceinline__ float tap_weight(float w_luma, float depth_diff, float dist, const float3 n, const float3 cn) {
-    const float w_normal = pow128(ming(maxg(dot3(n.x, n.y, n.z, cn.x, cn.y, cn.z), 0.001f), 1.0f));
-    const float w_depth = __fdiv_rn(depth_diff, __fadd_rn(dist, 0.001f));
-    return __fmul_rn(post_exp(-__fadd_rn(w_luma, w_depth)), w_normal);
+// ---- filter taps ----------------------------------------------------------------------------------------------------------
+// The à-trous passes are INSTRUCTION-bound, not memory-bound (first B200 run: 0.8 ms per 4K pass for 32 B/px of HBM traffic,
+// ~90 instructions per tap), so the tap is spelled for the SM's pipes while producing the oracle's bits:
+//   * pow(clamp(dot(n, cn), .001, 1), 128): normals are integer vectors, so the dot product is an integer, the clamp gives 1
+//     (dot >= 1) or 0.001, and seven squarings give exactly 1.0f or 0.0f — computed as an integer dot product and a select;
+//   * exp(): rint() through the 1.5*2^23 magic add (FADD on the FMA pipe instead of FRND/F2I on the quarter-rate pipe), the
+//     2^n scaling as an integer add on the exponent field (exact, like the multiplication it replaces);
+//   * the two quotients are a * (1/b) by definition (oracle header); 1/lumaPhi is per pixel, 1/(length + 0.001) per tap and
+//     computed on the host (IEEE sqrt and division), so no division is left in the loop;
+//   * kernels are templated on the pass number: tap offsets and kernel weights are immediates, the 25 record addresses are
+//     five row pointers plus constant offsets; CTAs whose taps all fall inside the image skip the bounds tests.
+__device__ __forceinline__ float post_exp_neg(float x) {  // == post_exp(x), restated (x <= 0 or NaN in the filters)
+    if (x != x) return x;
+    if (!(x > -87.0f)) return 0.0f;
+    if (x > 88.0f) x = 88.0f;
+    const float tm = __fadd_rn(__fmul_rn(x, 1.44269502f), 12582912.0f);  // low mantissa bits = rint(t), two's complement
+    const float n = __fsub_rn(tm, 12582912.0f);
+    float r = __fmaf_rn(n, -0.693145752f, x);
+    r = __fmaf_rn(n, -1.42860677e-06f, r);
+    float p = 1.38888892e-03f;
+    p = __fmaf_rn(p, r, 8.33333377e-03f);
+    p = __fmaf_rn(p, r, 4.16666679e-02f);
+    p = __fmaf_rn(p, r, 1.66666672e-01f);
+    p = __fmaf_rn(p, r, 0.5f);
+    p = __fmaf_rn(p, r, 1.0f);
+    p = __fmaf_rn(p, r, 1.0f);
+    return __int_as_float(__float_as_int(p) + ((__float_as_int(tm) - 0x4B400000) << 23));  // p in [0.7, 1.42), n >= -126: stays normal
+}
+// integer components of unpackGNormal: each in {-1, 0, 1, 2}
+struct INormal {
+    int x, y, z;
+};
+__device__ __forceinline__ INormal inormal(uint32_t albedo_normal) {
+    const uint32_t a = albedo_normal >> 24;
+    return {(int)(a & 3u) - 1, (int)((a >> 2) & 3u) - 1, (int)((a >> 4) & 3u) - 1};
+}
+// exp(-(w_luma + w_depth)) * w_normal
+__device__ __forceinline__ float tap_weight(float w_luma, float w_depth, const INormal n, const INormal cn) {
+    const float w_normal = (n.x * cn.x + n.y * cn.y + n.z * cn.z) >= 1 ? 1.0f : 0.0f;
+    return __fmul_rn(post_exp_neg(-__fadd_rn(w_luma, w_depth)), w_normal);
 }
 
+struct TapRcp {
+    float v[49];  // 1 / (length(offset) + 0.001) per tap, row-major over the (2R+1)^2 window
+};
+
 // ---- Filter.comp pass -1: varianceEstim (:17-68).  in = IrradianceTex records, io_temp = TempIrradianceTex records -------
-__global__ void __launch_bounds__(256) k_variance(const uint4* __restrict__ in, const uint8_t* __restrict__ hist, uint4* io_temp, int w, int h) {
+__global__ void __launch_bounds__(256) k_variance(const uint4* __restrict__ in, const uint8_t* __restrict__ hist, uint4* io_temp, int w, int h,
+                                                  const __grid_constant__ TapRcp rcp) {
     const int x = blockIdx.x * 32 + threadIdx.x, y = blockIdx.y * 8 + threadIdx.y;
     if (x >= w || y >= h) return;
     const size_t i = (size_t)y * w + x;
@@ -250,20 +291,21 @@ __global__ void __launch_bounds__(256) k_variance(const uint4* __restrict__ in, 
     }
     const Rec stale = unpack(io_temp[i]);  // :26 reads the centre from the TEMP texture
     const float cl = luminance(stale.r, stale.g, stale.b);
-    const float3 cn = unpack_normal(c.albedo);
+    const INormal cn = inormal(c.albedo);
     float sr = 0.0f, sg = 0.0f, sb = 0.0f, s0 = 0.0f, s1 = 0.0f, wsum = 0.0f;
+#pragma unroll
     for (int ky = -3; ky <= 3; ky++) {
         const int sy = y + ky;
         if ((uint32_t)sy >= (uint32_t)h) continue;
+        const uint4* row = in + (size_t)sy * w + x;
 #pragma unroll
         for (int kx = -3; kx <= 3; kx++) {
-            const int sx = x + kx;
-            if ((uint32_t)sx >= (uint32_t)w) continue;
-            const Rec t = unpack(__ldg(in + (size_t)sy * w + sx));
+            if ((uint32_t)(x + kx) >= (uint32_t)w) continue;
+            const Rec t = unpack(__ldg(row + kx));
             const float l = luminance(t.r, t.g, t.b);
-            const float w_luma = __fdiv_rn(fabsf(__fsub_rn(l, cl)), 10.0f);
-            const float dist = __fsqrt_rn(__fadd_rn(__fmul_rn((float)kx, (float)kx), __fmul_rn((float)ky, (float)ky)));
-            const float wgt = tap_weight(w_luma, fabsf(__fsub_rn(c.depth, t.depth)), dist, unpack_normal(t.albedo), cn);
+            const float w_luma = __fmul_rn(fabsf(__fsub_rn(l, cl)), 0.1f);  // 1/lumaPhi, lumaPhi = 10
+            const float w_depth = __fmul_rn(fabsf(__fsub_rn(c.depth, t.depth)), rcp.v[(ky + 3) * 7 + (kx + 3)]);
+            const float wgt = tap_weight(w_luma, w_depth, inormal(t.albedo), cn);
             sr = __fadd_rn(sr, __fmul_rn(t.r, wgt));
             sg = __fadd_rn(sg, __fmul_rn(t.g, wgt));
             sb = __fadd_rn(sb, __fmul_rn(t.b, wgt));
@@ -281,11 +323,12 @@ __global__ void __launch_bounds__(256) k_variance(const uint4* __restrict__ in, 
 }
 
 // ---- Filter.comp pass >= 0: svgfAtrous + getFilteredVariance (:70-135) -------------------------------------------------
-__global__ void __launch_bounds__(256) k_atrous(const uint4* __restrict__ in, uint4* __restrict__ out, int w, int h, int pass_no) {
-    const int x = blockIdx.x * 32 + threadIdx.x, y = blockIdx.y * 8 + threadIdx.y;
-    if (x >= w || y >= h) return;
+template <int PASS, bool INTERIOR>
+__device__ __forceinline__ void atrous_pixel(const uint4* __restrict__ in, uint4* __restrict__ out, int x, int y, int w, int h, const TapRcp& rcp) {
+    constexpr int D = 1 << PASS;
     const size_t i = (size_t)y * w + x;
-    const uint4 cq = __ldg(in + i);
+    const uint4* centre = in + i;
+    const uint4 cq = __ldg(centre);
     const Rec c = unpack(cq);
     if (c.depth < 0.0f) {
         out[i] = cq;
@@ -296,31 +339,29 @@ __global__ void __launch_bounds__(256) k_atrous(const uint4* __restrict__ in, ui
     for (int ky = -1; ky <= 1; ky++)
 #pragma unroll
         for (int kx = -1; kx <= 1; kx++) {
-            const int sx = x + kx, sy = y + ky;
             float v = 0.0f;  // imageLoad outside the image returns 0
-            if ((uint32_t)sx < (uint32_t)w && (uint32_t)sy < (uint32_t)h) v = h2f(__ldg(&in[(size_t)sy * w + sx].y) >> 16);
+            if ((uint32_t)(x + kx) < (uint32_t)w && (uint32_t)(y + ky) < (uint32_t)h) v = h2f(__ldg(&(centre + (ptrdiff_t)ky * w + kx)->y) >> 16);
             const float k = (kx == 0 ? 0.25f : 0.125f) * (ky == 0 ? 1.0f : 0.5f);  // kernel[|kx|][|ky|] = {1/4,1/8;1/8,1/16}
             cv = __fadd_rn(cv, __fmul_rn(v, k));
         }
-    const float3 cn = unpack_normal(c.albedo);
+    const INormal cn = inormal(c.albedo);
     const float cl = luminance(c.r, c.g, c.b);
-    const float luma_phi = __fmul_rn(__fsqrt_rn(maxg(0.0001f, cv)), 4.0f);
+    const float inv_phi = __fdiv_rn(1.0f, __fmul_rn(__fsqrt_rn(maxg(0.0001f, cv)), 4.0f));
     float sr = c.r, sg = c.g, sb = c.b, sv = c.var, wsum = 1.0f;
 #pragma unroll
     for (int ky = -2; ky <= 2; ky++) {
-        const int oy = ky * (1 << pass_no), sy = y + oy;
-        if ((uint32_t)sy >= (uint32_t)h) continue;
+        if (!INTERIOR && (uint32_t)(y + ky * D) >= (uint32_t)h) continue;
+        const uint4* row = centre + (ptrdiff_t)(ky * D) * w;
 #pragma unroll
         for (int kx = -2; kx <= 2; kx++) {
             if (kx == 0 && ky == 0) continue;
-            const int ox = kx * (1 << pass_no), sx = x + ox;
-            if ((uint32_t)sx >= (uint32_t)w) continue;
-            const Rec t = unpack(__ldg(in + (size_t)sy * w + sx));
-            const float w_luma = __fdiv_rn(fabsf(__fsub_rn(luminance(t.r, t.g, t.b), cl)), luma_phi);
-            const float dist = __fsqrt_rn(__fadd_rn(__fmul_rn((float)ox, (float)ox), __fmul_rn((float)oy, (float)oy)));
+            if (!INTERIOR && (uint32_t)(x + kx * D) >= (uint32_t)w) continue;
+            const Rec t = unpack(__ldg(row + kx * D));
+            const float w_luma = __fmul_rn(fabsf(__fsub_rn(luminance(t.r, t.g, t.b), cl)), inv_phi);
+            const float w_depth = __fmul_rn(fabsf(__fsub_rn(c.depth, t.depth)), rcp.v[(ky + 2) * 5 + (kx + 2)]);
             const float kxw = kx == 0 ? 0.375f : ((kx == 1 || kx == -1) ? 0.25f : 0.0625f);
             const float kyw = ky == 0 ? 0.375f : ((ky == 1 || ky == -1) ? 0.25f : 0.0625f);
-            const float wgt = __fmul_rn(__fmul_rn(kxw, kyw), tap_weight(w_luma, fabsf(__fsub_rn(c.depth, t.depth)), dist, unpack_normal(t.albedo), cn));
+            const float wgt = __fmul_rn(kxw * kyw, tap_weight(w_luma, w_depth, inormal(t.albedo), cn));
             sr = __fadd_rn(sr, __fmul_rn(t.r, wgt));
             sg = __fadd_rn(sg, __fmul_rn(t.g, wgt));
             sb = __fadd_rn(sb, __fmul_rn(t.b, wgt));
@@ -330,6 +371,20 @@ __global__ void __launch_bounds__(256) k_atrous(const uint4* __restrict__ in, ui
     }
     if (wsum < 0.001f) wsum = 0.001f;
     out[i] = pack(__fdiv_rn(sr, wsum), __fdiv_rn(sg, wsum), __fdiv_rn(sb, wsum), __fdiv_rn(sv, __fmul_rn(wsum, wsum)), c.depth, c.albedo);
+}
+
+template <int PASS>
+__global__ void __launch_bounds__(256) k_atrous(const uint4* __restrict__ in, uint4* __restrict__ out, int w, int h, const __grid_constant__ TapRcp rcp) {
+    constexpr int R = 2 << PASS;
+    const int x0 = blockIdx.x * 32, y0 = blockIdx.y * 8;
+    const int x = x0 + threadIdx.x, y = y0 + threadIdx.y;
+    const bool interior = x0 >= R && y0 >= R && x0 + 31 + R < w && y0 + 7 + R < h;  // uniform per CTA
+    if (interior) {
+        atrous_pixel<PASS, true>(in, out, x, y, w, h, rcp);
+    } else {
+        if (x >= w || y >= h) return;
+        atrous_pixel<PASS, false>(in, out, x, y, w, h, rcp);
+    }
 }
 
 // ---- GBufferBlit.frag:8-46 ------------------------------------------------------------------------------------------------
@@ -431,6 +486,22 @@ int gfail(VrtGBuffer* g, int status, const std::string& msg) {
         cudaError_t e__ = (call);                                                                                    \
         if (e__ != cudaSuccess) return gfail(gb, VRT_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e__)); \
     } while (0)
+
+// 1 / (length(offset) + 0.001) for the (2r+1)^2 taps at dilation d: IEEE sqrt, add, divide, as the oracle computes them per tap
+TapRcp tap_rcp(int r, int d) {
+    TapRcp t{};
+    const int n = 2 * r + 1;
+    for (int ky = -r; ky <= r; ky++)
+        for (int kx = -r; kx <= r; kx++) {
+            const float fx = (float)(kx * d), fy = (float)(ky * d);
+            volatile float sq = fx * fx;  // volatile: no contraction of fx*fx + fy*fy by the host compiler
+            volatile float sq2 = fy * fy;
+            volatile float len = std::sqrt((float)(sq + sq2));
+            volatile float den = len + 0.001f;
+            t.v[(ky + r) * n + (kx + r)] = 1.0f / den;
+        }
+    return t;
+}
 
 void free_planes(VrtGBuffer* g) {
     void* ps[] = {g->irr, g->prev_irr, g->temp_irr, g->moments, g->prev_moments, g->hist, g->hist_prev, g->d_tiles, g->d_rgba};
@@ -568,12 +639,19 @@ VRT_API int vrt_gbuffer_denoise_present_device(VrtGBuffer* gb, const void* d_til
         k_reproject<<<grid, block, 0, s>>>(tiles, gb->prev_irr, gb->prev_moments, gb->hist_prev, gb->irr, gb->moments, gb->hist, P);
         launches++;
         if (gb->num_passes > 0) {
-            k_variance<<<grid, block, 0, s>>>(gb->irr, gb->hist, gb->temp_irr, w, h);
+            k_variance<<<grid, block, 0, s>>>(gb->irr, gb->hist, gb->temp_irr, w, h, tap_rcp(3, 1));
             launches++;
             for (uint32_t i = 0; i < gb->num_passes; i++) {  // GBuffer.h:103-121
                 const uint4* in = i == 1 ? gb->prev_irr : (i % 2 == 0 ? gb->temp_irr : gb->irr);
                 uint4* out = i % 2 == 0 ? gb->irr : gb->temp_irr;
-                k_atrous<<<grid, block, 0, s>>>(in, out, w, h, (int)i);
+                const TapRcp tr = tap_rcp(2, 1 << i);
+                switch (i) {
+                case 0: k_atrous<0><<<grid, block, 0, s>>>(in, out, w, h, tr); break;
+                case 1: k_atrous<1><<<grid, block, 0, s>>>(in, out, w, h, tr); break;
+                case 2: k_atrous<2><<<grid, block, 0, s>>>(in, out, w, h, tr); break;
+                case 3: k_atrous<3><<<grid, block, 0, s>>>(in, out, w, h, tr); break;
+                default: k_atrous<4><<<grid, block, 0, s>>>(in, out, w, h, tr); break;
+                }
                 launches++;
                 if (i == 0) std::swap(gb->prev_irr, gb->irr);
             }
