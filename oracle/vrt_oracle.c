@@ -790,3 +790,182 @@ void orc_render(const OrcMap* m, const VrtFrame* f, void* out, VrtHit* aux_hits,
     }
     if (stats) *stats = total;
 }
+
+/* ------------------------------------------------------------------------------------------ */
+/* GLSL-renderer ray casts: rayCast / rayCastCoarse / getStepPos of the     */
+/* reference's GPU renderer, VoxelRT/Shaders/VoxelTraversal.glsl:14-52,92-131,162-243, with      */
+/* VoxelMap.glsl:28-76 addressing.  PARITY UNPINNED (GLSL needs a GL device).  Canonical          */
+/* arithmetic: IEEE binary32 RN, one operation at a time, no FMA; min(a,b) = b<a ? b : a,         */
+/* max(a,b) = a<b ? b : a; ivec3(floor(x)) of NaN / out-of-range values = INT_MIN (out of grid).  */
+/* ------------------------------------------------------------------------------------------ */
+static inline float glsl_min(float a, float b) { return b < a ? b : a; }
+static inline float glsl_max(float a, float b) { return a < b ? b : a; }
+static inline int32_t glsl_floor2i(float x) {
+    float f = floorf(x);
+    return (f >= -2147483648.0f && f < 2147483648.0f) ? (int32_t)f : (int32_t)0x80000000;
+}
+
+/* GenerateRayCellInteractionMaskLUT, VoxelRT/GpuRenderer.cpp:193-210: for every direction octant and origin cell of a
+ * 4x4x4 mask, the cells a ray travelling in that octant can still reach. */
+void orc_interaction_lut(uint64_t table[512]) {
+    for (uint32_t oct = 0; oct < 8; oct++) {
+        int dir[3] = {(int)(oct & 1) * 2 - 1, (int)((oct >> 1) & 1) * 2 - 1, (int)((oct >> 2) & 1) * 2 - 1}; /* x, y, z */
+        for (uint32_t origin = 0; origin < 64; origin++) {
+            int o[3] = {(int)(origin & 3), (int)((origin >> 4) & 3), (int)((origin >> 2) & 3)}; /* MaskIndexer: x | z<<2 | y<<4 */
+            uint64_t mask = 0;
+            for (uint32_t j = 0; j < 64; j++) {
+                int p[3] = {o[0] + (int)(j & 3) * dir[0], o[1] + (int)((j >> 4) & 3) * dir[1], o[2] + (int)((j >> 2) & 3) * dir[2]};
+                if ((unsigned)p[0] < 4 && (unsigned)p[1] < 4 && (unsigned)p[2] < 4) mask |= 1ull << (p[0] | p[2] << 2 | p[1] << 4);
+            }
+            table[origin + oct * 64] = mask;
+        }
+    }
+}
+
+/* SectorMasks[] of the GPU storage (GpuRenderer.cpp:134-142): bit = sector has any brick allocated */
+static uint64_t sector_group_mask(const OrcMap* m, uint32_t gx, uint32_t gy, uint32_t gz) {
+    uint64_t g = 0;
+    for (uint32_t i = 0; i < 64; i++) {
+        uint32_t si = sector_index(m, (int32_t)(gx * 4 + (i & 3)), (int32_t)(gy * 4 + ((i >> 4) & 3)), (int32_t)(gz * 4 + ((i >> 2) & 3)));
+        if (m->sector_masks[si]) g |= 1ull << i;
+    }
+    return g;
+}
+
+/* getStepPos, VoxelTraversal.glsl:92-131.  Returns 1 when the ray may step on (p moved to the far corner of the empty
+ * cell), 0 on a hit (coarse hits move p to an occupied voxel of the 4^3 cell, :127). */
+static int glsl_step_pos(const OrcMap* m, int32_t p[3], const float d[3], int coarse, int aniso, const uint64_t* lut, CastCounters* c) {
+    uint32_t si = sector_index(m, p[0] >> 5, p[1] >> 5, p[2] >> 5);
+    uint64_t mask = m->sector_masks[si]; /* BrickMasks[] = allocation mask */
+    c->sector_fetches++;
+    uint32_t idx = ((uint32_t)(p[0] >> 3) & 3) | (((uint32_t)(p[2] >> 3) & 3) << 2) | (((uint32_t)(p[1] >> 3) & 3) << 4);
+    int scale = 8;
+    if ((mask >> idx) & 1) { /* isFineLod: brick allocated -> its 4^3 cell mask (:101-109) */
+        uint32_t cell = ((uint32_t)(p[0] >> 2) & 1) | (((uint32_t)(p[2] >> 2) & 1) << 1) | (((uint32_t)(p[1] >> 2) & 1) << 2);
+        mask = m->sector_cells[si] ? m->sector_cells[si][idx * 8 + cell] : 0;
+        c->cell_fetches++;
+        idx = ((uint32_t)p[0] & 3) | (((uint32_t)p[2] & 3) << 2) | (((uint32_t)p[1] & 3) << 4);
+        scale = 1;
+        if ((mask >> idx) & 1) return 0;
+    } else if (mask == 0) { /* sector without bricks -> the 128^3 level (:110-114) */
+        mask = sector_group_mask(m, (uint32_t)(p[0] >> 7), (uint32_t)(p[1] >> 7), (uint32_t)(p[2] >> 7));
+        idx = ((uint32_t)(p[0] >> 5) & 3) | (((uint32_t)(p[2] >> 5) & 3) << 2) | (((uint32_t)(p[1] >> 5) & 3) << 4);
+        scale = 32;
+    }
+    if (aniso) { /* :116-121 */
+        uint32_t oct = (d[0] < 0 ? 0u : 1u) + (d[1] < 0 ? 0u : 2u) + (d[2] < 0 ? 0u : 4u);
+        mask &= lut[idx + oct * 64];
+    }
+    uint32_t half = idx < 32 ? (uint32_t)mask : (uint32_t)(mask >> 32);
+    int lod = (mask == 0 ? 4 : (((half >> (idx & 0xA)) & 0x00330033u) == 0 ? 2 : 1)) * scale; /* getIsotropicLod :22-32 */
+    if (coarse && lod < 4) { /* findAnyOccupiedPos :40-52 */
+        uint32_t cur = (uint32_t)mask, bit = 0;
+        if (cur == 0) { bit = 32; cur = (uint32_t)(mask >> 32); }
+        bit += (uint32_t)__builtin_ctz(cur);
+        p[0] = (p[0] & ~3) | (int32_t)(bit & 3);
+        p[1] = (p[1] & ~3) | (int32_t)((bit >> 4) & 3);
+        p[2] = (p[2] & ~3) | (int32_t)((bit >> 2) & 3);
+        return 0;
+    }
+    int32_t cm = lod - 1;
+    for (int a = 0; a < 3; a++) p[a] = d[a] < 0 ? (p[a] & ~cm) : (p[a] | cm); /* alignToCellBoundaries :33-39 */
+    return 1;
+}
+
+/* clipRayToAABB, VoxelTraversal.glsl:133-145 with the bounds rayCast passes (:173,207) */
+static void glsl_clip(const OrcMap* m, const float o[3], const float d[3], const int32_t wo[3], float out[3]) {
+    float grid[3] = {(float)(1u << (m->shift_xz + 5)), (float)(1u << (m->shift_y + 5)), (float)(1u << (m->shift_xz + 5))};
+    float t1[3], t2[3];
+    for (int a = 0; a < 3; a++) {
+        float inv = 1.0f / d[a];
+        float lo = (float)(int32_t)(1u - (uint32_t)wo[a]);        /* -u_WorldOrigin + 1 (integer arithmetic) */
+        float hi = (grid[a] - (float)wo[a]) - 1.0f;               /* vec3(GRID) - u_WorldOrigin - 1          */
+        float a1 = (lo - o[a]) * inv, a2 = (hi - o[a]) * inv;
+        t1[a] = glsl_min(a1, a2);
+        t2[a] = glsl_max(a1, a2);
+    }
+    float tmin = glsl_max(t1[0], glsl_max(t1[1], t1[2]));
+    float tmax = glsl_min(t2[0], glsl_min(t2[1], t2[2]));
+    int clip = tmin > 0.0f && tmin < tmax;
+    for (int a = 0; a < 3; a++) out[a] = clip ? o[a] + d[a] * tmin : o[a];
+}
+
+static void glsl_cast(const OrcMap* m, const float o_in[3], const float d[3], const int32_t wo[3], uint32_t flags, const uint64_t* lut,
+                      VrtHit* out, CastCounters* cnt) {
+    const int coarse_mode = (flags & VRT_GLSL_COARSE) != 0, aniso = (flags & VRT_GLSL_ANISOTROPIC) != 0;
+    const uint32_t cap = coarse_mode ? 96u : 256u; /* :176,211 */
+    float o[3] = {o_in[0], o_in[1], o_in[2]}, start[3], inv[3], ts[3], sd[3] = {0, 0, 0}, cur[3] = {0, 0, 0};
+    glsl_clip(m, o, d, wo, start);
+    if (coarse_mode) memcpy(o, start, sizeof(o)); /* rayCastCoarse moves the origin itself (:207) */
+    for (int a = 0; a < 3; a++) {
+        inv[a] = 1.0f / d[a];
+        ts[a] = ((d[a] < 0.0f ? 0.0f : 1.0f) - o[a]) * inv[a]; /* (step(0, dir) - origin) * invDir */
+    }
+    int32_t p[3];
+    for (int a = 0; a < 3; a++) p[a] = (int32_t)((uint32_t)wo[a] + (uint32_t)glsl_floor2i(start[a]));
+    int hit = 0, inb = 1;
+    float tmin = 0.0f;
+    uint32_t i = 0;
+    for (; i < cap; i++) {
+        cnt->iters++;
+        for (int a = 0; a < 3; a++) sd[a] = ts[a] + (float)(int32_t)((uint32_t)p[a] - (uint32_t)wo[a]) * inv[a];
+        tmin = glsl_min(glsl_min(sd[0], sd[1]), sd[2]);
+        tmin = coarse_mode ? tmin + 0.001f : u2f(f2u(tmin) + 5u); /* :215 / :179-180 */
+        for (int a = 0; a < 3; a++) cur[a] = o[a] + tmin * d[a];
+        for (int a = 0; a < 3; a++) p[a] = (int32_t)((uint32_t)wo[a] + (uint32_t)glsl_floor2i(cur[a]));
+        inb = inbound(m, p[0], p[1], p[2]);
+        if (!inb) break;
+        if (!glsl_step_pos(m, p, d, coarse_mode && i > 30, aniso, lut, cnt)) { /* :218 coarse = i > 30 */
+            hit = 1;
+            break;
+        }
+    }
+    int capped = i >= cap;
+    int sm[3] = {tmin >= sd[0], tmin >= sd[1], tmin >= sd[2]}; /* :198,228 */
+    int nrm[3];
+    for (int a = 0; a < 3; a++) nrm[a] = sm[a] ? (d[a] > 0.0f ? -1 : (d[a] < 0.0f ? 1 : 0)) : 0; /* mix(0, -sign(dir), sideMask) */
+    out->vx = p[0];
+    out->vy = p[1];
+    out->vz = p[2];
+    out->material = hit ? voxel_material(m, p[0], p[1], p[2]) : 0u;
+    out->dist = tmin;
+    out->px = cur[0];
+    out->py = cur[1];
+    out->pz = cur[2];
+    float fu = sm[0] ? cur[1] : cur[0], fv = sm[2] ? cur[1] : cur[2]; /* fract(mix(currPos.xz, currPos.yy, sideMask.xz)) */
+    out->u = hit ? fu - floorf(fu) : 0.0f;
+    out->v = hit ? fv - floorf(fv) : 0.0f;
+    uint32_t iters_done = capped ? cap : i;
+    out->flags = (hit ? (uint32_t)((nrm[0] + 1) | ((nrm[1] + 1) << 2) | ((nrm[2] + 1) << 4)) : 21u) | (hit ? VRT_HIT_HIT : 0) |
+                 (inb ? VRT_HIT_INBOUND : 0) | (capped ? VRT_HIT_CAPPED : 0) | (iters_done << VRT_HIT_ITERS_SHIFT);
+    out->_pad = 0;
+}
+
+void orc_trace_glsl(const OrcMap* m, uint64_t n, const float* origin3, const float* dir3, const int32_t wo[3], uint32_t flags,
+                    VrtHit* out, OrcStats* stats, int threads) {
+    uint64_t lut[512];
+    orc_interaction_lut(lut);
+    OrcStats total;
+    memset(&total, 0, sizeof(total));
+#ifdef _OPENMP
+    if (threads <= 0) threads = omp_get_max_threads();
+#pragma omp parallel num_threads(threads)
+#endif
+    {
+        OrcStats local;
+        memset(&local, 0, sizeof(local));
+#ifdef _OPENMP
+#pragma omp for schedule(dynamic, 4096)
+#endif
+        for (int64_t i = 0; i < (int64_t)n; i++) {
+            CastCounters c = {0, 0, 0, {0}};
+            glsl_cast(m, origin3 + 3 * i, dir3 + 3 * i, wo, flags, lut, &out[i], &c);
+            stats_add(&local, &c, &out[i]);
+        }
+#ifdef _OPENMP
+#pragma omp critical
+#endif
+        stats_merge(&total, &local);
+    }
+    if (stats) *stats = total;
+}
