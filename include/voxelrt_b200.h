@@ -189,6 +189,20 @@ VRT_API int vrt_trace(VrtContext* ctx, uint64_t n, const float* origin3, const f
 VRT_API int vrt_trace_device(VrtContext* ctx, uint64_t n, const float* d_origin3, const float* d_dir3,
                              const int32_t world_origin[3], uint32_t max_iters, VrtHit* d_out, void* stream);
 
+/* ---- ray cast with the GPU renderer's semantics ------------------------------- */
+/* rayCast / rayCastCoarse of the reference's GLSL renderer (Shaders/VoxelTraversal.glsl:162-243) with its
+ * getStepPos (:92-131): the extra 128^3 level (SectorMasks, one bit per sector of a 4x4x4 group), origins
+ * outside the grid clipped to its box (:133-145), +5-ulp bias and 256 iterations — or, with VRT_GLSL_COARSE,
+ * rayCastCoarse: +0.001 bias, 96 iterations, after 30 of them any occupied 4^3 cell counts as a hit (what the
+ * GPU renderer uses for bounce and sun-shadow rays, VoxelRender.comp:58-83).  VRT_GLSL_ANISOTROPIC masks every
+ * occupancy word with the ray/cell interaction LUT first (u_UseAnisotropicLods, GpuRenderer.cpp:193-210).
+ * These rays visit other cells than the CPU renderer's, so normals / iteration counts differ from vrt_trace;
+ * VrtHit fields: dist = biased tmin, flags carry -sign(dir) normals (code 21 = none on a miss), u/v as the shader. */
+#define VRT_GLSL_COARSE 1u
+#define VRT_GLSL_ANISOTROPIC 2u
+VRT_API int vrt_trace_glsl(VrtContext* ctx, uint64_t n, const float* origin3, const float* dir3, const int32_t world_origin[3],
+                           uint32_t flags, VrtHit* out);
+
 /* ---- hit query (picking) ---------------------------------------------------------------------- */
 /* HitResult VoxelMap::RayCast(dvec3 origin, dvec3 dir, maxIters=1024) (VoxelMap.cpp:140-170),
  * batched.  The reference walks the unbounded sector hash; here sectors outside the resident

@@ -74,6 +74,10 @@ def load():
     lib.orc_set_sky.restype = None
     lib.orc_trace.argtypes = [vp, u64, vp, vp, C.POINTER(C.c_int32), u32, vp, C.POINTER(OrcStats), C.c_int]
     lib.orc_trace.restype = None
+    lib.orc_trace_glsl.argtypes = [vp, u64, vp, vp, C.POINTER(C.c_int32), u32, vp, C.POINTER(OrcStats), C.c_int]
+    lib.orc_trace_glsl.restype = None
+    lib.orc_interaction_lut.argtypes = [vp]
+    lib.orc_interaction_lut.restype = None
     lib.orc_hit_query.argtypes = [vp, u64, vp, vp, u32, vp, C.c_int]
     lib.orc_hit_query.restype = None
     lib.orc_render.argtypes = [vp, C.POINTER(VrtFrame), vp, vp, C.POINTER(OrcStats), C.c_int, u32, u32]
@@ -146,6 +150,16 @@ class OracleMap:
         self.lib.orc_trace(self.h, o.shape[0], o.ctypes.data, d.ctypes.data, wo, max_iters, out.ctypes.data, C.byref(st), threads)
         return out, st
 
+    def trace_glsl(self, origin3, dir3, world_origin, flags=0, threads=0):
+        """rayCast / rayCastCoarse of the GLSL renderer (VoxelTraversal.glsl:162-243); flags = VRT_GLSL_*."""
+        o = np.ascontiguousarray(origin3, dtype=np.float32).reshape(-1, 3)
+        d = np.ascontiguousarray(dir3, dtype=np.float32).reshape(-1, 3)
+        out = np.zeros(o.shape[0], HIT_DTYPE)
+        st = OrcStats()
+        wo = (C.c_int32 * 3)(*[int(v) for v in world_origin])
+        self.lib.orc_trace_glsl(self.h, o.shape[0], o.ctypes.data, d.ctypes.data, wo, int(flags), out.ctypes.data, C.byref(st), threads)
+        return out, st
+
     def hit_query(self, origin3, dir3, max_iters=1024, threads=0):
         o = np.ascontiguousarray(origin3, dtype=np.float64).reshape(-1, 3)
         d = np.ascontiguousarray(dir3, dtype=np.float64).reshape(-1, 3)
@@ -214,3 +228,10 @@ def pack_r11g11b10f(r, g, b):
 
 def num_threads():
     return int(load().orc_num_threads())
+
+
+def interaction_lut() -> np.ndarray:
+    """GenerateRayCellInteractionMaskLUT (GpuRenderer.cpp:193-210) as the oracle restates it: 512 u64."""
+    t = np.zeros(512, np.uint64)
+    load().orc_interaction_lut(t.ctypes.data)
+    return t

@@ -910,7 +910,7 @@ static void glsl_cast(const OrcMap* m, const float o_in[3], const float d[3], co
         cnt->iters++;
         for (int a = 0; a < 3; a++) sd[a] = ts[a] + (float)(int32_t)((uint32_t)p[a] - (uint32_t)wo[a]) * inv[a];
         tmin = glsl_min(glsl_min(sd[0], sd[1]), sd[2]);
-        tmin = coarse_mode ? tmin + 0.001f : u2f(f2u(tmin) + 5u); /* :215 / :179-180 */
+        tmin = coarse_mode ? tmin + 0.001f : (tmin == tmin ? u2f(f2u(tmin) + 5u) : tmin); /* :215 / :179-180; a NaN stays a NaN whatever its payload */
         for (int a = 0; a < 3; a++) cur[a] = o[a] + tmin * d[a];
         for (int a = 0; a < 3; a++) p[a] = (int32_t)((uint32_t)wo[a] + (uint32_t)glsl_floor2i(cur[a]));
         inb = inbound(m, p[0], p[1], p[2]);

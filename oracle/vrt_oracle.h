@@ -84,6 +84,13 @@ uint32_t orc_pack_unorm8x4(float r, float g, float b, float a);
 uint32_t orc_pack_half2(float x, float y);
 void orc_sincos_2pi(float x, float* s, float* c);
 
+/* rayCast / rayCastCoarse + getStepPos of the GLSL renderer (Shaders/VoxelTraversal.glsl:92-243); flags = VRT_GLSL_*.
+ * Parity unpinned (GLSL needs a GL device); canonical arithmetic in vrt_oracle.c. */
+void orc_trace_glsl(const OrcMap* m, uint64_t n, const float* origin3, const float* dir3, const int32_t world_origin[3], uint32_t flags,
+                    VrtHit* out, OrcStats* stats, int threads);
+/* GenerateRayCellInteractionMaskLUT, GpuRenderer.cpp:193-210 */
+void orc_interaction_lut(uint64_t table[512]);
+
 int orc_num_threads(void);
 
 #ifdef __cplusplus

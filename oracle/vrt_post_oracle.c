@@ -27,6 +27,8 @@
  * smallest normal.  The two per-tap quotients of the filters (w_luma = |dl| / lumaPhi, w_depth = |dd| / (length + 0.001),
  * Filter.comp:51,57,117,123) are evaluated as a * (1/b) with a correctly rounded reciprocal — what GPU GLSL compilers emit
  * for `/` (the spec allows 2.5 ulp), and the divisor is per pixel / per tap, so the reciprocal is shared by all taps.
+ * The luminance dot product and the running sums of the two filters (sum += value * weight, Filter.comp:60-62,128-129, and
+ * the 3x3 variance prefilter :79) are FMAs — the contraction GPU compilers apply to GLSL `a += b * c`; nothing else is fused.
  * Out-of-range image loads return 0 (robust buffer access).
  *
  * One documented deviation: Reproject.comp reads u_HistoryLenTex at NEIGHBOUR positions (:78) while
@@ -162,7 +164,7 @@ static inline void unpack_normal(uint32_t albedo_normal, float n[3]) { /* unpack
     n[0] = (float)(a & 3u) - 1.0f; n[1] = (float)((a >> 2) & 3u) - 1.0f; n[2] = (float)((a >> 4) & 3u) - 1.0f;
 }
 static inline float dot3(const float a[3], const float b[3]) { return a[0] * b[0] + a[1] * b[1] + a[2] * b[2]; }
-static inline float luminance(const float c[3]) { return c[0] * 0.299f + c[1] * 0.587f + c[2] * 0.114f; }
+static inline float luminance(const float c[3]) { return fmaf(c[2], 0.114f, fmaf(c[1], 0.587f, c[0] * 0.299f)); }
 static inline void load_h4(const Half4* t, size_t i, float v[4]) { for (int k = 0; k < 4; k++) v[k] = f16_to_f32(t[i].c[k]); }
 static inline void store_h4(Half4* t, size_t i, const float v[4]) { for (int k = 0; k < 4; k++) t[i].c[k] = f32_to_f16(v[k]); }
 static inline void mat_vec(const float m[16], float x, float y, float z, float w, float r[4]) {
@@ -323,8 +325,8 @@ static void variance_pass(PostOracle* o) {
                     float w_normal = pow128(fmin_g(fmax_g(dot3(n, cn), 0.001f), 1.0f));
                     float w_depth = fabsf(cd - o->depth[j]) * (1.0f / (sqrtf((float)kx * (float)kx + (float)ky * (float)ky) + 0.001f));
                     float w = post_exp(-(w_luma + w_depth)) * w_normal;
-                    for (int k = 0; k < 3; k++) si[k] = si[k] + v[k] * w;
-                    sm[0] = sm[0] + l * w; sm[1] = sm[1] + (l * l) * w;
+                    for (int k = 0; k < 3; k++) si[k] = fmaf(v[k], w, si[k]);
+                    sm[0] = fmaf(l, w, sm[0]); sm[1] = fmaf(l * l, w, sm[1]);
                     wsum = wsum + w;
                 }
             wsum = fmax_g(wsum, 0.001f);
@@ -353,7 +355,7 @@ static void atrous_pass(PostOracle* o, const Half4* in, Half4* out, int pass_no)
             for (int ky = -1; ky <= 1; ky++)
                 for (int kx = -1; kx <= 1; kx++) {
                     float v = in_bounds(o, x + kx, y + ky) ? f16_to_f32(in[(size_t)(y + ky) * o->w + (x + kx)].c[3]) : 0.0f;
-                    cv = cv + v * kvar[abs(kx)][abs(ky)];
+                    cv = fmaf(v, kvar[abs(kx)][abs(ky)], cv);
                 }
             float cn[3];
             unpack_normal(o->albedo[i], cn);
@@ -375,8 +377,8 @@ static void atrous_pass(PostOracle* o, const Half4* in, Half4* out, int pass_no)
                     float w_depth = fabsf(cd - o->depth[j]) * (1.0f / (sqrtf((float)ox * (float)ox + (float)oy * (float)oy) + 0.001f));
                     float w = kern[abs(kx)] * kern[abs(ky)];
                     w = w * (post_exp(-(w_luma + w_depth)) * w_normal);
-                    for (int k = 0; k < 3; k++) sum[k] = sum[k] + v[k] * w;
-                    sum[3] = sum[3] + v[3] * (w * w);
+                    for (int k = 0; k < 3; k++) sum[k] = fmaf(v[k], w, sum[k]);
+                    sum[3] = fmaf(v[3], w * w, sum[3]);
                     wsum = wsum + w;
                 }
             if (wsum < 0.001f) wsum = 0.001f;

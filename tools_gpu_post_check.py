@@ -85,6 +85,60 @@ if not PERF_ONLY:
     res["traced"] = worst
     gb.close()
     gb2.close()
+    # vrt_trace_glsl (the GLSL renderer's rayCast / rayCastCoarse) against orc_trace_glsl
+    from oracle import pyoracle  # noqa: E402
+
+    omap = pyoracle.OracleMap(6, 4)
+    omap.set_palette(scene["palette"])
+    omap.sync(terrain.scene_records(scene))
+
+    def hits_differ(a, b):
+        n = 0
+        for name in a.dtype.names:
+            x, y = a[name], b[name]
+            if x.dtype.kind == "f":
+                nan = np.isnan(x) & np.isnan(y)
+                n += int(((x.view(np.uint32) != y.view(np.uint32)) & ~nan).sum())
+            else:
+                n += int((x != y).sum())
+        return n
+
+    rng = np.random.default_rng(11)
+    vals = np.array([0.0, -0.0, 1.0, -1.0, 1e-39, -1e-39, 1e30, np.inf, -np.inf, np.nan, 0.3, -0.7], np.float32)
+    d_sp = np.array([(a, b, c) for a in vals for b in vals for c in vals], np.float32)
+    o_sp = np.tile(np.array([[0.25, 0.5, 0.75]], np.float32), (len(d_sp), 1))
+    o_sp[::7, 0] = np.nan
+    glsl = {}
+    for flags in (0, 1, 2, 3):
+        bad = 0
+        for k in range(3):
+            wo_ = (int(rng.integers(2, 190)), int(rng.integers(2, 126)), int(rng.integers(2, 190)))
+            o_ = rng.random((20000, 3)).astype(np.float32)
+            d_ = rng.normal(size=(20000, 3))
+            d_ = (d_ / np.linalg.norm(d_, axis=1, keepdims=True)).astype(np.float32)
+            bad += hits_differ(ctx.trace_glsl(o_, d_, wo_, flags), omap.trace_glsl(o_, d_, wo_, flags)[0])
+        o_ = (rng.uniform(-100, 100, (20000, 3))).astype(np.float32)  # far origins (bounce-like) around (96, 64, 96)
+        bad += hits_differ(ctx.trace_glsl(o_, d_, (96, 64, 96), flags), omap.trace_glsl(o_, d_, (96, 64, 96), flags)[0])
+        o_ = (rng.random((5000, 3)) - 0.5).astype(np.float32)  # camera above the view box
+        d2 = rng.normal(size=(5000, 3)) * 0.08
+        d2[:, 1] = -1.0
+        d2 = (d2 / np.linalg.norm(d2, axis=1, keepdims=True)).astype(np.float32)
+        want = omap.trace_glsl(o_, d2, (96, 600, 96), flags)[0]
+        bad += hits_differ(ctx.trace_glsl(o_, d2, (96, 600, 96), flags), want)
+        bad_sp = hits_differ(ctx.trace_glsl(o_sp, d_sp, (90, 70, 90), flags), omap.trace_glsl(o_sp, d_sp, (90, 70, 90), flags)[0])
+        glsl[f"flags{flags}"] = {"mismatching_fields": bad, "special_directions": bad_sp, "outside_hit_fraction": float(((want["flags"] & 0x100) != 0).mean())}
+        say(f"trace_glsl flags={flags}: {glsl[f'flags{flags}']}")
+    recs2 = [(40, 10, 40, 1 << 21, 1 << 21, np.full((1, 512), 250, np.uint8)), (2, 1, 2, 0, 0xFFFFFFFFFFFFFFFF, None, True)]
+    ctx.sync(recs2)
+    omap.sync(recs2)
+    wo2 = (40 * 32 + 5, 10 * 32 + 60, 40 * 32 + 7)
+    o2 = rng.random((4000, 3)).astype(np.float32)
+    d3 = np.tile(np.array([[0.05, -1.0, 0.08]], np.float32), (4000, 1)) + rng.normal(size=(4000, 3)).astype(np.float32) * 0.1
+    want = omap.trace_glsl(o2, d3, wo2, 0)[0]
+    glsl["after_edit"] = {"mismatching_fields": hits_differ(ctx.trace_glsl(o2, d3, wo2, 0), want) + hits_differ(ctx.trace_glsl(o_, d_, (96, 64, 96), 1), omap.trace_glsl(o_, d_, (96, 64, 96), 1)[0]),
+                          "lone_brick_hits": int(((want["flags"] & 0x100) != 0).sum())}
+    say(f"trace_glsl after edits: {glsl['after_edit']}")
+    res["trace_glsl"] = glsl
     ctx.close()
     import subprocess  # noqa: E402
 

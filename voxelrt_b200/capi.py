@@ -21,6 +21,8 @@ VRT_HIT_HIT = 0x100
 VRT_HIT_INBOUND = 0x200
 VRT_HIT_CAPPED = 0x400
 VRT_HIT_ITERS_SHIFT = 16
+VRT_GLSL_COARSE = 1
+VRT_GLSL_ANISOTROPIC = 2
 VRT_FRAME_LINEAR_OUTPUT = 1
 VRT_FRAME_AUX_HITS = 2
 VRT_FRAME_PART_ROWS = 8
@@ -147,6 +149,7 @@ EXPORTS = [
     "vrt_read_sector",
     "vrt_trace",
     "vrt_trace_device",
+    "vrt_trace_glsl",
     "vrt_hit_query",
     "vrt_set_blue_noise",
     "vrt_set_sky",
@@ -188,6 +191,7 @@ def load(path: os.PathLike | None = None) -> C.CDLL:
     lib.vrt_read_sector.argtypes = [vp, C.c_int32, C.c_int32, C.c_int32, C.POINTER(u64), C.POINTER(u32), vp, vp]
     lib.vrt_trace.argtypes = [vp, u64, vp, vp, i32p, u32, vp]
     lib.vrt_trace_device.argtypes = [vp, u64, vp, vp, i32p, u32, vp, vp]
+    lib.vrt_trace_glsl.argtypes = [vp, u64, vp, vp, i32p, u32, vp]
     lib.vrt_hit_query.argtypes = [vp, u64, vp, vp, u32, vp]
     lib.vrt_set_blue_noise.argtypes = [vp, vp, C.c_size_t]
     lib.vrt_set_sky.argtypes = [vp, C.POINTER(VrtSkyDesc), vp]
@@ -326,6 +330,16 @@ class Context:
         out = np.zeros(o.shape[0], HIT_DTYPE)
         wo = (C.c_int32 * 3)(*[int(v) for v in world_origin])
         self._chk(self.lib.vrt_trace(self.h, o.shape[0], o.ctypes.data, d.ctypes.data, wo, max_iters, out.ctypes.data))
+        return out
+
+    def trace_glsl(self, origin3, dir3, world_origin, flags=0):
+        """Ray casts with the GLSL renderer's semantics (rayCast / rayCastCoarse, VoxelTraversal.glsl:162-243)."""
+        o = np.ascontiguousarray(origin3, dtype=np.float32).reshape(-1, 3)
+        d = np.ascontiguousarray(dir3, dtype=np.float32).reshape(-1, 3)
+        assert o.shape == d.shape
+        out = np.zeros(o.shape[0], HIT_DTYPE)
+        wo = (C.c_int32 * 3)(*[int(v) for v in world_origin])
+        self._chk(self.lib.vrt_trace_glsl(self.h, o.shape[0], o.ctypes.data, d.ctypes.data, wo, int(flags), out.ctypes.data))
         return out
 
     def trace_device(self, n, d_origin, d_dir, world_origin, max_iters, d_out, stream=0):

@@ -14,6 +14,7 @@
 #include <vector>
 
 #include "slot_allocator.h"
+#include "vrt_glsl.cuh"
 #include "vrt_kernels.cuh"
 
 using namespace vrt;
@@ -76,6 +77,9 @@ struct VrtContext {
 
     uint32_t* d_sat = nullptr;  // summed-volume table of the box builder
     bool boxes_stale = true;    // some sector's emptiness changed since the boxes were built
+    uint2* d_groups = nullptr;  // vrt_trace_glsl: SectorMasks of the GLSL renderer (one u64 per 4x4x4 sectors), built on demand
+    uint2* d_lut = nullptr;     // vrt_trace_glsl: ray/cell interaction LUT
+    bool groups_stale = true;
     int macro_on = 1;  // 0 off, 1 on, 2 on + "metrics" launches count the macro loop's own trips (diagnostic)
     DevMetrics* d_metrics = nullptr;
     bool metrics_on = false;
@@ -640,6 +644,8 @@ extern "C" void vrt_destroy(VrtContext* ctx) {
     cudaFree(ctx->d_sky);
     cudaFree(ctx->d_metrics);
     cudaFree(ctx->d_sat);
+    cudaFree(ctx->d_groups);
+    cudaFree(ctx->d_lut);
     if (ctx->ev_sync) cudaEventDestroy(ctx->ev_sync);
     for (auto& e : ctx->ev_render) if (e) cudaEventDestroy(e);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -770,6 +776,7 @@ extern "C" int vrt_sync(VrtContext* ctx, uint32_t n, const VrtDirtySector* recs)
             if ((old.mask == 0) != (new_mask == 0)) {
                 ctx->resident_sectors += new_mask ? 1 : -1;
                 ctx->boxes_stale = true;
+                ctx->groups_stale = true;
                 ctx->scene_epoch++;
             }
             ctx->sectors[si] = cur;
@@ -934,6 +941,64 @@ extern "C" int vrt_trace(VrtContext* ctx, uint64_t n, const float* origin3, cons
     CU(cudaMemcpyAsync(ctx->d_rays_d.p, dir3, n * 12, cudaMemcpyHostToDevice, ctx->stream));
     st = launch_trace(ctx, n, (const float*)ctx->d_rays_o.p, (const float*)ctx->d_rays_d.p, wo, max_iters, (VrtHit*)ctx->d_hits.p, ctx->stream);
     if (st) return st;
+    CU(cudaMemcpyAsync(out, ctx->d_hits.p, n * sizeof(VrtHit), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return VRT_OK;
+}
+
+// GenerateRayCellInteractionMaskLUT (GpuRenderer.cpp:193-210): cells of a 4x4x4 mask a ray of a given octant can reach from a cell
+static void interaction_lut(uint64_t table[512]) {
+    for (int oct = 0; oct < 8; oct++) {
+        const int sx = (oct & 1) ? 1 : -1, sy = (oct & 2) ? 1 : -1, sz = (oct & 4) ? 1 : -1;
+        for (int origin = 0; origin < 64; origin++) {
+            const int ox = origin & 3, oz = (origin >> 2) & 3, oy = origin >> 4;
+            uint64_t m = 0;
+            for (int jy = 0; jy < 4; jy++)
+                for (int jz = 0; jz < 4; jz++)
+                    for (int jx = 0; jx < 4; jx++) {
+                        const int x = ox + jx * sx, y = oy + jy * sy, z = oz + jz * sz;
+                        if (x >= 0 && x < 4 && y >= 0 && y < 4 && z >= 0 && z < 4) m |= 1ull << (x + 4 * z + 16 * y);
+                    }
+            table[origin + 64 * oct] = m;
+        }
+    }
+}
+
+extern "C" int vrt_trace_glsl(VrtContext* ctx, uint64_t n, const float* origin3, const float* dir3, const int32_t wo[3], uint32_t flags,
+                              VrtHit* out) {
+    if (!ctx || !wo || (n && (!origin3 || !dir3 || !out))) return VRT_ERR_INVALID;
+    if (flags & ~(VRT_GLSL_COARSE | VRT_GLSL_ANISOTROPIC)) return fail(ctx, VRT_ERR_INVALID, "vrt_trace_glsl: unknown flag");
+    if (ctx->sxz < 2 || ctx->sy < 2) return fail(ctx, VRT_ERR_UNSUPPORTED, "vrt_trace_glsl: the view must span at least 4 sectors per axis (128^3 level)");
+    if (n == 0) return VRT_OK;
+    if (n > 0x7FFFFFFFull * 128ull) return fail(ctx, VRT_ERR_INVALID, "too many rays for one launch");
+    DeviceGuard g(ctx->device);
+    int st;
+    const uint32_t gxz = ctx->sxz - 2, n_groups = 1u << (2 * gxz + ctx->sy - 2);
+    uint64_t launches = 0;
+    if (!ctx->d_lut) {
+        uint64_t table[512];
+        interaction_lut(table);
+        CU(cudaMalloc((void**)&ctx->d_lut, sizeof(table)));
+        CU(cudaMemcpy(ctx->d_lut, table, sizeof(table), cudaMemcpyHostToDevice));
+    }
+    if (!ctx->d_groups) CU(cudaMalloc((void**)&ctx->d_groups, (size_t)n_groups * 8));
+    DevScene S = dev_scene(ctx);
+    if (ctx->groups_stale) {
+        k_build_groups<<<(n_groups + 127) / 128, 128, 0, ctx->stream>>>(S, ctx->d_groups, gxz, n_groups);
+        ctx->groups_stale = false;
+        launches++;
+    }
+    if ((st = ensure(ctx, ctx->d_rays_o, n * 12))) return st;
+    if ((st = ensure(ctx, ctx->d_rays_d, n * 12))) return st;
+    if ((st = ensure(ctx, ctx->d_hits, n * sizeof(VrtHit)))) return st;
+    CU(cudaMemcpyAsync(ctx->d_rays_o.p, origin3, n * 12, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemcpyAsync(ctx->d_rays_d.p, dir3, n * 12, cudaMemcpyHostToDevice, ctx->stream));
+    GlslScene G{ctx->d_groups, ctx->d_lut, gxz};
+    k_trace_glsl<<<(unsigned)((n + 127) / 128), 128, 0, ctx->stream>>>(S, G, wo[0], wo[1], wo[2], (const float*)ctx->d_rays_o.p,
+                                                                      (const float*)ctx->d_rays_d.p, flags, n, (VrtHit*)ctx->d_hits.p);
+    launches++;
+    CU(cudaGetLastError());
+    ctx->stats.last_launches = launches;
     CU(cudaMemcpyAsync(out, ctx->d_hits.p, n * sizeof(VrtHit), cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
     return VRT_OK;

@@ -83,7 +83,7 @@ __global__ void __launch_bounds__(128) k_trace_glsl(DevScene S, GlslScene G, int
 #pragma unroll
         for (int a = 0; a < 3; a++) sd[a] = __fadd_rn(ts[a], __fmul_rn((float)(int)((uint32_t)p[a] - (uint32_t)wo[a]), inv[a]));
         tmin = glsl_min(glsl_min(sd[0], sd[1]), sd[2]);
-        tmin = coarse_mode ? __fadd_rn(tmin, 0.001f) : __uint_as_float(__float_as_uint(tmin) + 5u);
+        tmin = coarse_mode ? __fadd_rn(tmin, 0.001f) : (tmin == tmin ? __uint_as_float(__float_as_uint(tmin) + 5u) : tmin);  // a NaN stays a NaN whatever its payload
 #pragma unroll
         for (int a = 0; a < 3; a++) {
             cur[a] = __fadd_rn(o[a], __fmul_rn(tmin, d[a]));

@@ -81,7 +81,8 @@ __device__ __forceinline__ float pow128(float x) {
 __device__ __forceinline__ float dot3(float ax, float ay, float az, float bx, float by, float bz) {
     return __fadd_rn(__fadd_rn(__fmul_rn(ax, bx), __fmul_rn(ay, by)), __fmul_rn(az, bz));
 }
-__device__ __forceinline__ float luminance(float r, float g, float b) { return dot3(r, g, b, 0.299f, 0.587f, 0.114f); }
+// dot(color, vec3(0.299, 0.587, 0.114)) as a multiply and two FMAs (the contraction GPU GLSL compilers apply; oracle: same)
+__device__ __forceinline__ float luminance(float r, float g, float b) { return __fmaf_rn(b, 0.114f, __fmaf_rn(g, 0.587f, __fmul_rn(r, 0.299f))); }
 // GLSL mat4 * vec4, accumulated left to right
 __device__ __forceinline__ float4 mat_vec(const Mat4& M, float x, float y, float z, float w) {
     float r[4];
@@ -266,11 +267,17 @@ __device__ __forceinline__ INormal inormal(uint32_t albedo_normal) {
     const uint32_t a = albedo_normal >> 24;
     return {(int)(a & 3u) - 1, (int)((a >> 2) & 3u) - 1, (int)((a >> 4) & 3u) - 1};
 }
-// exp(-(w_luma + w_depth)) * w_normal
-__device__ __forceinline__ float tap_weight(float w_luma, float w_depth, const INormal n, const INormal cn) {
-    const float w_normal = (n.x * cn.x + n.y * cn.y + n.z * cn.z) >= 1 ? 1.0f : 0.0f;
+// exp(-(w_luma + w_depth)) * w_normal.  Almost every tap has the centre's normal code: then dot(n, cn) = |cn|^2 and w_normal is
+// the per-pixel constant `self`; only other codes take the integer dot product.
+__device__ __forceinline__ float tap_weight(float w_luma, float w_depth, uint32_t tap_albedo, uint32_t centre_albedo, const INormal cn, float self) {
+    float w_normal = self;
+    if ((tap_albedo ^ centre_albedo) >> 24) {
+        const INormal n = inormal(tap_albedo);
+        w_normal = (n.x * cn.x + n.y * cn.y + n.z * cn.z) >= 1 ? 1.0f : 0.0f;
+    }
     return __fmul_rn(post_exp_neg(-__fadd_rn(w_luma, w_depth)), w_normal);
 }
+__device__ __forceinline__ float self_weight(const INormal cn) { return (cn.x * cn.x + cn.y * cn.y + cn.z * cn.z) >= 1 ? 1.0f : 0.0f; }
 
 struct TapRcp {
     float v[49];  // 1 / (length(offset) + 0.001) per tap, row-major over the (2R+1)^2 window
@@ -292,6 +299,7 @@ __global__ void __launch_bounds__(256) k_variance(const uint4* __restrict__ in, 
     const Rec stale = unpack(io_temp[i]);  // :26 reads the centre from the TEMP texture
     const float cl = luminance(stale.r, stale.g, stale.b);
     const INormal cn = inormal(c.albedo);
+    const float self = self_weight(cn);
     float sr = 0.0f, sg = 0.0f, sb = 0.0f, s0 = 0.0f, s1 = 0.0f, wsum = 0.0f;
 #pragma unroll
     for (int ky = -3; ky <= 3; ky++) {
@@ -305,12 +313,12 @@ __global__ void __launch_bounds__(256) k_variance(const uint4* __restrict__ in, 
             const float l = luminance(t.r, t.g, t.b);
             const float w_luma = __fmul_rn(fabsf(__fsub_rn(l, cl)), 0.1f);  // 1/lumaPhi, lumaPhi = 10
             const float w_depth = __fmul_rn(fabsf(__fsub_rn(c.depth, t.depth)), rcp.v[(ky + 3) * 7 + (kx + 3)]);
-            const float wgt = tap_weight(w_luma, w_depth, inormal(t.albedo), cn);
-            sr = __fadd_rn(sr, __fmul_rn(t.r, wgt));
-            sg = __fadd_rn(sg, __fmul_rn(t.g, wgt));
-            sb = __fadd_rn(sb, __fmul_rn(t.b, wgt));
-            s0 = __fadd_rn(s0, __fmul_rn(l, wgt));
-            s1 = __fadd_rn(s1, __fmul_rn(__fmul_rn(l, l), wgt));
+            const float wgt = tap_weight(w_luma, w_depth, t.albedo, c.albedo, cn, self);
+            sr = __fmaf_rn(t.r, wgt, sr);  // sums are FMAs (oracle: same)
+            sg = __fmaf_rn(t.g, wgt, sg);
+            sb = __fmaf_rn(t.b, wgt, sb);
+            s0 = __fmaf_rn(l, wgt, s0);
+            s1 = __fmaf_rn(__fmul_rn(l, l), wgt, s1);
             wsum = __fadd_rn(wsum, wgt);
         }
     }
@@ -342,9 +350,10 @@ __device__ __forceinline__ void atrous_pixel(const uint4* __restrict__ in, uint4
             float v = 0.0f;  // imageLoad outside the image returns 0
             if ((uint32_t)(x + kx) < (uint32_t)w && (uint32_t)(y + ky) < (uint32_t)h) v = h2f(__ldg(&(centre + (ptrdiff_t)ky * w + kx)->y) >> 16);
             const float k = (kx == 0 ? 0.25f : 0.125f) * (ky == 0 ? 1.0f : 0.5f);  // kernel[|kx|][|ky|] = {1/4,1/8;1/8,1/16}
-            cv = __fadd_rn(cv, __fmul_rn(v, k));
+            cv = __fmaf_rn(v, k, cv);
         }
     const INormal cn = inormal(c.albedo);
+    const float self = self_weight(cn);
     const float cl = luminance(c.r, c.g, c.b);
     const float inv_phi = __fdiv_rn(1.0f, __fmul_rn(__fsqrt_rn(maxg(0.0001f, cv)), 4.0f));
     float sr = c.r, sg = c.g, sb = c.b, sv = c.var, wsum = 1.0f;
@@ -361,11 +370,11 @@ __device__ __forceinline__ void atrous_pixel(const uint4* __restrict__ in, uint4
             const float w_depth = __fmul_rn(fabsf(__fsub_rn(c.depth, t.depth)), rcp.v[(ky + 2) * 5 + (kx + 2)]);
             const float kxw = kx == 0 ? 0.375f : ((kx == 1 || kx == -1) ? 0.25f : 0.0625f);
             const float kyw = ky == 0 ? 0.375f : ((ky == 1 || ky == -1) ? 0.25f : 0.0625f);
-            const float wgt = __fmul_rn(kxw * kyw, tap_weight(w_luma, w_depth, inormal(t.albedo), cn));
-            sr = __fadd_rn(sr, __fmul_rn(t.r, wgt));
-            sg = __fadd_rn(sg, __fmul_rn(t.g, wgt));
-            sb = __fadd_rn(sb, __fmul_rn(t.b, wgt));
-            sv = __fadd_rn(sv, __fmul_rn(t.var, __fmul_rn(wgt, wgt)));
+            const float wgt = __fmul_rn(kxw * kyw, tap_weight(w_luma, w_depth, t.albedo, c.albedo, cn, self));
+            sr = __fmaf_rn(t.r, wgt, sr);
+            sg = __fmaf_rn(t.g, wgt, sg);
+            sb = __fmaf_rn(t.b, wgt, sb);
+            sv = __fmaf_rn(t.var, __fmul_rn(wgt, wgt), sv);
             wsum = __fadd_rn(wsum, wgt);
         }
     }
