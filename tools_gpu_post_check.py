@@ -135,7 +135,7 @@ if not PERF_ONLY:
     o2 = rng.random((4000, 3)).astype(np.float32)
     d3 = np.tile(np.array([[0.05, -1.0, 0.08]], np.float32), (4000, 1)) + rng.normal(size=(4000, 3)).astype(np.float32) * 0.1
     want = omap.trace_glsl(o2, d3, wo2, 0)[0]
-    glsl["after_edit"] = {"mismatching_fields": hits_differ(ctx.trace_glsl(o2, d3, wo2, 0), want) + hits_differ(ctx.trace_glsl(o_, d_, (96, 64, 96), 1), omap.trace_glsl(o_, d_, (96, 64, 96), 1)[0]),
+    glsl["after_edit"] = {"mismatching_fields": hits_differ(ctx.trace_glsl(o2, d3, wo2, 0), want) + hits_differ(ctx.trace_glsl(o_, d2, (96, 64, 96), 1), omap.trace_glsl(o_, d2, (96, 64, 96), 1)[0]),
                           "lone_brick_hits": int(((want["flags"] & 0x100) != 0).sum())}
     say(f"trace_glsl after edits: {glsl['after_edit']}")
     res["trace_glsl"] = glsl
