@@ -20,6 +20,10 @@ def pytest_configure(config):
 
 
 def _cuda_available() -> bool:
+    import os
+
+    if os.environ.get("VRT_ASSUME_CUDA") == "1":  # quick GPU sessions: skip the (slow on a fresh box) torch import
+        return True
     try:
         import torch
 
