@@ -21,6 +21,8 @@ N > 1   screen split of the SAME frame (strong scaling): rank r renders the 8-pi
         is traced (presenting GPU = frame % N).  value = K frames back to back including the last
         gather, max over ranks; gather.* carries the non-pipelined frame latency and a trace-only figure.
 --workload  sponza | large | edits: the other BASELINE configs (non-default bench lines).
+--present   additionally time the step after the path (the reference's GBuffer: blit + reprojection + SVGF + present,
+        include/voxelrt_b200_post.h) on the traced frames and add a "present" block (N = 1 only; opt-in).
 """
 from __future__ import annotations
 
@@ -342,7 +344,7 @@ def present_block(args, ctx, frame, stream, fb, w, h, peak):
     import torch
 
     from scenes import camera as _camera
-    from voxelrt_b200 import post
+    from voxelrt_b200 import capi, post
 
     gb = post.GBuffer(torch.cuda.current_device())
     gb.set_passes(args.present_passes)
