@@ -12,9 +12,9 @@ timeout 300 python tools_gpu_post_check.py > /dev/null 2>&1; tail -4 gpurun_out/
 timeout 120 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1; tail -2 gpurun_out/smoke.log
 timeout 600 python bench.py > gpurun_out/bench.json 2> gpurun_out/bench.err; tail -3 gpurun_out/bench.err; cat gpurun_out/bench.json
 timeout 300 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_ref.json 2>> gpurun_out/bench.err; cat gpurun_out/bench_ref.json
-timeout 600 python bench.py --present --bounces 1 --steps 10 --warmup 3 --no-cpu > gpurun_out/bench_present.json 2> gpurun_out/bench_present.err; tail -1 gpurun_out/bench_present.json | cut -c1-400
+timeout 600 python bench.py --bounces 1 --steps 10 --warmup 3 --no-cpu > gpurun_out/bench_present.json 2> gpurun_out/bench_present.err; tail -1 gpurun_out/bench_present.json | cut -c1-400
 if [ "$1" != "noprof" ]; then
-timeout 600 ncu --set full --clock-control none -k regex:k_atrous -s 2 -c 5 -f -o gpurun_out/prof_atrous python bench.py --present --bounces 1 --steps 2 --warmup 1 --no-cpu > gpurun_out/ncu_atrous.log 2>&1
+timeout 600 ncu --set full --clock-control none -k regex:k_atrous -s 2 -c 5 -f -o gpurun_out/prof_atrous python bench.py --bounces 1 --steps 2 --warmup 1 --no-cpu > gpurun_out/ncu_atrous.log 2>&1
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches.csv python bench.py --steps 3 --warmup 3 --no-cpu > gpurun_out/bench_under_ncu.log 2>&1
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_render -s 4 -c 2 -f -o gpurun_out/prof_render python bench.py --steps 3 --warmup 3 --no-cpu > gpurun_out/ncu_full.log 2>&1
 ncu -i gpurun_out/prof_render.ncu-rep --page source --csv > gpurun_out/prof_render_source.csv 2>/dev/null
