@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Kernel-only A/B timing of the 4K primary frame under different vrt_set_option settings (GPU box).
 
-    python tools_exp.py "persistent=0" "persistent=1" "persistent=2,macro_steps=1" ...
+    python tools/exp.py "persistent=0" "persistent=1" "persistent=2,macro_steps=1" ...
 Prints ms/frame (CUDA events on the launching stream, L2 flushed between frames, median and min of N).
 """
 import sys

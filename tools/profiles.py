@@ -1,7 +1,7 @@
 #!/usr/bin/env python
-"""Turn a gpurun_out/ session (tools_gpu_round.sh) into the tracked summaries under profiles/.
+"""Turn a gpurun_out/ session (tools/gpu_round.sh) into the tracked summaries under profiles/.
 
-    python tools_profiles.py [tag]          # tag defaults to r01
+    python tools/profiles.py [tag]          # tag defaults to r01
 """
 import csv
 import json
@@ -10,7 +10,7 @@ import subprocess
 import sys
 from pathlib import Path
 
-ROOT = Path(__file__).resolve().parent
+ROOT = Path(__file__).resolve().parents[1]
 OUT = ROOT / "gpurun_out"
 PROF = ROOT / "profiles"
 METRICS = """gpu__time_duration.sum dram__bytes_read.sum dram__bytes_write.sum l1tex__t_sector_hit_rate.pct
@@ -45,7 +45,7 @@ def main():
     if (OUT / "prof_bounce.ncu-rep").exists():
         summarise(OUT / "prof_bounce.ncu-rep", f"{tag}_ncu_k_render_bounce1")
         if (OUT / "prof_bounce_source.csv").exists():
-            subprocess.run([sys.executable, str(ROOT / "tools_regions.py"), str(OUT / "prof_bounce_source.csv"), str(PROF / f"{tag}_ncu_k_render_bounce1_source_regions.txt")],
+            subprocess.run([sys.executable, str(ROOT / "tools" / "regions.py"), str(OUT / "prof_bounce_source.csv"), str(PROF / f"{tag}_ncu_k_render_bounce1_source_regions.txt")],
                            stdout=subprocess.DEVNULL)
     if (OUT / "prof_wave.ncu-rep").exists():
         summarise(OUT / "prof_wave.ncu-rep", f"{tag}_ncu_k_wave_trace_2bounces")
@@ -75,7 +75,7 @@ def main():
                       "capture": f"profiles/{tag}_ncu_k_render_raw_summary.csv launch0"}
             (PROF / "traffic.json").write_text(json.dumps(t, indent=2) + "\n")
     if (OUT / "prof_render_source.csv").exists():
-        subprocess.run([sys.executable, str(ROOT / "tools_regions.py"), str(OUT / "prof_render_source.csv"), str(PROF / f"{tag}_ncu_k_render_source_regions.txt")],
+        subprocess.run([sys.executable, str(ROOT / "tools" / "regions.py"), str(OUT / "prof_render_source.csv"), str(PROF / f"{tag}_ncu_k_render_source_regions.txt")],
                        stdout=subprocess.DEVNULL)
     for src, dst in (("bench.json", f"{tag}_bench_4k_primary.json"), ("bench_ref.json", f"{tag}_bench_reference_arm.json"),
                      ("launches.csv", f"{tag}_launches_4k_primary.csv"), ("bench_sponza.json", f"{tag}_bench_sponza_1080p_1bounce.json"),

@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Where the frame kernel's instructions go, by SOURCE region.
 
-    python tools_regions.py [gpurun_out/prof_render_source.csv] [out.txt]
+    python tools/regions.py [gpurun_out/prof_render_source.csv] [out.txt]
 
 Joins the per-SASS-instruction counters of an `ncu --set full --import-source on` capture (exported with
 `ncu -i rep --page source --csv`) with the line table of the very library that was profiled (`nvdisasm -g` on the
@@ -15,7 +15,7 @@ import sys
 import tempfile
 from pathlib import Path
 
-ROOT = Path(__file__).resolve().parent
+ROOT = Path(__file__).resolve().parents[1]
 LIB = ROOT / "voxelrt_b200" / "lib" / "libvoxelrt_b200.so"
 SRC = ROOT / "voxelrt_b200" / "csrc"
 
