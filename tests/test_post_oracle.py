@@ -231,3 +231,34 @@ def test_regression_fixture(pp):
         assert np.array_equal(img, z["rgba"][f]), f"frame {f}"
     assert np.array_equal(orc.read(orc.HIST), z["hist"]) and np.array_equal(orc.read(orc.MOMENTS), z["moments"])
     assert np.array_equal(orc.read(orc.PREV_IRR), z["prev_irr"])
+
+
+@pytest.mark.parametrize("passes,moving", [(5, True), (0, True), (2, True), (3, False)])
+def test_oracle_agrees_with_an_independent_float64_model(pp, passes, moving):
+    """tests/gbuffer_model_np.py restates the same shaders a second time (numpy, float64, vectorised, written from the GLSL).
+    Threshold tests (plane distance, bounds after truncation, wsum) can flip on rounding, so a small fraction of pixels may
+    differ; everywhere else the planes agree to f16 precision and the image to one 8-bit step."""
+    from gbuffer_model_np import NumpyGBuffer
+
+    w, h = SIZE
+    seq = pu.synthetic_sequence(w, h, 5, seed=40 + passes, moving=moving)
+    orc, mdl = pp.PostOracle(w, h), NumpyGBuffer(w, h)
+    orc.set_passes(passes)
+    for f, (proj, inv, pos, tiles) in enumerate(seq):
+        reset = f == 3
+        orc.set_camera(proj, inv, pos, reset_history=reset)
+        mdl.set_camera(proj, inv, pos)
+        img = orc.denoise_present(tiles)
+        rgb = mdl.frame(tiles, reset=reset, passes=passes)
+        hist_o = orc.read(orc.HIST).reshape(h, w).astype(np.int64)
+        same_hist = hist_o == mdl.hist
+        assert same_hist.mean() > 0.99, (f, same_hist.mean())
+        for plane_o, plane_m, name in ((orc.IRR, mdl.irr, "irr"), (orc.PREV_IRR, mdl.prev_irr, "prev"), (orc.TEMP_IRR, mdl.temp_irr, "temp")):
+            got = pu.f16_to_f32(orc.read(plane_o).reshape(h, w, 4)).astype(np.float64)
+            err = np.abs(got - plane_m) / np.maximum(1e-2, np.abs(plane_m))
+            close = (err < 4e-3).all(axis=-1)
+            assert close.mean() > 0.985, (f, name, close.mean(), float(np.nanmax(err)))
+        mom = pu.f16_to_f32(orc.read(orc.MOMENTS).reshape(h, w, 2)).astype(np.float64)
+        assert (np.abs(mom - mdl.moments) < 4e-3 * np.maximum(1.0, np.abs(mdl.moments))).all(axis=-1).mean() > 0.985
+        ch = np.stack([(img >> s) & 255 for s in (0, 8, 16)], -1).astype(np.int64)
+        assert (np.abs(ch - rgb) <= 1).all(axis=-1).mean() > 0.985, f
