@@ -190,6 +190,7 @@ PO_API void post_oracle_set_camera(PostOracle* o, const float proj[16], const fl
 /* CopyTiledFramebuffer.comp:10-37 with TileShiftX = TileShiftY = 2 (16-lane packets) */
 static void blit_tiles(PostOracle* o, const uint32_t* tiles) {
     const uint32_t stride = (uint32_t)o->w >> 2, field = 16, tile_words = 64;
+#pragma omp parallel for schedule(static)
     for (int y = 0; y < o->h; y++)
         for (int x = 0; x < o->w; x++) {
             uint32_t off = (((uint32_t)x >> 2) + ((uint32_t)y >> 2) * stride) * tile_words + ((uint32_t)x & 3) + (((uint32_t)y & 3) << 2);
@@ -289,6 +290,7 @@ static void reproject_pass(PostOracle* o, int reset) {
     float delta[3];
     for (int k = 0; k < 3; k++) delta[k] = (float)(o->cur_pos[k] - o->hist_pos[k]); /* GBuffer.h:82 */
     memcpy(o->hist_snapshot, o->hist, (size_t)o->w * o->h);
+#pragma omp parallel for schedule(static)
     for (int y = 0; y < o->h; y++)
         for (int x = 0; x < o->w; x++)
             if (!reproject_px(o, x, y, delta, reset)) { /* main(), Reproject.comp:104-108 */
@@ -300,6 +302,7 @@ static void reproject_pass(PostOracle* o, int reset) {
 /* varianceEstim, Filter.comp:17-68: in u_IrradianceTex, out u_TempIrradianceTex; note that the centre
  * luminance is read from the TEMP texture (:26), i.e. whatever the previous frame left there. */
 static void variance_pass(PostOracle* o) {
+#pragma omp parallel for schedule(static) /* every pixel reads o->irr and its OWN temp texel only */
     for (int y = 0; y < o->h; y++)
         for (int x = 0; x < o->w; x++) {
             size_t i = (size_t)y * o->w + x;
@@ -344,6 +347,7 @@ static void variance_pass(PostOracle* o) {
 static void atrous_pass(PostOracle* o, const Half4* in, Half4* out, int pass_no) {
     static const float kvar[2][2] = {{0.25f, 0.125f}, {0.125f, 0.0625f}};
     static const float kern[3] = {0.375f, 0.25f, 0.0625f};
+#pragma omp parallel for schedule(static)
     for (int y = 0; y < o->h; y++)
         for (int x = 0; x < o->w; x++) {
             size_t i = (size_t)y * o->w + x;
@@ -402,7 +406,9 @@ static uint32_t unorm8(float c) {
 }
 /* GBufferBlit.frag:18-46 */
 static void present_pass(const PostOracle* o, int debug_channel, uint32_t* rgba) {
-    for (size_t i = 0, n = (size_t)o->w * o->h; i < n; i++) {
+    const int64_t n = (int64_t)o->w * o->h;
+#pragma omp parallel for schedule(static)
+    for (int64_t i = 0; i < n; i++) {
         uint32_t a = o->albedo[i];
         float alb[3] = {(float)(a & 255u) / 255.0f, (float)((a >> 8) & 255u) / 255.0f, (float)((a >> 16) & 255u) / 255.0f};
         float irr[4], c[3];

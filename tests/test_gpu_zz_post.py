@@ -63,6 +63,14 @@ def test_synthetic_sequence_bit_exact(passes):
     _run_both(seq, w, h, passes, reset_at=(4,), what=f"passes={passes}")
 
 
+def test_full_size_3840x2160_bit_exact():
+    """BASELINE's frame size: two 4K frames (the second one reprojects), five passes, every plane and the image bit-exact —
+    covers interior CTAs of every pass and 64-bit indexing.  The oracle runs its passes on all host threads."""
+    w, h = 3840, 2160
+    seq = pu.synthetic_sequence(w, h, 2, seed=77)
+    _run_both(seq, w, h, 5, what="4K")
+
+
 def test_static_camera_long_history_bit_exact():
     w, h = 64, 48
     seq = pu.synthetic_sequence(w, h, 70, seed=7, moving=False)
