@@ -61,6 +61,7 @@ def test_argument_validation_without_a_gpu():
     assert lib.vrt_create(C.byref(bad), C.byref(h)) == -1
     assert b"struct_size" in lib.vrt_last_error(None)
     assert lib.vrt_sync(None, 0, None) == -1 and lib.vrt_render(None, None, None, None) == -1
+    assert lib.vrt_trace_glsl(None, 0, None, None, None, 0, None) == -1
 
 
 def test_product_never_imports_the_oracle():
@@ -69,6 +70,7 @@ def test_product_never_imports_the_oracle():
         if p.suffix in (".py", ".cu", ".cuh", ".cpp", ".h", ".hpp") or p.name == "Makefile":
             t = p.read_text(errors="ignore")
             assert "pyoracle" not in t and "liboracle" not in t and "vrt_oracle" not in t and "refharness" not in t, p
+            assert "pypostoracle" not in t and "post_oracle" not in t and "orc_trace" not in t, p
 
 
 def test_post_header_symbols_all_exported():

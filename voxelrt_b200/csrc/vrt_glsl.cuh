@@ -5,7 +5,7 @@
 // and the optional ray/cell interaction-mask LUT (GpuRenderer.cpp:193-210).  These change which cells a ray visits and
 // therefore normals and iteration counts relative to the CPU renderer, so they live in their OWN entry point
 // (vrt_trace_glsl) and never touch the bit-exact frame kernels.  Arithmetic: fp32 RN, one operation at a time, no FMA
-// (the canonical form the oracle's orc_trace_glsl defines; GLSL itself leaves contraction to the compiler).
+// (the canonical form the parity oracle defines for this entry point; GLSL itself leaves contraction to the compiler).
 #pragma once
 #include "vrt_device.cuh"
 
