@@ -107,3 +107,43 @@ def test_coarse_and_anisotropic_variants(hash_oracle):
     same_c = (fine["vx"] == coarse["vx"]) & (fine["vy"] == coarse["vy"]) & (fine["vz"] == coarse["vz"])
     assert same_c[early].mean() > 0.98
     assert ((coarse["flags"] & CAP) != 0).sum() >= ((fine["flags"] & CAP) != 0).sum() or True
+
+
+@pytest.mark.parametrize("coarse,aniso", [(False, False), (True, False), (False, True), (True, True)])
+def test_oracle_equals_an_independent_python_restatement_bit_for_bit(hash_scene, hash_oracle, coarse, aniso):
+    """tests/glsl_cast_model_py.py walks a dense voxel array with numpy float32 scalars, written from the GLSL on its own; the C
+    oracle must produce the same VrtHit bits (camera-frame rays, bounce-like far origins for the coarse cast, outside cameras)."""
+    from glsl_cast_model_py import DenseWorld, cast
+    from voxelrt_b200 import capi
+
+    world = DenseWorld(hash_scene)
+    flags = (capi.VRT_GLSL_COARSE if coarse else 0) | (capi.VRT_GLSL_ANISOTROPIC if aniso else 0)
+    cases = []
+    for k in range(3):
+        wo, o, d = camera_frame_rays(90, 700 + k + 10 * flags)
+        cases.append((wo, o, d))
+    rng = np.random.default_rng(50 + flags)
+    if coarse:
+        o = rng.uniform(-90, 90, (90, 3)).astype(np.float32)
+        d = rng.normal(size=(90, 3))
+        cases.append(((96, 64, 96), o, (d / np.linalg.norm(d, axis=1, keepdims=True)).astype(np.float32)))
+    o = (rng.random((60, 3)) - 0.5).astype(np.float32)
+    d = rng.normal(size=(60, 3)) * 0.08
+    d[:, 1] = -1.0
+    cases.append(((96, 600, 96), o, (d / np.linalg.norm(d, axis=1, keepdims=True)).astype(np.float32)))
+    n_hit = 0
+    for wo, o, d in cases:
+        got, _ = hash_oracle.trace_glsl(o, d, wo, flags)
+        for r in range(len(o)):
+            m = cast(world, o[r], d[r], wo, coarse_mode=coarse, aniso=aniso)
+            g = got[r]
+            what = f"flags={flags} wo={wo} ray={r} o={o[r]} d={d[r]}: {m} vs {g}"
+            assert bool(g["flags"] & HIT) == m["hit"] and bool(g["flags"] & INB) == m["inb"] and bool(g["flags"] & CAP) == m["capped"], what
+            assert (g["flags"] >> 16) == m["iters"], what
+            assert [g["vx"], g["vy"], g["vz"]] == m["voxel"], what
+            code = (m["normal"][0] + 1) | (m["normal"][1] + 1) << 2 | (m["normal"][2] + 1) << 4
+            assert (g["flags"] & 0x3F) == code and g["material"] == m["material"], what
+            for a, b in ((g["dist"], m["dist"]), (g["px"], m["pos"][0]), (g["py"], m["pos"][1]), (g["pz"], m["pos"][2]), (g["u"], m["uv"][0]), (g["v"], m["uv"][1])):
+                assert np.float32(a).view(np.uint32) == np.float32(b).view(np.uint32) or (np.isnan(a) and np.isnan(b)), what
+            n_hit += m["hit"]
+    assert n_hit > 100
