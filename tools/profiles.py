@@ -49,6 +49,8 @@ def main():
                            stdout=subprocess.DEVNULL)
     if (OUT / "prof_wave.ncu-rep").exists():
         summarise(OUT / "prof_wave.ncu-rep", f"{tag}_ncu_k_wave_trace_2bounces")
+    if (OUT / "prof_atrous.ncu-rep").exists():  # the GBuffer step's filter kernel
+        summarise(OUT / "prof_atrous.ncu-rep", f"{tag}_ncu_k_atrous")
     rep = OUT / "prof_render.ncu-rep"
     if rep.exists():
         det = subprocess.run(["ncu", "-i", str(rep), "--page", "details"], capture_output=True, text=True).stdout
@@ -81,7 +83,9 @@ def main():
                      ("launches.csv", f"{tag}_launches_4k_primary.csv"), ("bench_sponza.json", f"{tag}_bench_sponza_1080p_1bounce.json"),
                      ("bench_large.json", f"{tag}_bench_large_4k_2bounces.json"), ("bench_edits.json", f"{tag}_bench_edits_4k.json"), ("bench_edits_brush.json", f"{tag}_bench_edits_brush_4k.json"),
                      ("bench_2gpu.json", f"{tag}_bench_4k_primary_2gpu.json"), ("bench_4gpu.json", f"{tag}_bench_4k_primary_4gpu.json"),
-                     ("bench_8gpu.json", f"{tag}_bench_4k_primary_8gpu.json"), ("macro_stats.log", f"{tag}_macro_stats.txt")):
+                     ("bench_8gpu.json", f"{tag}_bench_4k_primary_8gpu.json"), ("macro_stats.log", f"{tag}_macro_stats.txt"),
+                     ("launches_post.csv", f"{tag}_launches_post_4k.csv"), ("post_check.log", f"{tag}_post_check.log"), ("post_check.json", f"{tag}_post_check.json"),
+                     ("bench_present.json", f"{tag}_bench_present_1bounce.json")):
         if (OUT / src).exists() and (OUT / src).stat().st_size:
             shutil.copy(OUT / src, PROF / dst)
 
