@@ -380,7 +380,23 @@ def present_block(args, ctx, frame, stream, fb, w, h, peak):
         gb.render_present(ctx, fr)
     e2e_ms = (time.perf_counter() - t0) * 1e3 / args.steps
     gb.close()
+    cpu = None
+    if not args.no_cpu:
+        # reported baseline, not a target: the image-space ORACLE (a scalar C port of the shaders, OpenMP over rows) on one traced frame —
+        # the reference itself runs this step as GLSL on a GPU and has no CPU implementation of it
+        from oracle import pypostoracle
+
+        tiles_host = fb.cpu().numpy()
+        po = pypostoracle.PostOracle(w, h)
+        po.set_passes(n)
+        proj, inv, _, _ = base.matrices(w, h)
+        po.set_camera(proj, inv, base.pos)
+        t0 = time.perf_counter()
+        po.denoise_present(tiles_host)
+        cpu = {"ms_per_frame": (time.perf_counter() - t0) * 1e3, "kind": "port", "cores": os.cpu_count(),
+               "sample": f"one {w}x{h} frame without history (every pixel takes the 7x7 variance pass), {n} passes"}
     return {
+        "cpu_baseline": cpu,
         "what": "CopyTiledFramebuffer + Reproject + Filter(-1, 0..%d) + GBufferBlit as CUDA kernels on the traced frame" % (n - 1),
         "passes": n,
         "ms_per_frame": ms,
