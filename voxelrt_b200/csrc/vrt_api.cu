@@ -894,9 +894,7 @@ extern "C" int vrt_read_sector(VrtContext* ctx, int32_t sx, int32_t sy, int32_t 
     if (((uint32_t)(sx | sz) >> ctx->sxz) != 0 || ((uint32_t)sy >> ctx->sy) != 0) return fail(ctx, VRT_ERR_INVALID, "sector outside the view");
     DeviceGuard g(ctx->device);
     CU(cudaStreamSynchronize(ctx->stream));
-    uint32_t si = (uint32_t)sx | ((uint32_t)sz << ctx->sxz) | ((uint32_t)sy << (2 * ctx->sxz));
     uint4 h;
-    (void)si;
     CU(cudaMemcpy(&h, ctx->d_hdr + hdr_index(ctx->sxp, ctx->sxp * ctx->sxp, sx, sy, sz), sizeof(h),
                   cudaMemcpyDeviceToHost));  // the DEVICE copy is what is inspected
     uint64_t mask = (uint64_t)h.x | ((uint64_t)h.y << 32);
