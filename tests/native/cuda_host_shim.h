@@ -1,0 +1,50 @@
+// The few CUDA device-side names voxelrt_b200/csrc/vrt_post.cu uses, defined for a HOST build (tests/native/emu_post.cpp): the
+// kernels of the GBuffer step are plain per-thread functions (no shared memory, no barriers), so running every (block, thread) of
+// the grid in a loop executes exactly the arithmetic the GPU executes.  Build with -ffp-contract=off: __fmul_rn(a,b) + c must not
+// fuse, FMAs happen only where the source says __fmaf_rn.  TEST INFRASTRUCTURE ONLY.
+#pragma once
+#include <immintrin.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstddef>
+#include <cstdint>
+#include <cstring>
+
+#define __device__
+#define __global__
+#define __forceinline__ inline
+#define __launch_bounds__(...)
+#define __grid_constant__
+
+struct uint2 { unsigned x, y; };
+struct uint4 { unsigned x, y, z, w; };
+struct float3 { float x, y, z; };
+struct float4 { float x, y, z, w; };
+struct dim3 { unsigned x = 1, y = 1, z = 1; };
+static inline uint2 make_uint2(unsigned x, unsigned y) { return {x, y}; }
+static inline uint4 make_uint4(unsigned x, unsigned y, unsigned z, unsigned w) { return {x, y, z, w}; }
+static inline float3 make_float3(float x, float y, float z) { return {x, y, z}; }
+static inline float4 make_float4(float x, float y, float z, float w) { return {x, y, z, w}; }
+
+static thread_local dim3 blockIdx, threadIdx, blockDim;
+
+template <class T>
+static inline T __ldg(const T* p) { return *p; }
+static inline float __fmaf_rn(float a, float b, float c) { return std::fmaf(a, b, c); }
+static inline float __fmul_rn(float a, float b) { return a * b; }
+static inline float __fadd_rn(float a, float b) { return a + b; }
+static inline float __fsub_rn(float a, float b) { return a - b; }
+static inline float __fdiv_rn(float a, float b) { return a / b; }
+static inline float __fsqrt_rn(float a) { return std::sqrt(a); }
+static inline unsigned __float_as_uint(float f) { unsigned u; std::memcpy(&u, &f, 4); return u; }
+static inline int __float_as_int(float f) { int u; std::memcpy(&u, &f, 4); return u; }
+static inline float __uint_as_float(unsigned u) { float f; std::memcpy(&f, &u, 4); return f; }
+static inline float __int_as_float(int u) { float f; std::memcpy(&f, &u, 4); return f; }
+struct __half { unsigned short v; };
+static inline __half __ushort_as_half(unsigned short u) { return {u}; }
+static inline unsigned short __half_as_ushort(__half h) { return h.v; }
+static inline float __half2float(__half h) { return _cvtsh_ss(h.v); }                                              // vcvtph2ps: exact
+static inline __half __float2half_rn(float f) { return {(unsigned short)_cvtss_sh(f, _MM_FROUND_TO_NEAREST_INT)}; }  // vcvtps2ph, RNE
+using std::max;
+using std::min;

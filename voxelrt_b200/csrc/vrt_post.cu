@@ -9,8 +9,12 @@
 // blit is fused into the reprojection kernel (each thread unpacks its own pixel from the tile framebuffer), so a frame
 // is 1 + 1 + N + 1 launches.  Arithmetic is spelled operation by operation (the library is built with -fmad=false) in
 // the canonical order the parity oracle defines; exp/log are the same polynomial forms.
+// (tests/native/emu_post.cpp compiles the device half of this file for the HOST behind a small shim, VRT_HOST_EMULATION, so
+// that the CPU test tier checks these very kernels against the oracle without a GPU.)
+#ifndef VRT_HOST_EMULATION
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
+#endif
 
 #include <cmath>
 #include <cstdio>
@@ -282,6 +286,22 @@ __device__ __forceinline__ float self_weight(const INormal cn) { return (cn.x * 
 struct TapRcp {
     float v[49];  // 1 / (length(offset) + 0.001) per tap, row-major over the (2R+1)^2 window
 };
+// 1 / (length(offset) + 0.001) for the (2r+1)^2 taps at dilation d: IEEE sqrt, add, divide, as the oracle computes them per tap
+inline TapRcp tap_rcp(int r, int d) {
+    TapRcp t{};
+    const int n = 2 * r + 1;
+    for (int ky = -r; ky <= r; ky++)
+        for (int kx = -r; kx <= r; kx++) {
+            const float fx = (float)(kx * d), fy = (float)(ky * d);
+            volatile float sq = fx * fx;  // volatile: no contraction of fx*fx + fy*fy by the host compiler
+            volatile float sq2 = fy * fy;
+            volatile float len = std::sqrt((float)(sq + sq2));
+            volatile float den = len + 0.001f;
+            t.v[(ky + r) * n + (kx + r)] = 1.0f / den;
+        }
+    return t;
+}
+
 
 // ---- Filter.comp pass -1: varianceEstim (:17-68).  in = IrradianceTex records, io_temp = TempIrradianceTex records -------
 __global__ void __launch_bounds__(256) k_variance(const uint4* __restrict__ in, const uint8_t* __restrict__ hist, uint4* io_temp, int w, int h,
@@ -461,6 +481,7 @@ __global__ void __launch_bounds__(256) k_blit_only(const uint32_t* __restrict__ 
 
 }  // namespace vrtpost
 
+#ifndef VRT_HOST_EMULATION
 using namespace vrtpost;
 
 struct VrtGBuffer {
@@ -495,22 +516,6 @@ int gfail(VrtGBuffer* g, int status, const std::string& msg) {
         cudaError_t e__ = (call);                                                                                    \
         if (e__ != cudaSuccess) return gfail(gb, VRT_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e__)); \
     } while (0)
-
-// 1 / (length(offset) + 0.001) for the (2r+1)^2 taps at dilation d: IEEE sqrt, add, divide, as the oracle computes them per tap
-TapRcp tap_rcp(int r, int d) {
-    TapRcp t{};
-    const int n = 2 * r + 1;
-    for (int ky = -r; ky <= r; ky++)
-        for (int kx = -r; kx <= r; kx++) {
-            const float fx = (float)(kx * d), fy = (float)(ky * d);
-            volatile float sq = fx * fx;  // volatile: no contraction of fx*fx + fy*fy by the host compiler
-            volatile float sq2 = fy * fy;
-            volatile float len = std::sqrt((float)(sq + sq2));
-            volatile float den = len + 0.001f;
-            t.v[(ky + r) * n + (kx + r)] = 1.0f / den;
-        }
-    return t;
-}
 
 void free_planes(VrtGBuffer* g) {
     void* ps[] = {g->irr, g->prev_irr, g->temp_irr, g->moments, g->prev_moments, g->hist, g->hist_prev, g->d_tiles, g->d_rgba};
@@ -741,3 +746,4 @@ VRT_API int vrt_gbuffer_last_launches(const VrtGBuffer* gb, uint64_t* out) {
 }
 
 }  // extern "C"
+#endif  // !VRT_HOST_EMULATION
