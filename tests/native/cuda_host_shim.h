@@ -1,5 +1,5 @@
-// The few CUDA device-side names voxelrt_b200/csrc/vrt_post.cu uses, defined for a HOST build (tests/native/emu_post.cpp): the
-// kernels of the GBuffer step are plain per-thread functions (no shared memory, no barriers), so running every (block, thread) of
+// The few CUDA device-side names voxelrt_b200/csrc/vrt_post.cu and vrt_glsl.cuh use, defined for a HOST build (tests/native/emu_*.cpp):
+// those kernels are plain per-thread functions (no shared memory, no barriers), so running every (block, thread) of
 // the grid in a loop executes exactly the arithmetic the GPU executes.  Build with -ffp-contract=off: __fmul_rn(a,b) + c must not
 // fuse, FMAs happen only where the source says __fmaf_rn.  TEST INFRASTRUCTURE ONLY.
 #pragma once
@@ -12,6 +12,7 @@
 #include <cstring>
 
 #define __device__
+#define __host__
 #define __global__
 #define __forceinline__ inline
 #define __launch_bounds__(...)
@@ -46,5 +47,10 @@ static inline __half __ushort_as_half(unsigned short u) { return {u}; }
 static inline unsigned short __half_as_ushort(__half h) { return h.v; }
 static inline float __half2float(__half h) { return _cvtsh_ss(h.v); }                                              // vcvtph2ps: exact
 static inline __half __float2half_rn(float f) { return {(unsigned short)_cvtss_sh(f, _MM_FROUND_TO_NEAREST_INT)}; }  // vcvtps2ph, RNE
+static inline int __popc(unsigned x) { return __builtin_popcount(x); }
+static inline int __ffs(int x) { return __builtin_ffs(x); }
+static inline int __float2int_rd(float x) { return (int)std::floor(x); }
+static inline int __float2int_rn(float x) { return (int)std::lrintf(x); }
+static inline float __int2float_rn(int x) { return (float)x; }
 using std::max;
 using std::min;
