@@ -6,6 +6,7 @@
 #include <immintrin.h>
 
 #include <algorithm>
+#include <cfenv>
 #include <cmath>
 #include <cstddef>
 #include <cstdint>
@@ -52,5 +53,29 @@ static inline int __ffs(int x) { return __builtin_ffs(x); }
 static inline int __float2int_rd(float x) { return (int)std::floor(x); }
 static inline int __float2int_rn(float x) { return (int)std::lrintf(x); }
 static inline float __int2float_rn(int x) { return (float)x; }
+// directed rounding (FADD.RM & co.): the x87/SSE rounding mode is switched around ONE volatile operation
+static inline float __fadd_rd(float a, float b) { std::fesetround(FE_DOWNWARD); volatile float x = a, y = b; volatile float r = x + y; std::fesetround(FE_TONEAREST); return r; }
+static inline float __fsub_rd(float a, float b) { std::fesetround(FE_DOWNWARD); volatile float x = a, y = b; volatile float r = x - y; std::fesetround(FE_TONEAREST); return r; }
+static inline float __fmaf_rd(float a, float b, float c) { std::fesetround(FE_DOWNWARD); volatile float x = a, y = b, z = c; volatile float r = __builtin_fmaf(x, y, z); std::fesetround(FE_TONEAREST); return r; }
+static inline float __frcp_rn(float x) { return 1.0f / x; }
+static inline unsigned __byte_perm(unsigned x, unsigned y, unsigned s) {
+    const unsigned long long v = (unsigned long long)x | ((unsigned long long)y << 32);
+    unsigned r = 0;
+    for (int i = 0; i < 4; i++) {
+        const unsigned sel = (s >> (4 * i)) & 0xF;
+        unsigned b = (unsigned)(v >> (8 * (sel & 7))) & 0xFF;
+        if (sel & 8) b = (b & 0x80) ? 0xFF : 0x00;
+        r |= b << (8 * i);
+    }
+    return r;
+}
+// one lane at a time: a warp of one (the traversal's results are defined per lane, whatever the warp it runs in)
+static inline unsigned __activemask() { return 1u; }
+static inline int __all_sync(unsigned, int p) { return p; }
+static inline int __any_sync(unsigned, int p) { return p; }
+template <class... A> static inline void __syncwarp(A...) {}
+template <class T> static inline T __shfl_down_sync(unsigned, T v, unsigned) { return v; }
+template <class T, class U> static inline T atomicAdd(T* p, U v) { T o = *p; *p = (T)(o + v); return o; }
+using std::isinf;
 using std::max;
 using std::min;

@@ -40,10 +40,15 @@ class DeviceLayout:
 
         self.sxz, self.sy = sxz, sy
         sxp, syp = (1 << sxz) + 2, (1 << sy) + 2
-        self.hdr = np.zeros((sxp * sxp * syp, 4), np.uint32)
+        # k_init_headers: the bordered grid with 2 * sxp^2 OUTSIDE guard entries before and after it (the fast traversal loop does
+        # not clamp its header index)
+        n, guard = sxp * sxp * syp, 2 * sxp * sxp
+        self.hdr_all = np.zeros((n + 2 * guard, 4), np.uint32)
+        self.hdr_all[:, 3] = 0x80000000  # VRT_HDR_OUTSIDE
+        self.hdr = self.hdr_all[guard : guard + n]  # a view: entry 0 of the grid
         inside = np.zeros((syp, sxp, sxp), bool)  # [y, z, x] of the bordered grid
         inside[1:-1, 1:-1, 1:-1] = True
-        self.hdr[~inside.reshape(-1), 3] = 0x80000000  # VRT_HDR_OUTSIDE on the border
+        self.hdr[inside.reshape(-1), 3] = 0
         n_bricks = sum(bin(int(m)).count("1") for m, _ in scene["sectors"].values())
         self.cells = np.zeros((n_bricks * 8, 2), np.uint32)
         self.voxels = np.zeros(n_bricks * 512, np.uint8)

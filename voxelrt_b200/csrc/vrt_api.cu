@@ -227,34 +227,7 @@ DevScene dev_scene(const VrtContext* ctx) {
 }
 
 // Constants of the traversal frame for a world origin (see RayFrame).
-RayFrame ray_frame(const VrtContext* ctx, const int32_t wo[3]) {
-    const int MAGIC_BITS = VRT_MAGIC_BITS;
-    RayFrame W;
-    W.wx = wo[0];
-    W.wy = wo[1];
-    W.wz = wo[2];
-    const int lox = wo[0] & 31, loy = wo[1] & 31, loz = wo[2] & 31;
-    W.mgx = 12582912.0f + (float)lox;  // exact: integers below 2^24
-    W.mgy = 12582912.0f + (float)loy;
-    W.mgz = 12582912.0f + (float)loz;
-    const int bx = wo[0] - lox, by = wo[1] - loy, bz = wo[2] - loz;  // wo & ~31
-    // (unsigned arithmetic: the MAGIC_BITS offsets wrap around by design and cancel in the kernel)
-    W.hx = (int)((uint32_t)bx - (uint32_t)MAGIC_BITS);
-    W.hy = (int)((uint32_t)by - (uint32_t)MAGIC_BITS);
-    W.hz = (int)((uint32_t)bz - (uint32_t)MAGIC_BITS);
-    const int lim = 1 << 20;
-    W.fast_ok = (wo[0] >= -lim && wo[0] <= lim && wo[1] >= -lim && wo[1] <= lim && wo[2] >= -lim && wo[2] <= lim) ? 1 : 0;
-    W.macro = ctx->macro_on;
-    W.hsx = (int)((uint32_t)(bx >> 5) - (uint32_t)MAGIC_BITS), W.hsy = (int)((uint32_t)(by >> 5) - (uint32_t)MAGIC_BITS),
-    W.hsz = (int)((uint32_t)(bz >> 5) - (uint32_t)MAGIC_BITS);
-    W.klx = (int)((uint32_t)MAGIC_BITS - (uint32_t)bx), W.kly = (int)((uint32_t)MAGIC_BITS - (uint32_t)by), W.klz = (int)((uint32_t)MAGIC_BITS - (uint32_t)bz);
-    // hdr_index of the (possibly far out-of-view) sector holding the frame origin, minus MAGIC_BITS on every axis: the
-    // loop adds SQ * stride per axis (SQ = MAGIC_BITS + sector coordinate relative to that sector), which brings the
-    // (wrapping) sum back inside the header grid
-    const uint32_t sxp = ctx->sxp, sxzp = ctx->sxp * ctx->sxp, MB = (uint32_t)MAGIC_BITS;
-    W.hoff = W.fast_ok ? (int)(((uint32_t)(bx >> 5) + 1u - MB) + ((uint32_t)(bz >> 5) + 1u - MB) * sxp + ((uint32_t)(by >> 5) + 1u - MB) * sxzp) : 0;
-    return W;
-}
+RayFrame ray_frame(const VrtContext* ctx, const int32_t wo[3]) { return make_ray_frame(ctx->sxp, ctx->macro_on, wo); }
 
 // Rebuilds the empty-sector boxes (k_box_*) on the context stream when they are stale.
 int rebuild_boxes(VrtContext* ctx) {
