@@ -18,6 +18,8 @@
 #define __forceinline__ inline
 #define __launch_bounds__(...)
 #define __grid_constant__
+#define __shared__
+#define __align__(n) alignas(n)
 
 struct uint2 { unsigned x, y; };
 struct uint4 { unsigned x, y, z, w; };
@@ -74,6 +76,9 @@ static inline unsigned __activemask() { return 1u; }
 static inline int __all_sync(unsigned, int p) { return p; }
 static inline int __any_sync(unsigned, int p) { return p; }
 template <class... A> static inline void __syncwarp(A...) {}
+static inline void __syncthreads() {}
+static inline unsigned __ballot_sync(unsigned, int p) { return p ? 1u : 0u; }
+template <class T> static inline T __shfl_sync(unsigned, T v, int) { return v; }
 template <class T> static inline T __shfl_down_sync(unsigned, T v, unsigned) { return v; }
 template <class T, class U> static inline T atomicAdd(T* p, U v) { T o = *p; *p = (T)(o + v); return o; }
 using std::isinf;

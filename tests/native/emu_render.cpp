@@ -1,0 +1,54 @@
+// libemu_render.so — the per-pixel body of the FRAME kernels (voxelrt_b200/csrc/vrt_shade.cuh: primary_ray, cast_ray, shade_pixel_primary
+// for bounces = 0 and shade_pixel for frames with blue-noise bounces and the sky cube) compiled for the host and run pixel by pixel; the
+// frame constants come from the product's own fill_frame_params.  Output: the 16 B/px tile framebuffer (VrtTile) like store_pixel writes
+// it.  Macro steps off (they need the box builder).  TEST INFRASTRUCTURE ONLY.
+#define VRT_HOST_EMULATION 1
+#include "cuda_host_shim.h"
+#include "../../voxelrt_b200/csrc/vrt_shade.cuh"
+
+using namespace vrt;
+
+extern "C" {
+#define EMU_API __attribute__((visibility("default")))
+
+struct EmuScene {
+    const uint4* hdr;
+    const uint2* cells;
+    const uint8_t* voxels;
+    const uint2* palette;
+    uint32_t sxz, sy;
+};
+
+EMU_API void emu_render(const EmuScene* e, const VrtFrame* f, const uint8_t* blue_noise, const uint32_t* sky, const VrtSkyDesc* sky_desc, VrtTile* out,
+                        VrtHit* aux) {
+    DevScene S{};
+    S.hdr = e->hdr, S.cells = e->cells, S.voxels = e->voxels, S.palette = e->palette;
+    S.sxz = e->sxz, S.sy = e->sy;
+    S.lim_xz = 32u << e->sxz, S.lim_y = 32u << e->sy;
+    S.sxp = (1u << e->sxz) + 2, S.sxzp = S.sxp * S.sxp;
+    S.n_hdr = S.sxzp * ((1u << e->sy) + 2);
+    uint32_t albedo[256];  // k_palette_albedo: albedo_rgb_bits of every palette entry
+    for (int i = 0; i < 256; i++) albedo[i] = albedo_rgb_bits(e->palette[i].x);
+    S.albedo = albedo;
+    FrameParams F;
+    fill_frame_params(F, f, S.sxp, 0, blue_noise, sky, sky_desc);
+    F.aux = aux;
+    const int w = (int)f->width, h = (int)f->height;
+#pragma omp parallel for schedule(dynamic, 4)
+    for (int y = 0; y < h; y++) {
+        blockDim.x = 128, blockDim.y = blockDim.z = 1;
+        for (int x = 0; x < w; x++) {
+            threadIdx.x = (unsigned)(x & 31);
+            PixelOut P;
+            if (F.bounces == 0) shade_pixel_primary<false>(S, F, (uint32_t)x, (uint32_t)y, true, P);
+            else shade_pixel<false, false>(S, F, (uint32_t)x, (uint32_t)y, true, P);
+            VrtTile* t = out + ((size_t)(y >> 2) * (size_t)(w >> 2) + (size_t)(x >> 2));
+            const int lane = (x & 3) | ((y & 3) << 2);
+            t->albedo[lane] = P.albedo;
+            t->depth[lane] = P.depth;
+            t->irr_rg[lane] = P.irr_rg;
+            t->irr_bx[lane] = P.irr_bx;
+        }
+    }
+}
+}

@@ -1,0 +1,71 @@
+"""The per-pixel body of the FRAME kernels in the CPU tier: voxelrt_b200/csrc/vrt_shade.cuh (primary_ray with the unguarded rcp / sqrt forms,
+cast_ray, shade_pixel_primary for bounces = 0, shade_pixel with blue-noise bounces and the sky cube, G-buffer packing) compiled for the
+host and run pixel by pixel with the product's own fill_frame_params — against the oracle's RenderRow restatement, byte for byte
+(16 B/px tile framebuffer) and hit record for hit record.  Hardware behaviour and the warp-level forms (wavefront passes, CTA compaction,
+macro steps) remain the GPU tests' business."""
+from __future__ import annotations
+
+import ctypes as C
+import subprocess
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+from conftest import assert_hits_equal
+from test_glsl_kernel_on_cpu import DeviceLayout, EmuScene
+
+NATIVE = Path(__file__).resolve().parent / "native"
+
+
+@pytest.fixture(scope="module")
+def emu():
+    from voxelrt_b200 import capi
+
+    subprocess.run(["make", "-s", "-C", str(NATIVE), "libemu_render.so"], check=True)
+    lib = C.CDLL(str(NATIVE / "libemu_render.so"))
+    lib.emu_render.argtypes = [C.POINTER(EmuScene), C.POINTER(capi.VrtFrame), C.c_void_p, C.c_void_p, C.POINTER(capi.VrtSkyDesc), C.c_void_p, C.c_void_p]
+    lib.emu_render.restype = None
+    return lib
+
+
+@pytest.fixture(scope="module")
+def layout(hash_scene):
+    return DeviceLayout(hash_scene)
+
+
+def _frames(w, h, bounces, frame_nos=(1,)):
+    from scenes import camera
+    from voxelrt_b200 import capi
+
+    cams = [camera.Camera(pos=(96.3, 90.2, 20.7), yaw=0.2, pitch=-0.45), camera.Camera(pos=(20.5, 70.1, 150.25), yaw=2.4, pitch=-0.3),
+            camera.Camera(pos=(100.0, 200.0, 100.0), yaw=1.0, pitch=-1.2)]
+    for cam in cams:
+        for fno in frame_nos:
+            proj, inv, wo, frac = cam.matrices(w, h)
+            yield capi.make_frame(w, h, inv, proj, wo, frac, frame_no=fno, bounces=bounces)
+
+
+@pytest.mark.parametrize("bounces", [0, 1, 2])
+def test_frame_kernel_source_equals_oracle(emu, layout, hash_oracle, shading_inputs, bounces):
+    from voxelrt_b200 import capi
+
+    (bn, _), (desc, tex, _) = shading_inputs
+    hash_oracle.set_blue_noise(bn)
+    hash_oracle.set_sky(desc, tex)
+    bn_a = np.ascontiguousarray(bn, np.uint8)
+    tex_a = np.ascontiguousarray(tex, np.uint32)
+    w, h = 320, 180
+    n_hits = 0
+    for frame in _frames(w, h, bounces, frame_nos=(1, 2, 77) if bounces else (1,)):
+        got = np.zeros(w * h // 16, capi.TILE_DTYPE)
+        aux = np.zeros(w * h, capi.HIT_DTYPE)
+        emu.emu_render(C.byref(layout.c), C.byref(frame), bn_a.ctypes.data, tex_a.ctypes.data, C.byref(desc), got.ctypes.data, aux.ctypes.data)
+        f2 = capi.make_frame(w, h, list(frame.inv_proj), list(frame.proj), list(frame.world_origin), list(frame.origin_frac), frame_no=frame.frame_no, bounces=bounces)
+        want, want_aux, _ = hash_oracle.render(f2, want_aux=True)
+        for field in ("albedo", "depth", "irr_rg", "irr_bx"):
+            a, b = got[field].view(np.uint32), want[field].view(np.uint32)
+            assert np.array_equal(a, b), f"bounces={bounces} frame_no={frame.frame_no}: {field} differs at {(a != b).sum()} pixels"
+        assert_hits_equal(aux, want_aux, f"bounces={bounces}: aux hit records")
+        n_hits += int(((want_aux["flags"] & 0x100) != 0).sum())
+    assert n_hits > 10000

@@ -294,46 +294,7 @@ int launch_render(VrtContext* ctx, const VrtFrame* f, void* d_out, VrtHit* d_aux
     if (f->part_index >= part_count) return fail(ctx, VRT_ERR_INVALID, "part_index >= part_count");
 
     FrameParams F;
-    memset(&F, 0, sizeof(F));
-    F.width = f->width;
-    F.height = f->height;
-    memcpy(F.inv_proj, f->inv_proj, sizeof(F.inv_proj));
-    memcpy(F.proj, f->proj, sizeof(F.proj));
-    F.ray_finite = 1u;
-    for (int k = 0; k < 16; k++)
-        if (!(fabsf(f->inv_proj[k]) <= 1.0995116e12f)) F.ray_finite = 0u;  // NaN, inf or > 2^40
-    for (int k = 0; k < 3; k++)
-        if (!(fabsf(f->origin_frac[k]) <= 1.0995116e12f)) F.ray_finite = 0u;
-    for (int k = 0; k < 4; k++) {  // SIMD.h:207-214 with z = 0, w = 1 (IEEE binary32, one rounding per operation as on the device)
-        volatile float t = f->inv_proj[12 + k] * 1.0f;
-        F.ray_c[k] = fmaf(f->inv_proj[8 + k], 0.0f, t);
-    }
-    F.W = ray_frame(ctx, f->world_origin);
-    for (int a = 0; a < 3; a++) F.frac[a] = f->origin_frac[a];
-    F.frame_no = f->frame_no;
-    F.bounces = f->bounces;
-    F.max_iters = f->max_iters ? f->max_iters : VRT_MAX_ITERS_DEFAULT;
-    F.flags = f->flags;
-    F.part_index = f->part_index;
-    F.part_count = part_count;
-    for (uint32_t i = 0; i < 8; i++) {  // CpuRenderer.cpp:258-259, scalar glm on the host there too
-        volatile float fi = (float)i;
-        volatile float ox = fi * 0.75487766624669276005f, oy = fi * 0.56984029099805326591f;
-        float sx = ox + 0.5f, sy = oy + 0.5f;
-        sx -= floorf(sx);
-        sy -= floorf(sy);
-        F.bn_off[i][0] = (uint32_t)(sx * 128.0f);
-        F.bn_off[i][1] = (uint32_t)(sy * 128.0f);
-    }
-    F.bn = ctx->d_bn;
-    F.sky = ctx->d_sky;
-    if (ctx->d_sky) {
-        F.sky_face = ctx->sky.face_size;
-        F.sky_mips = ctx->sky.mip_levels;
-        F.sky_layer_shift = ctx->sky.layer_shift;
-        F.sky_row_shift = (uint32_t)__builtin_ctz(ctx->sky.face_size);
-        for (int i = 0; i < 16; i++) F.sky_mip_offset[i] = ctx->sky.mip_offset[i];
-    }
+    fill_frame_params(F, f, ctx->sxp, ctx->macro_on, ctx->d_bn, ctx->d_sky, &ctx->sky);
     F.out = d_out;
     F.aux = (f->flags & VRT_FRAME_AUX_HITS) ? d_aux : nullptr;
     F.metrics = ctx->d_metrics;
