@@ -32,6 +32,15 @@ def emu():
     return lib
 
 
+def aligned_zeros(shape, dtype, align=256):
+    """cudaMalloc returns 256-byte aligned memory and the fast traversal loop relies on it (it ORs the 8 * cell offset into the
+    address of a brick's 64-byte cell-mask block); numpy only promises 16 bytes."""
+    n = int(np.prod(shape)) * np.dtype(dtype).itemsize
+    raw = np.zeros(n + align, np.uint8)
+    off = (-raw.ctypes.data) % align
+    return raw[off : off + n].view(dtype).reshape(shape)
+
+
 class DeviceLayout:
     """The resident brickmap as the kernels see it, built from a scene dict without any product code."""
 
@@ -43,15 +52,15 @@ class DeviceLayout:
         # k_init_headers: the bordered grid with 2 * sxp^2 OUTSIDE guard entries before and after it (the fast traversal loop does
         # not clamp its header index)
         n, guard = sxp * sxp * syp, 2 * sxp * sxp
-        self.hdr_all = np.zeros((n + 2 * guard, 4), np.uint32)
+        self.hdr_all = aligned_zeros((n + 2 * guard, 4), np.uint32)
         self.hdr_all[:, 3] = 0x80000000  # VRT_HDR_OUTSIDE
         self.hdr = self.hdr_all[guard : guard + n]  # a view: entry 0 of the grid
         inside = np.zeros((syp, sxp, sxp), bool)  # [y, z, x] of the bordered grid
         inside[1:-1, 1:-1, 1:-1] = True
         self.hdr[inside.reshape(-1), 3] = 0
         n_bricks = sum(bin(int(m)).count("1") for m, _ in scene["sectors"].values())
-        self.cells = np.zeros((n_bricks * 8, 2), np.uint32)
-        self.voxels = np.zeros(n_bricks * 512, np.uint8)
+        self.cells = aligned_zeros((n_bricks * 8, 2), np.uint32)
+        self.voxels = aligned_zeros(n_bricks * 512, np.uint8)
         slot = 0
         xs, zs, ys = np.meshgrid(np.arange(4), np.arange(4), np.arange(4), indexing="ij")
         for (sx, sy_, sz), (mask, bricks) in sorted(scene["sectors"].items()):
