@@ -31,7 +31,7 @@ static inline uint4 make_uint4(unsigned x, unsigned y, unsigned z, unsigned w) {
 static inline float3 make_float3(float x, float y, float z) { return {x, y, z}; }
 static inline float4 make_float4(float x, float y, float z, float w) { return {x, y, z, w}; }
 
-static thread_local dim3 blockIdx, threadIdx, blockDim;
+static thread_local dim3 blockIdx, threadIdx, blockDim, gridDim;
 
 template <class T>
 static inline T __ldg(const T* p) { return *p; }
@@ -60,6 +60,12 @@ static inline float __fadd_rd(float a, float b) { std::fesetround(FE_DOWNWARD); 
 static inline float __fsub_rd(float a, float b) { std::fesetround(FE_DOWNWARD); volatile float x = a, y = b; volatile float r = x - y; std::fesetround(FE_TONEAREST); return r; }
 static inline float __fmaf_rd(float a, float b, float c) { std::fesetround(FE_DOWNWARD); volatile float x = a, y = b, z = c; volatile float r = __builtin_fmaf(x, y, z); std::fesetround(FE_TONEAREST); return r; }
 static inline float __frcp_rn(float x) { return 1.0f / x; }
+static inline unsigned __umulhi(unsigned a, unsigned b) { return (unsigned)(((unsigned long long)a * b) >> 32); }
+static inline double __ddiv_rn(double a, double b) { return a / b; }
+static inline double __dmul_rn(double a, double b) { return a * b; }
+static inline double __dadd_rn(double a, double b) { return a + b; }
+static inline double __dsub_rn(double a, double b) { return a - b; }
+static inline double __fma_rn(double a, double b, double c) { return std::fma(a, b, c); }
 static inline unsigned __byte_perm(unsigned x, unsigned y, unsigned s) {
     const unsigned long long v = (unsigned long long)x | ((unsigned long long)y << 32);
     unsigned r = 0;
@@ -79,6 +85,7 @@ template <class... A> static inline void __syncwarp(A...) {}
 static inline void __syncthreads() {}
 static inline unsigned __ballot_sync(unsigned, int p) { return p ? 1u : 0u; }
 template <class T> static inline T __shfl_sync(unsigned, T v, int) { return v; }
+template <class T> static inline T __shfl_xor_sync(unsigned, T v, int) { return v; }  // (kernels that really exchange data between lanes are not emulated)
 template <class T> static inline T __shfl_down_sync(unsigned, T v, unsigned) { return v; }
 template <class T, class U> static inline T atomicAdd(T* p, U v) { T o = *p; *p = (T)(o + v); return o; }
 using std::isinf;

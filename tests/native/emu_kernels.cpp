@@ -1,0 +1,71 @@
+// libemu_kernels.so — per-thread kernels of voxelrt_b200/csrc/vrt_kernels.cuh compiled for the host: K_hit_query (the fp64 picking ray of
+// VoxelMap::RayCast) and the header / empty-box builders (k_init_headers, k_write_headers, k_box_occupancy, k_box_scan, k_box_grow), run
+// thread by thread; with the boxes in place the traversal can be emulated WITH macro steps.  TEST INFRASTRUCTURE ONLY.
+#define VRT_HOST_EMULATION 1
+#include "cuda_host_shim.h"
+#include "../../voxelrt_b200/csrc/vrt_kernels.cuh"
+
+using namespace vrt;
+
+template <class F>
+static void run_1d(uint64_t n, unsigned block, F kernel) {
+    const int64_t blocks = (int64_t)((n + block - 1) / block);
+#pragma omp parallel for schedule(dynamic, 16)
+    for (int64_t b = 0; b < blocks; b++) {
+        blockDim.x = block, blockDim.y = blockDim.z = 1;
+        blockIdx.x = (unsigned)b;
+        for (unsigned t = 0; t < block; t++) {
+            threadIdx.x = t;
+            kernel();
+        }
+    }
+}
+
+extern "C" {
+#define EMU_API __attribute__((visibility("default")))
+
+struct EmuScene {
+    uint4* hdr;  // entry 0 of the bordered grid; 2 * sxp^2 guard entries precede and follow it
+    const uint2* cells;
+    const uint8_t* voxels;
+    const uint2* palette;
+    uint32_t sxz, sy;
+};
+static DevScene scene_of(const EmuScene* e) {
+    DevScene S{};
+    S.hdr = e->hdr, S.cells = e->cells, S.voxels = e->voxels, S.palette = e->palette;
+    S.sxz = e->sxz, S.sy = e->sy;
+    S.lim_xz = 32u << e->sxz, S.lim_y = 32u << e->sy;
+    S.sxp = (1u << e->sxz) + 2, S.sxzp = S.sxp * S.sxp;
+    S.n_hdr = S.sxzp * ((1u << e->sy) + 2);
+    return S;
+}
+
+EMU_API void emu_hit_query(const EmuScene* e, const double* o3, const double* d3, uint32_t max_iters, uint64_t n, VrtHitD* out) {
+    const DevScene S = scene_of(e);
+    run_1d(n, 128, [&] { k_hit_query(S, o3, d3, max_iters, n, out); });
+}
+
+// vrt_create + vrt_sync's header path: k_init_headers, then one HeaderUpdate per resident sector through k_write_headers
+EMU_API void emu_build_headers(const EmuScene* e, const uint32_t* index, const uint32_t* mask_lo, const uint32_t* mask_hi, const uint32_t* base, uint32_t n) {
+    const DevScene S = scene_of(e);
+    const uint32_t syp = (1u << e->sy) + 2, guard = 2u * S.sxzp;
+    run_1d((uint64_t)S.n_hdr + 2u * guard, 256, [&] { k_init_headers(e->hdr, S.sxp, syp, guard); });
+    HeaderUpdate* upd = new HeaderUpdate[n ? n : 1];
+    for (uint32_t i = 0; i < n; i++) upd[i] = HeaderUpdate{index[i], mask_lo[i], mask_hi[i], base[i]};
+    run_1d(n, 128, [&] { k_write_headers(upd, n, e->hdr); });
+    delete[] upd;
+}
+
+// rebuild_boxes of vrt_api.cu: the same five launches, in order
+EMU_API void emu_build_boxes(const EmuScene* e, uint32_t* sat) {
+    const DevScene S = scene_of(e);
+    const uint32_t sxp = S.sxp, syp = (1u << e->sy) + 2, sxzp = S.sxzp, n = S.n_hdr;
+    run_1d(n, 256, [&] { k_box_occupancy(e->hdr, sat, n); });
+    run_1d(sxp * syp, 128, [&] { k_box_scan(sat, sxp * syp, sxp, 1u, sxp * syp, sxp, 0u); });
+    run_1d(sxp * syp, 128, [&] { k_box_scan(sat, sxp * syp, sxp, sxp, sxp, 1u, sxzp); });
+    run_1d(sxzp, 128, [&] { k_box_scan(sat, sxzp, syp, sxzp, sxzp, 1u, 0u); });
+    const uint32_t n_view = 1u << (2 * e->sxz + e->sy);
+    run_1d(n_view, 128, [&] { k_box_grow(e->hdr, sat, sxp, sxzp, 1 << e->sxz, 1 << e->sy); });
+}
+}

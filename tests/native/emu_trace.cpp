@@ -20,7 +20,8 @@ struct EmuScene {
     uint32_t sxz, sy;
 };
 
-// mode 0: cast_ray as k_trace calls it; 1: force the generic loop (what special rays take)
+// mode 0: cast_ray as k_trace calls it, macro steps off; 1: force the generic loop (what special rays take);
+// 2: macro steps ON (the headers must carry the boxes of the box builder, tests/native/emu_kernels.cpp)
 EMU_API void emu_trace(const EmuScene* e, const int32_t wo[3], const float* o3, const float* d3, uint32_t max_iters, uint64_t n, VrtHit* out,
                        int mode, uint64_t* n_fast) {
     DevScene S{};
@@ -29,7 +30,7 @@ EMU_API void emu_trace(const EmuScene* e, const int32_t wo[3], const float* o3, 
     S.lim_xz = 32u << e->sxz, S.lim_y = 32u << e->sy;
     S.sxp = (1u << e->sxz) + 2, S.sxzp = S.sxp * S.sxp;
     S.n_hdr = S.sxzp * ((1u << e->sy) + 2);
-    RayFrame W = make_ray_frame(S.sxp, 0, wo);
+    RayFrame W = make_ray_frame(S.sxp, mode == 2 ? 1 : 0, wo);
     if (mode == 1) W.fast_ok = 0;
     if (max_iters == 0) max_iters = VRT_MAX_ITERS_DEFAULT;
     uint64_t fast = 0;
