@@ -69,3 +69,24 @@ def test_frame_kernel_source_equals_oracle(emu, layout, hash_oracle, shading_inp
         assert_hits_equal(aux, want_aux, f"bounces={bounces}: aux hit records")
         n_hits += int(((want_aux["flags"] & 0x100) != 0).sum())
     assert n_hits > 10000
+
+
+def test_bench_terrain_frame_reference_camera(emu, bench_scene, bench_oracle):
+    """BASELINE configs[0]/[1]'s scene (the FastNoise2 terrain, or the hash terrain over the same sectors where the reference's
+    FastNoise2 is not in the tree) and the reference's camera (Main.cpp:76-78), primary rays: the frame kernel's pixel source
+    reproduces the oracle's G-buffer bytes and hit records at 640x360."""
+    from scenes import camera
+    from voxelrt_b200 import capi
+
+    L = DeviceLayout(bench_scene)
+    w, h = 640, 360
+    proj, inv, wo, frac = camera.Camera().matrices(w, h)
+    frame = capi.make_frame(w, h, inv, proj, wo, frac, frame_no=1, bounces=0)
+    got = np.zeros(w * h // 16, capi.TILE_DTYPE)
+    aux = np.zeros(w * h, capi.HIT_DTYPE)
+    emu.emu_render(C.byref(L.c), C.byref(frame), None, None, None, got.ctypes.data, aux.ctypes.data)
+    want, want_aux, st = bench_oracle.render(capi.make_frame(w, h, inv, proj, wo, frac, frame_no=1, bounces=0), want_aux=True)
+    assert got.tobytes() == want.tobytes()
+    assert_hits_equal(aux, want_aux, "bench terrain, reference camera")
+    hits = int(((want_aux["flags"] & 0x100) != 0).sum())
+    assert 0.6 < hits / (w * h) < 0.9  # SURVEY probe: 75 % of the primary rays hit

@@ -62,22 +62,22 @@ class DeviceLayout:
         self.cells = aligned_zeros((n_bricks * 8, 2), np.uint32)
         self.voxels = aligned_zeros(n_bricks * 512, np.uint8)
         slot = 0
-        xs, zs, ys = np.meshgrid(np.arange(4), np.arange(4), np.arange(4), indexing="ij")
+        weights = (np.uint64(1) << (np.arange(4, dtype=np.uint64)[None, None, :] + np.uint64(4) * np.arange(4, dtype=np.uint64)[None, :, None]
+                                    + np.uint64(16) * np.arange(4, dtype=np.uint64)[:, None, None]))  # [y, z, x] -> bit x + 4 z + 16 y
         for (sx, sy_, sz), (mask, bricks) in sorted(scene["sectors"].items()):
             mask = int(mask)
             lo, hi = mask & 0xFFFFFFFF, mask >> 32
             self.hdr[(sx + 1) + (sz + 1) * sxp + (sy_ + 1) * sxp * sxp] = (lo, hi, slot, slot + bin(lo).count("1"))
-            for k in range(bin(mask).count("1")):
-                vox = np.asarray(bricks[k], np.uint8).reshape(8, 8, 8)  # [y, z, x]
-                self.voxels[slot * 512 : slot * 512 + 512] = vox.reshape(-1)
-                for c in range(8):
-                    cx, cz, cy = c & 1, (c >> 1) & 1, c >> 2
-                    sub = vox[cy * 4 : cy * 4 + 4, cz * 4 : cz * 4 + 4, cx * 4 : cx * 4 + 4] != 0  # [y, z, x]
-                    bits = 0
-                    for y, z, x in zip(*np.nonzero(sub)):
-                        bits |= 1 << (int(x) + 4 * int(z) + 16 * int(y))
-                    self.cells[slot * 8 + c] = (bits & 0xFFFFFFFF, bits >> 32)
-                slot += 1
+            k = bin(mask).count("1")
+            vox = np.asarray(bricks, np.uint8).reshape(k, 8, 8, 8)  # [brick, y, z, x]
+            self.voxels[slot * 512 : (slot + k) * 512] = vox.reshape(-1)
+            # cell c = cx | cz<<1 | cy<<2 holds voxels [4cy:4cy+4, 4cz:4cz+4, 4cx:4cx+4]
+            sub = (vox != 0).reshape(k, 2, 4, 2, 4, 2, 4).transpose(0, 1, 3, 5, 2, 4, 6)  # [brick, cy, cz, cx, y, z, x]
+            bits = (sub.astype(np.uint64) * weights).sum(axis=(4, 5, 6), dtype=np.uint64).reshape(k, 8)  # index cy*4 + cz*2 + cx
+            cells = self.cells[slot * 8 : (slot + k) * 8].reshape(k, 8, 2)
+            cells[..., 0] = (bits & np.uint64(0xFFFFFFFF)).astype(np.uint32)
+            cells[..., 1] = (bits >> np.uint64(32)).astype(np.uint32)
+            slot += k
         pal = np.asarray(scene["palette"], np.uint64)
         self.palette = np.stack([(pal & np.uint64(0xFFFFFFFF)).astype(np.uint32), (pal >> np.uint64(32)).astype(np.uint32)], axis=1).copy()
         lut = [interaction_mask(i, o) for o in range(8) for i in range(64)]
