@@ -90,3 +90,35 @@ def test_bench_terrain_frame_reference_camera(emu, bench_scene, bench_oracle):
     assert_hits_equal(aux, want_aux, "bench terrain, reference camera")
     hits = int(((want_aux["flags"] & 0x100) != 0).sum())
     assert 0.6 < hits / (w * h) < 0.9  # SURVEY probe: 75 % of the primary rays hit
+
+
+def test_sponza_frames_one_bounce(emu, shading_inputs):
+    """BASELINE configs[2]'s scene (the bundled Sponza model voxelised into 1024^3, view 32x16x32 sectors), one bounce of blue-noise diffuse
+    rays inside the atrium: the frame kernel's pixel source against the oracle at 384x216, two cameras and frame numbers."""
+    from oracle import pyoracle
+    from scenes import camera, models, terrain
+    from voxelrt_b200 import capi
+
+    if not models.sponza_available(1024):
+        pytest.skip("scenes/_ref/sponza_1024.dat absent (built by __graft_entry__.build() where the reference assets exist)")
+    scene = models.sponza(1024)
+    (bn, _), (desc, tex, _) = shading_inputs
+    orc = pyoracle.OracleMap(5, 4)
+    orc.set_palette(scene["palette"])
+    orc.sync(terrain.scene_records(scene))
+    orc.set_blue_noise(bn)
+    orc.set_sky(desc, tex)
+    L = DeviceLayout(scene, sxz=5, sy=4)
+    bn_a, tex_a = np.ascontiguousarray(bn, np.uint8), np.ascontiguousarray(tex, np.uint32)
+    w, h = 384, 216
+    cams = [camera.Camera(pos=(210.3, 80.2, 505.7), yaw=1.5, pitch=-0.15), camera.Camera(pos=(700.1, 300.4, 520.2), yaw=-1.2, pitch=-0.6)]
+    for frame_no, cam in ((1, cams[0]), (3, cams[1])):
+        proj, inv, wo, frac = cam.matrices(w, h)
+        frame = capi.make_frame(w, h, inv, proj, wo, frac, frame_no=frame_no, bounces=1)
+        got = np.zeros(w * h // 16, capi.TILE_DTYPE)
+        aux = np.zeros(w * h, capi.HIT_DTYPE)
+        emu.emu_render(C.byref(L.c), C.byref(frame), bn_a.ctypes.data, tex_a.ctypes.data, C.byref(desc), got.ctypes.data, aux.ctypes.data)
+        want, want_aux, st = orc.render(capi.make_frame(w, h, inv, proj, wo, frac, frame_no=frame_no, bounces=1), want_aux=True)
+        assert st.hits > w * h
+        assert got.tobytes() == want.tobytes(), f"sponza frame {frame_no}"
+        assert_hits_equal(aux, want_aux, f"sponza frame {frame_no}")
