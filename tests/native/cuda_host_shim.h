@@ -85,7 +85,29 @@ template <class... A> static inline void __syncwarp(A...) {}
 static inline void __syncthreads() {}
 static inline unsigned __ballot_sync(unsigned, int p) { return p ? 1u : 0u; }
 template <class T> static inline T __shfl_sync(unsigned, T v, int) { return v; }
-template <class T> static inline T __shfl_xor_sync(unsigned, T v, int) { return v; }  // (kernels that really exchange data between lanes are not emulated)
+// Warp REPLAY for kernels whose lanes exchange data through a fixed sequence of xor-shuffles and have no divergent control flow around
+// them (the warp-per-brick occupancy build): the emulator runs all 32 lanes once per shuffle call; call #k of round r returns what lane
+// (l ^ mask) passed to call #k in the PREVIOUS round — correct for every k < r by induction, a placeholder otherwise — so after
+// (number of calls + 1) rounds every lane has computed with the right values (stores of earlier rounds are simply overwritten).
+struct ShflReplay {
+    unsigned prev[64][32], cur[64][32];
+    int call;   // index of the next shuffle call of the running lane
+    int lane;
+};
+static thread_local ShflReplay* g_shfl_replay = nullptr;
+template <class T> static inline T __shfl_xor_sync(unsigned, T v, int mask) {
+    ShflReplay* r = g_shfl_replay;
+    if (!r) return v;  // one-lane warp
+    static_assert(sizeof(T) == 4, "replay handles 32-bit values");
+    unsigned bits;
+    std::memcpy(&bits, &v, 4);
+    const int k = r->call++;
+    r->cur[k][r->lane] = bits;
+    const unsigned other = r->prev[k][r->lane ^ mask];
+    T out;
+    std::memcpy(&out, &other, 4);
+    return out;
+}
 template <class T> static inline T __shfl_down_sync(unsigned, T v, unsigned) { return v; }
 template <class T, class U> static inline T atomicAdd(T* p, U v) { T o = *p; *p = (T)(o + v); return o; }
 using std::isinf;

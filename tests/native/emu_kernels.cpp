@@ -57,6 +57,30 @@ EMU_API void emu_build_headers(const EmuScene* e, const uint32_t* index, const u
     delete[] upd;
 }
 
+// K_upload (K2, one WARP per brick: voxel copy + the eight 4x4x4 occupancy masks through xor-shuffle OR-reductions), by warp replay
+EMU_API void emu_upload_bricks(const uint4* staging, const uint32_t* slots, uint32_t n, uint8_t* voxels, uint2* cells) {
+#pragma omp parallel for schedule(dynamic, 8)
+    for (int64_t w = 0; w < (int64_t)n; w++) {
+        ShflReplay R;
+        std::memset(&R, 0, sizeof(R));
+        g_shfl_replay = &R;
+        blockDim.x = 32, blockDim.y = blockDim.z = 1;
+        blockIdx.x = (unsigned)w;
+        int calls = 0;
+        for (int round = 0; round <= 64; round++) {
+            for (unsigned lane = 0; lane < 32; lane++) {
+                threadIdx.x = lane;
+                R.lane = (int)lane, R.call = 0;
+                k_upload_bricks(staging, slots, n, voxels, cells);
+                calls = R.call;
+            }
+            std::memcpy(R.prev, R.cur, sizeof(R.prev));
+            if (round >= calls) break;  // every call has seen correct inputs
+        }
+        g_shfl_replay = nullptr;
+    }
+}
+
 // rebuild_boxes of vrt_api.cu: the same five launches, in order
 EMU_API void emu_build_boxes(const EmuScene* e, uint32_t* sat) {
     const DevScene S = scene_of(e);

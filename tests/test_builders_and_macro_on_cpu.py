@@ -139,3 +139,36 @@ def test_boxes_are_empty_and_macro_steps_change_nothing(libs, layout, hash_scene
         n_iter_diff += int(((got["flags"] >> 16) != (want["flags"] >> 16)).sum())
         assert_hits_equal(trace(o, d, wo, 0), want, f"step by step, wo={wo}")
     assert n_iter_diff < 100  # and it is almost always exact
+
+
+def test_occupancy_build_kernel_by_warp_replay(libs, layout, hash_scene):
+    """K_upload (one warp per dirty brick: copy + the eight 4x4x4 occupancy masks, FlatVoxelStorage::UpdateOccupancy) — its lanes OR their
+    partial masks together through xor-shuffles, so the emulator replays the warp once per shuffle call (cuda_host_shim.h: ShflReplay).
+    Result against the numpy layout (bit = x + 4z + 16y of every non-empty voxel) and the oracle's orc_build_occupancy, which is pinned
+    to the reference's UpdateOccupancy."""
+    from oracle import pyoracle
+
+    k, _ = libs
+    k.emu_upload_bricks.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p]
+    k.emu_upload_bricks.restype = None
+    bricks = np.concatenate([np.asarray(b, np.uint8).reshape(-1, 512) for _, (m, b) in sorted(hash_scene["sectors"].items())])
+    n = len(bricks)
+    assert n * 512 == layout.voxels.size
+    rng = np.random.default_rng(12)
+    slots = rng.permutation(n).astype(np.uint32)  # bricks land in arbitrary slots
+    staging = aligned_zeros(n * 512, np.uint8)
+    staging[:] = bricks.reshape(-1)
+    voxels = aligned_zeros(n * 512, np.uint8)
+    cells = aligned_zeros((n * 8, 2), np.uint32)
+    cells[:] = 0xFFFFFFFF
+    k.emu_upload_bricks(staging.ctypes.data, slots.ctypes.data, n, voxels.ctypes.data, cells.ctypes.data)
+    want_vox = layout.voxels.reshape(n, 512)
+    want_cells = layout.cells.reshape(n, 8, 2)
+    assert np.array_equal(voxels.reshape(n, 512)[slots], want_vox)
+    assert np.array_equal(cells.reshape(n, 8, 2)[slots], want_cells)
+    lib = pyoracle.load()
+    for i in rng.choice(n, 200, replace=False):
+        out = np.zeros(8, np.uint64)
+        lib.orc_build_occupancy(bricks[i].ctypes.data, out.ctypes.data)
+        got = cells.reshape(n, 8, 2)[slots[i]]
+        assert np.array_equal(got[:, 0].astype(np.uint64) | (got[:, 1].astype(np.uint64) << np.uint64(32)), out)
