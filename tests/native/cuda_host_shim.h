@@ -83,7 +83,6 @@ static inline int __all_sync(unsigned, int p) { return p; }
 static inline int __any_sync(unsigned, int p) { return p; }
 template <class... A> static inline void __syncwarp(A...) {}
 static inline void __syncthreads() {}
-static inline unsigned __ballot_sync(unsigned, int p) { return p ? 1u : 0u; }
 template <class T> static inline T __shfl_sync(unsigned, T v, int) { return v; }
 // Warp REPLAY for kernels whose lanes exchange data through a fixed sequence of xor-shuffles and have no divergent control flow around
 // them (the warp-per-brick occupancy build): the emulator runs all 32 lanes once per shuffle call; call #k of round r returns what lane
@@ -107,6 +106,15 @@ template <class T> static inline T __shfl_xor_sync(unsigned, T v, int mask) {
     T out;
     std::memcpy(&out, &other, 4);
     return out;
+}
+static inline unsigned __ballot_sync(unsigned, int p) {
+    ShflReplay* r = g_shfl_replay;
+    if (!r) return p ? 1u : 0u;  // one-lane warp
+    const int k = r->call++;
+    r->cur[k][r->lane] = p ? 1u : 0u;
+    unsigned word = 0;
+    for (int l = 0; l < 32; l++) word |= (r->prev[k][l] & 1u) << l;
+    return word;
 }
 template <class T> static inline T __shfl_down_sync(unsigned, T v, unsigned) { return v; }
 template <class T, class U> static inline T atomicAdd(T* p, U v) { T o = *p; *p = (T)(o + v); return o; }

@@ -81,6 +81,28 @@ EMU_API void emu_upload_bricks(const uint4* staging, const uint32_t* slots, uint
     }
 }
 
+// k_build_occ (one ballot per warp of 32 header entries) by warp replay: the one-bit-per-entry table of the OCC traversal loop
+EMU_API void emu_build_occ(const uint4* hdr_all, uint32_t n_all, uint32_t* occ) {
+    const int64_t warps = ((int64_t)n_all + 31) / 32;
+#pragma omp parallel for schedule(static)
+    for (int64_t w = 0; w < warps; w++) {
+        ShflReplay R;
+        std::memset(&R, 0, sizeof(R));
+        g_shfl_replay = &R;
+        blockDim.x = 32, blockDim.y = blockDim.z = 1;
+        blockIdx.x = (unsigned)w;
+        for (int round = 0; round < 2; round++) {
+            for (unsigned lane = 0; lane < 32; lane++) {
+                threadIdx.x = lane;
+                R.lane = (int)lane, R.call = 0;
+                k_build_occ(hdr_all, n_all, occ);
+            }
+            std::memcpy(R.prev, R.cur, sizeof(R.prev));
+        }
+        g_shfl_replay = nullptr;
+    }
+}
+
 // rebuild_boxes of vrt_api.cu: the same five launches, in order
 EMU_API void emu_build_boxes(const EmuScene* e, uint32_t* sat) {
     const DevScene S = scene_of(e);

@@ -21,7 +21,11 @@ struct EmuScene {
 };
 
 // mode 0: cast_ray as k_trace calls it, macro steps off; 1: force the generic loop (what special rays take);
-// 2: macro steps ON (the headers must carry the boxes of the box builder, tests/native/emu_kernels.cpp)
+// 2: macro steps ON (the headers must carry the boxes of the box builder, tests/native/emu_kernels.cpp);
+// 3: the OCC form of the step-by-step loop (big views: a one-bit sector table is consulted before the header)
+static const uint32_t* g_occ = nullptr;  // mode 3: the one-bit table of k_build_occ (bit index = header index + guard)
+EMU_API void emu_set_occ(const uint32_t* occ) { g_occ = occ; }
+
 EMU_API void emu_trace(const EmuScene* e, const int32_t wo[3], const float* o3, const float* d3, uint32_t max_iters, uint64_t n, VrtHit* out,
                        int mode, uint64_t* n_fast) {
     DevScene S{};
@@ -30,6 +34,7 @@ EMU_API void emu_trace(const EmuScene* e, const int32_t wo[3], const float* o3, 
     S.lim_xz = 32u << e->sxz, S.lim_y = 32u << e->sy;
     S.sxp = (1u << e->sxz) + 2, S.sxzp = S.sxp * S.sxp;
     S.n_hdr = S.sxzp * ((1u << e->sy) + 2);
+    S.occ = g_occ, S.occ_bias = 2u * S.sxzp;
     RayFrame W = make_ray_frame(S.sxp, mode == 2 ? 1 : 0, wo);
     if (mode == 1) W.fast_ok = 0;
     if (max_iters == 0) max_iters = VRT_MAX_ITERS_DEFAULT;
@@ -45,7 +50,8 @@ EMU_API void emu_trace(const EmuScene* e, const int32_t wo[3], const float* o3, 
         H.hit = false;
         const float ox = o3[3 * i], oy = o3[3 * i + 1], oz = o3[3 * i + 2], dx = d3[3 * i], dy = d3[3 * i + 1], dz = d3[3 * i + 2];
         fast += (W.fast_ok && ray_is_fast(ox, oy, oz, dx, dy, dz)) ? 1 : 0;
-        cast_ray<false>(S, W, ox, oy, oz, dx, dy, dz, max_iters, H, R);
+        if (mode == 3) cast_ray<false, true, true>(S, W, ox, oy, oz, dx, dy, dz, max_iters, H, R);
+        else cast_ray<false>(S, W, ox, oy, oz, dx, dy, dz, max_iters, H, R);
         store_hit(out + i, H, R);
     }
     if (n_fast) *n_fast = fast;

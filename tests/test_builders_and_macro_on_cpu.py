@@ -172,3 +172,35 @@ def test_occupancy_build_kernel_by_warp_replay(libs, layout, hash_scene):
         lib.orc_build_occupancy(bricks[i].ctypes.data, out.ctypes.data)
         got = cells.reshape(n, 8, 2)[slots[i]]
         assert np.array_equal(got[:, 0].astype(np.uint64) | (got[:, 1].astype(np.uint64) << np.uint64(32)), out)
+
+
+def test_one_bit_sector_table_and_the_occ_loop(libs, layout, hash_oracle):
+    """k_build_occ (a ballot per 32 header entries, by warp replay) against its definition, and the OCC form of the step-by-step loop (what the
+    frame kernels of big views run for bounce rays) against the oracle."""
+    from voxelrt_b200 import capi
+
+    k, t = libs
+    k.emu_build_occ.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p]
+    k.emu_build_occ.restype = None
+    t.emu_set_occ.argtypes = [C.c_void_p]
+    t.emu_set_occ.restype = None
+    n_all = len(layout.hdr_all)
+    occ = np.zeros((n_all + 31) // 32 + 1, np.uint32)
+    k.emu_build_occ(layout.hdr_all.ctypes.data, n_all, occ.ctypes.data)
+    h = layout.hdr_all
+    want_bits = ((h[:, 0] | h[:, 1]) != 0) | ((h[:, 3] & OUTSIDE) != 0)
+    got_bits = ((occ[np.arange(n_all) >> 5] >> (np.arange(n_all) & 31).astype(np.uint32)) & 1).astype(bool)
+    assert np.array_equal(got_bits, want_bits) and want_bits.any() and not want_bits.all()
+    t.emu_set_occ(occ.ctypes.data)
+    try:
+        rng = np.random.default_rng(31)
+        for wo in ((96, 64, 96), (600, 200, 1500), (30, 500, 30)):
+            o = rng.uniform(-60, 60, (40000, 3)).astype(np.float32)
+            d = rng.normal(size=(40000, 3))
+            d = (d / np.linalg.norm(d, axis=1, keepdims=True)).astype(np.float32)
+            out = np.zeros(len(o), capi.HIT_DTYPE)
+            w = (C.c_int32 * 3)(*wo)
+            t.emu_trace(C.byref(layout.c), w, o.ctypes.data, d.ctypes.data, 0, len(o), out.ctypes.data, 3, None)
+            assert_hits_equal(out, hash_oracle.trace(o, d, wo)[0], f"OCC loop wo={wo}")
+    finally:
+        t.emu_set_occ(None)
