@@ -103,6 +103,40 @@ EMU_API void emu_build_occ(const uint4* hdr_all, uint32_t n_all, uint32_t* occ) 
     }
 }
 
+// k_render itself (one-thread-per-pixel frame kernel: warp tiles of 8x4 pixels numbered inside macro tiles or bands, the multi-GPU screen
+// split, store_pixel), launched like launch_render does: fill_frame_params + fill_frame_partition, blocks of VRT_RENDER_THREADS threads.
+EMU_API int emu_render_kernel(const EmuScene* e, const VrtFrame* f, const uint8_t* bn, const uint32_t* sky, const VrtSkyDesc* sky_desc, void* out,
+                              uint32_t row0, uint32_t row1) {
+    DevScene S = scene_of(e);
+    uint32_t albedo[256];
+    for (int i = 0; i < 256; i++) albedo[i] = albedo_rgb_bits(e->palette[i].x);
+    S.albedo = albedo;
+    FrameParams F;
+    fill_frame_params(F, f, S.sxp, 0, bn, sky, sky_desc);
+    F.out = out;
+    if (!fill_frame_partition(F, f, row0, row1)) return -1;
+    if (F.n_work <= F.work_offset) return 0;
+    const unsigned wpb = VRT_RENDER_THREADS / 32;
+    const int64_t blocks = (F.n_work - F.work_offset + wpb - 1) / wpb;
+    const bool rows = (F.flags & VRT_FRAME_PART_ROWS) != 0u, primary = F.bounces == 0;
+#pragma omp parallel for schedule(dynamic, 8)
+    for (int64_t b = 0; b < blocks; b++) {
+        blockDim.x = VRT_RENDER_THREADS, blockDim.y = blockDim.z = 1;
+        blockIdx.x = (unsigned)b;
+        for (unsigned t = 0; t < VRT_RENDER_THREADS; t++) {
+            threadIdx.x = t;
+            if (primary) {
+                if (rows) k_render<false, true, true>(S, F);
+                else k_render<false, true, false>(S, F);
+            } else {
+                if (rows) k_render<false, false, true>(S, F);
+                else k_render<false, false, false>(S, F);
+            }
+        }
+    }
+    return (int)blocks;
+}
+
 // rebuild_boxes of vrt_api.cu: the same five launches, in order
 EMU_API void emu_build_boxes(const EmuScene* e, uint32_t* sat) {
     const DevScene S = scene_of(e);

@@ -122,3 +122,61 @@ def test_sponza_frames_one_bounce(emu, shading_inputs):
         assert st.hits > w * h
         assert got.tobytes() == want.tobytes(), f"sponza frame {frame_no}"
         assert_hits_equal(aux, want_aux, f"sponza frame {frame_no}")
+
+
+@pytest.fixture(scope="module")
+def kern():
+    from voxelrt_b200 import capi
+
+    subprocess.run(["make", "-s", "-C", str(NATIVE), "libemu_kernels.so"], check=True)
+    lib = C.CDLL(str(NATIVE / "libemu_kernels.so"))
+    lib.emu_render_kernel.argtypes = [C.POINTER(EmuScene), C.POINTER(capi.VrtFrame), C.c_void_p, C.c_void_p, C.POINTER(capi.VrtSkyDesc), C.c_void_p, C.c_uint32, C.c_uint32]
+    lib.emu_render_kernel.restype = C.c_int
+    return lib
+
+
+@pytest.mark.parametrize("size", [(320, 180), (36, 4), (260, 148)])
+def test_k_render_grid_and_the_screen_split(kern, layout, hash_oracle, shading_inputs, size):
+    """k_render as launched (fill_frame_params + fill_frame_partition, warp tiles numbered inside 32x32 macro tiles or 8-pixel bands, store_pixel):
+    the whole frame equals the oracle; for N = 2, 3, 8 ranks — by macro tile and by band (VRT_FRAME_PART_ROWS) — the parts are disjoint and
+    their union is the whole frame, byte for byte (N-GPU == 1-GPU); row ranges (the band-pipelined host path) likewise."""
+    from scenes import camera
+    from voxelrt_b200 import capi
+
+    (bn, _), (desc, tex, _) = shading_inputs
+    hash_oracle.set_blue_noise(bn)
+    hash_oracle.set_sky(desc, tex)
+    bn_a, tex_a = np.ascontiguousarray(bn, np.uint8), np.ascontiguousarray(tex, np.uint32)
+    w, h = size
+    cam = camera.Camera(pos=(96.3, 90.2, 20.7), yaw=0.2, pitch=-0.45)
+    proj, inv, wo, frac = cam.matrices(w, h)
+    SENT = 0xA5A5A5A5
+
+    def run(bounces, part_index=0, part_count=1, flags=0, row0=0, row1=0, into=None):
+        fr = capi.make_frame(w, h, inv, proj, wo, frac, frame_no=5, bounces=bounces, flags=flags, part_index=part_index, part_count=part_count)
+        out = into if into is not None else np.full(w * h * 4, SENT, np.uint32)
+        assert kern.emu_render_kernel(C.byref(layout.c), C.byref(fr), bn_a.ctypes.data, tex_a.ctypes.data, C.byref(desc), out.ctypes.data, row0, row1) >= 0
+        return out
+
+    for bounces in (0, 1):
+        want = hash_oracle.render(capi.make_frame(w, h, inv, proj, wo, frac, frame_no=5, bounces=bounces))[0]
+        want_u = np.frombuffer(want.tobytes(), np.uint32)
+        whole = run(bounces)
+        assert np.array_equal(whole, want_u), f"bounces={bounces}"
+        for flags in (0, capi.VRT_FRAME_PART_ROWS):
+            for n in (2, 3, 8):
+                covered = np.zeros(w * h * 4, bool)
+                acc = np.full(w * h * 4, SENT, np.uint32)
+                for r in range(n):
+                    part = run(bounces, r, n, flags)
+                    mine = part != SENT
+                    assert not (covered & mine).any(), f"parts overlap (n={n}, flags={flags})"
+                    covered |= mine
+                    acc[mine] = part[mine]
+                assert np.array_equal(acc, want_u), f"union of {n} parts (flags={flags}, bounces={bounces})"
+    # row ranges of an unpartitioned frame, written into one buffer
+    acc = np.full(w * h * 4, SENT, np.uint32)
+    rows_total = (h + 31) // 32
+    for r0 in range(0, rows_total, 2):
+        run(0, row0=r0, row1=min(r0 + 2, rows_total), into=acc)
+    assert np.array_equal(acc, np.frombuffer(hash_oracle.render(capi.make_frame(w, h, inv, proj, wo, frac, frame_no=5, bounces=0))[0].tobytes(), np.uint32))

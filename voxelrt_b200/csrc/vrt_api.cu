@@ -299,23 +299,7 @@ int launch_render(VrtContext* ctx, const VrtFrame* f, void* d_out, VrtHit* d_aux
     F.aux = (f->flags & VRT_FRAME_AUX_HITS) ? d_aux : nullptr;
     F.metrics = ctx->d_metrics;
 
-    uint32_t macros_x = (f->width + 31) / 32, macros_y = (f->height + 31) / 32;
-    uint32_t macros = macros_x * macros_y;
-    uint32_t my_macros = macros / part_count + ((macros % part_count) > f->part_index ? 1u : 0u);
-    F.n_work = my_macros * 32u;
-    if (f->flags & VRT_FRAME_PART_ROWS) {  // bands of VRT_BAND_ROWS pixels, 8 warp tiles per 32-pixel group of a band
-        const uint32_t bands = (f->height + VRT_BAND_ROWS - 1) / VRT_BAND_ROWS;
-        const uint32_t mine = bands / part_count + ((bands % part_count) > f->part_index ? 1u : 0u);
-        F.n_work = mine * macros_x * 8u;
-    }
-    F.work_offset = 0;
-    if (row1 != 0 && part_count == 1) {
-        F.work_offset = std::min(row0, macros_y) * macros_x * 32u;
-        F.n_work = std::min(row1, macros_y) * macros_x * 32u;
-    }
-    F.macros_x = macros_x;
-    F.macros_x_magic = macros_x > 1 ? (uint32_t)((0x100000000ull + macros_x - 1) / macros_x) : 0u;
-    if ((uint64_t)macros * macros_x >= 0xFFFFFFFFull) return fail(ctx, VRT_ERR_INVALID, "frame too large");
+    if (!fill_frame_partition(F, f, row0, row1)) return fail(ctx, VRT_ERR_INVALID, "frame too large");
     if (F.n_work <= F.work_offset) return VRT_OK;
     DevScene S = dev_scene(ctx);
     const unsigned wpb = VRT_RENDER_THREADS / 32;
