@@ -1,5 +1,5 @@
-"""Shared fixtures.  `-m "not gpu"` runs here (no GPU): oracle vs golden vectors, host logic, ABI
-exports.  `-m gpu` runs on a B200: the parity tests proper, every one of them through the C ABI of
+"""Shared fixtures.  `-m "not gpu"` runs here (no GPU): oracle vs golden vectors and independent restatements, host logic, ABI
+exports, and the kernels' own source compiled for the host (tests/native/emu_*.cpp behind cuda_host_shim.h; test_*_on_cpu.py).  `-m gpu` runs on a B200: the parity tests proper, every one of them through the C ABI of
 libvoxelrt_b200.so (voxelrt_b200.capi is a 1:1 ctypes binding of include/voxelrt_b200.h)."""
 from __future__ import annotations
 
