@@ -180,3 +180,23 @@ def test_k_render_grid_and_the_screen_split(kern, layout, hash_oracle, shading_i
     for r0 in range(0, rows_total, 2):
         run(0, row0=r0, row1=min(r0 + 2, rows_total), into=acc)
     assert np.array_equal(acc, np.frombuffer(hash_oracle.render(capi.make_frame(w, h, inv, proj, wo, frac, frame_no=5, bounces=0))[0].tobytes(), np.uint32))
+
+
+def test_k_render_linear_output(kern, layout, hash_oracle):
+    """VRT_FRAME_LINEAR_OUTPUT: four planes (albedo, depth, irrRG, irrBX) of w*h words instead of 4x4 tiles — same values."""
+    from scenes import camera
+    from voxelrt_b200 import capi
+
+    w, h = 132, 68
+    cam = camera.Camera(pos=(20.5, 70.1, 150.25), yaw=2.4, pitch=-0.3)
+    proj, inv, wo, frac = cam.matrices(w, h)
+    fr = capi.make_frame(w, h, inv, proj, wo, frac, frame_no=2, bounces=0, flags=capi.VRT_FRAME_LINEAR_OUTPUT)
+    out = np.zeros(4 * w * h, np.uint32)
+    assert kern.emu_render_kernel(C.byref(layout.c), C.byref(fr), None, None, None, out.ctypes.data, 0, 0) > 0
+    want_lin = hash_oracle.render(capi.make_frame(w, h, inv, proj, wo, frac, frame_no=2, bounces=0, flags=capi.VRT_FRAME_LINEAR_OUTPUT))[0]
+    assert np.array_equal(out, np.ascontiguousarray(want_lin).view(np.uint32).reshape(-1))
+    want_tiles = hash_oracle.render(capi.make_frame(w, h, inv, proj, wo, frac, frame_no=2, bounces=0))[0]
+    t = want_tiles.reshape(h // 4, w // 4)
+    for k, name in enumerate(("albedo", "depth", "irr_rg", "irr_bx")):
+        plane = t[name].view(np.uint32).reshape(h // 4, w // 4, 4, 4).transpose(0, 2, 1, 3).reshape(h, w)
+        assert np.array_equal(out[k * w * h : (k + 1) * w * h].reshape(h, w), plane), name
