@@ -22,7 +22,9 @@ struct EmuScene {
 
 // mode 0: cast_ray as k_trace calls it, macro steps off; 1: force the generic loop (what special rays take);
 // 2: macro steps ON (the headers must carry the boxes of the box builder, tests/native/emu_kernels.cpp);
-// 3: the OCC form of the step-by-step loop (big views: a one-bit sector table is consulted before the header)
+// 3: the OCC form of the step-by-step loop (big views: a one-bit sector table is consulted before the header);
+// 4: the METRICS instantiation (what bench.py's roofline counters come from); n_fast then receives 6 words: fast rays, iterations, sector-mask
+//    fetches, cell-mask fetches, hits, capped rays (DevMetrics, summed here instead of through the warp-aggregated atomics)
 static const uint32_t* g_occ = nullptr;  // mode 3: the one-bit table of k_build_occ (bit index = header index + guard)
 EMU_API void emu_set_occ(const uint32_t* occ) { g_occ = occ; }
 
@@ -38,8 +40,8 @@ EMU_API void emu_trace(const EmuScene* e, const int32_t wo[3], const float* o3, 
     RayFrame W = make_ray_frame(S.sxp, mode == 2 ? 1 : 0, wo);
     if (mode == 1) W.fast_ok = 0;
     if (max_iters == 0) max_iters = VRT_MAX_ITERS_DEFAULT;
-    uint64_t fast = 0;
-#pragma omp parallel for schedule(dynamic, 1024) reduction(+ : fast)
+    uint64_t fast = 0, m_it = 0, m_ns = 0, m_nc = 0, m_hit = 0, m_cap = 0;
+#pragma omp parallel for schedule(dynamic, 1024) reduction(+ : fast, m_it, m_ns, m_nc, m_hit, m_cap)
     for (int64_t i = 0; i < (int64_t)n; i++) {
         blockDim.x = 128, blockDim.y = blockDim.z = 1;
         threadIdx.x = (unsigned)(i & 127);
@@ -50,10 +52,16 @@ EMU_API void emu_trace(const EmuScene* e, const int32_t wo[3], const float* o3, 
         H.hit = false;
         const float ox = o3[3 * i], oy = o3[3 * i + 1], oz = o3[3 * i + 2], dx = d3[3 * i], dy = d3[3 * i + 1], dz = d3[3 * i + 2];
         fast += (W.fast_ok && ray_is_fast(ox, oy, oz, dx, dy, dz)) ? 1 : 0;
-        if (mode == 3) cast_ray<false, true, true>(S, W, ox, oy, oz, dx, dy, dz, max_iters, H, R);
+        if (mode == 4) {
+            cast_ray<true>(S, W, ox, oy, oz, dx, dy, dz, max_iters, H, R);
+            m_it += R.iters, m_ns += R.n_sector, m_nc += R.n_cell, m_hit += H.hit ? 1 : 0, m_cap += R.capped ? 1 : 0;
+        } else if (mode == 3) cast_ray<false, true, true>(S, W, ox, oy, oz, dx, dy, dz, max_iters, H, R);
         else cast_ray<false>(S, W, ox, oy, oz, dx, dy, dz, max_iters, H, R);
         store_hit(out + i, H, R);
     }
-    if (n_fast) *n_fast = fast;
+    if (n_fast) {
+        n_fast[0] = fast;
+        if (mode == 4) n_fast[1] = m_it, n_fast[2] = m_ns, n_fast[3] = m_nc, n_fast[4] = m_hit, n_fast[5] = m_cap;
+    }
 }
 }

@@ -100,3 +100,25 @@ def test_traversal_source_reproduces_the_reference_golden_vectors(emu, layout, h
     for f in ("vx", "vy", "vz"):
         assert np.array_equal(got[f][hit], want[f][hit]), f
     assert hit.sum() > 1000 and nf > 0
+
+
+def test_traversal_counters_equal_the_oracle(emu, layout, hash_oracle):
+    """The METRICS instantiation of the traversal (bench.py's roofline numerator: B = 8 I_s + 8 I_c + 9 H + 16 P is computed from these counters):
+    iterations, sector-mask fetches, cell-mask fetches, hits and capped rays, summed over 150 k rays, equal the oracle's OrcStats."""
+    from voxelrt_b200 import capi
+
+    for k, cap in ((0, 0), (1, 40), (2, 0)):
+        if k < 2:
+            wo, o, d = camera_frame_rays(50000, 2500 + k)
+        else:
+            wo = (96, 64, 96)
+            o, d = random_rays(np.random.default_rng(77), 50000, 192, 128, wo)
+        out = np.zeros(len(o), capi.HIT_DTYPE)
+        w = (C.c_int32 * 3)(*[int(v) for v in wo])
+        words = (C.c_uint64 * 6)()
+        emu.emu_trace(C.byref(layout.c), w, np.ascontiguousarray(o).ctypes.data, np.ascontiguousarray(d).ctypes.data, cap, len(o), out.ctypes.data, 4,
+                      C.cast(words, C.POINTER(C.c_uint64)))
+        want, st = hash_oracle.trace(o, d, wo, max_iters=cap)
+        assert_hits_equal(out, want, f"metrics instantiation, case {k}")
+        assert (int(words[1]), int(words[2]), int(words[3]), int(words[4]), int(words[5])) == (st.iters, st.sector_fetches, st.cell_fetches, st.hits, st.capped), (list(words), st.as_dict())
+        assert st.algorithmic_bytes(0) == 8 * int(words[2]) + 8 * int(words[3]) + 9 * int(words[4])
