@@ -19,6 +19,9 @@ struct EmuScene {
     uint32_t sxz, sy;
 };
 
+static const uint32_t* g_occ = nullptr;  // non-null: frames with bounces run the OCC instantiation (big views), bit index = header index + guard
+EMU_API void emu_render_set_occ(const uint32_t* occ) { g_occ = occ; }
+
 EMU_API void emu_render(const EmuScene* e, const VrtFrame* f, const uint8_t* blue_noise, const uint32_t* sky, const VrtSkyDesc* sky_desc, VrtTile* out,
                         VrtHit* aux) {
     DevScene S{};
@@ -30,6 +33,7 @@ EMU_API void emu_render(const EmuScene* e, const VrtFrame* f, const uint8_t* blu
     uint32_t albedo[256];  // k_palette_albedo: albedo_rgb_bits of every palette entry
     for (int i = 0; i < 256; i++) albedo[i] = albedo_rgb_bits(e->palette[i].x);
     S.albedo = albedo;
+    S.occ = g_occ, S.occ_bias = 2u * S.sxzp;
     FrameParams F;
     fill_frame_params(F, f, S.sxp, 0, blue_noise, sky, sky_desc);
     F.aux = aux;
@@ -41,6 +45,7 @@ EMU_API void emu_render(const EmuScene* e, const VrtFrame* f, const uint8_t* blu
             threadIdx.x = (unsigned)(x & 31);
             PixelOut P;
             if (F.bounces == 0) shade_pixel_primary<false>(S, F, (uint32_t)x, (uint32_t)y, true, P);
+            else if (g_occ) shade_pixel<false, true>(S, F, (uint32_t)x, (uint32_t)y, true, P);
             else shade_pixel<false, false>(S, F, (uint32_t)x, (uint32_t)y, true, P);
             VrtTile* t = out + ((size_t)(y >> 2) * (size_t)(w >> 2) + (size_t)(x >> 2));
             const int lane = (x & 3) | ((y & 3) << 2);

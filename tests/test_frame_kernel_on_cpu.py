@@ -200,3 +200,41 @@ def test_k_render_linear_output(kern, layout, hash_oracle):
     for k, name in enumerate(("albedo", "depth", "irr_rg", "irr_bx")):
         plane = t[name].view(np.uint32).reshape(h // 4, w // 4, 4, 4).transpose(0, 2, 1, 3).reshape(h, w)
         assert np.array_equal(out[k * w * h : (k + 1) * w * h].reshape(h, w), plane), name
+
+
+def test_big_view_two_bounces_occ_form(emu, kern, hash_scene, shading_inputs):
+    """BASELINE configs[3]'s shape in small: a 4096x512x4096 view (128x16x128 sectors), two bounces — the frame kernels of big views consult the
+    one-bit sector table before the header (OCC instantiation).  Pixel source against the oracle, table from the emulated k_build_occ."""
+    from oracle import pyoracle
+    from scenes import camera, terrain
+    from voxelrt_b200 import capi
+
+    (bn, _), (desc, tex, _) = shading_inputs
+    orc = pyoracle.OracleMap(7, 4)
+    orc.set_palette(hash_scene["palette"])
+    orc.sync(terrain.scene_records(hash_scene))
+    orc.set_blue_noise(bn)
+    orc.set_sky(desc, tex)
+    L = DeviceLayout(hash_scene, sxz=7, sy=4)
+    kern.emu_build_occ.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p]
+    kern.emu_build_occ.restype = None
+    n_all = len(L.hdr_all)
+    occ = np.zeros((n_all + 31) // 32 + 1, np.uint32)
+    kern.emu_build_occ(L.hdr_all.ctypes.data, n_all, occ.ctypes.data)
+    emu.emu_render_set_occ.argtypes = [C.c_void_p]
+    emu.emu_render_set_occ.restype = None
+    emu.emu_render_set_occ(occ.ctypes.data)
+    try:
+        bn_a, tex_a = np.ascontiguousarray(bn, np.uint8), np.ascontiguousarray(tex, np.uint32)
+        w, h = 320, 180
+        for cam in (camera.Camera(pos=(96.3, 90.2, 20.7), yaw=0.2, pitch=-0.45), camera.Camera(pos=(400.5, 260.1, 380.25), yaw=-2.3, pitch=-0.55)):
+            proj, inv, wo, frac = cam.matrices(w, h)
+            frame = capi.make_frame(w, h, inv, proj, wo, frac, frame_no=9, bounces=2)
+            got = np.zeros(w * h // 16, capi.TILE_DTYPE)
+            aux = np.zeros(w * h, capi.HIT_DTYPE)
+            emu.emu_render(C.byref(L.c), C.byref(frame), bn_a.ctypes.data, tex_a.ctypes.data, C.byref(desc), got.ctypes.data, aux.ctypes.data)
+            want, want_aux, _ = orc.render(capi.make_frame(w, h, inv, proj, wo, frac, frame_no=9, bounces=2), want_aux=True)
+            assert got.tobytes() == want.tobytes()
+            assert_hits_equal(aux, want_aux, "big view, OCC form")
+    finally:
+        emu.emu_render_set_occ(None)
