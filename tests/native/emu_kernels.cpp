@@ -81,6 +81,12 @@ EMU_API void emu_upload_bricks(const uint4* staging, const uint32_t* slots, uint
     }
 }
 
+// K_move: device-side relocation of resident bricks ({src slot, dst slot} pairs, one warp per brick, no lane exchange).  All reads of a launch
+// precede its writes on the GPU only per warp, so (as in vrt_sync) sources and destinations of one launch must not overlap.
+EMU_API void emu_move_bricks(const uint2* pairs, uint32_t n, uint8_t* voxels, uint2* cells) {
+    run_1d((uint64_t)n * 32u, 256, [&] { k_move_bricks(pairs, n, voxels, cells); });
+}
+
 // k_build_occ (one ballot per warp of 32 header entries) by warp replay: the one-bit-per-entry table of the OCC traversal loop
 EMU_API void emu_build_occ(const uint4* hdr_all, uint32_t n_all, uint32_t* occ) {
     const int64_t warps = ((int64_t)n_all + 31) / 32;

@@ -204,3 +204,24 @@ def test_one_bit_sector_table_and_the_occ_loop(libs, layout, hash_oracle):
             assert_hits_equal(out, hash_oracle.trace(o, d, wo)[0], f"OCC loop wo={wo}")
     finally:
         t.emu_set_occ(None)
+
+
+def test_brick_relocation_kernel(libs, layout):
+    """K_move (slot ranges that shift when a sector gains or loses bricks are moved on the device): voxels and cell masks arrive intact."""
+    k, _ = libs
+    k.emu_move_bricks.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p]
+    k.emu_move_bricks.restype = None
+    n = layout.voxels.size // 512
+    m = min(n // 2, 3000)
+    voxels = aligned_zeros(2 * n * 512, np.uint8)
+    cells = aligned_zeros((2 * n * 8, 2), np.uint32)
+    voxels[: n * 512] = layout.voxels
+    cells[: n * 8] = layout.cells
+    rng = np.random.default_rng(5)
+    src = rng.choice(n, m, replace=False).astype(np.uint32)
+    dst = (n + rng.choice(n, m, replace=False)).astype(np.uint32)  # disjoint from every source
+    pairs = np.stack([src, dst], axis=1).copy()
+    k.emu_move_bricks(pairs.ctypes.data, m, voxels.ctypes.data, cells.ctypes.data)
+    assert np.array_equal(voxels.reshape(-1, 512)[dst], layout.voxels.reshape(-1, 512)[src])
+    assert np.array_equal(cells.reshape(-1, 8, 2)[dst], layout.cells.reshape(-1, 8, 2)[src])
+    assert np.array_equal(voxels[: n * 512], layout.voxels) and np.array_equal(cells[: n * 8], layout.cells)
