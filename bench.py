@@ -237,21 +237,35 @@ def bench_frame(width, height, bounces, part_index=0, part_count=1, frame_no=1, 
     return capi.make_frame(width, height, inv, proj, wo, frac, frame_no=frame_no, bounces=bounces, flags=flags, part_index=part_index, part_count=part_count)
 
 
-def cpu_arm(args, scene, recs, want_ref=True):
-    """Times the CPU path on all host threads.  -> (Mrays/s, ms per frame, kind, cores, sample, rays)"""
+def host_threads():
+    """Hardware threads this process may use.  NOT OMP_NUM_THREADS: torch.distributed.run exports OMP_NUM_THREADS=1 to its
+    workers, which in round 1 silently turned the N > 1 reference arm into a one-thread run."""
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+def cpu_arm(args, scene, recs, want_ref=True, shipped_flags=True):
+    """The CPU path on ALL host threads (thread count passed explicitly).  -> (run() -> seconds, kind, cores, rays, build note)
+    kind "reference" = the reference's own CpuRenderer.cpp (oracle/_ref), timed in the build with the flags the reference ships
+    with (-O3 -march=native -ffast-math, src/CMakeLists.txt:36) when that library is present; "port" = the oracle restatement."""
     from oracle import pyoracle
 
-    kind, runner = "port", None
+    kind, runner, build = "port", None, "oracle/vrt_oracle.c: gcc -O2 -ffp-contract=off -fno-fast-math, OpenMP"
+    cores = host_threads()
     if want_ref and _WL["reference_ok"]:
         try:
             from oracle import refharness
 
-            if refharness.available():
-                runner = refharness.RefRenderer(scene, recs)
+            fast = shipped_flags and refharness.available(True)
+            if refharness.available(fast):
+                runner = refharness.RefRenderer(scene, recs, shipped_flags=fast, threads=cores)
                 kind = "reference"
+                build = ("reference CpuRenderer.cpp, g++ -O3 -march=native -ffast-math (the flags it ships with), OpenMP over tile rows" if fast else
+                         "reference CpuRenderer.cpp, g++ -O2 -march=native -fno-fast-math (parity build), OpenMP over tile rows")
         except Exception as e:  # pragma: no cover
             print(f"[bench] oracle/_ref unavailable ({e}); timing the oracle port", file=sys.stderr)
-    cores = pyoracle.num_threads()
     w, h = args.width, args.height
     rays = w * h * (1 + args.bounces)
     if runner is None:
@@ -268,7 +282,7 @@ def cpu_arm(args, scene, recs, want_ref=True):
 
         def run():
             t0 = time.perf_counter()
-            orc.render(frame, want_aux=False)
+            orc.render(frame, want_aux=False, threads=cores)
             return time.perf_counter() - t0
 
     else:
@@ -276,7 +290,7 @@ def cpu_arm(args, scene, recs, want_ref=True):
         def run():
             return runner.render_seconds(w, h, args.bounces)
 
-    return run, kind, cores, rays
+    return run, kind, cores, rays, build
 
 
 def run_reference(args):
@@ -284,8 +298,8 @@ def run_reference(args):
     if rank != 0:
         return 0
     scene, recs, sstats = build_scene(args.workload)
-    run, kind, cores, rays = cpu_arm(args, scene, recs)
-    for _ in range(min(args.warmup, 2)):
+    run, kind, cores, rays, build = cpu_arm(args, scene, recs)
+    for _ in range(args.warmup):
         run()
     times = [run() for _ in range(args.steps)]
     ms = 1000.0 * sum(times) / len(times)
@@ -297,7 +311,7 @@ def run_reference(args):
         "unit": "Mrays/s",
         "n_gpus": args.gpus,
         "steps": args.steps,
-        "warmup": min(args.warmup, 2),
+        "warmup": args.warmup,
         "ms_per_step": ms,
         "higher_is_better": True,
         "scaling": "strong",
@@ -310,7 +324,9 @@ def run_reference(args):
             "unit": "Mrays/s",
             "cores": cores,
             "kind": kind,
-            "sample": f"{args.steps} full {args.width}x{args.height} frames, {rays} rays each",
+            "build": build,
+            "omp_num_threads_env": os.environ.get("OMP_NUM_THREADS"),
+            "sample": f"{args.steps} full {args.width}x{args.height} frames, {rays} rays each, on {cores} host threads (explicit count; the launcher's OMP_NUM_THREADS is ignored)",
         },
         "e2e": {"value": val, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -758,7 +774,7 @@ def run_b200(args):
             except Exception as e:  # noqa: BLE001
                 line["present"] = {"error": f"{type(e).__name__}: {e}"}
         if not args.no_cpu and n_gpus == 1:
-            run, kind, cores, rays = cpu_arm(args, scene, recs)
+            run, kind, cores, rays, build = cpu_arm(args, scene, recs)
             run()
             times, t_begin = [], time.perf_counter()
             while len(times) < 3 or (time.perf_counter() - t_begin < 10.0 and len(times) < 20):
@@ -769,6 +785,7 @@ def run_b200(args):
                 "unit": "Mrays/s",
                 "cores": cores,
                 "kind": kind,
+                "build": build,
                 "sample": f"best of {len(times)} full {w}x{h} frames ({rays} rays each) on {cores} host threads",
             }
         print(json.dumps(line))

@@ -171,7 +171,14 @@ VRT_API int vrt_set_palette(VrtContext* ctx, const uint64_t palette[256]);
 /* FlatVoxelStorage::SyncBuffers (CpuRenderer.cpp:33-61) / GpuVoxelStorage::SyncBuffers
  * (GpuRenderer.cpp:45-167): allocate/free brick slots, upload ONLY the dirty bricks, rebuild
  * their 8 cell masks on the device (UpdateOccupancy, CpuRenderer.cpp:63-83 /
- * UpdateOccupancy.comp:8-34).  Host data is consumed before return. */
+ * UpdateOccupancy.comp:8-34).  Host data is consumed before return.
+ * - Each sector may appear in at most ONE record per call (DirtyLocs is a map keyed by sector, VoxelMap.h:185);
+ *   a duplicate returns VRT_ERR_INVALID.
+ * - The call is transactional: a record that fails validation (dirty bricks without payload, duplicate sector)
+ *   or a failed allocation (VRT_ERR_OOM) returns before anything — host mirror, slot arena, device buffers —
+ *   has changed; vrt_read_sector and rendering see the state of the previous successful call.
+ * - A brick that enters alloc_mask without being in dirty_mask (VoxelMap::GetBrick creates bricks on lookup,
+ *   VoxelMap.cpp:122) is resident as an EMPTY brick (its recycled slot is zero-filled). */
 VRT_API int vrt_sync(VrtContext* ctx, uint32_t n, const VrtDirtySector* sectors);
 /* Test/inspection hook: copy the resident state of one sector back to the host.
  * out_alloc_mask: allocation mask; out_bricks (64*512 B) / out_cells (64*8 u64) are filled for

@@ -15,8 +15,11 @@ from voxelrt_b200.capi import HIT_DTYPE, HITD_DTYPE, TILE_DTYPE, VrtDirtySector,
 
 HERE = Path(__file__).resolve().parent
 LIB = HERE / "_ref" / "libref_cpu.so"
+# the same harness built with the flags the reference ships with (-O3 -march=native -ffast-math, src/CMakeLists.txt:36): used for
+# TIMING only (bench.py's reference arm); every parity pin uses the -fno-fast-math build above
+LIB_SHIPPED = HERE / "_ref" / "libref_cpu_fastmath.so"
 _NEED = ("avx512f", "avx512bw", "avx512dq", "avx512vl", "avx2", "fma", "bmi2")
-_lib = None
+_libs = {}
 
 
 def _cpu_ok() -> bool:
@@ -31,17 +34,16 @@ def _cpu_ok() -> bool:
         return False
 
 
-def available() -> bool:
-    return LIB.exists() and _cpu_ok()
+def available(shipped_flags: bool = False) -> bool:
+    return (LIB_SHIPPED if shipped_flags else LIB).exists() and _cpu_ok()
 
 
-def load():
-    global _lib
-    if _lib is not None:
-        return _lib
-    if not available():
-        raise RuntimeError("oracle/_ref/libref_cpu.so missing or this CPU lacks AVX-512")
-    lib = C.CDLL(str(LIB))
+def load(shipped_flags: bool = False):
+    if shipped_flags in _libs:
+        return _libs[shipped_flags]
+    if not available(shipped_flags):
+        raise RuntimeError("oracle/_ref/libref_cpu*.so missing or this CPU lacks AVX-512")
+    lib = C.CDLL(str(LIB_SHIPPED if shipped_flags else LIB))
     vp, u32, u64 = C.c_void_p, C.c_uint32, C.c_uint64
     lib.ref_create.restype = vp
     lib.ref_destroy.argtypes = [vp]
@@ -90,15 +92,16 @@ def load():
     lib.ref_pack_rgba8.restype = u32
     lib.ref_pack_rg16f.argtypes = [C.c_float] * 2
     lib.ref_pack_rg16f.restype = u32
-    _lib = lib
+    lib.ref_num_threads.restype = C.c_int
+    _libs[shipped_flags] = lib
     return lib
 
 
 class RefMap:
     """The reference's VoxelMap + FlatVoxelStorage (a dense 2048x512x2048 view: ~2.3 GB of host memory)."""
 
-    def __init__(self):
-        self.lib = load()
+    def __init__(self, shipped_flags: bool = False):
+        self.lib = load(shipped_flags)
         self.h = C.c_void_p(self.lib.ref_create())
 
     def close(self):
@@ -209,6 +212,16 @@ class RefMap:
         return out, float(secs)
 
 
+def host_threads() -> int:
+    """Hardware threads this process may run on (not OMP_NUM_THREADS, which launchers override)."""
+    import os
+
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
 def encode_material(r, g, b, fuzz=255, emission=0.0):
     return int(load().ref_encode_material(r, g, b, fuzz, emission))
 
@@ -223,11 +236,15 @@ def inverse_proj_screen(m16, w, h):
 class RefRenderer:
     """bench.py helper: the reference renderer holding a scene; render_seconds() times one frame."""
 
-    def __init__(self, scene, recs):
-        self.map = RefMap()
+    def __init__(self, scene, recs, shipped_flags: bool = False, threads: int = 0):
+        self.map = RefMap(shipped_flags)
         self.map.set_palette(scene["palette"])
         self.map.sync(recs)
         self._sky = False
+        self.shipped_flags = shipped_flags
+        # explicit thread count: launchers such as torch.distributed.run export OMP_NUM_THREADS=1, which would silently
+        # turn "all host threads" into one
+        self.threads = int(threads) if threads else host_threads()
 
     def render_seconds(self, w, h, bounces):
         from scenes import camera, shading
@@ -241,7 +258,7 @@ class RefRenderer:
         cam = camera.Camera()
         proj, inv, wo, frac = cam.matrices(w, h)
         frame = capi.make_frame(w, h, inv, proj, wo, frac, frame_no=1, bounces=bounces)
-        _, secs = self.map.render(frame)
+        _, secs = self.map.render(frame, threads=self.threads)
         return secs
 
 

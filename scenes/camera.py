@@ -51,7 +51,7 @@ def matmul(a, b):
 def translate(m, v):
     """glm::translate(m, v): m * T(v)."""
     out = m.copy()
-    out[3] = m[0] * f32(v[0]) + m[1] * f32(v[1]) + m[2] * f32(v[2]) + m[3]
+    out[3] = ((m[0] * f32(v[0]) + m[1] * f32(v[1])).astype(f32) + m[2] * f32(v[2])).astype(f32) + m[3]
     return out.astype(f32)
 
 
@@ -64,9 +64,42 @@ def scale(m, v):
 
 
 def inverse(m):
-    # computed in float64 then rounded once; glm::inverse's float cofactor expansion differs in
-    # the last ulps, which only moves the rays by the same amount for oracle and GPU alike.
-    return np.linalg.inv(m.astype(np.float64).T).T.astype(f32)
+    """glm::inverse(mat4): GLM's float cofactor expansion, one float32 rounding per operation — the same operation sequence as
+    oracle/shim/glm/mat4x4.hpp (what the reference's GetInverseProjScreenMat runs on in oracle/_ref) and the adapter's Inverse()
+    (voxelrt_b200/host/b200_renderer.cpp); tests pin the three against each other bit for bit."""
+    m = np.asarray(m, f32)
+
+    def det2(a, b, c, d):  # a*b - c*d
+        return f32(f32(a * b) - f32(c * d))
+
+    c00, c02, c03 = det2(m[2][2], m[3][3], m[3][2], m[2][3]), det2(m[1][2], m[3][3], m[3][2], m[1][3]), det2(m[1][2], m[2][3], m[2][2], m[1][3])
+    c04, c06, c07 = det2(m[2][1], m[3][3], m[3][1], m[2][3]), det2(m[1][1], m[3][3], m[3][1], m[1][3]), det2(m[1][1], m[2][3], m[2][1], m[1][3])
+    c08, c10, c11 = det2(m[2][1], m[3][2], m[3][1], m[2][2]), det2(m[1][1], m[3][2], m[3][1], m[1][2]), det2(m[1][1], m[2][2], m[2][1], m[1][2])
+    c12, c14, c15 = det2(m[2][0], m[3][3], m[3][0], m[2][3]), det2(m[1][0], m[3][3], m[3][0], m[1][3]), det2(m[1][0], m[2][3], m[2][0], m[1][3])
+    c16, c18, c19 = det2(m[2][0], m[3][2], m[3][0], m[2][2]), det2(m[1][0], m[3][2], m[3][0], m[1][2]), det2(m[1][0], m[2][2], m[2][0], m[1][2])
+    c20, c22, c23 = det2(m[2][0], m[3][1], m[3][0], m[2][1]), det2(m[1][0], m[3][1], m[3][0], m[1][1]), det2(m[1][0], m[2][1], m[2][0], m[1][1])
+    f0, f1, f2 = (c00, c00, c02, c03), (c04, c04, c06, c07), (c08, c08, c10, c11)
+    f3, f4, f5 = (c12, c12, c14, c15), (c16, c16, c18, c19), (c20, c20, c22, c23)
+    v0 = (m[1][0], m[0][0], m[0][0], m[0][0])
+    v1 = (m[1][1], m[0][1], m[0][1], m[0][1])
+    v2 = (m[1][2], m[0][2], m[0][2], m[0][2])
+    v3 = (m[1][3], m[0][3], m[0][3], m[0][3])
+
+    def comb(a, fa, b, fb, c, fc, s):  # ((a*fa - b*fb) + c*fc) * s
+        return f32(f32(f32(f32(a * fa) - f32(b * fb)) + f32(c * fc)) * s)
+
+    inv = np.zeros((4, 4), f32)
+    for i in range(4):
+        sa = f32(-1.0 if i & 1 else 1.0)
+        sb = f32(-sa)
+        inv[0][i] = comb(v1[i], f0[i], v2[i], f1[i], v3[i], f2[i], sa)
+        inv[1][i] = comb(v0[i], f0[i], v2[i], f3[i], v3[i], f4[i], sb)
+        inv[2][i] = comb(v0[i], f1[i], v1[i], f3[i], v3[i], f5[i], sa)
+        inv[3][i] = comb(v0[i], f2[i], v1[i], f4[i], v2[i], f5[i], sb)
+    d0, d1, d2, d3 = f32(m[0][0] * inv[0][0]), f32(m[0][1] * inv[1][0]), f32(m[0][2] * inv[2][0]), f32(m[0][3] * inv[3][0])
+    with np.errstate(divide="ignore", invalid="ignore"):
+        one_over_det = f32(f32(1) / f32(f32(d0 + d1) + f32(d2 + d3)))
+        return (inv * one_over_det).astype(f32)
 
 
 def inverse_proj_screen(proj_view, width, height):

@@ -126,3 +126,76 @@ def test_delta_upload_moves_only_dirty_bricks(hash_scene):
     gm, base, gb, gc = ctx.read_sector(sx, sy, sz)
     assert np.array_equal(gb[b0], edited)
     ctx.close()
+
+
+def test_allocated_but_not_dirty_bricks_are_empty():
+    """A brick that enters alloc_mask without being dirty (VoxelMap::GetBrick creates bricks on lookup, quirk Q5) must be resident
+    as an EMPTY brick even when its slot is recycled from a freed sector (recycled slots held stale voxels)."""
+    from oracle import pyoracle
+    from voxelrt_b200 import capi
+
+    rng = np.random.default_rng(5)
+    ctx = capi.Context(2, 1, device=0, initial_brick_capacity=64)
+    orc = pyoracle.OracleMap(2, 1)
+    pal = rng.integers(0, 1 << 40, 256, dtype=np.uint64)
+    ctx.set_palette(pal)
+    orc.set_palette(pal)
+    full = (1 << 64) - 1
+    solid = np.stack([_rand_brick(rng, 0.9) for _ in range(64)])
+    for m in (ctx, orc):
+        m.sync([(0, 0, 0, full, full, solid)])           # fills the whole 64-slot arena with solid bricks
+        m.sync([(0, 0, 0, 0, full, None, True)])         # ... and frees it again: every slot now holds stale voxels
+    dirty = 0b11111
+    alloc = 0b1111111111 | (1 << 40)
+    payload = np.stack([_rand_brick(rng, 0.5) for _ in range(5)])
+    for m in (ctx, orc):
+        m.sync([(1, 0, 2, alloc, dirty, payload)])       # bricks 5-9 and 40: allocated, never written
+    _compare_all(ctx, orc, 4, 2)
+    gm, base, gb, gc = ctx.read_sector(1, 0, 2)
+    assert gm == alloc and not gb[5:10].any() and not gb[40].any() and not gc[5:10].any() and not gc[40].any()
+    # same through the relocation path: the sector gains a low brick (everything moves) plus one more empty brick
+    alloc2 = alloc | (1 << 3 << 8) | (1 << 50)
+    one = _rand_brick(rng, 0.7)[None]
+    for m in (ctx, orc):
+        m.sync([(1, 0, 2, alloc2, 1 << 11, one)])
+    _compare_all(ctx, orc, 4, 2)
+    o, d = random_rays(rng, 20_000, 128, 64, (0, 0, 0))
+    assert_hits_equal(ctx.trace(o, d, (0, 0, 0)), orc.trace(o, d, (0, 0, 0))[0], "fresh bricks", ignore_iters=True)
+    ctx.close()
+
+
+def test_sync_is_transactional_on_bad_records(hash_scene):
+    """A record that fails validation in the MIDDLE of a batch, or a duplicate sector, leaves residency and rendering unchanged
+    (VERDICT r1 weak #8 / ADVICE: earlier records of the batch used to mutate the host mirror before the error return)."""
+    import ctypes as C
+
+    from conftest import ctx_for
+    from voxelrt_b200 import capi
+
+    ctx = ctx_for(hash_scene)
+    rng = np.random.default_rng(9)
+    keys = sorted(hash_scene["sectors"])[:3]
+    before = [ctx.read_sector(*k) for k in keys]
+    stats0 = ctx.stats()
+    o, d = random_rays(rng, 20_000, 128, 64, (0, 0, 0))
+    hits0 = ctx.trace(o, d, (0, 0, 0))
+    full = (1 << 64) - 1
+    solid = np.full((64, 512), 3, np.uint8)
+    # record 0 would re-allocate its sector to 64 bricks (relocation + growth); record 1 claims dirty bricks but has no payload
+    arr, keep, n = capi.make_records([(*keys[0], full, full, solid), (*keys[1], full, full, None), (*keys[2], full, full, solid)])
+    assert ctx.lib.vrt_sync(ctx.h, n, arr) == capi.VRT_ERR_INVALID
+    assert b"nothing was changed" in ctx.lib.vrt_last_error(ctx.h)
+    # the same sector twice in one call
+    arr2, keep2, n2 = capi.make_records([(*keys[0], full, full, solid), (*keys[2], 1, 1, solid[:1]), (*keys[0], 1, 1, solid[:1])])
+    assert ctx.lib.vrt_sync(ctx.h, n2, arr2) == capi.VRT_ERR_INVALID
+    after = [ctx.read_sector(*k) for k in keys]
+    for (m0, b0, v0, c0), (m1, b1, v1, c1) in zip(before, after):
+        assert m0 == m1 and b0 == b1 and np.array_equal(v0, v1) and np.array_equal(c0, c1)
+    st = ctx.stats()
+    assert (st.resident_bricks, st.resident_sectors, st.free_ranges) == (stats0.resident_bricks, stats0.resident_sectors, stats0.free_ranges)
+    assert_hits_equal(ctx.trace(o, d, (0, 0, 0)), hits0, "after rejected syncs")
+    # and the context still works: the valid part of the batch goes through afterwards
+    ctx.sync([(*keys[0], full, full, solid), (*keys[2], full, full, solid)])
+    gm, _, gb, _ = ctx.read_sector(*keys[0])
+    assert gm == full and np.array_equal(gb, solid)
+    ctx.close()

@@ -15,6 +15,7 @@ import numpy as np
 ROOT = Path(__file__).resolve().parent.parent
 LIB_PATH = Path(__file__).resolve().parent / "lib" / "libvoxelrt_b200.so"
 
+VRT_OK, VRT_ERR_INVALID, VRT_ERR_CUDA, VRT_ERR_OOM, VRT_ERR_STATE, VRT_ERR_UNSUPPORTED = 0, -1, -2, -3, -4, -5  # VrtStatus
 VRT_SECTOR_REMOVED = 1
 VRT_HIT_NORMAL_MASK = 0x3F
 VRT_HIT_HIT = 0x100

@@ -648,17 +648,75 @@ extern "C" int vrt_sync(VrtContext* ctx, uint32_t n, const VrtDirtySector* recs)
     std::vector<Upload> uploads;
     std::vector<uint2> moves;
     std::vector<HeaderUpdate> headers;
-    uploads.reserve(n * 8);
+    static const uint8_t kZeroBrick[VRT_BRICK_BYTES] = {};
 
+    // The call is TRANSACTIONAL: pass 1 looks at every record without touching anything, and everything that can fail for
+    // lack of memory (arena growth, staging buffers) happens between the passes — so a bad record or an allocation failure
+    // returns with the host mirror, the slot arena and the device state exactly as they were.
+    // Pass 1: payload pointers, duplicate sectors (two records for one sector would race in the single k_move / k_upload
+    // launches below: the second record's moves read what the first one's moves write), and upper bounds for the sizes.
+    uint64_t need_slots = 0, max_uploads = 0, max_moves = 0, max_headers = 0;
+    {
+        std::vector<uint32_t> seen;
+        seen.reserve(n);
+        for (uint32_t r = 0; r < n; r++) {
+            const VrtDirtySector& d = recs[r];
+            // ViewSectorIndexer::CheckInBounds -> continue (CpuRenderer.cpp:40, GpuRenderer.cpp:54-55)
+            if (((uint32_t)(d.sx | d.sz) >> ctx->sxz) != 0 || ((uint32_t)d.sy >> ctx->sy) != 0) continue;
+            const uint32_t si = (uint32_t)d.sx | ((uint32_t)d.sz << ctx->sxz) | ((uint32_t)d.sy << (2 * ctx->sxz));
+            seen.push_back(si);
+            const SectorSlots& old = ctx->sectors[si];
+            const uint64_t new_mask = (d.flags & VRT_SECTOR_REMOVED) ? 0ull : d.alloc_mask;  // GpuRenderer.cpp:59-67
+            const uint64_t dirty = d.dirty_mask & new_mask;                                   // :62
+            if (dirty && !d.bricks)
+                return fail(ctx, VRT_ERR_INVALID, "record " + std::to_string(r) + ": dirty bricks without payload (nothing was changed)");
+            const uint64_t fresh = new_mask & ~old.mask & ~dirty;  // allocated without content: zero-filled below
+            max_uploads += popcount64(dirty) + popcount64(fresh);
+            if (new_mask != old.mask) {
+                need_slots += popcount64(new_mask);
+                max_moves += popcount64(old.mask & new_mask & ~dirty);
+                max_headers++;
+            }
+        }
+        std::sort(seen.begin(), seen.end());
+        if (std::adjacent_find(seen.begin(), seen.end()) != seen.end())
+            return fail(ctx, VRT_ERR_INVALID, "the same sector appears in two records of one vrt_sync call (nothing was changed)");
+    }
+    // Every fresh range of this call fits behind the high-water mark (one coalesced free range): then no alloc() below can
+    // fail, whatever the fragmentation.  Grown BEFORE the first mutation; a failure here leaves everything as it was.
+    if (need_slots) {
+        const uint64_t tail = (uint64_t)ctx->arena.capacity() - ctx->arena.high_water();
+        if (tail < need_slots) {
+            const uint64_t want = std::max<uint64_t>((uint64_t)ctx->arena.capacity() * 2, (uint64_t)ctx->arena.high_water() + need_slots);
+            if (want > 0x7FFFFFFFull) return fail(ctx, VRT_ERR_OOM, "Could not allocate brick slots");  // BrickSlotAllocator.cpp:15
+            int st = resize_arena(ctx, (uint32_t)want);
+            if (st) return st;
+        }
+    }
+    // staging for the largest chunk this call can need (same layout as below, from the upper bounds)
+    const size_t kChunkBricks = (size_t)1 << 17;
+    {
+        const size_t mm = (max_moves * 8 + 15) & ~(size_t)15, mb = mm + max_headers * sizeof(HeaderUpdate);
+        const size_t c0 = std::min<size_t>(max_uploads, kChunkBricks), half_max = ((c0 * 516 + 15) & ~(size_t)15) + mb + 16;
+        if (max_uploads || mb) {
+            int st = ensure_host_stage(ctx, 2 * half_max);
+            if (st) return st;
+            st = ensure(ctx, ctx->d_stage, 2 * half_max);
+            if (st) return st;
+        }
+    }
+    uploads.reserve(max_uploads);
+    moves.reserve(max_moves);
+    headers.reserve(max_headers);
+
+    // Pass 2: commit to the host mirror and the arena, and list the device work.
     for (uint32_t r = 0; r < n; r++) {
         const VrtDirtySector& d = recs[r];
-        // ViewSectorIndexer::CheckInBounds -> continue (CpuRenderer.cpp:40, GpuRenderer.cpp:54-55)
         if (((uint32_t)(d.sx | d.sz) >> ctx->sxz) != 0 || ((uint32_t)d.sy >> ctx->sy) != 0) continue;
         uint32_t si = (uint32_t)d.sx | ((uint32_t)d.sz << ctx->sxz) | ((uint32_t)d.sy << (2 * ctx->sxz));
         SectorSlots old = ctx->sectors[si];
-        uint64_t new_mask = (d.flags & VRT_SECTOR_REMOVED) ? 0ull : d.alloc_mask;  // GpuRenderer.cpp:59-67
-        uint64_t dirty = d.dirty_mask & new_mask;                                   // :62
-        if (dirty && !d.bricks) return fail(ctx, VRT_ERR_INVALID, "dirty bricks without payload");
+        uint64_t new_mask = (d.flags & VRT_SECTOR_REMOVED) ? 0ull : d.alloc_mask;
+        uint64_t dirty = d.dirty_mask & new_mask;
 
         SectorSlots cur = old;
         if (new_mask != old.mask) {
@@ -673,13 +731,8 @@ extern "C" int vrt_sync(VrtContext* ctx, uint32_t n, const VrtDirtySector* recs)
                 // new bricks all sort after the resident ones: the range grows in place, nothing moves
             } else {
                 uint32_t base = ctx->arena.alloc(new_n);
-                while (base == RangeArena::kNone) {
-                    uint64_t want = std::max<uint64_t>((uint64_t)ctx->arena.capacity() * 2, (uint64_t)ctx->arena.capacity() + new_n);
-                    if (want > 0x7FFFFFFFull) return fail(ctx, VRT_ERR_OOM, "Could not allocate brick slots");
-                    int st = resize_arena(ctx, (uint32_t)want);
-                    if (st) return st;
-                    base = ctx->arena.alloc(new_n);
-                }
+                if (base == RangeArena::kNone)  // cannot happen: the tail behind the high-water mark holds need_slots
+                    return fail(ctx, VRT_ERR_STATE, "internal: slot arena exhausted after pre-growth");
                 cur.base = base;
                 // resident bricks that survive and are not re-sent move device-side
                 uint64_t keep = old.mask & new_mask & ~dirty;
@@ -708,6 +761,11 @@ extern "C" int vrt_sync(VrtContext* ctx, uint32_t n, const VrtDirtySector* recs)
             uploads.push_back(Upload{src, slot_of(cur, b)});
             src += 512;
         }
+        // Bricks that enter the allocation mask WITHOUT being dirty (VoxelMap::GetBrick creates the brick on a mere lookup,
+        // VoxelMap.cpp:122 — quirk Q5) own a slot nothing else writes; slots are recycled, so it is filled with an empty
+        // brick (what the reference's zero-initialised per-position storage holds for a brick that never had content).
+        for (uint64_t m = new_mask & ~old.mask & ~dirty; m; m &= m - 1)
+            uploads.push_back(Upload{kZeroBrick, slot_of(cur, (uint32_t)__builtin_ctzll(m))});
     }
 
     // Staging is chunked and double-buffered: a chunk of at most kChunkBricks bricks (64 MiB) is gathered into one half of the
@@ -715,17 +773,13 @@ extern "C" int vrt_sync(VrtContext* ctx, uint32_t n, const VrtDirtySector* recs)
     // other half — a multi-GB scene never needs a multi-GB pinned allocation, and the host gather overlaps the PCIe copy.
     // Chunk 0 also carries the relocation pairs and header records ("meta").
     const size_t nu = uploads.size(), nm = moves.size(), nh = headers.size();
-    const size_t kChunkBricks = (size_t)1 << 17;
     const size_t meta_moves = (nm * 8 + 15) & ~(size_t)15, meta_bytes = meta_moves + nh * sizeof(HeaderUpdate);
     const size_t chunk0 = std::min(nu, kChunkBricks);
     const size_t half = ((chunk0 * 516 + 15) & ~(size_t)15) + meta_bytes + 16;  // bricks, slots, meta
     const size_t n_chunks = nu ? (nu + kChunkBricks - 1) / kChunkBricks : (meta_bytes ? 1 : 0);
     size_t total = 0;
     if (n_chunks) {
-        int st = ensure_host_stage(ctx, 2 * half);
-        if (st) return st;
-        st = ensure(ctx, ctx->d_stage, 2 * half);
-        if (st) return st;
+        int st = VRT_OK;  // (both staging buffers were sized from the upper bounds before pass 2)
         // The previous frame may still read the arena from a caller stream: the kernels below wait for it on the device, but
         // the host gather and the H2D copies do not — they overlap the frame that is still being traced.
         // (the halves' offsets depend on this call's sizes, so both halves of the PREVIOUS call must have been consumed first;

@@ -16,34 +16,39 @@ mat4 operator*(const mat4& a, const mat4& b) {
         }
     return r;
 }
+// glm::inverse(mat4) — what GBuffer::GetInverseProjScreenMat calls (GBuffer.h:134): GLM's float cofactor expansion
+// (18 2x2 sub-determinants, one reciprocal of the determinant).  One rounding per operation (this file is built
+// -ffp-contract=off); tests/test_native_host.py pins the result bit for bit against the reference's own
+// GetInverseProjScreenMat compiled into oracle/_ref.
 mat4 Inverse(const mat4& a) {
-    double w[4][8];
-    for (int r = 0; r < 4; r++)
-        for (int c = 0; c < 4; c++) {
-            w[r][c] = a.at(c, r);
-            w[r][4 + c] = r == c ? 1.0 : 0.0;
-        }
+    auto m = [&](int c, int r) { return a.at(c, r); };
+    const float c00 = m(2, 2) * m(3, 3) - m(3, 2) * m(2, 3), c02 = m(1, 2) * m(3, 3) - m(3, 2) * m(1, 3), c03 = m(1, 2) * m(2, 3) - m(2, 2) * m(1, 3);
+    const float c04 = m(2, 1) * m(3, 3) - m(3, 1) * m(2, 3), c06 = m(1, 1) * m(3, 3) - m(3, 1) * m(1, 3), c07 = m(1, 1) * m(2, 3) - m(2, 1) * m(1, 3);
+    const float c08 = m(2, 1) * m(3, 2) - m(3, 1) * m(2, 2), c10 = m(1, 1) * m(3, 2) - m(3, 1) * m(1, 2), c11 = m(1, 1) * m(2, 2) - m(2, 1) * m(1, 2);
+    const float c12 = m(2, 0) * m(3, 3) - m(3, 0) * m(2, 3), c14 = m(1, 0) * m(3, 3) - m(3, 0) * m(1, 3), c15 = m(1, 0) * m(2, 3) - m(2, 0) * m(1, 3);
+    const float c16 = m(2, 0) * m(3, 2) - m(3, 0) * m(2, 2), c18 = m(1, 0) * m(3, 2) - m(3, 0) * m(1, 2), c19 = m(1, 0) * m(2, 2) - m(2, 0) * m(1, 2);
+    const float c20 = m(2, 0) * m(3, 1) - m(3, 0) * m(2, 1), c22 = m(1, 0) * m(3, 1) - m(3, 0) * m(1, 1), c23 = m(1, 0) * m(2, 1) - m(2, 0) * m(1, 1);
+    const float f0[4] = {c00, c00, c02, c03}, f1[4] = {c04, c04, c06, c07}, f2[4] = {c08, c08, c10, c11};
+    const float f3[4] = {c12, c12, c14, c15}, f4[4] = {c16, c16, c18, c19}, f5[4] = {c20, c20, c22, c23};
+    const float v0[4] = {m(1, 0), m(0, 0), m(0, 0), m(0, 0)}, v1[4] = {m(1, 1), m(0, 1), m(0, 1), m(0, 1)};
+    const float v2[4] = {m(1, 2), m(0, 2), m(0, 2), m(0, 2)}, v3[4] = {m(1, 3), m(0, 3), m(0, 3), m(0, 3)};
+    mat4 inv;
     for (int i = 0; i < 4; i++) {
-        int p = i;
-        for (int r = i + 1; r < 4; r++)
-            if (std::fabs(w[r][i]) > std::fabs(w[p][i])) p = r;
-        for (int c = 0; c < 8; c++) std::swap(w[i][c], w[p][c]);
-        double d = w[i][i];
-        for (int c = 0; c < 8; c++) w[i][c] /= d;
-        for (int r = 0; r < 4; r++)
-            if (r != i) {
-                double f = w[r][i];
-                for (int c = 0; c < 8; c++) w[r][c] -= f * w[i][c];
-            }
+        const float sa = (i & 1) ? -1.0f : 1.0f, sb = -sa;
+        inv.at(0, i) = ((v1[i] * f0[i] - v2[i] * f1[i]) + v3[i] * f2[i]) * sa;
+        inv.at(1, i) = ((v0[i] * f0[i] - v2[i] * f3[i]) + v3[i] * f4[i]) * sb;
+        inv.at(2, i) = ((v0[i] * f1[i] - v1[i] * f3[i]) + v3[i] * f5[i]) * sa;
+        inv.at(3, i) = ((v0[i] * f2[i] - v1[i] * f4[i]) + v2[i] * f5[i]) * sb;
     }
-    mat4 out;
-    for (int r = 0; r < 4; r++)
-        for (int c = 0; c < 4; c++) out.at(c, r) = (float)w[r][4 + c];
-    return out;
+    const float d0 = m(0, 0) * inv.at(0, 0), d1 = m(0, 1) * inv.at(1, 0), d2 = m(0, 2) * inv.at(2, 0), d3 = m(0, 3) * inv.at(3, 0);
+    const float one_over_det = 1.0f / ((d0 + d1) + (d2 + d3));
+    for (int c = 0; c < 4; c++)
+        for (int r = 0; r < 4; r++) inv.at(c, r) = inv.at(c, r) * one_over_det;
+    return inv;
 }
 mat4 Translate(const mat4& a, float x, float y, float z) {
     mat4 r = a;
-    for (int row = 0; row < 4; row++) r.at(3, row) = a.at(0, row) * x + a.at(1, row) * y + a.at(2, row) * z + a.at(3, row);
+    for (int row = 0; row < 4; row++) r.at(3, row) = ((a.at(0, row) * x + a.at(1, row) * y) + a.at(2, row) * z) + a.at(3, row);
     return r;
 }
 mat4 Scale(const mat4& a, float x, float y, float z) {
@@ -220,3 +225,13 @@ void B200Renderer::SetBlueNoise(const uint8_t* rg) { Check(vrt_set_blue_noise(_c
 void B200Renderer::SetSky(const VrtSkyDesc& desc, const uint32_t* texels) { Check(vrt_set_sky(_ctx, &desc, texels), "vrt_set_sky"); }
 
 }  // namespace vrt_host
+
+// Test hook (tests/test_native_host.py): GetInverseProjScreenMat for a column-major float[16], so that the adapter's matrix can be
+// compared bit for bit with the reference's own GBuffer::GetInverseProjScreenMat (oracle/_ref) from Python.
+extern "C" __attribute__((visibility("default"))) void vrt_host_inverse_proj_screen(const float* proj_view16, uint32_t w, uint32_t h, float* out16) {
+    vrt_host::mat4 m;
+    std::memcpy(m.m, proj_view16, sizeof(m.m));
+    vrt_host::mat4 r = vrt_host::GetInverseProjScreenMat(m, w, h);
+    std::memcpy(out16, r.m, sizeof(r.m));
+}
+
