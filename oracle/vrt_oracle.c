@@ -9,6 +9,7 @@
  * so the compiler neither fuses nor splits anything.
  */
 #include "vrt_oracle.h"
+#include "x86_approx14_tables.h"
 
 #include <math.h>
 #include <stdlib.h>
@@ -199,10 +200,59 @@ static inline float x86_fract(float x) {
     if ((double)r > e) r = nextafterf(r, -INFINITY);
     return r;
 }
-/* canonical replacements of the hardware approximations:
- * approx_rsqrt = _mm512_rsqrt14_ps, approx_rcp = _mm512_rcp14_ps (SIMD_AVX512.h:140-142) */
-static inline float canon_rsqrt(float x) { return 1.0f / sqrtf(x); }
-static inline float canon_rcp(float x) { return 1.0f / x; }
+/* approx_rsqrt = _mm512_rsqrt14_ps, approx_rcp = _mm512_rcp14_ps (SIMD_AVX512.h:136-138), bit-exact: both instructions are
+ * architecturally defined; measured on the instruction, the result is a 64-segment piecewise-linear function of the top
+ * mantissa bits in integer arithmetic (x86_approx14_tables.h), exact for powers of two (four).  orc_x86_rcp14 / orc_x86_rsqrt14
+ * are compared with the instructions on ALL 2^32 inputs by tests/test_x86_approx14.py (needs an AVX-512 host). */
+float orc_x86_rsqrt14(float x) {
+    uint32_t u = f2u(x), sign = u & 0x80000000u, a = u & 0x7FFFFFFFu;
+    if (a > 0x7F800000u) return u2f(u | 0x00400000u); /* NaN -> quiet, payload kept */
+    if (a == 0) return u2f(sign | 0x7F800000u);       /* +-0 -> +-inf */
+    if (sign) return u2f(0xFFC00000u);                /* negative -> real indefinite */
+    if (a == 0x7F800000u) return 0.0f;
+    int e = (int)(a >> 23);
+    uint32_t mant = a & 0x7FFFFFu;
+    if (e == 0) { /* denormal argument */
+        int sh = __builtin_clz(mant) - 8;
+        mant = (mant << sh) & 0x7FFFFFu;
+        e = 1 - sh;
+    }
+    int E = e - 127, odd = E & 1, k = (E - odd) / 2; /* x = (1.m * 2^odd) * 4^k */
+    uint32_t rb = 0x3F800000u;
+    if (mant != 0 || odd) {
+        const uint32_t* c = orc_rsqrt14_coef[((uint32_t)odd << 5) | (mant >> 18)];
+        rb = ((c[0] - c[1] * ((mant >> 8) & 0x3FFu)) >> 9) << 7;
+    }
+    return u2f(rb - ((uint32_t)k << 23));
+}
+float orc_x86_rcp14(float x) {
+    uint32_t u = f2u(x), sign = u & 0x80000000u, a = u & 0x7FFFFFFFu;
+    if (a > 0x7F800000u) return u2f(u | 0x00400000u);
+    if (a == 0x7F800000u) return u2f(sign);
+    if (a == 0) return u2f(sign | 0x7F800000u);
+    int e = (int)(a >> 23);
+    uint32_t mant = a & 0x7FFFFFu;
+    if (e == 0) {
+        int sh = __builtin_clz(mant) - 8;
+        mant = (mant << sh) & 0x7FFFFFu;
+        e = 1 - sh;
+    }
+    uint32_t rb = 0x3F800000u;
+    if (mant != 0) {
+        const uint32_t* c = orc_rcp14_coef[mant >> 17];
+        rb = ((c[0] - c[1] * ((mant >> 7) & 0x3FFu)) >> 9) << 7;
+    }
+    int re = (int)(rb >> 23) - (e - 127);
+    uint32_t rm = rb & 0x7FFFFFu;
+    if (re >= 255) return u2f(sign | 0x7F800000u);
+    if (re <= 0) { /* denormal result, truncated */
+        int sh = 1 - re;
+        return u2f(sh > 24 ? sign : (sign | ((rm | 0x800000u) >> sh)));
+    }
+    return u2f(sign | ((uint32_t)re << 23) | rm);
+}
+static inline float approx_rsqrt(float x) { return orc_x86_rsqrt14(x); }
+static inline float approx_rcp(float x) { return orc_x86_rcp14(x); }
 
 /* f16 <-> f32, IEEE RNE (Texture.h:101-116 uses vcvtps2ph/vcvtph2ps); NaN canonicalised */
 static uint16_t f32_to_f16(float f) {
@@ -305,8 +355,15 @@ static inline int step_pos(const OrcMap* m, int32_t p[3], const float d[3], Cast
 }
 
 /* RayCast, VoxelRT/CpuRenderer.cpp:172-224, one lane. */
+static void cast_ray_ex(const OrcMap* m, const float o[3], const float d[3], const int32_t wo[3], uint32_t max_iters,
+                        VrtHit* out, CastCounters* cnt, uint32_t* trips_out);
 static void cast_ray(const OrcMap* m, const float o[3], const float d[3], const int32_t wo[3], uint32_t max_iters,
                      VrtHit* out, CastCounters* cnt) {
+    cast_ray_ex(m, o, d, wo, max_iters, out, cnt, NULL);
+}
+/* trips_out: loop trips started before the lane stopped (1 = stopped in the first trip); max_iters for a capped lane */
+static void cast_ray_ex(const OrcMap* m, const float o[3], const float d[3], const int32_t wo[3], uint32_t max_iters,
+                        VrtHit* out, CastCounters* cnt, uint32_t* trips_out) {
     float inv[3], ts[3], sd[3] = {0, 0, 0}, cur[3];
     int32_t p[3] = {0, 0, 0};
     for (int a = 0; a < 3; a++) {
@@ -354,6 +411,7 @@ static void cast_ray(const OrcMap* m, const float o[3], const float d[3], const 
     out->u = x86_fract(fu); /* fract = _mm512_reduce_ps(x, TO_NEG_INF) (SIMD_AVX512.h:116) */
     out->v = x86_fract(fv);
     uint32_t iters_done = it < max_iters ? it + 1 : max_iters;
+    if (trips_out) *trips_out = iters_done;
     if (iters_done > 0xFFFF) iters_done = 0xFFFF;
     out->flags = (uint32_t)((nx + 1) | ((ny + 1) << 2) | ((nz + 1) << 4)) | ((!active && inb) ? VRT_HIT_HIT : 0) | /* :222 */
                  (inb ? VRT_HIT_INBOUND : 0) | (active ? VRT_HIT_CAPPED : 0) | (iters_done << VRT_HIT_ITERS_SHIFT);
@@ -502,9 +560,9 @@ static inline void transform_vec4(const float m[16], const float v[4], float r[4
     for (int row = 0; row < 4; row++)
         r[row] = fmaf(m[0 + row], v[0], fmaf(m[4 + row], v[1], fmaf(m[8 + row], v[2], m[12 + row] * v[3])));
 }
-/* simd::normalize, SIMD.h:109-115 (approx_rsqrt -> canonical 1/sqrt) */
+/* simd::normalize, SIMD.h:109-115: a * approx_rsqrt(dot(a, a)) */
 static inline void normalize3(float a[3]) {
-    float len = canon_rsqrt(fmaf(a[0], a[0], fmaf(a[1], a[1], a[2] * a[2])));
+    float len = approx_rsqrt(fmaf(a[0], a[0], fmaf(a[1], a[1], a[2] * a[2])));
     a[0] *= len;
     a[1] *= len;
     a[2] *= len;
@@ -538,17 +596,33 @@ static inline void sincos_2pi(float x, float* s, float* c) {
     *c = u2f(f2u(cc) | (f2u(xr) & 0x80000000u));
 }
 
-/* SampleDirection, CpuRenderer.cpp:273-291.  approx_sqrt(v) = rsqrt14(v) * v (SIMD_AVX512.h:140);
- * v = 0 gives inf * 0 = NaN (quirk Q7) in the canonical form too. */
+/* SampleDirection, CpuRenderer.cpp:273-291.  approx_sqrt(v) = rsqrt14(v) * v (SIMD_AVX512.h:136);
+ * v = 0 gives inf * 0 = NaN (quirk Q7). */
 void orc_sample_direction(float sx, float sy, float out[3]) {
     float y = fmaf(sy, 2.0f, -1.0f); /* :284 (exact either way) */
     float x, z;
     sincos_2pi(sx, &x, &z);          /* :287 */
     float v = fmaf(-y, y, 1.0f);     /* :288, 1 - y*y contracted */
-    float s = canon_rsqrt(v) * v;
+    float s = approx_rsqrt(v) * v;
     out[0] = x * s;
     out[1] = y;
     out[2] = z * s;
+}
+
+/* dir = normalize(hit.Normal + SampleDirection(bn)), CpuRenderer.cpp:392.  SampleDirection is inlined into RenderRow, and the reference's
+ * compilers contract `Normal.x + x * sy` / `Normal.z + z * sy` into FMAs (the same -ffp-contract=fast that fuses sideDist and
+ * currPos in RayCast; found by a 1-ulp direction difference that turned a stalled ray of the reference into a hit).  The y
+ * component has no product: plain add. */
+static inline void bounce_direction(const float nrm[3], float sx, float sy, float dir[3]) {
+    float y = fmaf(sy, 2.0f, -1.0f);
+    float x, z;
+    sincos_2pi(sx, &x, &z);
+    float v = fmaf(-y, y, 1.0f);
+    float s = approx_rsqrt(v) * v;
+    dir[0] = fmaf(x, s, nrm[0]);
+    dir[1] = nrm[1] + y;
+    dir[2] = fmaf(z, s, nrm[2]);
+    normalize3(dir);
 }
 
 /* VBlueNoise::Sample, CpuRenderer.cpp:254-270, for the 16-lane (4x4 tile) build: the R2 offset
@@ -588,16 +662,18 @@ void orc_sky_sample(const OrcMap* m, const float dir[3], uint32_t mip, float out
         out[0] = out[1] = out[2] = 0.0f;
         return;
     }
+    /* VFloat operator> is _mm512_cmp_ps_mask(a, b, _MM_CMPINT_GT) (SIMD_AVX512.h:83): the INTEGER predicate 6 read as a float predicate is
+     * _CMP_NLE_US, "not less-or-equal" — TRUE when either operand is NaN.  A NaN direction (quirk Q7) therefore selects face 4 / 5. */
     float w = dir[0];
-    int wy = fabsf(dir[1]) > fabsf(w);
+    int wy = !(fabsf(dir[1]) <= fabsf(w));
     w = wy ? dir[1] : w;
-    int wz = fabsf(dir[2]) > fabsf(w);
+    int wz = !(fabsf(dir[2]) <= fabsf(w));
     w = wz ? dir[2] : w;
     int wx = wy | wz;
     wy &= !wz;
     uint32_t face = wz ? 4u : (wy ? 2u : 0u);
     face += f2u(w) >> 31;
-    w = canon_rcp(fabsf(w)) * 0.5f; /* approx_rcp -> canonical */
+    w = approx_rcp(fabsf(w)) * 0.5f; /* Texture.h:285 */
     float u = fmaf(wx ? dir[0] : dir[2], w, 0.5f);
     float v = fmaf(wy ? dir[2] : dir[1], w, 0.5f);
 
@@ -633,8 +709,8 @@ uint32_t orc_pack_unorm8x4(float r, float g, float b, float a) {
 uint32_t orc_pack_half2(float x, float y) { return (uint32_t)f32_to_f16(x) | ((uint32_t)f32_to_f16(y) << 16); }
 void orc_sincos_2pi(float x, float* s, float* c) { sincos_2pi(x, s, c); }
 
-/* RenderRow body for one pixel, CpuRenderer.cpp:326-402 (lane-wise: a lane whose mask bit is
- * off does nothing further — the packet-coupled leftovers are listed in DESIGN.md §3). */
+/* RenderRow body for one pixel, CpuRenderer.cpp:326-402, LANE-WISE (a lane whose mask bit is off does nothing further): only the
+ * debugging aid orc_debug_pixel uses it; frames are rendered by render_tile below, which carries the packet semantics. */
 /* optional capture of every ray a pixel casts (debugging aid for the parity tests) */
 typedef struct {
     float* rays; /* per bounce: origin xyz, dir xyz */
@@ -644,10 +720,6 @@ typedef struct {
 
 static void render_pixel_ex(const OrcMap* m, const VrtFrame* f, uint32_t x, uint32_t y, uint32_t* o_albedo, float* o_depth,
                             uint32_t* o_rg, uint32_t* o_bx, VrtHit* aux, OrcStats* stats, PixelTrace* pt);
-static void render_pixel(const OrcMap* m, const VrtFrame* f, uint32_t x, uint32_t y, uint32_t* o_albedo, float* o_depth,
-                         uint32_t* o_rg, uint32_t* o_bx, VrtHit* aux, OrcStats* stats) {
-    render_pixel_ex(m, f, x, y, o_albedo, o_depth, o_rg, o_bx, aux, stats, NULL);
-}
 uint32_t orc_debug_pixel(const OrcMap* m, const VrtFrame* f, uint32_t x, uint32_t y, float* rays6, VrtHit* hits, uint32_t out4[4]) {
     PixelTrace pt = {rays6, hits, 0};
     float dep;
@@ -722,17 +794,157 @@ static void render_pixel_ex(const OrcMap* m, const VrtFrame* f, uint32_t x, uint
         origin[0] = fmaf(nrm[0], 0.01f, hit.px); /* :389 */
         origin[1] = fmaf(nrm[1], 0.01f, hit.py);
         origin[2] = fmaf(nrm[2], 0.01f, hit.pz);
-        float bn[2], sdv[3];
+        float bn[2];
         orc_blue_noise_sample(m, x, y, f->frame_no, i, bn); /* :391 */
-        orc_sample_direction(bn[0], bn[1], sdv);
-        for (int a = 0; a < 3; a++) dir[a] = nrm[a] + sdv[a]; /* :392 */
-        normalize3(dir);
+        bounce_direction(nrm, bn[0], bn[1], dir);           /* :392 */
     }
     *o_albedo = albedo;
     *o_depth = depth;
     *o_rg = (uint32_t)f32_to_f16(irr[0]) | ((uint32_t)f32_to_f16(irr[1]) << 16); /* :398 */
     uint32_t hz = f32_to_f16(irr[2]);
     *o_bx = hz | (hz << 16); /* :399 Pack({z}) -> VFloat2(v){x=y=v} (SIMD.h:32) */
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/* The 16-lane PACKET semantics of RayCast / RenderRow.                                          */
+/* The reference traces 4x4-pixel tiles as one SIMD packet (AVX-512: simd::VectorWidth = 16,      */
+/* TileWidth = TileHeight = 4), and a few statements of RayCast and RenderRow are not masked, so   */
+/* what a lane returns depends on its 15 neighbours (DESIGN.md §3, quirks Q2 / Q10 and the          */
+/* "zombie" lanes).  orc_render reproduces all of it; orc_trace stays lane-wise (one ray per packet).*/
+/* ------------------------------------------------------------------------------------------ */
+typedef struct {
+    float pos[3];      /* VHitResult::Pos      */
+    uint32_t material; /* MaterialData (low 32 bits of the palette entry) */
+    int n[3];          /* Normal               */
+    int hit;           /* Mask                 */
+} PacketLane;
+
+/* RayCast (CpuRenderer.cpp:172-224) for one packet.  `active` = the activeMask argument.  Per lane, the loop of an ACTIVE lane is the
+ * lane-wise cast_ray; the coupling is:
+ *  - the loop runs until no lane is active, and `currPos = origin + tmin * dir` (:200-201) is not masked: a lane that stopped in
+ *    the FIRST trip, or was never active, still has sideDist = 0, so once the packet goes on past its first trip its currPos
+ *    becomes origin + 0.001 * dir, and voxelPos / inboundMask follow (:186-188) (Q10);
+ *  - when some lane is still active after the last trip (iteration cap), the loop ends right after `voxelPos -= worldOrigin` (:195),
+ *    so GetVoxelMaterial (:210) reads voxel (voxelPos - worldOrigin) for every stopped lane of that packet (Q2);
+ *  - MaterialData is gathered for every lane that is not active at the end, never-active lanes included (:210), and
+ *    Mask = ~activeMask & inboundMask (:222) can be set for a never-active lane. */
+static void cast_packet(const OrcMap* m, float o[16][3], float d[16][3], uint32_t active, const int32_t wo[3], uint32_t max_iters,
+                        PacketLane out[16], VrtHit lane_hits[16], OrcStats* stats) {
+    uint32_t trips[16];
+    int capped[16];
+    int pk_multi = 0, pk_capped = 0;
+    for (int l = 0; l < 16; l++) {
+        trips[l] = 0;
+        capped[l] = 0;
+        if (!((active >> l) & 1)) continue;
+        CastCounters c = {0, 0, 0, {0}};
+        cast_ray_ex(m, o[l], d[l], wo, max_iters, &lane_hits[l], &c, &trips[l]);
+        if (stats) stats_add(stats, &c, &lane_hits[l]);
+        capped[l] = (lane_hits[l].flags & VRT_HIT_CAPPED) != 0;
+        if (capped[l]) pk_capped = 1;
+        if (capped[l] || trips[l] >= 2) pk_multi = 1; /* still active after the first trip */
+    }
+    for (int l = 0; l < 16; l++) {
+        const int was_active = (int)((active >> l) & 1);
+        const int first = !was_active || (trips[l] == 1 && !capped[l]);
+        PacketLane* r = &out[l];
+        int32_t p[3];
+        int inb;
+        if (first) {
+            float sd0 = 0.0f;
+            float tmin = x86_min(x86_min(sd0, sd0), sd0) + 0.001f; /* :200 with sideDist = 0 */
+            for (int a = 0; a < 3; a++) {
+                r->pos[a] = pk_multi ? fmaf(tmin, d[l][a], o[l][a]) : o[l][a]; /* :201, :181 */
+                p[a] = (int32_t)((uint32_t)wo[a] + (uint32_t)x86_floor2i(r->pos[a])); /* :186 */
+            }
+            inb = inbound(m, p[0], p[1], p[2]); /* :188 */
+            /* :204-216 with sideDist = 0: X and Y both match */
+            r->n[0] = (f2u(d[l][0]) >> 31) ? 1 : -1;
+            r->n[1] = (f2u(d[l][1]) >> 31) ? 1 : -1;
+            r->n[2] = 0;
+        } else {
+            const VrtHit* h = &lane_hits[l];
+            r->pos[0] = h->px, r->pos[1] = h->py, r->pos[2] = h->pz;
+            p[0] = h->vx, p[1] = h->vy, p[2] = h->vz;
+            inb = (h->flags & VRT_HIT_INBOUND) != 0;
+            r->n[0] = (int)(h->flags & 3) - 1, r->n[1] = (int)((h->flags >> 2) & 3) - 1, r->n[2] = (int)((h->flags >> 4) & 3) - 1;
+        }
+        if (capped[l]) { /* still active: not gathered (:210), Mask clear (:222) */
+            r->material = 0;
+            r->hit = 0;
+        } else {
+            if (pk_capped)
+                for (int a = 0; a < 3; a++) p[a] = (int32_t)((uint32_t)p[a] - (uint32_t)wo[a]); /* :195 without the matching += */
+            r->material = voxel_material(m, p[0], p[1], p[2]);
+            r->hit = inb;
+        }
+    }
+}
+
+/* RenderRow body for one 4x4 tile = one packet, CpuRenderer.cpp:332-400.  Lane l = pixel (x0 + l % 4, y0 + l / 4) (SIMD.h TileOffsets).
+ * Everything after RayCast is unmasked in the reference except the sky lookup (:348-369) and the depth of missed primary rays (:377):
+ * lanes whose path has ended keep accumulating `throughput * emission` of whatever voxel their stale position maps to and keep
+ * producing new origins / directions for as long as some lane of the packet is alive. */
+static void render_tile(const OrcMap* m, const VrtFrame* f, uint32_t x0, uint32_t y0, uint32_t albedo[16], float depth[16], uint32_t irr_rg[16],
+                        uint32_t irr_bx[16], VrtHit* aux /* frame-sized, row-major, or NULL */, OrcStats* stats) {
+    float origin[16][3], dir[16][3], irr[16][3], thr[16][3];
+    const uint32_t max_iters = f->max_iters ? f->max_iters : VRT_MAX_ITERS_DEFAULT;
+    for (int l = 0; l < 16; l++) {
+        orc_primary_ray(f, x0 + (uint32_t)(l & 3), y0 + (uint32_t)(l >> 2), origin[l], dir[l]); /* :327-334 */
+        for (int a = 0; a < 3; a++) irr[l][a] = 0.0f, thr[l][a] = 1.0f;                          /* :338-339 */
+        albedo[l] = 0;
+        depth[l] = 0.0f;
+    }
+    uint32_t mask = 0xFFFFu;
+    for (uint32_t i = 0; i <= f->bounces && mask; i++) { /* :342 */
+        PacketLane hit[16];
+        VrtHit lane_hits[16];
+        cast_packet(m, origin, dir, mask, f->world_origin, max_iters, hit, lane_hits, stats); /* :343 */
+        for (int l = 0; l < 16; l++) {
+            const uint32_t x = x0 + (uint32_t)(l & 3), y = y0 + (uint32_t)(l >> 2);
+            if (i == 0 && aux) aux[(size_t)y * f->width + x] = lane_hits[l]; /* the lane-wise RayCast record of the primary ray */
+            const uint32_t md = hit[l].material;
+            float col[3] = {(float)((md >> 11) & 31) * (1.0f / 31), (float)((md >> 5) & 63) * (1.0f / 63), (float)(md & 31) * (1.0f / 31)}; /* :97-104 */
+            for (int a = 0; a < 3; a++) col[a] = col[a] * col[a];
+            float emission = f16_to_f32((uint16_t)(md >> 16)); /* :105-107 */
+            const int miss = (int)((mask >> l) & 1) && !hit[l].hit; /* :346 missMask = mask & ~hit.Mask */
+            if (miss) {                                            /* :347-369 */
+                float sky[3];
+                orc_sky_sample(m, dir[l], i == 0 ? 1 : 3, sky);
+                if (i == 0) irr[l][0] = sky[0], irr[l][1] = sky[1], irr[l][2] = sky[2];
+                else col[0] = sky[0], col[1] = sky[1], col[2] = sky[2], emission = 1.0f;
+            }
+            if (i == 0) { /* :370-382 */
+                albedo[l] = pack_unorm8(col[0]) | (pack_unorm8(col[1]) << 8) | (pack_unorm8(col[2]) << 16) | (pack_unorm8(0.0f) << 24);
+                albedo[l] |= (uint32_t)(hit[l].n[0] + 1) << 24;
+                albedo[l] |= (uint32_t)(hit[l].n[1] + 1) << 26;
+                albedo[l] |= (uint32_t)(hit[l].n[2] + 1) << 28;
+                float pp[4] = {hit[l].pos[0] / 16.0f, hit[l].pos[1] / 16.0f, hit[l].pos[2] / 16.0f, 1.0f}, pr[4];
+                transform_vec4(f->proj, pp, pr);
+                depth[l] = miss ? -1.0f : pr[2] / pr[3];
+                if (f->bounces == 0) { /* :379-382 */
+                    irr[l][0] = irr[l][1] = irr[l][2] = 1.0f;
+                    continue;
+                }
+            } else {
+                for (int a = 0; a < 3; a++) thr[l][a] = thr[l][a] * col[a]; /* :384 */
+            }
+            for (int a = 0; a < 3; a++) irr[l][a] = fmaf(thr[l][a], emission, irr[l][a]); /* :386 */
+            const float nrm[3] = {(float)hit[l].n[0], (float)hit[l].n[1], (float)hit[l].n[2]};
+            for (int a = 0; a < 3; a++) origin[l][a] = fmaf(nrm[a], 0.01f, hit[l].pos[a]); /* :389 */
+            float bn[2];
+            orc_blue_noise_sample(m, x, y, f->frame_no, i, bn); /* :391 */
+            bounce_direction(nrm, bn[0], bn[1], dir[l]);        /* :392 */
+        }
+        if (f->bounces == 0) break;
+        for (int l = 0; l < 16; l++)
+            if (!hit[l].hit) mask &= ~(1u << l); /* :387 mask &= hit.Mask */
+    }
+    for (int l = 0; l < 16; l++) {
+        irr_rg[l] = (uint32_t)f32_to_f16(irr[l][0]) | ((uint32_t)f32_to_f16(irr[l][1]) << 16); /* :398 */
+        uint32_t hz = f32_to_f16(irr[l][2]);
+        irr_bx[l] = hz | (hz << 16); /* :399 Pack({z}) -> VFloat2(v){x=y=v} (SIMD.h:32) */
+    }
 }
 
 void orc_render(const OrcMap* m, const VrtFrame* f, void* out, VrtHit* aux_hits, OrcStats* stats, int threads,
@@ -754,31 +966,30 @@ void orc_render(const OrcMap* m, const VrtFrame* f, void* out, VrtHit* aux_hits,
 #pragma omp for schedule(dynamic, 1)
 #endif
         for (int64_t ty = row0 / 4; ty < (int64_t)(row1 / 4); ty++) { /* :455-462 one tile row */
-            for (uint32_t x = 0; x < w; x++) {
-                for (uint32_t yy = 0; yy < 4; yy++) {
-                    uint32_t y = (uint32_t)ty * 4 + yy;
-                    if (part_count > 1) {
-                        uint32_t t = (f->flags & VRT_FRAME_PART_ROWS) ? (y / VRT_BAND_ROWS) : (y / 32) * tiles_x + (x / 32);
-                        if (t % part_count != f->part_index) continue;
-                    }
-                    uint32_t alb, rg, bx;
-                    float dep;
-                    render_pixel(m, f, x, y, &alb, &dep, &rg, &bx, aux_hits ? &aux_hits[(size_t)y * w + x] : NULL,
-                                 stats ? &local : NULL);
+            for (uint32_t x0 = 0; x0 + 4 <= w; x0 += 4) {             /* :329 one packet */
+                const uint32_t y0 = (uint32_t)ty * 4;
+                if (part_count > 1) { /* a 4x4 tile never straddles two parts (bands are 8 rows, macro tiles 32x32) */
+                    uint32_t t = (f->flags & VRT_FRAME_PART_ROWS) ? (y0 / VRT_BAND_ROWS) : (y0 / 32) * tiles_x + (x0 / 32);
+                    if (t % part_count != f->part_index) continue;
+                }
+                uint32_t alb[16], rg[16], bx[16];
+                float dep[16];
+                render_tile(m, f, x0, y0, alb, dep, rg, bx, aux_hits, stats ? &local : NULL);
+                for (uint32_t l = 0; l < 16; l++) {
+                    const uint32_t x = x0 + (l & 3), y = y0 + (l >> 2);
                     if (f->flags & VRT_FRAME_LINEAR_OUTPUT) {
                         uint32_t* o = (uint32_t*)out;
                         size_t n = (size_t)w * h, p = (size_t)y * w + x;
-                        o[p] = alb;
-                        memcpy(&o[n + p], &dep, 4);
-                        o[2 * n + p] = rg;
-                        o[3 * n + p] = bx;
+                        o[p] = alb[l];
+                        memcpy(&o[n + p], &dep[l], 4);
+                        o[2 * n + p] = rg[l];
+                        o[3 * n + p] = bx[l];
                     } else { /* Framebuffer::Tile, :299-309, tile = (y/4)*TileStride + x/4 (:459) */
                         VrtTile* t = (VrtTile*)out + ((size_t)(y / 4) * (w / 4) + x / 4);
-                        uint32_t lane = (x & 3) | ((y & 3) << 2);
-                        t->albedo[lane] = alb;
-                        t->depth[lane] = dep;
-                        t->irr_rg[lane] = rg;
-                        t->irr_bx[lane] = bx;
+                        t->albedo[l] = alb[l];
+                        t->depth[l] = dep[l];
+                        t->irr_rg[l] = rg[l];
+                        t->irr_bx[l] = bx[l];
                     }
                 }
             }

@@ -9,8 +9,9 @@
  * Parity status: PINNED for the traversal (a7-a10 of SURVEY §8a) against the reference's own
  * CpuRenderer.cpp compiled from /root/reference by oracle/Makefile (oracle/_ref/, see
  * oracle/ref_harness.cpp and tests/golden/); the reference ships no tests or golden vectors
- * of its own.  Shading follows the canonical arithmetic documented in DESIGN.md §3 (the
- * reference's rsqrt14/rcp14 approximations are hardware-defined and replaced by IEEE ops).
+ * of its own.  Ray generation and shading are PINNED too: whole frames of orc_render equal the reference's RenderRow output byte
+ * for byte (tests/test_ref_pin.py) — rsqrt14 / rcp14 are reproduced bit-exactly and the 16-lane packet coupling of RayCast / RenderRow
+ *  is part of orc_render's semantics.
  *
  * The structs are the public ABI's (include/voxelrt_b200.h) so tests feed identical bytes
  * to both sides.
@@ -90,6 +91,10 @@ void orc_trace_glsl(const OrcMap* m, uint64_t n, const float* origin3, const flo
                     VrtHit* out, OrcStats* stats, int threads);
 /* GenerateRayCellInteractionMaskLUT, GpuRenderer.cpp:193-210 */
 void orc_interaction_lut(uint64_t table[512]);
+
+/* _mm512_rsqrt14_ps / _mm512_rcp14_ps (SIMD_AVX512.h:136-138), bit-exact for every argument */
+float orc_x86_rsqrt14(float x);
+float orc_x86_rcp14(float x);
 
 int orc_num_threads(void);
 

@@ -11,6 +11,10 @@
 #include <cstddef>
 #include <cstdint>
 #include <cstring>
+#include <ucontext.h>
+
+#include <cstdlib>
+#include <vector>
 
 #define __device__
 #define __host__
@@ -23,11 +27,13 @@
 
 struct uint2 { unsigned x, y; };
 struct uint4 { unsigned x, y, z, w; };
+struct float2 { float x, y; };
 struct float3 { float x, y, z; };
 struct float4 { float x, y, z, w; };
 struct dim3 { unsigned x = 1, y = 1, z = 1; };
 static inline uint2 make_uint2(unsigned x, unsigned y) { return {x, y}; }
 static inline uint4 make_uint4(unsigned x, unsigned y, unsigned z, unsigned w) { return {x, y, z, w}; }
+static inline float2 make_float2(float x, float y) { return {x, y}; }
 static inline float3 make_float3(float x, float y, float z) { return {x, y, z}; }
 static inline float4 make_float4(float x, float y, float z, float w) { return {x, y, z, w}; }
 
@@ -77,13 +83,96 @@ static inline unsigned __byte_perm(unsigned x, unsigned y, unsigned s) {
     }
     return r;
 }
-// one lane at a time: a warp of one (the traversal's results are defined per lane, whatever the warp it runs in)
-static inline unsigned __activemask() { return 1u; }
-static inline int __all_sync(unsigned, int p) { return p; }
-static inline int __any_sync(unsigned, int p) { return p; }
+// ---- warps ------------------------------------------------------------------------------------------------------------------------
+// Three ways to run device code that talks to the other lanes of its warp:
+//  (1) one lane at a time, a warp of one: votes see only the caller (per-lane functions: the traversal's results are defined per lane);
+//  (2) LOCKSTEP (EmuWarp, run_warp_lockstep): the 32 lanes of a warp are 32 host threads and every collective is a rendezvous — what the
+//      frame kernels need now that a half-warp is one SIMD packet of the reference (packet_votes), and what the persistent trace pass needs
+//      (its loop control is a vote per trip).  A lane that returns leaves the rendezvous (it votes 0 from then on, like an exited thread);
+//  (3) shuffle REPLAY (ShflReplay below) for the straight-line warp-per-brick kernels.
+struct EmuWarp {
+    ucontext_t sched;      // the scheduler (run_warp_lockstep's own context)
+    ucontext_t ctx[32];    // one fiber per lane, all on the calling OS thread
+    bool done[32];
+    unsigned xchg[32];     // words deposited at the current rendezvous (0 for lanes that have returned)
+    unsigned result[32];   // snapshot handed to the lanes when they resume
+    unsigned block_idx, block_dim, tid0;
+    void (*body)(void*, int);
+    void* arg;
+};
+static thread_local EmuWarp* t_emu_warp = nullptr;
+static thread_local int t_emu_lane = 0;
+static inline void emu_enter_lane(EmuWarp* w, int l) {  // (all fibers share the OS thread's thread_locals: set them on every switch)
+    blockIdx.x = w->block_idx, blockIdx.y = blockIdx.z = 0;
+    blockDim.x = w->block_dim, blockDim.y = blockDim.z = 1;
+    threadIdx.x = w->tid0 + (unsigned)l, threadIdx.y = threadIdx.z = 0;
+    t_emu_lane = l;
+}
+static inline unsigned emu_exchange(unsigned mine, unsigned out[32]) {  // every live lane deposits a word, then all read all of them
+    EmuWarp* w = t_emu_warp;
+    const int l = t_emu_lane;
+    w->xchg[l] = mine;
+    swapcontext(&w->ctx[l], &w->sched);  // back to the scheduler until every live lane has arrived
+    for (int k = 0; k < 32; k++) out[k] = w->result[k];
+    return 0;
+}
+static void emu_lane_entry(unsigned lo, unsigned hi) {
+    EmuWarp* w = reinterpret_cast<EmuWarp*>(((unsigned long long)hi << 32) | lo);
+    const int l = t_emu_lane;
+    w->body(w->arg, l);
+    w->done[l] = true;
+    w->xchg[l] = 0u;  // an exited lane votes 0 / false from now on
+    swapcontext(&w->ctx[l], &w->sched);
+}
+// runs fn(lane) for the 32 lanes of one warp in LOCKSTEP: 32 fibers on the calling thread; a collective hands control back to the
+// scheduler, which resumes the lanes in turn until all of them wait at the same rendezvous (or have returned), then publishes the words
+template <class F>
+static void run_warp_lockstep(unsigned block_idx, unsigned block_dim, unsigned tid0, F fn) {
+    static thread_local char* stacks = nullptr;
+    const size_t kStack = 256u << 10;
+    if (!stacks) stacks = static_cast<char*>(std::malloc(32 * kStack));
+    EmuWarp w;
+    w.block_idx = block_idx, w.block_dim = block_dim, w.tid0 = tid0;
+    w.body = [](void* a, int lane) { (*static_cast<F*>(a))(lane); };
+    w.arg = &fn;
+    const unsigned long long wp = reinterpret_cast<unsigned long long>(&w);
+    for (int l = 0; l < 32; l++) {
+        w.done[l] = false;
+        w.xchg[l] = w.result[l] = 0u;
+        getcontext(&w.ctx[l]);
+        w.ctx[l].uc_stack.ss_sp = stacks + (size_t)l * kStack;
+        w.ctx[l].uc_stack.ss_size = kStack;
+        w.ctx[l].uc_link = nullptr;
+        makecontext(&w.ctx[l], reinterpret_cast<void (*)()>(emu_lane_entry), 2, (unsigned)(wp & 0xFFFFFFFFu), (unsigned)(wp >> 32));
+    }
+    EmuWarp* outer = t_emu_warp;
+    t_emu_warp = &w;
+    for (;;) {
+        bool any = false;
+        for (int l = 0; l < 32; l++)
+            if (!w.done[l]) {
+                any = true;
+                emu_enter_lane(&w, l);
+                swapcontext(&w.sched, &w.ctx[l]);  // until the lane reaches a collective or returns
+            }
+        if (!any) break;
+        for (int l = 0; l < 32; l++) w.result[l] = w.xchg[l];
+    }
+    t_emu_warp = outer;
+}
+static inline unsigned __activemask() { return t_emu_warp ? 0xFFFFFFFFu : 1u; }
 template <class... A> static inline void __syncwarp(A...) {}
 static inline void __syncthreads() {}
-template <class T> static inline T __shfl_sync(unsigned, T v, int) { return v; }
+template <class T> static inline T __shfl_sync(unsigned, T v, int src) {
+    if (!t_emu_warp) return v;
+    static_assert(sizeof(T) == 4, "lockstep shuffles handle 32-bit values");
+    unsigned bits, all[32];
+    std::memcpy(&bits, &v, 4);
+    emu_exchange(bits, all);
+    T out;
+    std::memcpy(&out, &all[src & 31], 4);
+    return out;
+}
 // Warp REPLAY for kernels whose lanes exchange data through a fixed sequence of xor-shuffles and have no divergent control flow around
 // them (the warp-per-brick occupancy build): the emulator runs all 32 lanes once per shuffle call; call #k of round r returns what lane
 // (l ^ mask) passed to call #k in the PREVIOUS round — correct for every k < r by induction, a placeholder otherwise — so after
@@ -107,7 +196,13 @@ template <class T> static inline T __shfl_xor_sync(unsigned, T v, int mask) {
     std::memcpy(&out, &other, 4);
     return out;
 }
-static inline unsigned __ballot_sync(unsigned, int p) {
+static inline unsigned __ballot_sync(unsigned mask, int p) {
+    if (t_emu_warp) {
+        unsigned all[32], word = 0;
+        emu_exchange(p ? 1u : 0u, all);
+        for (int l = 0; l < 32; l++) word |= (all[l] & 1u) << l;
+        return word & mask;
+    }
     ShflReplay* r = g_shfl_replay;
     if (!r) return p ? 1u : 0u;  // one-lane warp
     const int k = r->call++;
@@ -116,8 +211,12 @@ static inline unsigned __ballot_sync(unsigned, int p) {
     for (int l = 0; l < 32; l++) word |= (r->prev[k][l] & 1u) << l;
     return word;
 }
+static inline int __any_sync(unsigned mask, int p) { return t_emu_warp ? (__ballot_sync(mask, p) != 0u) : p; }
+// (only ever used with the mask of the lanes that entered a branch together; the emulated cast_ray takes that decision per lane)
+static inline int __all_sync(unsigned, int p) { return p; }
 template <class T> static inline T __shfl_down_sync(unsigned, T v, unsigned) { return v; }
-template <class T, class U> static inline T atomicAdd(T* p, U v) { T o = *p; *p = (T)(o + v); return o; }
+template <class T, class U> static inline T atomicAdd(T* p, U v) { return __atomic_fetch_add(p, (T)v, __ATOMIC_RELAXED); }
+
 using std::isinf;
 using std::max;
 using std::min;

@@ -126,11 +126,8 @@ EMU_API int emu_render_kernel(const EmuScene* e, const VrtFrame* f, const uint8_
     const int64_t blocks = (F.n_work - F.work_offset + wpb - 1) / wpb;
     const bool rows = (F.flags & VRT_FRAME_PART_ROWS) != 0u, primary = F.bounces == 0;
 #pragma omp parallel for schedule(dynamic, 8)
-    for (int64_t b = 0; b < blocks; b++) {
-        blockDim.x = VRT_RENDER_THREADS, blockDim.y = blockDim.z = 1;
-        blockIdx.x = (unsigned)b;
-        for (unsigned t = 0; t < VRT_RENDER_THREADS; t++) {
-            threadIdx.x = t;
+    for (int64_t w = 0; w < blocks * (int64_t)wpb; w++) {  // every warp of the grid, its 32 lanes in lockstep (packet votes)
+        run_warp_lockstep((unsigned)(w / wpb), VRT_RENDER_THREADS, (unsigned)(w % wpb) * 32u, [&](int) {
             if (primary) {
                 if (rows) k_render<false, true, true>(S, F);
                 else k_render<false, true, false>(S, F);
@@ -138,9 +135,56 @@ EMU_API int emu_render_kernel(const EmuScene* e, const VrtFrame* f, const uint8_
                 if (rows) k_render<false, false, true>(S, F);
                 else k_render<false, false, false>(S, F);
             }
-        }
+        });
     }
     return (int)blocks;
+}
+
+// The WAVEFRONT form of a frame with bounces, launched like launch_render does: k_wave_primary, then per bounce level k_wave_trace (the
+// persistent, lane-refilling trace pass with the branch-lean trip) and k_wave_shade.  Warps run in lockstep; the trace pass runs `trace_warps`
+// persistent warps one after the other (the first ones drain most of the queue — results do not depend on who traces a ray).
+EMU_API int emu_wave_frame(const EmuScene* e, const VrtFrame* f, const uint8_t* bn, const uint32_t* sky, const VrtSkyDesc* sky_desc, void* out, VrtHit* aux,
+                           uint32_t trace_warps) {
+    DevScene S = scene_of(e);
+    uint32_t albedo[256];
+    for (int i = 0; i < 256; i++) albedo[i] = albedo_rgb_bits(e->palette[i].x);
+    S.albedo = albedo;
+    FrameParams F;
+    fill_frame_params(F, f, S.sxp, 0, bn, sky, sky_desc);
+    F.out = out;
+    F.aux = aux;
+    if (!fill_frame_partition(F, f, 0, 0)) return -1;
+    if (F.n_work <= F.work_offset || F.bounces == 0) return 0;
+    const unsigned wpb = VRT_RENDER_THREADS / 32;
+    const int64_t warps = (int64_t)((F.n_work - F.work_offset + wpb - 1) / wpb) * wpb;
+    const bool rows = (F.flags & VRT_FRAME_PART_ROWS) != 0u;
+    const size_t cap = (size_t)(F.n_work - F.work_offset) * 32u;
+    std::vector<RayRec> rays(cap);
+    std::vector<HitRec> hits(cap);
+    std::vector<float4> path_a(cap);
+    std::vector<float2> path_b(cap);
+    std::vector<uint16_t> pk(cap / 16 + 1);
+    uint32_t counters[20] = {};
+    WaveBuffers B{rays.data(), counters, counters + 10, hits.data(), path_a.data(), path_b.data(), pk.data()};
+#pragma omp parallel for schedule(dynamic, 8)
+    for (int64_t w = 0; w < warps; w++)
+        run_warp_lockstep((unsigned)(w / wpb), VRT_RENDER_THREADS, (unsigned)(w % wpb) * 32u, [&](int) {
+            if (rows) k_wave_primary<true>(S, F, B);
+            else k_wave_primary<false>(S, F, B);
+        });
+    for (uint32_t level = 1; level <= F.bounces; level++) {
+        TraceArgs A{B.rays, B.n_rays + level, B.head + level, B.hits, F.max_iters};
+#pragma omp parallel for schedule(dynamic, 1)
+        for (int64_t w = 0; w < (int64_t)trace_warps; w++)
+            run_warp_lockstep((unsigned)(w / wpb), VRT_RENDER_THREADS, (unsigned)(w % wpb) * 32u, [&](int) { k_wave_trace(S, F.W, A); });
+#pragma omp parallel for schedule(dynamic, 8)
+        for (int64_t w = 0; w < warps; w++)
+            run_warp_lockstep((unsigned)(w / wpb), VRT_RENDER_THREADS, (unsigned)(w % wpb) * 32u, [&](int) {
+                if (rows) k_wave_shade<true>(S, F, B, level);
+                else k_wave_shade<false>(S, F, B, level);
+            });
+    }
+    return (int)counters[1];
 }
 
 // rebuild_boxes of vrt_api.cu: the same five launches, in order

@@ -1,5 +1,6 @@
 // libemu_render.so — the per-pixel body of the FRAME kernels (voxelrt_b200/csrc/vrt_shade.cuh: primary_ray, cast_ray, shade_pixel_primary
-// for bounces = 0 and shade_pixel for frames with blue-noise bounces and the sky cube) compiled for the host and run pixel by pixel; the
+// for bounces = 0 and shade_pixel for frames with blue-noise bounces and the sky cube) compiled for the host and run warp tile by warp tile
+// (8x4 pixels = 32 lanes in LOCKSTEP: a half-warp is one 4x4 packet of the reference, and the packet coupling is carried by warp votes); the
 // frame constants come from the product's own fill_frame_params.  Output: the 16 B/px tile framebuffer (VrtTile) like store_pixel writes
 // it.  Macro steps off (they need the box builder).  TEST INFRASTRUCTURE ONLY.
 #define VRT_HOST_EMULATION 1
@@ -38,22 +39,26 @@ EMU_API void emu_render(const EmuScene* e, const VrtFrame* f, const uint8_t* blu
     fill_frame_params(F, f, S.sxp, 0, blue_noise, sky, sky_desc);
     F.aux = aux;
     const int w = (int)f->width, h = (int)f->height;
+    const int tiles_x = (w + 7) / 8, tiles_y = (h + 3) / 4;
+    const bool occ = g_occ != nullptr;
 #pragma omp parallel for schedule(dynamic, 4)
-    for (int y = 0; y < h; y++) {
-        blockDim.x = 128, blockDim.y = blockDim.z = 1;
-        for (int x = 0; x < w; x++) {
-            threadIdx.x = (unsigned)(x & 31);
+    for (int t = 0; t < tiles_x * tiles_y; t++) {
+        const int x0 = (t % tiles_x) * 8, y0 = (t / tiles_x) * 4;
+        run_warp_lockstep((unsigned)t, 32, 0, [&](int lane) {
+            const int x = x0 + ((lane >> 4) << 2) + (lane & 3), y = y0 + ((lane >> 2) & 3);  // render_warp_tile's lane -> pixel map
+            const bool valid = x < w && y < h;
             PixelOut P;
-            if (F.bounces == 0) shade_pixel_primary<false>(S, F, (uint32_t)x, (uint32_t)y, true, P);
-            else if (g_occ) shade_pixel<false, true>(S, F, (uint32_t)x, (uint32_t)y, true, P);
-            else shade_pixel<false, false>(S, F, (uint32_t)x, (uint32_t)y, true, P);
-            VrtTile* t = out + ((size_t)(y >> 2) * (size_t)(w >> 2) + (size_t)(x >> 2));
-            const int lane = (x & 3) | ((y & 3) << 2);
-            t->albedo[lane] = P.albedo;
-            t->depth[lane] = P.depth;
-            t->irr_rg[lane] = P.irr_rg;
-            t->irr_bx[lane] = P.irr_bx;
-        }
+            if (F.bounces == 0) shade_pixel_primary<false>(S, F, (uint32_t)x, (uint32_t)y, valid, P);
+            else if (occ) shade_pixel<false, true>(S, F, (uint32_t)x, (uint32_t)y, valid, P);
+            else shade_pixel<false, false>(S, F, (uint32_t)x, (uint32_t)y, valid, P);
+            if (!valid) return;
+            VrtTile* tile = out + ((size_t)(y >> 2) * (size_t)(w >> 2) + (size_t)(x >> 2));
+            const int l = (x & 3) | ((y & 3) << 2);
+            tile->albedo[l] = P.albedo;
+            tile->depth[l] = P.depth;
+            tile->irr_rg[l] = P.irr_rg;
+            tile->irr_bx[l] = P.irr_bx;
+        });
     }
 }
 }

@@ -238,3 +238,44 @@ def test_big_view_two_bounces_occ_form(emu, kern, hash_scene, shading_inputs):
             assert_hits_equal(aux, want_aux, "big view, OCC form")
     finally:
         emu.emu_render_set_occ(None)
+
+
+@pytest.mark.parametrize("size,bounces,flags_parts", [((256, 144), 1, (0, 1)), ((256, 144), 3, (0, 1)), ((132, 76), 2, (8, 3)), ((36, 8), 2, (0, 2))])
+def test_wavefront_pipeline_source_equals_oracle(kern, layout, hash_oracle, shading_inputs, size, bounces, flags_parts):
+    """The WAVEFRONT form of a frame with bounces as launched (k_wave_primary, then per level k_wave_trace — persistent warps whose lanes are
+    refilled from the level's queue, the branch-lean trip, the one-trip shortcut for NaN directions — and k_wave_shade with the packet votes),
+    all warps in lockstep on the host: the frame equals the oracle (= the reference's RenderRow) byte for byte, hit records included; with a
+    screen split the parts are disjoint and their union is the frame."""
+    from scenes import camera
+    from voxelrt_b200 import capi
+
+    (bn, _), (desc, tex, _) = shading_inputs
+    hash_oracle.set_blue_noise(bn)
+    hash_oracle.set_sky(desc, tex)
+    bn_a, tex_a = np.ascontiguousarray(bn, np.uint8), np.ascontiguousarray(tex, np.uint32)
+    kern.emu_wave_frame.argtypes = [C.POINTER(EmuScene), C.POINTER(capi.VrtFrame), C.c_void_p, C.c_void_p, C.POINTER(capi.VrtSkyDesc), C.c_void_p, C.c_void_p, C.c_uint32]
+    kern.emu_wave_frame.restype = C.c_int
+    w, h = size
+    flags, parts = flags_parts
+    SENT = 0xA5A5A5A5
+    cams = [camera.Camera(pos=(96.3, 90.2, 20.7), yaw=0.2, pitch=-0.45), camera.Camera(pos=(60.3, 20.2, 40.7), yaw=1.2, pitch=-0.3),
+            camera.Camera(pos=(96.3, 126.9, 20.7), yaw=0.2, pitch=1.2)]
+    for k, cam in enumerate(cams):
+        proj, inv, wo, frac = cam.matrices(w, h)
+        want, want_aux, _ = hash_oracle.render(capi.make_frame(w, h, inv, proj, wo, frac, frame_no=3 + 64 * k, bounces=bounces), want_aux=True)
+        acc = np.full(w * h * 4, SENT, np.uint32)
+        aux = np.zeros(w * h, capi.HIT_DTYPE)
+        queued = 0
+        for r in range(parts):
+            fr = capi.make_frame(w, h, inv, proj, wo, frac, frame_no=3 + 64 * k, bounces=bounces, flags=flags, part_index=r, part_count=parts)
+            part = np.full(w * h * 4, SENT, np.uint32)
+            n1 = kern.emu_wave_frame(C.byref(layout.c), C.byref(fr), bn_a.ctypes.data, tex_a.ctypes.data, C.byref(desc), part.ctypes.data, aux.ctypes.data, 5)
+            assert n1 >= 0
+            queued += n1
+            mine = part != SENT
+            assert not ((acc != SENT) & mine).any()
+            acc[mine] = part[mine]
+        assert np.array_equal(acc, np.frombuffer(want.tobytes(), np.uint32)), f"camera {k}: {(acc != np.frombuffer(want.tobytes(), np.uint32)).sum()} words differ"
+        assert_hits_equal(aux, want_aux, f"camera {k}: aux hit records")
+        if k == 0:
+            assert queued > w * h // 4  # (bounce rays really went through the queues)

@@ -222,7 +222,7 @@ def test_render_persistent_kernel_equals_grid_kernel(bench_ctx, bench_oracle, sh
             got, _ = bench_ctx.render(_frame(cam, 1280, 720))
             assert got.tobytes() == out_c.tobytes()
     finally:
-        bench_ctx.set_option("persistent", 1)
+        bench_ctx.set_option("persistent", 0)
 
 
 @pytest.mark.parametrize("i", range(4))
@@ -262,8 +262,8 @@ def test_render_bounces(hash_scene, hash_oracle, shading_inputs, bounces):
 
 @pytest.mark.parametrize("size", [(320, 180), (36, 4), (260, 148)])
 def test_bounce_compaction_equals_per_pixel_path(bench_ctx, bench_oracle, shading_inputs, size):
-    """Frames with bounces: the wavefront passes (queues + trip budgets) and the CTA-compacted kernel give the bytes of the
-    one-thread-per-pixel kernel and of the oracle, incl. aux records, partitions and odd frame sizes."""
+    """Frames with bounces: the wavefront form (camera pass, then per level a persistent lane-refilling trace pass and a shade pass) gives the
+    bytes of the one-thread-per-pixel kernel and of the oracle, incl. aux records, partitions and odd frame sizes."""
     from scenes import camera
     from voxelrt_b200 import capi
 
@@ -277,8 +277,7 @@ def test_bounce_compaction_equals_per_pixel_path(bench_ctx, bench_oracle, shadin
     try:
         for bounces in (1, 3):
             want, aux_c, _ = bench_oracle.render(_frame(cam, w, h, bounces=bounces, frame_no=7), want_aux=True)
-            for mode in ("per-pixel", "compact", "wavefront"):
-                bench_ctx.set_option("compact_bounces", int(mode == "compact"))
+            for mode in ("per-pixel", "wavefront"):
                 bench_ctx.set_option("wavefront", int(mode == "wavefront"))
                 got, aux_g = bench_ctx.render(_frame(cam, w, h, bounces=bounces, frame_no=7), want_aux=True)
                 assert got.tobytes() == want.tobytes(), (size, bounces, mode)
@@ -289,8 +288,9 @@ def test_bounce_compaction_equals_per_pixel_path(bench_ctx, bench_oracle, shadin
                     bench_ctx._chk(bench_ctx.lib.vrt_render(bench_ctx.h, __import__("ctypes").byref(f), part.ctypes.data, None))
                 assert part.tobytes() == want.tobytes(), (size, bounces, mode, "band split")
     finally:
-        bench_ctx.set_option("compact_bounces", 0)
         bench_ctx.set_option("wavefront", 2)
+    with pytest.raises(capi.VrtError):  # round 1's CTA-level compaction is gone
+        bench_ctx.set_option("compact_bounces", 1)
 
 
 def test_wavefront_self_tuning_keeps_frames_identical(bench_ctx, bench_oracle, shading_inputs):

@@ -140,3 +140,48 @@ def test_sincos_and_blue_noise_match_reference(hash_oracle):
             for tx in range(4):
                 lib.orc_blue_noise_sample(hash_oracle.h, x0 + tx, y0 + ty, int(q[2]), int(q[3]), out)
                 assert np.float32(out[0]) == tile[ty, tx, 0] and np.float32(out[1]) == tile[ty, tx, 1]
+
+
+# ---- whole frames the REFERENCE rendered (tests/golden/ref_frames.npz) ---------------------------------------------------------
+def _golden_frames_or_skip():
+    import golden_frames as gf
+
+    z = gf.load()
+    if not gf.assets_match(z):
+        pytest.skip("scenes/_ref does not hold the blue-noise table / sky cube the golden frames were rendered with")
+    return gf, z
+
+
+@pytest.mark.parametrize("name", ["hash_b0", "hash_b1", "hash_b2", "hash_b3", "hash_inside_solid", "hash_outside_view"])
+def test_oracle_reproduces_reference_rendered_frames(name, hash_scene, hash_oracle):
+    """orc_render == the G-buffer the reference's own RenderRow produced (committed fixture), byte for byte: 0-3 bounces, a camera
+    inside solid rock, a camera outside the view."""
+    from scenes import shading, terrain
+
+    gf, z = _golden_frames_or_skip()
+    assert terrain.scene_digest(hash_scene) == str(z["hash_scene_digest"])
+    hash_oracle.set_blue_noise(shading.load_blue_noise()[0])
+    desc, texels, _ = shading.load_sky()
+    hash_oracle.set_sky(desc, texels)
+    got = hash_oracle.render(gf.frame_of(z, name))[0]
+    gf.assert_tiles_equal(got, z[name + "_tiles"], name)
+
+
+def test_oracle_reproduces_reference_bench_frames(bench_scene):
+    """BASELINE configs[0] / [1]: the 1280x720 frame (0 and 1 bounce) and the 3840x2160 primary frame equal the reference-rendered
+    ones (SHA-256 per plane; the frames are 15 / 133 MB)."""
+    from oracle import pyoracle
+    from scenes import shading, terrain
+
+    gf, z = _golden_frames_or_skip()
+    if terrain.scene_digest(bench_scene) != str(z["bench_scene_digest"]):
+        pytest.skip("bench terrain differs from the one the golden frames were rendered on (no FastNoise2 here?)")
+    orc = pyoracle.OracleMap(6, 4)
+    orc.set_palette(bench_scene["palette"])
+    orc.sync(terrain.scene_records(bench_scene))
+    orc.set_blue_noise(shading.load_blue_noise()[0])
+    desc, texels, _ = shading.load_sky()
+    orc.set_sky(desc, texels)
+    for name in gf.BENCH_NAMES:
+        gf.assert_digests_equal(orc.render(gf.frame_of(z, name))[0], z, name)
+    orc.close()

@@ -43,46 +43,76 @@ def test_raycast_lanewise_200k_rays(ref_map, hash_oracle):
         assert np.array_equal(got[f][hit], want[f][hit]), f
 
 
-def test_primary_rays_differ_only_by_rsqrt14(ref_map, hash_oracle):
-    """GetPrimaryRay normalises with rsqrt14 (rel. error 2^-14); the oracle's canonical form uses
-    1/sqrt.  Origins must be bit-equal, directions equal up to that scale factor — and tracing the
-    REFERENCE's rays through both gives identical hits (so the deviation cannot leak into parity)."""
+def test_primary_rays_equal_the_reference(ref_map, hash_oracle):
+    """GetPrimaryRay normalises with rsqrt14 (rel. error 2^-14, so |dir| != 1): origins AND directions are bit-equal now that the
+    oracle evaluates rsqrt14 exactly (round 1: canonical 1/sqrt, directions equal only up to a scale factor)."""
     from scenes import camera
     from voxelrt_b200 import capi
 
-    cam = camera.Camera(pos=(96.3, 90.2, 20.7), yaw=0.2, pitch=-0.45)
-    w, h = 256, 144
-    proj, inv, wo, frac = cam.matrices(w, h)
-    frame = capi.make_frame(w, h, inv, proj, wo, frac)
-    ro, rd = ref_map.primary_rays(frame)
-    oo, od = hash_oracle.primary_rays(frame)
-    assert np.array_equal(ro.view(np.uint32), oo.view(np.uint32))
-    scale = np.linalg.norm(rd.astype(np.float64), axis=1)
-    assert np.abs(scale - 1).max() < 2.0**-13
-    assert np.abs(rd / scale[:, None] - od).max() < 1e-6
-    want = ref_map.trace(ro, rd, wo, lanes_per_packet=1)
-    got, _ = hash_oracle.trace(ro, rd, wo)
-    assert np.array_equal(got["flags"] & 0x13F, want["flags"] & 0x13F)
-    assert np.array_equal(got["material"], want["material"])
-    assert _bits_equal(got["dist"], want["dist"]).all()
+    for cam, (w, h) in ((camera.Camera(pos=(96.3, 90.2, 20.7), yaw=0.2, pitch=-0.45), (256, 144)), (camera.Camera(), (640, 360))):
+        proj, inv, wo, frac = cam.matrices(w, h)
+        frame = capi.make_frame(w, h, inv, proj, wo, frac)
+        ro, rd = ref_map.primary_rays(frame)
+        oo, od = hash_oracle.primary_rays(frame)
+        assert np.array_equal(ro.view(np.uint32), oo.view(np.uint32))
+        assert np.array_equal(rd.view(np.uint32), od.view(np.uint32))
+        scale = np.linalg.norm(rd.astype(np.float64), axis=1)
+        assert 0 < np.abs(scale - 1).max() < 2.0**-13  # (the approximation is really there)
 
 
-def test_frame_agreement_rate(ref_map, hash_oracle):
-    """RenderRow (packets, rsqrt14) against the oracle frame (lane-wise, canonical arithmetic): the
-    G-buffer must agree on all but a sliver of pixels — the ones where a 2^-14 direction change moves
-    a ray across a voxel edge."""
-    from scenes import camera
+@pytest.mark.parametrize("w,h,bounces,frame_no,cam_kw", [
+    (512, 288, 0, 1, dict(pos=(96.3, 90.2, 20.7), yaw=0.2, pitch=-0.45)),
+    (512, 288, 1, 1, dict(pos=(96.3, 90.2, 20.7), yaw=0.2, pitch=-0.45)),
+    (384, 216, 2, 9, dict(pos=(140.3, 100.2, 120.7), yaw=3.9, pitch=-0.6)),
+    (260, 148, 3, 65, dict(pos=(30.7, 70.1, 150.2), yaw=2.4, pitch=-0.3)),
+    (256, 144, 2, 3, dict(pos=(60.3, 20.2, 40.7), yaw=1.2, pitch=-0.3)),    # camera inside solid rock: every primary ray stops in its first trip
+    (256, 144, 1, 3, dict(pos=(-50.3, 90.2, 20.7), yaw=1.2, pitch=-0.3)),   # camera outside the view
+    (256, 144, 1, 2, dict(pos=(96.3, 126.9, 20.7), yaw=0.2, pitch=1.2)),    # looking up: mostly sky, packets with dead lanes
+])
+def test_oracle_frames_equal_the_reference_byte_for_byte(ref_map, hash_oracle, w, h, bounces, frame_no, cam_kw):
+    """WHOLE FRAMES: orc_render == the reference's RenderRow (16-lane AVX-512 packets, rsqrt14 / rcp14) in every byte of the G-buffer
+    — albedo + normal, depth, irradiance — with bounces, blue noise, sky, emissive voxels, and the packet-coupled behaviour
+    (capped lanes, first-trip stoppers, finished lanes that keep accumulating).  Round 1 asserted "> 99.5 % of the texels"."""
+    from golden_frames import assert_tiles_equal
+    from scenes import camera, shading
     from voxelrt_b200 import capi
 
-    cam = camera.Camera(pos=(96.3, 90.2, 20.7), yaw=0.2, pitch=-0.45)
-    w, h = 512, 288
-    proj, inv, wo, frac = cam.matrices(w, h)
-    ref_tiles, _ = ref_map.render(capi.make_frame(w, h, inv, proj, wo, frac, bounces=0))
-    orc_tiles, _, _ = hash_oracle.render(capi.make_frame(w, h, inv, proj, wo, frac, bounces=0))
-    same_albedo = (ref_tiles["albedo"] == orc_tiles["albedo"]).mean()
-    depth_close = np.isclose(ref_tiles["depth"], orc_tiles["depth"], rtol=0, atol=2e-4).mean()
-    assert same_albedo > 0.995, same_albedo
-    assert depth_close > 0.995, depth_close
+    bn = shading.load_blue_noise()[0]
+    desc, texels, _ = shading.load_sky()
+    ref_map.set_blue_noise(bn)
+    ref_map.set_sky(desc, texels)
+    hash_oracle.set_blue_noise(bn)
+    hash_oracle.set_sky(desc, texels)
+    proj, inv, wo, frac = camera.Camera(**cam_kw).matrices(w, h)
+    ref_tiles, _ = ref_map.render(capi.make_frame(w, h, inv, proj, wo, frac, frame_no=frame_no, bounces=bounces))
+    orc_tiles = hash_oracle.render(capi.make_frame(w, h, inv, proj, wo, frac, frame_no=frame_no, bounces=bounces))[0]
+    assert_tiles_equal(orc_tiles, ref_tiles, f"{w}x{h} bounces={bounces}")
+
+
+def test_oracle_bench_terrain_frames_equal_the_reference(bench_scene):
+    """BASELINE configs[0] (1280x720) with 0 and 1 bounce, scene and camera of the reference's Main.cpp: every byte equal."""
+    from golden_frames import assert_tiles_equal
+    from oracle import pyoracle, refharness
+    from scenes import camera, shading, terrain
+    from voxelrt_b200 import capi
+
+    recs = terrain.scene_records(bench_scene)
+    ref = refharness.RefMap()
+    orc = pyoracle.OracleMap(6, 4)
+    bn = shading.load_blue_noise()[0]
+    desc, texels, _ = shading.load_sky()
+    for m in (ref, orc):
+        m.set_palette(bench_scene["palette"])
+        m.sync(recs)
+        m.set_blue_noise(bn)
+        m.set_sky(desc, texels)
+    w, h = 1280, 720
+    proj, inv, wo, frac = camera.Camera().matrices(w, h)
+    for bounces in (0, 1):
+        ref_tiles, _ = ref.render(capi.make_frame(w, h, inv, proj, wo, frac, frame_no=5, bounces=bounces))
+        orc_tiles = orc.render(capi.make_frame(w, h, inv, proj, wo, frac, frame_no=5, bounces=bounces))[0]
+        assert_tiles_equal(orc_tiles, ref_tiles, f"bench terrain 720p bounces={bounces}")
+    ref.close()
 
 
 def test_hit_query_20k(ref_map, hash_oracle):
@@ -108,9 +138,9 @@ def test_hit_query_20k(ref_map, hash_oracle):
         assert np.array_equal(got[f][hit].view(np.uint32), want[f][hit].view(np.uint32)), f
 
 
-def test_sample_direction_and_sky_within_approximation(ref_map, hash_oracle):
-    """SampleDirection uses rsqrt14 * v, ProjectCubemap uses rcp14: the canonical forms (IEEE) must
-    stay within those approximations' error."""
+def test_sample_direction_and_sky_equal_the_reference(ref_map, hash_oracle):
+    """SampleDirection (rsqrt14 * v, incl. the NaN of quirk Q7) and the sky lookup (ProjectCubemap with rcp14 and the reference's float
+    `>`, which is TRUE on NaN operands — _MM_CMPINT_GT read as a float predicate is _CMP_NLE_US, SIMD_AVX512.h:83): bit-equal."""
     import ctypes as C
 
     from oracle import pyoracle, refharness
@@ -119,22 +149,25 @@ def test_sample_direction_and_sky_within_approximation(ref_map, hash_oracle):
     rng = np.random.default_rng(4)
     lib = pyoracle.load()
     out = (C.c_float * 3)()
-    for _ in range(500):
-        sx, sy = float(np.float32(rng.random())), float(np.float32(rng.integers(1, 255) / 255))
+    for k in range(600):
+        sx, sy = float(np.float32(rng.random())), float(np.float32(rng.integers(0, 256) / 255 if k % 3 else (k % 2)))
         lib.orc_sample_direction(sx, sy, out)
         a = np.array(out[:], np.float32)
         b = refharness.sample_direction(sx, sy)
-        assert np.abs(a - b).max() < 3e-4, (sx, sy, a, b)
+        assert (a.view(np.uint32) == b.view(np.uint32)).all() or (np.isnan(a) == np.isnan(b)).all() and np.isnan(a).any(), (sx, sy, a, b)
     desc, tex, _ = shading.load_sky()
     ref_map.set_sky(desc, tex)
     hash_oracle.set_sky(desc, tex)
-    same = 0
-    dirs = rng.normal(size=(2000, 3)).astype(np.float32)
+    dirs = rng.normal(size=(4000, 3)).astype(np.float32)
+    dirs[:64] *= np.float32(1e-3)
+    dirs[64:128, rng.integers(0, 3, 64)] = 0.0
+    special = np.array([0x7FC00000, 0xFFC00000, 0x7F800000, 0xFF800000, 0, 0x80000000], np.uint32).view(np.float32)
+    dirs = np.concatenate([dirs, special[rng.integers(0, 6, (256, 3))], np.stack([special, special, special], 1)])
     for dvec in dirs:
+        dvec = np.ascontiguousarray(dvec)
         for mip in (1, 3):
             lib.orc_sky_sample(hash_oracle.h, dvec.ctypes.data, mip, out)
-            same += np.array_equal(np.array(out[:], np.float32), refharness.sky_sample(dvec, mip))
-    assert same / (2 * len(dirs)) > 0.99  # nearest-texel fetch: rcp14 moves < 1 % of samples to a neighbour
+            assert np.array_equal(np.array(out[:], np.float32).view(np.uint32), refharness.sky_sample(dvec, mip).view(np.uint32)), (dvec, mip)
 
 
 def test_cvox_files_are_wire_compatible_with_the_reference(ref_map, hash_scene, tmp_path):

@@ -4,6 +4,7 @@
     python tools/exp.py "persistent=0" "persistent=1" "persistent=2,macro_steps=1" ...
 Prints ms/frame (CUDA events on the launching stream, L2 flushed between frames, median and min of N).
 """
+import os
 import sys
 
 sys.path.insert(0, "/root/repo")
@@ -11,7 +12,7 @@ sys.path.insert(0, "/root/repo/tests")
 import numpy as np
 import torch
 
-import os
+
 
 from voxelrt_b200 import capi
 
@@ -21,7 +22,7 @@ import bench
 from conftest import ctx_for
 from scenes import terrain
 
-N = 40
+N = int(os.environ.get("VRT_EXP_N", "40"))
 workload = "terrain"
 bounces = None
 argv = sys.argv[1:]

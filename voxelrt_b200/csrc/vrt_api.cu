@@ -94,11 +94,9 @@ struct VrtContext {
     uint64_t wave_key = 0;        // (bounces, width, height, scene epoch) the decision was taken for
     uint64_t scene_epoch = 0;     // bumped when a sync changes some sector's emptiness
     cudaEvent_t ev_tune[4] = {};
-    DeviceBuffer d_wave_q[2], d_wave_c[2], d_wave_n;
+    DeviceBuffer d_wave_rays, d_wave_hits, d_wave_path, d_wave_n;
     cudaEvent_t ev_wave = nullptr;  // the queues are shared: a wave frame on another stream waits for the previous one
     bool wave_used = false;
-    int compact_on = 0;  // frames with bounces: pack the live bounce rays of a CTA between bounces (k_render_cta); measured 10 % SLOWER
-                         // (the bounce phase is latency-bound: fewer tracing warps hide less latency than idle lanes cost)
     int persist_on = 0;  // measured slower than the grid form on primary frames (tile order loses the L1 locality of 4 adjacent warp tiles per CTA)
     uint32_t* d_tickets = nullptr;
     uint32_t ticket_base[16] = {};
@@ -309,7 +307,7 @@ int launch_render(VrtContext* ctx, const VrtFrame* f, void* d_out, VrtHit* d_aux
     // which form traces a frame with bounces (see wave_on)
     bool use_wave = false;
     int tune_slot = -1;  // >= 0: this frame is one of the two timed ones (events tune_slot, tune_slot + 1)
-    if (!primary && !ctx->metrics_on && !ctx->compact_on && !ctx->persist_on && ctx->wave_on) {
+    if (!primary && !ctx->metrics_on && !ctx->persist_on && ctx->wave_on) {
         if (ctx->wave_on == 1) use_wave = true;
         else if (row0 != 0 || row1 != 0 || part_count > 1) use_wave = ctx->wave_choice == 1;  // band / partial launches never tune
         else {
@@ -342,59 +340,42 @@ int launch_render(VrtContext* ctx, const VrtFrame* f, void* d_out, VrtHit* d_aux
         }
     } tune_end{ctx, tune_slot, s};
     if (use_wave) {
-        // Wavefront: camera pass, then for each bounce level passes with trip budgets 16 / 32 / the rest (vrt_shade.cuh).
-        const size_t cap = (size_t)(F.n_work - F.work_offset) * 32u;  // at most one path per pixel of this launch
+        // Wavefront: camera pass, then per bounce level a trace pass (persistent, lanes refilled from the level's queue) and a shade
+        // pass (one thread per pixel in tile order: the packet coupling is two half-warp votes) — vrt_shade.cuh, vrt_kernels.cuh.
+        const size_t cap = (size_t)(F.n_work - F.work_offset) * 32u;  // pixel slots of this launch; at most one ray per slot and level
         int st2;
-        for (int k = 0; k < 2; k++) {
-            if ((st2 = ensure(ctx, ctx->d_wave_q[k], cap * sizeof(PathRec)))) return st2;
-            if ((st2 = ensure(ctx, ctx->d_wave_c[k], cap * sizeof(ContRec)))) return st2;
-        }
-        const uint32_t n_counters = 2u + 8u * 3u;
+        if ((st2 = ensure(ctx, ctx->d_wave_rays, cap * sizeof(RayRec)))) return st2;
+        if ((st2 = ensure(ctx, ctx->d_wave_hits, cap * sizeof(HitRec)))) return st2;
+        if ((st2 = ensure(ctx, ctx->d_wave_path, cap * (sizeof(float4) + sizeof(float2)) + (cap / 16u) * sizeof(uint16_t) + 64u))) return st2;
+        const uint32_t n_counters = 2u * 10u;  // rays queued per level [0..9], refill cursor per level
         if ((st2 = ensure(ctx, ctx->d_wave_n, n_counters * sizeof(uint32_t)))) return st2;
         if (ctx->wave_used) CU(cudaStreamWaitEvent(s, ctx->ev_wave, 0));
         tune_begin();
         uint32_t* cnt = static_cast<uint32_t*>(ctx->d_wave_n.p);
         CU(cudaMemsetAsync(cnt, 0, n_counters * sizeof(uint32_t), s));
-        PathRec* q[2] = {static_cast<PathRec*>(ctx->d_wave_q[0].p), static_cast<PathRec*>(ctx->d_wave_q[1].p)};
-        ContRec* c[2] = {static_cast<ContRec*>(ctx->d_wave_c[0].p), static_cast<ContRec*>(ctx->d_wave_c[1].p)};
-        // counters: [level] for the level queues (level 1 = cnt[1] ...), then 2 per level for the continuation queues
-        if (rows) k_wave_primary<true><<<blocks, VRT_RENDER_THREADS, 0, s>>>(S, F, q[1], cnt + 1);
-        else k_wave_primary<false><<<blocks, VRT_RENDER_THREADS, 0, s>>>(S, F, q[1], cnt + 1);
+        WaveBuffers B;
+        B.rays = static_cast<RayRec*>(ctx->d_wave_rays.p);
+        B.n_rays = cnt;
+        B.head = cnt + 10;
+        B.hits = static_cast<HitRec*>(ctx->d_wave_hits.p);
+        B.path_a = static_cast<float4*>(ctx->d_wave_path.p);
+        B.path_b = reinterpret_cast<float2*>(B.path_a + cap);
+        B.pk_alive = reinterpret_cast<uint16_t*>(B.path_b + cap);
+        if (rows) k_wave_primary<true><<<blocks, VRT_RENDER_THREADS, 0, s>>>(S, F, B);
+        else k_wave_primary<false><<<blocks, VRT_RENDER_THREADS, 0, s>>>(S, F, B);
         ctx->stats.last_launches += 1;
-        const bool occ = (size_t)ctx->n_hdr * sizeof(uint4) >= ((size_t)4 << 20);
-        const unsigned grid = (unsigned)std::min<size_t>((cap + VRT_RENDER_THREADS - 1) / VRT_RENDER_THREADS,
-                                                         (size_t)ctx->sm_count * VRT_RENDER_CTAS(false) * 4u);
+        const unsigned grid = (unsigned)std::min<size_t>((cap + VRT_RENDER_THREADS - 1) / VRT_RENDER_THREADS, (size_t)ctx->sm_count * VRT_TRACE_CTAS);
         for (uint32_t level = 1; level <= F.bounces; level++) {
-            uint32_t* n_level = cnt + level;                     // rays of this level (filled by the previous level / camera pass)
-            uint32_t* n_next = level < 8 ? cnt + level + 1 : cnt;  // (never written at the last level)
-            uint32_t* n_c = cnt + 9 + (level - 1) * 2;           // two continuation counters per level
-            WaveArgs A;
-            A.q_in = q[level & 1];
-            A.c_in = nullptr;
-            A.n_in = n_level;
-            A.q_out = q[(level + 1) & 1];
-            A.n_q_out = n_next;
-            A.c_out = c[0];
-            A.n_c_out = n_c;
-            A.budget = 16u;
-            if (occ) k_wave_trace<false, true><<<grid, VRT_RENDER_THREADS, 0, s>>>(S, F, A);
-            else k_wave_trace<false, false><<<grid, VRT_RENDER_THREADS, 0, s>>>(S, F, A);
-            A.q_in = nullptr;
-            A.c_in = c[0];
-            A.n_in = n_c;
-            A.c_out = c[1];
-            A.n_c_out = n_c + 1;
-            A.budget = 32u;
-            if (occ) k_wave_trace<true, true><<<grid, VRT_RENDER_THREADS, 0, s>>>(S, F, A);
-            else k_wave_trace<true, false><<<grid, VRT_RENDER_THREADS, 0, s>>>(S, F, A);
-            A.c_in = c[1];
-            A.n_in = n_c + 1;
-            A.c_out = nullptr;
-            A.n_c_out = nullptr;
-            A.budget = 0xFFFFFFFFu;
-            if (occ) k_wave_trace<true, true><<<grid, VRT_RENDER_THREADS, 0, s>>>(S, F, A);
-            else k_wave_trace<true, false><<<grid, VRT_RENDER_THREADS, 0, s>>>(S, F, A);
-            ctx->stats.last_launches += 3;
+            TraceArgs A;
+            A.rays = B.rays;
+            A.n = B.n_rays + level;
+            A.head = B.head + level;
+            A.hits = B.hits;
+            A.max_iters = F.max_iters;
+            k_wave_trace<<<grid, VRT_RENDER_THREADS, 0, s>>>(S, F.W, A);
+            if (rows) k_wave_shade<true><<<blocks, VRT_RENDER_THREADS, 0, s>>>(S, F, B, level);
+            else k_wave_shade<false><<<blocks, VRT_RENDER_THREADS, 0, s>>>(S, F, B, level);
+            ctx->stats.last_launches += 2;
         }
         CU(cudaEventRecord(ctx->ev_wave, s));
         ctx->wave_used = true;
@@ -402,13 +383,7 @@ int launch_render(VrtContext* ctx, const VrtFrame* f, void* d_out, VrtHit* d_aux
         return VRT_OK;
     }
     tune_begin();
-    if (!primary && ctx->compact_on && !ctx->persist_on) {
-        // frames with bounces: CTA-compacted bounce rays (k_render_cta)
-        const int v = (ctx->metrics_on ? 2 : 0) | (rows ? 1 : 0);
-        if (v == 0) k_render_cta<false, false><<<blocks, VRT_RENDER_THREADS, 0, s>>>(S, F);
-        else if (v == 1) k_render_cta<false, true><<<blocks, VRT_RENDER_THREADS, 0, s>>>(S, F);
-        else if (v == 2) k_render_cta<true, false><<<blocks, VRT_RENDER_THREADS, 0, s>>>(S, F);
-        else k_render_cta<true, true><<<blocks, VRT_RENDER_THREADS, 0, s>>>(S, F);
+    if (false) {
     } else if (ctx->persist_on && !ctx->metrics_on && !rows) {
         // one resident grid; warps pull tiles from a ticket counter (see k_render_persist)
         const unsigned resident = (unsigned)ctx->sm_count * (unsigned)VRT_RENDER_CTAS(primary) * (unsigned)ctx->persist_on;
@@ -543,7 +518,7 @@ extern "C" void vrt_destroy(VrtContext* ctx) {
     for (void* p : ctx->exported) cudaFree(p);
     if (ctx->ev_wave) cudaEventDestroy(ctx->ev_wave);
     for (auto& e : ctx->ev_tune) if (e) cudaEventDestroy(e);
-    DeviceBuffer* bufs[] = {&ctx->d_wave_q[0], &ctx->d_wave_q[1], &ctx->d_wave_c[0], &ctx->d_wave_c[1], &ctx->d_wave_n, &ctx->d_stage, &ctx->d_rays_o, &ctx->d_rays_d, &ctx->d_hits, &ctx->d_fb,
+    DeviceBuffer* bufs[] = {&ctx->d_wave_rays, &ctx->d_wave_hits, &ctx->d_wave_path, &ctx->d_wave_n, &ctx->d_stage, &ctx->d_rays_o, &ctx->d_rays_d, &ctx->d_hits, &ctx->d_fb,
                             &ctx->d_aux,   &ctx->d_q_o,    &ctx->d_q_d,    &ctx->d_q_out};
     for (auto* b : bufs)
         if (b->p) cudaFree(b->p);
@@ -593,7 +568,10 @@ extern "C" int vrt_set_option(VrtContext* ctx, const char* name, int64_t value) 
     if (!strcmp(name, "metrics")) ctx->metrics_on = value != 0;
     else if (!strcmp(name, "macro_steps")) ctx->macro_on = (int)value;
     else if (!strcmp(name, "persistent")) ctx->persist_on = (int)value;
-    else if (!strcmp(name, "compact_bounces")) ctx->compact_on = (int)value;
+    else if (!strcmp(name, "compact_bounces")) {
+        // round 1's CTA-level re-dealing of bounce rays (measured slower) is gone: the wavefront trace pass refills lanes from a queue
+        if (value != 0) return fail(ctx, VRT_ERR_UNSUPPORTED, "compact_bounces was removed; see the \"wavefront\" option");
+    }
     else if (!strcmp(name, "wavefront")) ctx->wave_on = (int)value;
     else return fail(ctx, VRT_ERR_INVALID, std::string("unknown option ") + name);
     return VRT_OK;

@@ -112,49 +112,140 @@ __global__ void __launch_bounds__(VRT_RENDER_THREADS, VRT_RENDER_CTAS(PRIMARY &&
     render_warp_tile<METRICS, PRIMARY, ROWS, OCC>(S, F, work);
 }
 
-// K_render for frames with bounces, CTA-compacted (shade_pixel_cta): same tiles, same pixels, but between bounces the CTA's
-// live rays are packed through shared memory so that its warps trace full batches.  No thread may leave before the last
-// barrier, so out-of-frame warps stay in the kernel with all lanes invalid.
-template <bool METRICS, bool ROWS>
-__global__ void __launch_bounds__(VRT_RENDER_THREADS, VRT_RENDER_CTAS(false)) k_render_cta(const __grid_constant__ DevScene S, const __grid_constant__ FrameParams F) {
-    __shared__ BounceExchange X;
-    const uint32_t work = F.work_offset + blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    uint32_t x0 = 0, y0 = 0;
-    const bool in_frame = work < F.n_work && warp_tile_origin<ROWS>(F, work, x0, y0);  // warp-uniform
-    const uint32_t lane = threadIdx.x & 31u;
-    const uint32_t x = x0 + ((lane >> 4) << 2) + (lane & 3u);
-    const uint32_t y = y0 + ((lane >> 2) & 3u);
-    const bool valid = in_frame && x < F.width && y < F.height;
-    PixelOut P;
-    shade_pixel_cta<METRICS>(S, F, x, y, valid, P, X);
-    if (valid) store_pixel(F, x, y, P);
-}
-
-// Wavefront form of a frame with bounces (vrt_shade.cuh): the camera pass, then per bounce level three budgeted passes.
+// ---------------------------------------------------------------------------------------------
+// Wavefront form of a frame with bounces (vrt_shade.cuh): camera pass, then per bounce level a TRACE pass and a SHADE pass.
+// ---------------------------------------------------------------------------------------------
 template <bool ROWS>
 __global__ void __launch_bounds__(VRT_RENDER_THREADS, VRT_RENDER_CTAS(false)) k_wave_primary(const __grid_constant__ DevScene S, const __grid_constant__ FrameParams F,
-                                                                                             PathRec* __restrict__ q, uint32_t* __restrict__ n_q) {
+                                                                                             const __grid_constant__ WaveBuffers B) {
     const uint32_t work = F.work_offset + blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (work >= F.n_work) return;  // warp-uniform
-    uint32_t x0, y0;
-    if (!warp_tile_origin<ROWS>(F, work, x0, y0)) return;
+    uint32_t x0 = 0, y0 = 0;
+    const bool in_frame = warp_tile_origin<ROWS>(F, work, x0, y0);  // warp-uniform; the warp stays for the votes
     const uint32_t lane = threadIdx.x & 31u;
     const uint32_t x = x0 + ((lane >> 4) << 2) + (lane & 3u);
     const uint32_t y = y0 + ((lane >> 2) & 3u);
-    wave_primary_pixel(S, F, x, y, x < F.width && y < F.height, q, n_q);
+    wave_primary_pixel(S, F, B, (work - F.work_offset) * 32u + lane, x, y, in_frame && x < F.width && y < F.height);
 }
-#ifndef VRT_WAVE_WARPS
-#define VRT_WAVE_WARPS 40
+template <bool ROWS>
+__global__ void __launch_bounds__(VRT_RENDER_THREADS) k_wave_shade(const __grid_constant__ DevScene S, const __grid_constant__ FrameParams F,
+                                                                   const __grid_constant__ WaveBuffers B, uint32_t level) {
+    const uint32_t work = F.work_offset + blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (work >= F.n_work) return;
+    uint32_t x0 = 0, y0 = 0;
+    const bool in_frame = warp_tile_origin<ROWS>(F, work, x0, y0);
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t x = x0 + ((lane >> 4) << 2) + (lane & 3u);
+    const uint32_t y = y0 + ((lane >> 2) & 3u);
+    wave_shade_pixel(S, F, B, (work - F.work_offset) * 32u + lane, x, y, in_frame && x < F.width && y < F.height, level);
+}
+
+// The trace pass: persistent warps, one ray per lane, lanes refilled from the level's queue whenever fewer than VRT_TRACE_REFILL of
+// the warp's 32 rays are still in flight (and once more when none is).  Rays outside the fast loop's domain (zero / denormal / huge
+// components, far origins, origins outside the view) are traced at once by the generic loop when they are pulled; rays whose
+// direction is NaN in all three components (quirk Q7: 0.8 % of all bounce rays) take ONE lean trip — the reference's second trip
+// lands at INT_MIN, outside the view, whatever the first one did — instead of dragging the warp through the generic loop.
+#ifndef VRT_TRACE_REFILL
+#define VRT_TRACE_REFILL 24
 #endif
-template <bool CONT, bool OCC>
-__global__ void __launch_bounds__(VRT_RENDER_THREADS, VRT_WAVE_WARPS * 32 / VRT_RENDER_THREADS) k_wave_trace(const __grid_constant__ DevScene S, const __grid_constant__ FrameParams F,
-                                                                                           const __grid_constant__ WaveArgs A) {
-    const uint32_t n = *A.n_in;
-    const uint32_t stride = gridDim.x * blockDim.x;
-    // whole warps iterate together (queue_push is a warp collective)
-    for (uint32_t base = (blockIdx.x * blockDim.x + threadIdx.x) & ~31u; base < n; base += stride) {
-        const uint32_t idx = base + (threadIdx.x & 31u);
-        wave_trace_one<CONT, OCC>(S, F, A, idx, idx < n);
+#ifndef VRT_TRACE_CTAS
+#define VRT_TRACE_CTAS 8
+#endif
+struct TraceArgs {
+    const RayRec* rays;
+    const uint32_t* n;  // rays queued for this level
+    uint32_t* head;     // refill cursor (zeroed per frame)
+    HitRec* hits;
+    uint32_t max_iters;
+};
+__global__ void __launch_bounds__(VRT_RENDER_THREADS, VRT_TRACE_CTAS) k_wave_trace(const __grid_constant__ DevScene S, const __grid_constant__ RayFrame W,
+                                                                                   const __grid_constant__ TraceArgs A) {
+    const uint32_t n = *A.n;
+    const unsigned lane = threadIdx.x & 31u, lt_mask = (1u << lane) - 1u;
+    LeanFrame C;
+    C.mgx = W.mgx, C.mgy = W.mgy, C.mgz = W.mgz, C.r32 = 0.03125f;
+    C.strz = (int)S.sxp, C.stry = (int)S.sxzp, C.hoff = W.hoff;
+    C.hdrp = S.hdr;
+    C.cellp = reinterpret_cast<const char*>(S.cells);
+    LeanRay r;
+    r.ox = r.oy = r.oz = r.dx = r.dy = r.dz = r.ix = r.iy = r.iz = r.tx = r.ty = r.tz = r.cx = r.cy = r.cz = r.sdx = r.sdy = r.sdz = 0.0f;
+    r.nmx = r.nmy = r.nmz = r.qx = r.qy = r.qz = 0;
+    uint32_t left = 0, budget = 0, slot = 0, hit_slot = 0;
+    int status = 0;        // how the ray in `r` ended: 1 solid voxel, 2 left the view, 3 out of trips
+    bool active = false;   // a ray is in flight in this lane
+    bool pending = false;  // it has ended and its record is not written yet
+    bool nan_ray = false;
+    bool more = true;      // the queue may still hold rays (warp-uniform)
+    for (;;) {
+        unsigned act = __ballot_sync(0xFFFFFFFFu, active);
+        if (act == 0u || (more && __popc(act) < VRT_TRACE_REFILL)) {
+            if (pending) {  // RayCast epilogue (CpuRenderer.cpp:204-223) of the ray that ended in this lane
+                pending = false;
+                if (nan_ray && status == 3) status = 2;  // the second trip of a NaN ray: currPos = NaN -> voxel INT_MIN -> outside
+                uint32_t flags = HITREC_CAST | normal_code(r.sdx, r.sdy, r.sdz, r.dx, r.dy, r.dz);
+                uint32_t material = 0u;  // (a miss's material is never used at bounce levels >= 1: RenderRow replaces it by the sky, :363-368)
+                if (status == 1) {
+                    const uint32_t vi = ((uint32_t)r.qx & 7u) | (((uint32_t)r.qz & 7u) << 3) | (((uint32_t)r.qy & 7u) << 6);
+                    material = ldg_u2(S.palette + __ldg(S.voxels + (size_t)hit_slot * 512u + vi)).x;  // :120-132
+                    flags |= HITREC_HIT;
+                } else if (status == 3) flags |= HITREC_CAPPED;
+                if (left == budget && status != 3) flags |= HITREC_FIRST;  // no completed step
+                store_hit_rec(A.hits + slot, r.cx, r.cy, r.cz, material, r.dx, r.dy, r.dz, flags);
+            }
+            if (more) {
+                const unsigned want = ~act;
+                const uint32_t cnt = (uint32_t)__popc(want);
+                uint32_t base = 0;
+                if (lane == (unsigned)(__ffs((int)want) - 1)) base = atomicAdd(A.head, cnt);
+                base = __shfl_sync(0xFFFFFFFFu, base, __ffs((int)want) - 1);
+                more = base + cnt < n;
+                const uint32_t idx = base + (uint32_t)__popc(want & lt_mask);
+                if (!active && idx < n) {
+                    const float4* rp = reinterpret_cast<const float4*>(A.rays + idx);
+                    const float4 r0 = __ldg(rp), r1 = __ldg(rp + 1);
+                    r.ox = r0.x, r.oy = r0.y, r.oz = r0.z, r.dx = r1.x, r.dy = r1.y, r.dz = r1.z;
+                    slot = __float_as_uint(r0.w);
+                    // the first position can be anywhere: bounds-test it here (GetInboundMask, :114-117), like cast_ray
+                    const float so = __fadd_rn(__fadd_rn(fabsf(r.ox), fabsf(r.oy)), fabsf(r.oz));
+                    bool start_ok = W.fast_ok && so <= 1048576.0f;
+                    if (start_ok) {
+                        const int px = W.wx + __float2int_rd(r.ox), py = W.wy + __float2int_rd(r.oy), pz = W.wz + __float2int_rd(r.oz);
+                        start_ok = (uint32_t)(px | pz) < S.lim_xz && (uint32_t)py < S.lim_y;
+                    }
+                    const bool fast = start_ok && A.max_iters != 0u && ray_is_fast(r.ox, r.oy, r.oz, r.dx, r.dy, r.dz);
+                    nan_ray = start_ok && A.max_iters >= 2u && r.dx != r.dx && r.dy != r.dy && r.dz != r.dz;
+                    if (fast || nan_ray) {
+                        r.ix = rcp_rn_normal(r.dx), r.iy = rcp_rn_normal(r.dy), r.iz = rcp_rn_normal(r.dz);  // :173 (== IEEE 1/x for fast rays; NaN stays NaN)
+                        r.tx = __fmul_rn(__fsub_rn(r.dx < 0.0f ? 0.0f : 1.0f, r.ox), r.ix);                  // :175-179
+                        r.ty = __fmul_rn(__fsub_rn(r.dy < 0.0f ? 0.0f : 1.0f, r.oy), r.iy);
+                        r.tz = __fmul_rn(__fsub_rn(r.dz < 0.0f ? 0.0f : 1.0f, r.oz), r.iz);
+                        r.nmx = __float_as_int(r.dx) >> 31, r.nmy = __float_as_int(r.dy) >> 31, r.nmz = __float_as_int(r.dz) >> 31;
+                        r.cx = r.ox, r.cy = r.oy, r.cz = r.oz;  // :181
+                        r.sdx = r.sdy = r.sdz = 0.0f;           // :180
+                        budget = left = nan_ray ? 1u : A.max_iters;
+                        active = true;
+                    } else {  // rare: the generic loop, to completion, right here
+                        CastResult R;
+                        HitLane H;
+                        cast_loop_generic(S, r.ox, r.oy, r.oz, r.dx, r.dy, r.dz, W.wx, W.wy, W.wz, A.max_iters, R);
+                        cast_finish<true>(S, R, r.dx, r.dy, r.dz, H);
+                        const uint32_t flags = HITREC_CAST | H.ncode | (H.hit ? HITREC_HIT : 0u) | (R.capped ? HITREC_CAPPED : 0u) |
+                                               ((R.iters == 1u && !R.capped) ? HITREC_FIRST : 0u);
+                        store_hit_rec(A.hits + slot, H.px, H.py, H.pz, H.material, r.dx, r.dy, r.dz, flags);
+                    }
+                }
+            }
+            act = __ballot_sync(0xFFFFFFFFu, active);
+            if (act == 0u) {
+                if (!more) break;
+                continue;
+            }
+        }
+        if (active) {
+            status = lean_trip(C, r, hit_slot);
+            if (status != 0) active = false, pending = true;
+            else if (--left == 0u) active = false, pending = true, status = 3;
+        }
     }
 }
 
