@@ -112,6 +112,11 @@ typedef struct VrtHitD {
  * Matrices are column-major float[16] exactly like glm::mat4 (m[col][row] = a[col*4+row]). */
 #define VRT_FRAME_LINEAR_OUTPUT 1u /* out = 4 planes (albedo, depth, irrRG, irrBX) of w*h u32  */
 #define VRT_FRAME_AUX_HITS 2u      /* also fill the VrtHit of every primary ray (aux_hits)     */
+#define VRT_FRAME_COMPACT 4u       /* bounces == 0 only: 8 B/px — per 4x4 tile {albedo[16], depth[16]} (VrtTileAD; with
+                                    * VRT_FRAME_LINEAR_OUTPUT: the two planes).  A primary-only frame's irradiance is the
+                                    * constant 1.0 in every pixel (CpuRenderer.cpp:379-381: IrradianceRG = IrradianceBX =
+                                    * 0x3C003C00), so half of the reference's 16 B/px tile carries no information; leaving it
+                                    * out halves the bytes over PCIe (vrt_render) and NVLink (vrt_render_gather), losslessly */
 #define VRT_FRAME_PART_ROWS 8u     /* multi-GPU split by BAND: rank r renders the VRT_BAND_ROWS-pixel-high
                                     * bands b with b % part_count == r (each band is one contiguous range
                                     * of the tile-layout framebuffer, so a rank's result moves with one
@@ -142,6 +147,12 @@ typedef struct VrtTile {
     uint32_t irr_rg[16];  /* 2 x f16                                                           */
     uint32_t irr_bx[16];  /* f16 | 0                                                           */
 } VrtTile;
+
+/* VRT_FRAME_COMPACT: the information-carrying half of a VrtTile of a primary-only frame. */
+typedef struct VrtTileAD {
+    uint32_t albedo[16];
+    float depth[16];
+} VrtTileAD;
 
 typedef struct VrtStats {
     uint64_t resident_bricks;   /* FreeList::NumAllocated                                      */
@@ -235,8 +246,11 @@ VRT_API int vrt_set_sky(VrtContext* ctx, const VrtSkyDesc* desc, const uint32_t*
 
 /* ---- frame ------------------------------------------------------------------------------------ */
 /* Renderer::RenderFrame minus present (Renderer.h:18; CpuRenderer.cpp:415-464 — everything
- * between SyncBuffers and the blit).  vrt_render writes w*h*16 bytes to HOST memory `out`
- * (tiles, or planes with VRT_FRAME_LINEAR_OUTPUT); aux_hits (host, w*h VrtHit, row-major
+ * between SyncBuffers and the blit).  vrt_render writes w*h*16 bytes (w*h*8 with VRT_FRAME_COMPACT) to HOST
+ * memory `out` (tiles, or planes with VRT_FRAME_LINEAR_OUTPUT).  With a screen split (part_count > 1 and
+ * VRT_FRAME_PART_ROWS) only this rank's 8-pixel bands are traced and written, at their offsets of the whole frame:
+ * N processes can fill ONE host frame (e.g. a shared, page-locked mapping) in parallel, each over its own PCIe link.
+ * aux_hits (host, w*h VrtHit, row-major
  * pixel order) is filled when VRT_FRAME_AUX_HITS is set.  vrt_render_device leaves the result
  * in device memory on `stream` — this is what a CUDA/GL-interop presenter would consume. */
 VRT_API int vrt_render(VrtContext* ctx, const VrtFrame* frame, void* out, VrtHit* aux_hits);

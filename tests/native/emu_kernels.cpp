@@ -164,8 +164,8 @@ EMU_API int emu_wave_frame(const EmuScene* e, const VrtFrame* f, const uint8_t* 
     std::vector<float4> path_a(cap);
     std::vector<float2> path_b(cap);
     std::vector<uint16_t> pk(cap / 16 + 1);
-    uint32_t counters[20] = {};
-    WaveBuffers B{rays.data(), counters, counters + 10, hits.data(), path_a.data(), path_b.data(), pk.data()};
+    uint32_t counters[30] = {};
+    WaveBuffers B{rays.data(), (uint32_t)cap, counters, counters + 20, counters + 10, hits.data(), path_a.data(), path_b.data(), pk.data()};
 #pragma omp parallel for schedule(dynamic, 8)
     for (int64_t w = 0; w < warps; w++)
         run_warp_lockstep((unsigned)(w / wpb), VRT_RENDER_THREADS, (unsigned)(w % wpb) * 32u, [&](int) {
@@ -173,10 +173,17 @@ EMU_API int emu_wave_frame(const EmuScene* e, const VrtFrame* f, const uint8_t* 
             else k_wave_primary<false>(S, F, B);
         });
     for (uint32_t level = 1; level <= F.bounces; level++) {
-        TraceArgs A{B.rays, B.n_rays + level, B.head + level, B.hits, F.max_iters};
+        TraceArgs A{B.rays, B.n_rays + level, B.head + level, B.hits, F.max_iters, 24u, B.n_generic + level, B.capacity};
 #pragma omp parallel for schedule(dynamic, 1)
         for (int64_t w = 0; w < (int64_t)trace_warps; w++)
             run_warp_lockstep((unsigned)(w / wpb), VRT_RENDER_THREADS, (unsigned)(w % wpb) * 32u, [&](int) { k_wave_trace(S, F.W, A); });
+        {
+            gridDim.x = 1, blockDim.x = 128, blockIdx.x = 0;
+            for (unsigned t = 0; t < 128; t++) {
+                threadIdx.x = t;
+                k_wave_trace_generic(S, F.W, A);
+            }
+        }
 #pragma omp parallel for schedule(dynamic, 8)
         for (int64_t w = 0; w < warps; w++)
             run_warp_lockstep((unsigned)(w / wpb), VRT_RENDER_THREADS, (unsigned)(w % wpb) * 32u, [&](int) {
@@ -184,7 +191,7 @@ EMU_API int emu_wave_frame(const EmuScene* e, const VrtFrame* f, const uint8_t* 
                 else k_wave_shade<false>(S, F, B, level);
             });
     }
-    return (int)counters[1];
+    return (int)(counters[1] + counters[21]);
 }
 
 // rebuild_boxes of vrt_api.cu: the same five launches, in order

@@ -391,6 +391,43 @@ def test_render_gather_row_bands(hash_ctx, parts):
         hash_ctx.render_gather(_frame(cam, 64, 36, part_index=0, part_count=2), local[0].data_ptr(), owner.data_ptr(), stream.cuda_stream)
 
 
+@pytest.mark.parametrize("parts", [1, 3, 8])
+def test_compact_output_is_the_varying_half_of_the_tile_framebuffer(hash_ctx, parts):
+    """VRT_FRAME_COMPACT (primary-only frames, 8 B/px): albedo + depth equal those of the full 16 B/px frame, whose irradiance words are the
+    constant 0x3C003C00 — through vrt_render (whole frame, band split into one host frame), the linear form, and vrt_render_gather."""
+    import ctypes as C
+
+    import torch
+
+    from scenes import camera
+    from voxelrt_b200 import capi
+
+    cam = camera.Camera(pos=(96.3, 90.2, 20.7), yaw=0.2, pitch=-0.45)
+    stream = torch.cuda.Stream()
+    for w, h in ((1280, 720), (416, 260), (64, 36)):
+        full, _ = hash_ctx.render(_frame(cam, w, h))
+        assert (full["irr_rg"] == 0x3C003C00).all() and (full["irr_bx"] == 0x3C003C00).all()
+        host = np.zeros(w * h // 16, capi.TILE_AD_DTYPE)
+        for p in range(parts):
+            f = _frame(cam, w, h, part_index=p, part_count=parts, flags=capi.VRT_FRAME_COMPACT | (capi.VRT_FRAME_PART_ROWS if parts > 1 else 0))
+            hash_ctx._chk(hash_ctx.lib.vrt_render(hash_ctx.h, C.byref(f), host.ctypes.data, None))
+        assert np.array_equal(host["albedo"], full["albedo"]) and host["depth"].tobytes() == full["depth"].tobytes(), (w, h, parts)
+        owner = torch.zeros(w * h * 2, dtype=torch.int32, device="cuda")
+        local = [torch.full((w * h * 2,), -1, dtype=torch.int32, device="cuda") for _ in range(capi.VRT_GATHER_DEPTH)]
+        torch.cuda.synchronize()
+        for p in range(parts):
+            f = _frame(cam, w, h, part_index=p, part_count=parts, flags=capi.VRT_FRAME_COMPACT | capi.VRT_FRAME_PART_ROWS)
+            hash_ctx.render_gather(f, local[p % capi.VRT_GATHER_DEPTH].data_ptr(), owner.data_ptr(), stream.cuda_stream)
+        hash_ctx.gather_wait(stream.cuda_stream)
+        stream.synchronize()
+        assert owner.cpu().numpy().tobytes() == host.tobytes(), (w, h, parts, "gather")
+    lin, _ = hash_ctx.render(_frame(cam, 132, 68, flags=capi.VRT_FRAME_LINEAR_OUTPUT | capi.VRT_FRAME_COMPACT))
+    lin_full, _ = hash_ctx.render(_frame(cam, 132, 68, flags=capi.VRT_FRAME_LINEAR_OUTPUT))
+    assert lin.shape == (2, 68, 132) and np.array_equal(lin, lin_full[:2])
+    with pytest.raises(capi.VrtError):  # with bounces the irradiance is not constant
+        hash_ctx.render(_frame(cam, 64, 36, bounces=1, flags=capi.VRT_FRAME_COMPACT))
+
+
 # ---------------------------------------------------------------------------------------------
 # hit query: vrt_hit_query == VoxelMap::RayCast (VoxelMap.cpp:140-170), fp64
 # ---------------------------------------------------------------------------------------------

@@ -16,8 +16,12 @@ import tempfile
 from pathlib import Path
 
 ROOT = Path(__file__).resolve().parents[1]
-LIB = ROOT / "voxelrt_b200" / "lib" / "libvoxelrt_b200.so"
-SRC = ROOT / "voxelrt_b200" / "csrc"
+import os
+
+# (a capture must be joined with the line table of the very build that was profiled: VRT_REGIONS_LIB / VRT_REGIONS_SRC point at it when
+# the tree has moved on since)
+LIB = Path(os.environ.get("VRT_REGIONS_LIB", ROOT / "voxelrt_b200" / "lib" / "libvoxelrt_b200.so"))
+SRC = Path(os.environ.get("VRT_REGIONS_SRC", ROOT / "voxelrt_b200" / "csrc"))
 
 
 def line_table(kernel_substr):
@@ -78,7 +82,8 @@ def source_regions():
     return out
 
 
-MAJOR = ("loop", "cast_loop_generic", "cast_finish", "voxel_palette_id", "primary_ray", "shade_pixel", "store_pixel", "store_hit", "warp_tile_origin",
+MAJOR = ("loop", "lean_trip", "k_wave_trace", "k_wave_shade", "k_wave_primary", "packet_lane", "packet_votes", "shade_bounce", "wave_", "bounce_direction",
+         "cast_loop_generic", "cast_finish", "voxel_palette_id", "primary_ray", "shade_pixel", "store_pixel", "store_hit", "warp_tile_origin",
          "cast_ray", "cast_loop_fast", "render_warp_tile", "k_render", "sky_sample", "blue_noise", "sample_direction")
 
 
@@ -114,7 +119,8 @@ def main():
             break
     ia, ie, it, isamp = hdr.index("Address"), hdr.index("Instructions Executed"), hdr.index("Thread Instructions Executed"), hdr.index("# Samples")
     flags = re.findall(r"\(bool\)([01])", kernel.split("(vrt::")[0])
-    base = "k_render_cta" if "k_render_cta" in kernel else ("k_render_persist" if "k_render_persist" in kernel else "k_render")
+    mname = re.search(r"vrt::(\w+)", kernel)
+    base = mname.group(1) if mname else "k_render"
     sub = f"{len(base)}{base}I" + "".join(f"Lb{f}E" for f in flags) if flags else base
     table, regs = line_table(sub), source_regions()
     base = int(data[0][ia], 16)

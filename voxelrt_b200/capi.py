@@ -26,6 +26,7 @@ VRT_GLSL_COARSE = 1
 VRT_GLSL_ANISOTROPIC = 2
 VRT_FRAME_LINEAR_OUTPUT = 1
 VRT_FRAME_AUX_HITS = 2
+VRT_FRAME_COMPACT = 4
 VRT_FRAME_PART_ROWS = 8
 VRT_GATHER_DEPTH = 8
 VRT_BLUE_NOISE_BYTES = 128 * 128 * 64 * 2
@@ -138,6 +139,8 @@ HITD_DTYPE = np.dtype(
 assert HITD_DTYPE.itemsize == 48
 TILE_DTYPE = np.dtype([("albedo", "<u4", 16), ("depth", "<f4", 16), ("irr_rg", "<u4", 16), ("irr_bx", "<u4", 16)])
 assert TILE_DTYPE.itemsize == 256
+TILE_AD_DTYPE = np.dtype([("albedo", "<u4", 16), ("depth", "<f4", 16)])  # VrtTileAD (VRT_FRAME_COMPACT)
+assert TILE_AD_DTYPE.itemsize == 128
 
 # every symbol include/voxelrt_b200.h declares (tests check the .so exports them all)
 EXPORTS = [
@@ -365,10 +368,11 @@ class Context:
     def render(self, frame: VrtFrame, want_aux=False):
         """Host-buffer render (the e2e path). Returns (out, aux) numpy arrays."""
         n = frame.width * frame.height
+        compact = bool(frame.flags & VRT_FRAME_COMPACT)
         if frame.flags & VRT_FRAME_LINEAR_OUTPUT:
-            out = np.zeros((4, frame.height, frame.width), np.uint32)
+            out = np.zeros((2 if compact else 4, frame.height, frame.width), np.uint32)
         else:
-            out = np.zeros(n // 16, TILE_DTYPE)
+            out = np.zeros(n // 16, TILE_AD_DTYPE if compact else TILE_DTYPE)
         aux = None
         if want_aux:
             frame.flags |= VRT_FRAME_AUX_HITS

@@ -89,6 +89,7 @@ struct VrtContext {
     // the default (2) measures: after every change of scene emptiness / bounce count / frame size the next two bounce frames
     // run one form each between CUDA events, and the faster one is kept.  0 / 1 force a form.
     int wave_on = 2;
+    int trace_refill = VRT_TRACE_REFILL;  // k_wave_trace: lanes in flight below which a warp refills (tuning knob, "trace_refill")
     int wave_choice = -1;         // -1 undecided, 0 per-pixel, 1 wavefront
     int wave_phase = 0;           // 0: time per-pixel next, 1: time wavefront next, 2: waiting for the events
     uint64_t wave_key = 0;        // (bounces, width, height, scene epoch) the decision was taken for
@@ -287,6 +288,8 @@ int launch_render(VrtContext* ctx, const VrtFrame* f, void* d_out, VrtHit* d_aux
     if (f->width == 0 || f->height == 0 || (f->width & 3u) || (f->height & 3u))
         return fail(ctx, VRT_ERR_INVALID, "frame size must be a non-zero multiple of 4 (CpuRenderer.cpp:419)");
     if (f->bounces > 7) return fail(ctx, VRT_ERR_INVALID, "bounces > 7");
+    if ((f->flags & VRT_FRAME_COMPACT) && f->bounces != 0)
+        return fail(ctx, VRT_ERR_INVALID, "VRT_FRAME_COMPACT drops the irradiance words, which are constant only for bounces == 0");
     if (f->bounces > 0 && ctx->d_bn == nullptr) return fail(ctx, VRT_ERR_STATE, "bounces > 0 needs vrt_set_blue_noise first");
     uint32_t part_count = f->part_count ? f->part_count : 1;
     if (f->part_index >= part_count) return fail(ctx, VRT_ERR_INVALID, "part_index >= part_count");
@@ -309,9 +312,11 @@ int launch_render(VrtContext* ctx, const VrtFrame* f, void* d_out, VrtHit* d_aux
     int tune_slot = -1;  // >= 0: this frame is one of the two timed ones (events tune_slot, tune_slot + 1)
     if (!primary && !ctx->metrics_on && !ctx->persist_on && ctx->wave_on) {
         if (ctx->wave_on == 1) use_wave = true;
-        else if (row0 != 0 || row1 != 0 || part_count > 1) use_wave = ctx->wave_choice == 1;  // band / partial launches never tune
+        else if (row0 != 0 || row1 != 0) use_wave = ctx->wave_choice == 1;  // row-range launches of the band-pipelined host path never tune
         else {
-            const uint64_t key = ((uint64_t)F.bounces << 56) ^ ((uint64_t)F.width << 40) ^ ((uint64_t)F.height << 24) ^ (ctx->scene_epoch & 0xFFFFFFu);
+            // (a rank of a screen split tunes on its own share of the frame; both forms give the same bytes, so ranks may differ)
+            const uint64_t key = ((uint64_t)F.bounces << 56) ^ ((uint64_t)F.width << 40) ^ ((uint64_t)F.height << 24) ^ ((uint64_t)part_count << 60) ^
+                                 ((uint64_t)(F.flags & VRT_FRAME_PART_ROWS) << 52) ^ (ctx->scene_epoch & 0xFFFFFFu);
             if (key != ctx->wave_key) ctx->wave_key = key, ctx->wave_choice = -1, ctx->wave_phase = 0;
             if (ctx->wave_choice < 0 && ctx->wave_phase == 2 && cudaEventQuery(ctx->ev_tune[3]) == cudaSuccess) {
                 float t_pixel = 0.0f, t_wave = 0.0f;
@@ -346,8 +351,9 @@ int launch_render(VrtContext* ctx, const VrtFrame* f, void* d_out, VrtHit* d_aux
         int st2;
         if ((st2 = ensure(ctx, ctx->d_wave_rays, cap * sizeof(RayRec)))) return st2;
         if ((st2 = ensure(ctx, ctx->d_wave_hits, cap * sizeof(HitRec)))) return st2;
+        if (cap > 0x7FFFFFFFull) return fail(ctx, VRT_ERR_INVALID, "frame too large for the wavefront form");
         if ((st2 = ensure(ctx, ctx->d_wave_path, cap * (sizeof(float4) + sizeof(float2)) + (cap / 16u) * sizeof(uint16_t) + 64u))) return st2;
-        const uint32_t n_counters = 2u * 10u;  // rays queued per level [0..9], refill cursor per level
+        const uint32_t n_counters = 3u * 10u;  // per level [0..9]: rays queued, refill cursor, generic rays queued
         if ((st2 = ensure(ctx, ctx->d_wave_n, n_counters * sizeof(uint32_t)))) return st2;
         if (ctx->wave_used) CU(cudaStreamWaitEvent(s, ctx->ev_wave, 0));
         tune_begin();
@@ -355,8 +361,10 @@ int launch_render(VrtContext* ctx, const VrtFrame* f, void* d_out, VrtHit* d_aux
         CU(cudaMemsetAsync(cnt, 0, n_counters * sizeof(uint32_t), s));
         WaveBuffers B;
         B.rays = static_cast<RayRec*>(ctx->d_wave_rays.p);
+        B.capacity = (uint32_t)cap;
         B.n_rays = cnt;
         B.head = cnt + 10;
+        B.n_generic = cnt + 20;
         B.hits = static_cast<HitRec*>(ctx->d_wave_hits.p);
         B.path_a = static_cast<float4*>(ctx->d_wave_path.p);
         B.path_b = reinterpret_cast<float2*>(B.path_a + cap);
@@ -372,10 +380,14 @@ int launch_render(VrtContext* ctx, const VrtFrame* f, void* d_out, VrtHit* d_aux
             A.head = B.head + level;
             A.hits = B.hits;
             A.max_iters = F.max_iters;
+            A.refill = (uint32_t)ctx->trace_refill;
+            A.n_generic = B.n_generic + level;
+            A.capacity = B.capacity;
             k_wave_trace<<<grid, VRT_RENDER_THREADS, 0, s>>>(S, F.W, A);
+            k_wave_trace_generic<<<(unsigned)ctx->sm_count, 128, 0, s>>>(S, F.W, A);
             if (rows) k_wave_shade<true><<<blocks, VRT_RENDER_THREADS, 0, s>>>(S, F, B, level);
             else k_wave_shade<false><<<blocks, VRT_RENDER_THREADS, 0, s>>>(S, F, B, level);
-            ctx->stats.last_launches += 2;
+            ctx->stats.last_launches += 3;
         }
         CU(cudaEventRecord(ctx->ev_wave, s));
         ctx->wave_used = true;
@@ -573,6 +585,7 @@ extern "C" int vrt_set_option(VrtContext* ctx, const char* name, int64_t value) 
         if (value != 0) return fail(ctx, VRT_ERR_UNSUPPORTED, "compact_bounces was removed; see the \"wavefront\" option");
     }
     else if (!strcmp(name, "wavefront")) ctx->wave_on = (int)value;
+    else if (!strcmp(name, "trace_refill")) ctx->trace_refill = (int)std::min<int64_t>(32, std::max<int64_t>(1, value));
     else return fail(ctx, VRT_ERR_INVALID, std::string("unknown option ") + name);
     return VRT_OK;
 }
@@ -1032,8 +1045,9 @@ extern "C" int vrt_render(VrtContext* ctx, const VrtFrame* frame, void* out, Vrt
     if ((frame->flags & VRT_FRAME_AUX_HITS) && !aux_hits) return fail(ctx, VRT_ERR_INVALID, "VRT_FRAME_AUX_HITS without aux buffer");
     DeviceGuard g(ctx->device);
     size_t npx = (size_t)frame->width * frame->height;
+    const size_t px_bytes = (frame->flags & VRT_FRAME_COMPACT) ? 8u : 16u, tile_bytes = px_bytes * 16u;
     int st;
-    if ((st = ensure(ctx, ctx->d_fb, npx * 16))) return st;
+    if ((st = ensure(ctx, ctx->d_fb, npx * px_bytes))) return st;
     bool aux = (frame->flags & VRT_FRAME_AUX_HITS) != 0;
     if (aux && (st = ensure(ctx, ctx->d_aux, npx * sizeof(VrtHit)))) return st;
     uint32_t part_count = frame->part_count ? frame->part_count : 1;
@@ -1044,19 +1058,19 @@ extern "C" int vrt_render(VrtContext* ctx, const VrtFrame* frame, void* out, Vrt
         ctx->stats.last_launches = 0;
         st = launch_render(ctx, frame, ctx->d_fb.p, nullptr, ctx->stream);
         if (st) return st;
-        const size_t band = (size_t)(frame->width / 4) * (VRT_BAND_ROWS / 4u) * sizeof(VrtTile);
+        const size_t band = (size_t)(frame->width / 4) * (VRT_BAND_ROWS / 4u) * tile_bytes;
         const uint32_t rows_full = frame->height / VRT_BAND_ROWS, rows_all = (frame->height + VRT_BAND_ROWS - 1u) / VRT_BAND_ROWS, r = frame->part_index;
         const uint32_t mine_full = rows_full > r ? (rows_full - r + part_count - 1) / part_count : 0u;
         if (mine_full) CU(cudaMemcpy2DAsync((char*)out + r * band, part_count * band, (char*)ctx->d_fb.p + r * band, part_count * band, band, mine_full, cudaMemcpyDeviceToHost, ctx->stream));
         if (rows_all > rows_full && rows_full % part_count == r) {
-            const size_t tail = (size_t)(frame->width / 4) * ((frame->height % VRT_BAND_ROWS) / 4u) * sizeof(VrtTile);
+            const size_t tail = (size_t)(frame->width / 4) * ((frame->height % VRT_BAND_ROWS) / 4u) * tile_bytes;
             CU(cudaMemcpyAsync((char*)out + rows_full * band, (char*)ctx->d_fb.p + rows_full * band, tail, cudaMemcpyDeviceToHost, ctx->stream));
         }
         CU(cudaStreamSynchronize(ctx->stream));
         return VRT_OK;
     }
     if (part_count > 1) {  // pixels of other ranks stay zero in a partial frame
-        CU(cudaMemsetAsync(ctx->d_fb.p, 0, npx * 16, ctx->stream));
+        CU(cudaMemsetAsync(ctx->d_fb.p, 0, npx * px_bytes, ctx->stream));
         if (aux) CU(cudaMemsetAsync(ctx->d_aux.p, 0, npx * sizeof(VrtHit), ctx->stream));
     }
     ctx->stats.last_launches = 0;
@@ -1067,7 +1081,7 @@ extern "C" int vrt_render(VrtContext* ctx, const VrtFrame* frame, void* out, Vrt
         // tiles are contiguous in the reference's tile order, so its D2H copy runs on a second stream
         // while the next band is being traced.  The PCIe copy, not the kernel, bounds this call.
         const uint32_t n_bands = 8, rows_per = (macros_y + n_bands - 1) / n_bands;
-        const size_t row_bytes = (size_t)32 * frame->width * 16;  // one macro row = 8 tile rows
+        const size_t row_bytes = (size_t)32 * frame->width * px_bytes;  // one macro row = 8 tile rows
         for (uint32_t b = 0; b < n_bands; b++) {
             uint32_t r0 = b * rows_per, r1 = std::min(macros_y, r0 + rows_per);
             if (r0 >= r1) break;
@@ -1075,7 +1089,7 @@ extern "C" int vrt_render(VrtContext* ctx, const VrtFrame* frame, void* out, Vrt
             if (st) return st;
             CU(cudaEventRecord(ctx->ev_band[b], ctx->stream));
             CU(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_band[b], 0));
-            size_t off = (size_t)r0 * row_bytes, end = std::min((size_t)r1 * row_bytes, npx * 16);
+            size_t off = (size_t)r0 * row_bytes, end = std::min((size_t)r1 * row_bytes, npx * px_bytes);
             CU(cudaMemcpyAsync((char*)out + off, (char*)ctx->d_fb.p + off, end - off, cudaMemcpyDeviceToHost, ctx->copy_stream));
         }
         CU(cudaStreamSynchronize(ctx->copy_stream));
@@ -1084,7 +1098,7 @@ extern "C" int vrt_render(VrtContext* ctx, const VrtFrame* frame, void* out, Vrt
     }
     st = launch_render(ctx, frame, ctx->d_fb.p, (VrtHit*)ctx->d_aux.p, ctx->stream);
     if (st) return st;
-    CU(cudaMemcpyAsync(out, ctx->d_fb.p, npx * 16, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaMemcpyAsync(out, ctx->d_fb.p, npx * px_bytes, cudaMemcpyDeviceToHost, ctx->stream));
     if (aux) CU(cudaMemcpyAsync(aux_hits, ctx->d_aux.p, npx * sizeof(VrtHit), cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
     return VRT_OK;
@@ -1169,7 +1183,8 @@ extern "C" int vrt_render_gather(VrtContext* ctx, const VrtFrame* frame, void* d
         cudaEvent_t ev = ctx->ev_gather_src[seq % (2u * VRT_GATHER_DEPTH)];
         CU(cudaEventRecord(ev, s));
         CU(cudaStreamWaitEvent(gs, ev, 0));
-        const size_t band = (size_t)(frame->width / 4) * (VRT_BAND_ROWS / 4u) * sizeof(VrtTile);
+        const size_t tile_bytes = (frame->flags & VRT_FRAME_COMPACT) ? sizeof(VrtTileAD) : sizeof(VrtTile);
+        const size_t band = (size_t)(frame->width / 4) * (VRT_BAND_ROWS / 4u) * tile_bytes;
         const uint32_t rows_full = frame->height / VRT_BAND_ROWS, rows_all = (frame->height + VRT_BAND_ROWS - 1u) / VRT_BAND_ROWS;
         const uint32_t r = frame->part_index;
         const uint32_t mine_full = rows_full > r ? (rows_full - r + part_count - 1) / part_count : 0u;
@@ -1183,7 +1198,7 @@ extern "C" int vrt_render_gather(VrtContext* ctx, const VrtFrame* frame, void* d
             }
         } else if (mine_full) CU(cudaMemcpy2DAsync(dst + r * band, part_count * band, src + r * band, part_count * band, band, mine_full, cudaMemcpyDeviceToDevice, gs));
         if (rows_all > rows_full && rows_full % part_count == r) {
-            const size_t tail = (size_t)(frame->width / 4) * ((frame->height % VRT_BAND_ROWS) / 4u) * sizeof(VrtTile);
+            const size_t tail = (size_t)(frame->width / 4) * ((frame->height % VRT_BAND_ROWS) / 4u) * tile_bytes;
             CU(cudaMemcpyAsync(dst + rows_full * band, src + rows_full * band, tail, cudaMemcpyDeviceToDevice, gs));
         }
         ctx->gather_pending = true;

@@ -62,7 +62,19 @@ __device__ __forceinline__ bool warp_tile_origin(const FrameParams& F, uint32_t 
 }
 
 __device__ __forceinline__ void store_pixel(const FrameParams& F, uint32_t x, uint32_t y, const PixelOut& P) {
-    if (F.flags & VRT_FRAME_LINEAR_OUTPUT) {
+    if (F.flags & VRT_FRAME_COMPACT) {  // primary-only frames: albedo + depth, the constant irradiance is not stored (include/voxelrt_b200.h)
+        if (F.flags & VRT_FRAME_LINEAR_OUTPUT) {
+            uint32_t* o = reinterpret_cast<uint32_t*>(F.out);
+            const size_t n = (size_t)F.width * F.height, p = (size_t)y * F.width + x;
+            o[p] = P.albedo;
+            o[n + p] = __float_as_uint(P.depth);
+        } else {
+            VrtTileAD* t = reinterpret_cast<VrtTileAD*>(F.out) + ((size_t)(y >> 2) * (F.width >> 2) + (x >> 2));
+            const uint32_t lane = (x & 3u) | ((y & 3u) << 2);
+            t->albedo[lane] = P.albedo;
+            t->depth[lane] = P.depth;
+        }
+    } else if (F.flags & VRT_FRAME_LINEAR_OUTPUT) {
         uint32_t* o = reinterpret_cast<uint32_t*>(F.out);
         size_t n = (size_t)F.width * F.height, p = (size_t)y * F.width + x;
         o[p] = P.albedo;
@@ -140,11 +152,12 @@ __global__ void __launch_bounds__(VRT_RENDER_THREADS) k_wave_shade(const __grid_
     wave_shade_pixel(S, F, B, (work - F.work_offset) * 32u + lane, x, y, in_frame && x < F.width && y < F.height, level);
 }
 
-// The trace pass: persistent warps, one ray per lane, lanes refilled from the level's queue whenever fewer than VRT_TRACE_REFILL of
-// the warp's 32 rays are still in flight (and once more when none is).  Rays outside the fast loop's domain (zero / denormal / huge
-// components, far origins, origins outside the view) are traced at once by the generic loop when they are pulled; rays whose
-// direction is NaN in all three components (quirk Q7: 0.8 % of all bounce rays) take ONE lean trip — the reference's second trip
-// lands at INT_MIN, outside the view, whatever the first one did — instead of dragging the warp through the generic loop.
+// The trace pass: persistent warps, one ray per lane, lanes refilled from the level's queue whenever fewer than `refill` of the warp's
+// 32 rays are still in flight (and once more when none is).  The queue holds FAST rays and rays whose direction is NaN in all three
+// components (quirk Q7: 0.8 % of all bounce rays; they take ONE lean trip — the reference's second trip lands at INT_MIN, outside the view,
+// whatever the first one did); rays outside the fast loop's domain (an exactly zero component: 0.4 % of the blue-noise samples; far or
+// outside origins) were queued apart by their producer and are traced by k_wave_trace_generic, 32 to a warp — one such ray traced inside
+// this kernel would drag its warp through the generic loop alone (measured: 10 % of the kernel's instructions at 1 thread per instruction).
 #ifndef VRT_TRACE_REFILL
 #define VRT_TRACE_REFILL 24
 #endif
@@ -153,99 +166,117 @@ __global__ void __launch_bounds__(VRT_RENDER_THREADS) k_wave_shade(const __grid_
 #endif
 struct TraceArgs {
     const RayRec* rays;
-    const uint32_t* n;  // rays queued for this level
+    const uint32_t* n;  // rays queued for this level (from the front of `rays`)
     uint32_t* head;     // refill cursor (zeroed per frame)
     HitRec* hits;
     uint32_t max_iters;
+    uint32_t refill;    // refill when fewer lanes than this are in flight
+    const uint32_t* n_generic;  // k_wave_trace_generic: rays queued from the end of `rays`
+    uint32_t capacity;
 };
 __global__ void __launch_bounds__(VRT_RENDER_THREADS, VRT_TRACE_CTAS) k_wave_trace(const __grid_constant__ DevScene S, const __grid_constant__ RayFrame W,
                                                                                    const __grid_constant__ TraceArgs A) {
     const uint32_t n = *A.n;
     const unsigned lane = threadIdx.x & 31u, lt_mask = (1u << lane) - 1u;
+    // loop constants pinned in registers (ptxas otherwise re-loads kernel parameters from the constant bank every trip: see cast_loop_fast)
+    const int opaque0 = (int)blockDim.z - 1;
+    const float opaque0f = __int_as_float(opaque0);
     LeanFrame C;
-    C.mgx = W.mgx, C.mgy = W.mgy, C.mgz = W.mgz, C.r32 = 0.03125f;
-    C.strz = (int)S.sxp, C.stry = (int)S.sxzp, C.hoff = W.hoff;
-    C.hdrp = S.hdr;
-    C.cellp = reinterpret_cast<const char*>(S.cells);
+    C.mgx = __fadd_rn(W.mgx, opaque0f), C.mgy = __fadd_rn(W.mgy, opaque0f), C.mgz = __fadd_rn(W.mgz, opaque0f), C.r32 = __fadd_rn(0.03125f, opaque0f);
+    C.strz = (int)S.sxp + opaque0, C.stry = (int)S.sxzp + opaque0, C.hoff = W.hoff + opaque0;
+    {
+        unsigned long long hp = (unsigned long long)S.hdr, cp = (unsigned long long)S.cells;
+#ifndef VRT_HOST_EMULATION
+        asm volatile("add.u64 %0, %0, %1;" : "+l"(hp) : "l"((unsigned long long)(unsigned)opaque0));
+        asm volatile("add.u64 %0, %0, %1;" : "+l"(cp) : "l"((unsigned long long)(unsigned)opaque0));
+#endif
+        C.hdrp = reinterpret_cast<const uint4*>(hp);
+        C.cellp = reinterpret_cast<const char*>(cp);
+    }
+    VRT_PIN_F(C.mgx);
+    VRT_PIN_F(C.mgy);
+    VRT_PIN_F(C.mgz);
+    VRT_PIN_F(C.r32);
+    VRT_PIN_R(C.strz);
+    VRT_PIN_R(C.stry);
+    VRT_PIN_R(C.hoff);
+    const uint32_t refill = A.refill + (uint32_t)opaque0;
     LeanRay r;
     r.ox = r.oy = r.oz = r.dx = r.dy = r.dz = r.ix = r.iy = r.iz = r.tx = r.ty = r.tz = r.cx = r.cy = r.cz = r.sdx = r.sdy = r.sdz = 0.0f;
     r.nmx = r.nmy = r.nmz = r.qx = r.qy = r.qz = 0;
     uint32_t left = 0, budget = 0, slot = 0, hit_slot = 0;
-    int status = 0;        // how the ray in `r` ended: 1 solid voxel, 2 left the view, 3 out of trips
-    bool active = false;   // a ray is in flight in this lane
-    bool pending = false;  // it has ended and its record is not written yet
-    bool nan_ray = false;
-    bool more = true;      // the queue may still hold rays (warp-uniform)
+    // lane state: 0 idle, 1 a ray is in flight, 2..4 it has ended (2 solid voxel, 3 left the view, 4 out of trips) and its record is not written yet
+    uint32_t state = 0;
+    uint32_t more = 1;  // the queue may still hold rays (warp-uniform)
     for (;;) {
-        unsigned act = __ballot_sync(0xFFFFFFFFu, active);
-        if (act == 0u || (more && __popc(act) < VRT_TRACE_REFILL)) {
-            if (pending) {  // RayCast epilogue (CpuRenderer.cpp:204-223) of the ray that ended in this lane
-                pending = false;
-                if (nan_ray && status == 3) status = 2;  // the second trip of a NaN ray: currPos = NaN -> voxel INT_MIN -> outside
+        unsigned act = __ballot_sync(0xFFFFFFFFu, state == 1u);
+        if (act == 0u || (more && (uint32_t)__popc(act) < refill)) {
+            if (state >= 2u) {  // RayCast epilogue (CpuRenderer.cpp:204-223) of the ray that ended in this lane
+                if (budget == 1u && state == 4u) state = 3u;  // the second trip of a NaN ray: currPos = NaN -> voxel INT_MIN -> outside
                 uint32_t flags = HITREC_CAST | normal_code(r.sdx, r.sdy, r.sdz, r.dx, r.dy, r.dz);
                 uint32_t material = 0u;  // (a miss's material is never used at bounce levels >= 1: RenderRow replaces it by the sky, :363-368)
-                if (status == 1) {
+                if (state == 2u) {
                     const uint32_t vi = ((uint32_t)r.qx & 7u) | (((uint32_t)r.qz & 7u) << 3) | (((uint32_t)r.qy & 7u) << 6);
                     material = ldg_u2(S.palette + __ldg(S.voxels + (size_t)hit_slot * 512u + vi)).x;  // :120-132
                     flags |= HITREC_HIT;
-                } else if (status == 3) flags |= HITREC_CAPPED;
-                if (left == budget && status != 3) flags |= HITREC_FIRST;  // no completed step
+                } else if (state == 4u) flags |= HITREC_CAPPED;
+                if (left == budget && state != 4u) flags |= HITREC_FIRST;  // no completed step
                 store_hit_rec(A.hits + slot, r.cx, r.cy, r.cz, material, r.dx, r.dy, r.dz, flags);
+                state = 0u;
             }
             if (more) {
                 const unsigned want = ~act;
                 const uint32_t cnt = (uint32_t)__popc(want);
+                const int leader = __ffs((int)want) - 1;
                 uint32_t base = 0;
-                if (lane == (unsigned)(__ffs((int)want) - 1)) base = atomicAdd(A.head, cnt);
-                base = __shfl_sync(0xFFFFFFFFu, base, __ffs((int)want) - 1);
-                more = base + cnt < n;
+                if ((int)lane == leader) base = atomicAdd(A.head, cnt);
+                base = __shfl_sync(0xFFFFFFFFu, base, leader);
+                more = base + cnt < n ? 1u : 0u;
                 const uint32_t idx = base + (uint32_t)__popc(want & lt_mask);
-                if (!active && idx < n) {
+                if (state == 0u && idx < n) {
                     const float4* rp = reinterpret_cast<const float4*>(A.rays + idx);
                     const float4 r0 = __ldg(rp), r1 = __ldg(rp + 1);
                     r.ox = r0.x, r.oy = r0.y, r.oz = r0.z, r.dx = r1.x, r.dy = r1.y, r.dz = r1.z;
                     slot = __float_as_uint(r0.w);
-                    // the first position can be anywhere: bounds-test it here (GetInboundMask, :114-117), like cast_ray
-                    const float so = __fadd_rn(__fadd_rn(fabsf(r.ox), fabsf(r.oy)), fabsf(r.oz));
-                    bool start_ok = W.fast_ok && so <= 1048576.0f;
-                    if (start_ok) {
-                        const int px = W.wx + __float2int_rd(r.ox), py = W.wy + __float2int_rd(r.oy), pz = W.wz + __float2int_rd(r.oz);
-                        start_ok = (uint32_t)(px | pz) < S.lim_xz && (uint32_t)py < S.lim_y;
-                    }
-                    const bool fast = start_ok && A.max_iters != 0u && ray_is_fast(r.ox, r.oy, r.oz, r.dx, r.dy, r.dz);
-                    nan_ray = start_ok && A.max_iters >= 2u && r.dx != r.dx && r.dy != r.dy && r.dz != r.dz;
-                    if (fast || nan_ray) {
-                        r.ix = rcp_rn_normal(r.dx), r.iy = rcp_rn_normal(r.dy), r.iz = rcp_rn_normal(r.dz);  // :173 (== IEEE 1/x for fast rays; NaN stays NaN)
-                        r.tx = __fmul_rn(__fsub_rn(r.dx < 0.0f ? 0.0f : 1.0f, r.ox), r.ix);                  // :175-179
-                        r.ty = __fmul_rn(__fsub_rn(r.dy < 0.0f ? 0.0f : 1.0f, r.oy), r.iy);
-                        r.tz = __fmul_rn(__fsub_rn(r.dz < 0.0f ? 0.0f : 1.0f, r.oz), r.iz);
-                        r.nmx = __float_as_int(r.dx) >> 31, r.nmy = __float_as_int(r.dy) >> 31, r.nmz = __float_as_int(r.dz) >> 31;
-                        r.cx = r.ox, r.cy = r.oy, r.cz = r.oz;  // :181
-                        r.sdx = r.sdy = r.sdz = 0.0f;           // :180
-                        budget = left = nan_ray ? 1u : A.max_iters;
-                        active = true;
-                    } else {  // rare: the generic loop, to completion, right here
-                        CastResult R;
-                        HitLane H;
-                        cast_loop_generic(S, r.ox, r.oy, r.oz, r.dx, r.dy, r.dz, W.wx, W.wy, W.wz, A.max_iters, R);
-                        cast_finish<true>(S, R, r.dx, r.dy, r.dz, H);
-                        const uint32_t flags = HITREC_CAST | H.ncode | (H.hit ? HITREC_HIT : 0u) | (R.capped ? HITREC_CAPPED : 0u) |
-                                               ((R.iters == 1u && !R.capped) ? HITREC_FIRST : 0u);
-                        store_hit_rec(A.hits + slot, H.px, H.py, H.pz, H.material, r.dx, r.dy, r.dz, flags);
-                    }
+                    r.ix = rcp_rn_normal(r.dx), r.iy = rcp_rn_normal(r.dy), r.iz = rcp_rn_normal(r.dz);  // :173 (== IEEE 1/x for fast rays; NaN stays NaN)
+                    r.tx = __fmul_rn(__fsub_rn(r.dx < 0.0f ? 0.0f : 1.0f, r.ox), r.ix);                  // :175-179
+                    r.ty = __fmul_rn(__fsub_rn(r.dy < 0.0f ? 0.0f : 1.0f, r.oy), r.iy);
+                    r.tz = __fmul_rn(__fsub_rn(r.dz < 0.0f ? 0.0f : 1.0f, r.oz), r.iz);
+                    r.nmx = __float_as_int(r.dx) >> 31, r.nmy = __float_as_int(r.dy) >> 31, r.nmz = __float_as_int(r.dz) >> 31;
+                    r.cx = r.ox, r.cy = r.oy, r.cz = r.oz;  // :181
+                    r.sdx = r.sdy = r.sdz = 0.0f;           // :180
+                    budget = left = __float_as_uint(r1.w) == RAY_NAN ? 1u : A.max_iters;
+                    state = 1u;
                 }
             }
-            act = __ballot_sync(0xFFFFFFFFu, active);
+            act = __ballot_sync(0xFFFFFFFFu, state == 1u);
             if (act == 0u) {
                 if (!more) break;
                 continue;
             }
         }
-        if (active) {
-            status = lean_trip(C, r, hit_slot);
-            if (status != 0) active = false, pending = true;
-            else if (--left == 0u) active = false, pending = true, status = 3;
+        if (state == 1u) {
+            const int st = lean_trip(C, r, hit_slot);
+            if (st != 0) state = 1u + (uint32_t)st;
+            else if (--left == 0u) state = 4u;
         }
+    }
+}
+
+// The rays outside the fast loop's domain (RAY_GENERIC, queued from the end of the ray buffer): cast_loop_generic spells out the x86
+// semantics (infinities and NaNs of zero components, cvtps2dq overflow).  One thread per ray; a few thousand rays per level.
+__global__ void __launch_bounds__(128) k_wave_trace_generic(const __grid_constant__ DevScene S, const __grid_constant__ RayFrame W,
+                                                            const __grid_constant__ TraceArgs A) {
+    const uint32_t n = *A.n_generic;
+    for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
+        const float4* rp = reinterpret_cast<const float4*>(A.rays + (A.capacity - 1u - k));
+        const float4 r0 = __ldg(rp), r1 = __ldg(rp + 1);
+        CastResult R;
+        HitLane H;
+        cast_loop_generic(S, r0.x, r0.y, r0.z, r1.x, r1.y, r1.z, W.wx, W.wy, W.wz, A.max_iters, R);
+        cast_finish<true>(S, R, r1.x, r1.y, r1.z, H);
+        const uint32_t flags = HITREC_CAST | H.ncode | (H.hit ? HITREC_HIT : 0u) | (R.capped ? HITREC_CAPPED : 0u) | ((R.iters == 1u && !R.capped) ? HITREC_FIRST : 0u);
+        store_hit_rec(A.hits + __float_as_uint(r0.w), H.px, H.py, H.pz, H.material, r1.x, r1.y, r1.z, flags);
     }
 }
 

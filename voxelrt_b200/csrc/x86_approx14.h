@@ -51,22 +51,7 @@ VRT_X86_TABLE Coef kRcp14[64] = {
 };
 // [0, 32): even exponent (argument mantissa in [1, 2)); [32, 64): odd exponent (argument taken as [2, 4))
 VRT_X86_TABLE Coef kRsqrt14[64] = {
-    {0xFDFFF480u, 1001u}, {0xFDF05080u, 955u}, {0xFDE16280u, 915u}, {0xFDD31900u, 877u},
-    {0xFDC56700u, 841u}, {0xFDB84380u, 807u}, {0xFDABA680u, 775u}, {0xFD9F8880u, 747u},
-    {0xFD93DD00u, 719u}, {0xFD88A080u, 693u}, {0xFD7DCB80u, 669u}, {0xFD735A00u, 647u},
-    {0xFD694100u, 625u}, {0xFD5F7D00u, 603u}, {0xFD560F80u, 585u}, {0xFD4CED80u, 567u},
-    {0xFD441380u, 549u}, {0xFD3B8180u, 533u}, {0xFD332F80u, 517u}, {0xFD2B1C00u, 501u},
-    {0xFD234680u, 487u}, {0xFD1BA980u, 473u}, {0xFD144400u, 461u}, {0xFD0D1180u, 449u},
-    {0xFD060F80u, 437u}, {0xFCFF3D80u, 425u}, {0xFCF89B00u, 415u}, {0xFCF21F00u, 403u},
-    {0xFCEBCF80u, 393u}, {0xFCE5AB00u, 385u}, {0xFCDFA780u, 375u}, {0xFCD9CD00u, 367u},
-    {0xFCD40A80u, 707u}, {0xFCC8FC80u, 675u}, {0xFCBE6E00u, 647u}, {0xFCB45200u, 619u},
-    {0xFCAAA600u, 595u}, {0xFCA15B80u, 571u}, {0xFC987080u, 549u}, {0xFC8FDC80u, 527u},
-    {0xFC879E80u, 509u}, {0xFC7FAD80u, 491u}, {0xFC780280u, 473u}, {0xFC709E80u, 457u},
-    {0xFC697A80u, 441u}, {0xFC629500u, 427u}, {0xFC5BE880u, 413u}, {0xFC557580u, 401u},
-    {0xFC4F3380u, 389u}, {0xFC492180u, 377u}, {0xFC433F80u, 365u}, {0xFC3D8C80u, 355u},
-    {0xFC380180u, 345u}, {0xFC329F00u, 335u}, {0xFC2D6200u, 325u}, {0xFC284C00u, 317u},
-    {0xFC235900u, 309u}, {0xFC1E8680u, 301u}, {0xFC19D380u, 293u}, {0xFC153F00u, 285u},
-    {0xFC10CA80u, 279u}, {0xFC0C6E80u, 271u}, {0xFC083000u, 265u}, {0xFC040B00u, 259u},
+#include "x86_approx14_rsqrt.inc"
 };
 
 VRT_X86_APPROX_QUAL uint32_t f2u(float f) {
@@ -113,6 +98,30 @@ VRT_X86_APPROX_QUAL float rsqrt14_pos_normal(float x) {
     uint32_t rb = ((c.c0 - c.c1 * t) >> 9) << 7;
     if ((u & 0x00FFFFFFu) == 0x00800000u) rb = 0x3F800000u;  // exact power of four
     // x = (1.m * 2^odd) * 4^k  ->  result = table value * 2^-k,  k = (e - 127 - odd) / 2
+    const int k = ((int)(u >> 23) - 127 - (int)(idx >> 5)) >> 1;
+    return u2f(rb - ((uint32_t)k << 23));
+}
+
+#if defined(__CUDACC__)
+// The same rsqrt14 coefficients in CONSTANT memory, for callers whose lanes mostly share the segment (camera rays: the squared length
+// of neighbouring pixels' directions differs in low mantissa bits): an indexed LDC instead of a global load in front of the traversal.
+__constant__ Coef kRsqrt14Const[64] = {
+#define VRT_X86_COEF_LIST_RSQRT
+#include "x86_approx14_rsqrt.inc"
+#undef VRT_X86_COEF_LIST_RSQRT
+};
+#endif
+VRT_X86_APPROX_QUAL float rsqrt14_pos_normal_uniform(float x) {
+    const uint32_t u = f2u(x);
+    const uint32_t idx = ((u >> 18) & 63u) ^ 32u;
+    const uint32_t t = (u >> 8) & 0x3FFu;
+#if defined(__CUDA_ARCH__)
+    const Coef c = kRsqrt14Const[idx];
+#else
+    const Coef c = kRsqrt14[idx];
+#endif
+    uint32_t rb = ((c.c0 - c.c1 * t) >> 9) << 7;
+    if ((u & 0x00FFFFFFu) == 0x00800000u) rb = 0x3F800000u;
     const int k = ((int)(u >> 23) - 127 - (int)(idx >> 5)) >> 1;
     return u2f(rb - ((uint32_t)k << 23));
 }
