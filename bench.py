@@ -53,12 +53,14 @@ def _peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def _traffic(args):
-    """DRAM bytes per launch of the dominant kernel from the committed ncu capture (null for other shapes)."""
+def _ncu_summary(args):
+    """What the committed ncu capture of the dominant kernel says (profiles/ncu_summary.json, written by tools/profiles.py from an
+    `ncu --set full` capture of the same command): DRAM / L2 bytes per launch, issue-slot and pipe utilisation, executed instructions.
+    None for shapes without a capture."""
     try:
-        d = json.loads((ROOT / "profiles" / "traffic.json").read_text())
-        e = d.get(f"k_render<false,true> {args.width}x{args.height} bounces={args.bounces}")
-        return (e["dram_read_bytes"] + e["dram_write_bytes"]) if e and args.gpus == 1 and args.workload == "terrain" else None
+        d = json.loads((ROOT / "profiles" / "ncu_summary.json").read_text())
+        key = f"{args.workload} {args.width}x{args.height} bounces={args.bounces} gpus={args.gpus}"
+        return d.get(key)
     except Exception:
         return None
 
@@ -190,8 +192,9 @@ _SCENE_FILE = [None]
 _WL = {"name": "terrain", "view": (6, 4), "cam": None, "label": None, "reference_ok": True}
 
 
-def build_scene(workload="terrain"):
-    """-> (scene, sync records, stats); fills _WL (view extent, camera, label) for the chosen workload."""
+def build_scene(workload="terrain", rank=0, world=1, barrier=None, large=(128, 24, 128, 512)):
+    """-> (scene, sync records, stats); fills _WL (view extent, camera, label) for the chosen workload.
+    rank / world / barrier: with several ranks on a node the big scene is generated once (rank 0, into /dev/shm) and mapped by the others."""
     from scenes import camera, terrain
 
     _WL["name"] = workload
@@ -207,9 +210,22 @@ def build_scene(workload="terrain"):
         _WL.update(view=(6, 5), cam=camera.Camera(pos=(420.3, 160.2, 1010.7), yaw=1.5, pitch=-0.15), reference_ok=False,
                    label="bundled assets/models/Sponza voxelised into 2048^3, camera (420,160,1011) yaw 1.5 pitch -0.15")
     elif workload == "large":
-        scene = terrain.terrain_fastnoise(128, 7, 128) if terrain.fastnoise_available() else terrain.terrain_hash(128, 7, 128, seed=12345, emissive=False)
-        _WL.update(view=(7, 4), cam=camera.Camera(pos=(2048.0, 128.0, 2048.0)), reference_ok=False,
-                   label=f"{scene.get('name', 'terrain')} in a 4096x512x4096 view, camera (2048,128,2048) yaw 1.52 pitch -0.5")
+        # BASELINE configs[3]: 4096-wide terrain with >= 10 GB of bricks: the reference's noise tree over 128 x ny x 128 sectors, raised by
+        # `shift` voxels (everything under the surface is solid rock whose voxel ids come from the noise, as TerrainGenerator.cpp:21-23 has it)
+        nx, ny, nz, shift = large
+        if terrain.fastnoise_available():
+            shared = "/dev/shm" if world > 1 and os.path.isdir("/dev/shm") else None
+            try:
+                scene = terrain.terrain_fastnoise_big(nx, ny, nz, y_shift=shift, shared_dir=shared, is_writer=rank == 0, wait=barrier)
+            except OSError as e:  # /dev/shm too small: every rank generates its own copy
+                print(f"[bench] shared scene failed ({e}); generating per rank", file=sys.stderr)
+                scene = terrain.terrain_fastnoise_big(nx, ny, nz, y_shift=shift)
+        else:
+            scene = terrain.terrain_hash(nx, min(ny, 7), nz, seed=12345, emissive=False)
+            shift = 0
+        sy_log2 = 4 if ny <= 16 else 5
+        _WL.update(view=(7, sy_log2), cam=camera.Camera(pos=(2048.0, 128.0 + shift, 2048.0)), reference_ok=False,
+                   label=f"{scene.get('name', 'terrain')} in a 4096x{32 << sy_log2}x4096 view, camera (2048,{128 + shift},2048) yaw 1.52 pitch -0.5")
     elif workload == "file":
         # any "cvox 0004" file the reference wrote (e.g. its logs/voxels_2k_sponza.dat, Main.cpp:38-49), read by scenes/cvox.py
         from scenes import cvox
@@ -352,6 +368,33 @@ def workload_config(args, scene, sstats):
     }
 
 
+def roofline_block(args, world, alg_bytes, ms_per_step, peak, peak_src, m, my_primary, launches):
+    """The path is NOT bandwidth-bound on the configs whose masks fit the 126 MB L2 (all but configs[3]'s bounce rays): ncu shows the frame
+    kernels limited by instruction ISSUE (70-80 % of the issue slots busy, ALU pipe ~60 %), DRAM traffic a few % of the algorithmic bytes.
+    `achieved / peak / frac` stay what the contract defines — algorithmic bytes (8 I_s + 8 I_c + 9 H + 16 P, with the REFERENCE's iteration
+    counts, which the metrics build of the kernel counts and tests tie to the oracle) over the measured HBM copy peak, a work-equivalent
+    figure — and `bound` says what really limits the kernel, with the ncu numbers of the committed capture beside it."""
+    achieved = alg_bytes / (ms_per_step * 1e-3) / 1e9
+    ncu = _ncu_summary(args)
+    kernel = ("vrt::k_render<false,true,%s>" % ("true" if world > 1 else "false")) if args.bounces == 0 else "vrt::k_wave_primary + k_wave_trace + k_wave_shade (or k_render<false,false,...>: self-tuned)"
+    return {
+        "bound": "issue",
+        "bound_note": "instruction-issue bound (see `ncu`); achieved/peak/frac = algorithmic bytes over the measured HBM copy peak, a work-equivalent figure",
+        "kernel": kernel,
+        "achieved": achieved,
+        "peak": peak,
+        "unit": "GB/s",
+        "frac": achieved / peak,
+        "peak_source": peak_src,
+        "algorithmic_bytes_per_launch": int(alg_bytes),
+        "bytes_per_ray": alg_bytes / max(1, my_primary * (1 + args.bounces)),
+        "traffic": None if ncu is None else ncu.get("dram_bytes"),
+        "ncu": ncu,
+        "launches_per_step": launches,
+        "counters": {"rays": m.rays, "reference_iterations": m.iters, "sector_fetches": m.sector_fetches, "cell_fetches": m.cell_fetches, "hits": m.hits, "capped": m.capped},
+    }
+
+
 def present_block(args, ctx, frame, stream, fb, w, h, peak):
     """--present: the step after the path — the reference's GBuffer (tile blit + reprojection + SVGF + tone-mapped present,
     include/voxelrt_b200_post.h) on the frames the bench just traced.  Device-timed with CUDA events on the launching
@@ -442,7 +485,11 @@ def run_b200(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     n_gpus = world
 
-    scene, recs, sstats = build_scene(args.workload)
+    def _barrier():
+        if world > 1:
+            dist.barrier()
+
+    scene, recs, sstats = build_scene(args.workload, rank, world, _barrier, large=(128, args.large_y, 128, args.large_shift))
     cap = 1 << 18
     while cap < sstats["bricks"] + 4096:
         cap <<= 1
@@ -457,13 +504,17 @@ def run_b200(args):
     t_up = time.perf_counter() - t_up
     up_stats = ctx.stats()
     # the same records once more (every brick dirty again, nothing allocated or moved): the steady-state rate of the upload path
-    t_re = time.perf_counter()
-    ctx.sync_records(rec_arr, rec_n)
-    torch.cuda.synchronize()
-    t_re = time.perf_counter() - t_re
+    t_re = None
+    if sstats["bricks"] <= 4_000_000:
+        t_re = time.perf_counter()
+        ctx.sync_records(rec_arr, rec_n)
+        torch.cuda.synchronize()
+        t_re = time.perf_counter() - t_re
     residency = {"scene_upload_ms": t_up * 1e3, "scene_upload_note": "first sync: includes the one-time pinned / device staging allocation",
+                 "scene_upload_GB_per_s": up_stats.bytes_uploaded / t_up / 1e9,
                  "bricks": int(up_stats.bricks_uploaded), "h2d_bytes": int(up_stats.bytes_uploaded),
-                 "reupload_ms": t_re * 1e3, "reupload_GB_per_s": up_stats.bytes_uploaded / t_re / 1e9, "device_bytes": int(up_stats.device_bytes)}
+                 "reupload_ms": None if t_re is None else t_re * 1e3, "reupload_GB_per_s": None if t_re is None else up_stats.bytes_uploaded / t_re / 1e9,
+                 "device_bytes": int(ctx.stats().device_bytes)}
     del rec_keep
     if args.bounces:
         from scenes import shading
@@ -471,10 +522,17 @@ def run_b200(args):
         ctx.set_blue_noise(shading.load_blue_noise()[0])
         d, t, _ = shading.load_sky()
         ctx.set_sky(d, t)
+    if args.wavefront is not None:
+        ctx.set_option("wavefront", args.wavefront)
 
     w, h = args.width, args.height
     npx = w * h
     rays_frame = npx * (1 + args.bounces)
+    # primary-only frames: 8 B/px (VRT_FRAME_COMPACT: albedo + normal, depth; the irradiance of such a frame is the constant 1.0 and is
+    # not moved) over NVLink and PCIe; the device-resident N = 1 frame keeps the reference's full 16 B/px tiles
+    compact = args.bounces == 0 and args.compact
+    xfer_px = 8 if compact else 16
+    xflag = capi.VRT_FRAME_COMPACT if compact else 0
     fb = torch.zeros(npx * 4, dtype=torch.int32, device="cuda")  # 16 B/px
     out_ptr = fb.data_ptr()
     # N > 1: pipelined tile gather over NVLink (vrt_render_gather).  Every rank renders its 8-pixel bands into its own
@@ -483,11 +541,11 @@ def run_b200(args):
     # display head per GPU), so no single NVLink port has to swallow 7/8 of every frame.
     owner_ptrs, local_fbs = None, None
     if world > 1:
-        handle, own_ptr = ctx.fb_export(npx * 16)
+        handle, own_ptr = ctx.fb_export(npx * xfer_px)
         handles = [None] * world
         dist.all_gather_object(handles, handle)
         owner_ptrs = [own_ptr if r == rank else ctx.fb_import(handles[r]) for r in range(world)]
-        local_fbs = [torch.zeros(npx * 4, dtype=torch.int32, device="cuda") for _ in range(capi.VRT_GATHER_DEPTH)]
+        local_fbs = [torch.zeros(npx * xfer_px // 4, dtype=torch.int32, device="cuda") for _ in range(capi.VRT_GATHER_DEPTH)]
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
     # a real (non-legacy) stream: handle 0 would mean "the context's own stream" to the C ABI and
     # torch events recorded on the legacy stream would not bracket the kernel
@@ -510,7 +568,7 @@ def run_b200(args):
         join_evs[0].record(stream)
         for s_ in streams[1:]:
             s_.wait_event(join_evs[0])
-    frame = bench_frame(w, h, args.bounces, part_index=rank, part_count=world, flags=capi.VRT_FRAME_PART_ROWS if world > 1 else 0)
+    frame = bench_frame(w, h, args.bounces, part_index=rank, part_count=world, flags=(capi.VRT_FRAME_PART_ROWS | xflag) if world > 1 else 0)
     frame_i = [0]
 
     # workload "edits" (BASELINE configs[4]): every frame is preceded by a batch of voxel edits whose dirty bricks are
@@ -552,6 +610,9 @@ def run_b200(args):
     ctx.set_option("metrics", 0)
     from voxelrt_b200 import partition
 
+    step()
+    torch.cuda.synchronize()
+    ctx_launches = int(ctx.stats().last_launches)  # kernels one step launches (1 for a primary frame; 1 + 3 per bounce level for a wavefront frame)
     my_primary = partition.pixels_of_rank(w, h, rank, world, rows=world > 1)
     alg_bytes = 8 * m.sector_fetches + 8 * m.cell_fetches + 9 * m.hits + 16 * my_primary
 
@@ -628,7 +689,7 @@ def run_b200(args):
     stepwise_ms = a.elapsed_time(b) / args.steps
     ctx.set_option("macro_steps", 1)
 
-    trace_only_ms, latency_ms, gather_ok = None, None, None
+    trace_only_ms, latency_ms, gather_ok, replicas_ok = None, None, None, None
     if world > 1:
         def local_step(k=0):  # the same split without the NVLink gather: every rank keeps its bands
             ctx.render_device(frame, local_fbs[k % len(local_fbs)].data_ptr(), None, streams[k % len(streams)].cuda_stream)
@@ -661,17 +722,32 @@ def run_b200(args):
         trace_only_ms, latency_ms = float(lt[0]), float(lt[1])
         # the frame assembled in rank 0's memory must equal the frame rank 0 renders alone
         dist.barrier()
-        if rank == 0 and edit_batches is None:
-            solo = torch.zeros(npx * 4, dtype=torch.int32, device="cuda")
-            ctx.render_device(bench_frame(w, h, args.bounces), solo.data_ptr(), None, stream.cuda_stream)
+        if rank == 0:
+            # (edits workload: every rank has applied the same edit batches, so rank 0 alone must still render the gathered frame)
+            solo = torch.zeros(npx * xfer_px // 4, dtype=torch.int32, device="cuda")
+            ctx.render_device(bench_frame(w, h, args.bounces, flags=xflag), solo.data_ptr(), None, stream.cuda_stream)
             torch.cuda.synchronize()
 
             class _DevPtr:  # view rank 0's exported framebuffer as a tensor
-                __cuda_array_interface__ = {"shape": (npx * 4,), "typestr": "<i4", "data": (int(owner_ptrs[0]), False), "version": 2}
+                __cuda_array_interface__ = {"shape": (npx * xfer_px // 4,), "typestr": "<i4", "data": (int(owner_ptrs[0]), False), "version": 2}
 
             gathered = torch.as_tensor(_DevPtr(), device="cuda")
             gather_ok = bool(torch.equal(solo, gathered))
         dist.barrier()
+        # replicas: the resident brickmap of every rank must be the same (same records, same allocator decisions) — compare a digest of
+        # the device state of a sample of sectors plus the allocator's statistics across the ranks
+        import hashlib as _hl
+
+        hsh = _hl.sha256()
+        keys = sorted(scene["sectors"].keys())
+        for key in keys[:: max(1, len(keys) // 64)][:64]:
+            m_, base_, bricks_, cells_ = ctx.read_sector(*key)
+            hsh.update(int(m_).to_bytes(8, "little") + int(base_).to_bytes(4, "little") + bricks_.tobytes() + cells_.tobytes())
+        st_ = ctx.stats()
+        hsh.update(f"{st_.resident_bricks},{st_.resident_sectors},{st_.free_ranges}".encode())
+        digests = [None] * world
+        dist.all_gather_object(digests, hsh.hexdigest())
+        replicas_ok = len(set(digests)) == 1
     tt = torch.tensor([total_ms, warm_ms], dtype=torch.float64, device="cuda")
     ab = torch.tensor([float(alg_bytes)], dtype=torch.float64, device="cuda")
     if world > 1:
@@ -680,12 +756,38 @@ def run_b200(args):
     ms_per_step = total_ms / args.steps
     value = rays_frame / (ms_per_step * 1e-3) / 1e6
 
-    # ---- e2e: host-buffer ABI call, pinned output, wall clock (rank-local partition) ----
-    host_out = torch.empty(npx * 4, dtype=torch.int32).pin_memory()
-    e2e_frame = bench_frame(w, h, args.bounces, part_index=rank, part_count=world, flags=capi.VRT_FRAME_PART_ROWS if world > 1 else 0)
+    # ---- e2e: the host-buffer ABI call (vrt_render), wall clock.  Frame constants in, G-buffer out into page-locked HOST memory.
+    # N = 1: the whole frame into a pinned buffer.  N > 1: ONE host frame shared by the ranks of the node (POSIX shared memory, page-locked
+    # in every process): each rank's vrt_render traces its 8-pixel bands and copies them to their place in that frame over its own PCIe
+    # link, so a complete frame exists on the host after every step and the copy bandwidth scales with the GPUs.
+    shm = None
+    if world == 1:
+        host_out = torch.empty(npx * xfer_px // 4, dtype=torch.int32).pin_memory()
+        host_ptr = host_out.data_ptr()
+    else:
+        from multiprocessing import shared_memory
 
-    def e2e_step():
-        st = ctx.lib.vrt_render(ctx.h, C.byref(e2e_frame), host_out.data_ptr(), None)
+        names = [None]
+        if rank == 0:
+            shm = shared_memory.SharedMemory(create=True, size=npx * xfer_px)
+            names[0] = shm.name
+        dist.broadcast_object_list(names, src=0)
+        if rank != 0:
+            shm = shared_memory.SharedMemory(name=names[0])
+        host_np = np.ndarray((npx * xfer_px // 4,), dtype=np.int32, buffer=shm.buf)
+        host_ptr = host_np.ctypes.data
+        rc = torch.cuda.cudart().cudaHostRegister(host_ptr, npx * xfer_px, 0)
+        if int(rc) != 0:
+            print(f"[bench] cudaHostRegister of the shared host frame failed ({rc}); copies go through pageable memory", file=sys.stderr)
+        dist.barrier()
+    e2e_frame = bench_frame(w, h, args.bounces, part_index=rank, part_count=world, flags=(capi.VRT_FRAME_PART_ROWS if world > 1 else 0) | xflag)
+
+    def e2e_step(fr=e2e_frame, ptr=None):
+        if edit_batches is not None:  # configs[4]: the frame's edits are part of the step
+            arr, keep, n = edit_batches[edit_i[0] % len(edit_batches)]
+            edit_i[0] += 1
+            ctx.sync_records(arr, n)
+        st = ctx.lib.vrt_render(ctx.h, C.byref(fr), host_ptr if ptr is None else ptr, None)
         if st != 0:
             ctx._chk(st)
 
@@ -696,12 +798,37 @@ def run_b200(args):
     t0 = time.perf_counter()
     for _ in range(args.steps):
         e2e_step()
+    if world > 1:
+        dist.barrier()  # the host frame is complete when every rank has delivered its bands
     e2e_s = time.perf_counter() - t0
     et = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(et, op=dist.ReduceOp.MAX)
     e2e_ms = float(et[0]) * 1000.0 / args.steps
     e2e_val = rays_frame / (e2e_ms * 1e-3) / 1e6
+    e2e_host_frame_ok = None
+    if world > 1:
+        if rank == 0 and edit_batches is None:  # the frame the ranks assembled on the host == the frame rank 0 delivers alone
+            solo_host = torch.empty(npx * xfer_px // 4, dtype=torch.int32).pin_memory()
+            e2e_step(bench_frame(w, h, args.bounces, flags=xflag), solo_host.data_ptr())
+            e2e_host_frame_ok = bool(np.array_equal(solo_host.numpy(), host_np))
+        dist.barrier()
+        torch.cuda.cudart().cudaHostUnregister(host_ptr)
+        del host_np
+        shm.close()
+        if rank == 0:
+            shm.unlink()
+    # the reference's full 16 B/px tile framebuffer through the same call, for comparison (N = 1)
+    e2e_full_val = None
+    if world == 1 and compact:
+        host_full = torch.empty(npx * 4, dtype=torch.int32).pin_memory()
+        full_frame = bench_frame(w, h, args.bounces)
+        for _ in range(2):
+            e2e_step(full_frame, host_full.data_ptr())
+        t0 = time.perf_counter()
+        for _ in range(max(3, args.steps // 2)):
+            e2e_step(full_frame, host_full.data_ptr())
+        e2e_full_val = rays_frame / ((time.perf_counter() - t0) / max(3, args.steps // 2)) / 1e6
 
     if rank == 0:
         peak, peak_src = _peaks()
@@ -729,11 +856,16 @@ def run_b200(args):
                 "value": e2e_val,
                 "unit": "Mrays/s",
                 "ms_per_step": e2e_ms,
-                "h2d_bytes_per_step": C.sizeof(capi.VrtFrame),
-                "d2h_bytes_per_step": npx * 16,
-                "api": "vrt_render (host buffers, pinned output)" + ("" if world == 1 else "; every rank delivers its own bands of the frame into its host buffer"),
+                "h2d_bytes_per_step": C.sizeof(capi.VrtFrame) * world + (int(timed_edit_stats["bytes"] / max(1, timed_edit_stats["syncs"])) * world if edit_batches is not None else 0),
+                "d2h_bytes_per_step": npx * xfer_px,
+                "payload": ("VRT_FRAME_COMPACT, 8 B/px: albedo + normal and depth; the irradiance words of a primary-only frame are the constant 1.0 "
+                            "(CpuRenderer.cpp:379-381) and are not moved" if compact else "the reference's 16 B/px tile framebuffer"),
+                "value_full_16B_per_px": e2e_full_val,
+                "api": "vrt_render (host buffers, page-locked output)" + ("" if world == 1 else
+                       "; ONE host frame in shared page-locked memory, every rank delivers its bands into it over its own PCIe link"),
+                "host_frame_equal_to_single_gpu_frame": e2e_host_frame_ok,
             },
-            "gpu_launches": args.steps + timed_edit_stats["launches"],
+            "gpu_launches": args.steps * ctx_launches + timed_edit_stats["launches"],
             "residency": residency,
             "edits": None if edit_batches is None else {
                 "mode": args.edit_mode,
@@ -746,26 +878,17 @@ def run_b200(args):
             },
             "gather": None if world == 1 else {
                 "how": "vrt_render_gather: 8-pixel bands rendered locally, one strided D2D copy per frame into the presenting GPU's framebuffer "
-                       "(CUDA IPC over NVLink) on the copy stream, overlapped with the next frame; presenting GPU = frame % N",
+                       "(CUDA IPC over NVLink; copy engines, not the SMs) on a copy stream, overlapped with the next frames; presenting GPU = frame % N; "
+                       "NCCL carries only the control plane (handles, barriers, timing reductions)",
                 "verified_equal_to_single_gpu_frame": gather_ok,
+                "replicas_identical": replicas_ok,
+                "payload_bytes_per_pixel": xfer_px,
                 "value_trace_only_warm_l2": rays_frame / (trace_only_ms * 1e-3) / 1e6,
                 "value_frame_latency_flushed_l2_owner0": rays_frame / (latency_ms * 1e-3) / 1e6,
                 "frame_latency_ms": latency_ms,
-                "bytes_over_nvlink_per_frame": npx * 16 * (world - 1) // world,
+                "bytes_over_nvlink_per_frame": npx * xfer_px * (world - 1) // world,
             },
-            "roofline": {
-                "bound": "hbm",
-                "kernel": "vrt::k_render<false,%s,%s>" % ("true" if args.bounces == 0 else "false", "true" if world > 1 else "false"),
-                "achieved": achieved,
-                "peak": peak,
-                "unit": "GB/s",
-                "frac": achieved / peak,
-                "peak_source": peak_src,
-                "algorithmic_bytes_per_launch": int(alg_bytes),
-                "bytes_per_ray": alg_bytes / max(1, my_primary * (1 + args.bounces)),
-                "traffic": _traffic(args),
-                "counters": {"rays": m.rays, "iters": m.iters, "sector_fetches": m.sector_fetches, "cell_fetches": m.cell_fetches, "hits": m.hits, "capped": m.capped},
-            },
+            "roofline": roofline_block(args, world, alg_bytes, ms_per_step, peak, peak_src, m, my_primary, ctx_launches),
         }
         if args.present and n_gpus == 1:
             # the step after the path; reported next to the headline, never allowed to take the bench line down with it
@@ -812,6 +935,10 @@ def main():
     ap.add_argument("--present-passes", type=int, default=5, help="GBuffer::NumDenoiserPasses for --present (0..5)")
     ap.add_argument("--scene-file", default=None, help="workload 'file': a cvox 0004 voxel-map file written by the reference (or by scenes/cvox.py)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--wavefront", type=int, default=None, choices=[0, 1, 2], help="frames with bounces: 0 one thread per pixel, 1 wavefront passes, 2 self-tuning (library default)")
+    ap.add_argument("--no-compact", dest="compact", action="store_false", default=True, help="move the full 16 B/px tiles of primary-only frames over NVLink / PCIe instead of the 8 B/px that carry information")
+    ap.add_argument("--large-y", type=int, default=24, help="workload 'large': sectors along y (24 with --large-shift 512 = 10 GB of bricks)")
+    ap.add_argument("--large-shift", type=int, default=512, help="workload 'large': voxels the terrain is raised by (solid rock below the surface)")
     args = ap.parse_args()
     _SCENE_FILE[0] = args.scene_file
     _, dw, dh, db = WORKLOADS[args.workload]

@@ -167,6 +167,47 @@ def terrain_fastnoise(nx=24, ny=7, nz=24, cache=True):
     return scene
 
 
+def terrain_fastnoise_big(nx=128, ny=24, nz=128, y_shift=512, shared_dir=None, is_writer=True, wait=None):
+    """BASELINE configs[3]: the reference's terrain over nx x ny x nz sectors, moved up by y_shift voxels (everything below the surface is
+    solid, so the shift sets the byte count: 128 x 24 x 128 sectors with y_shift = 512 hold ~20 M bricks = 10 GB of voxels).  Generated by
+    scenes/terrain_gen.c (OpenMP over sectors, FastNoise2 from the reference's vendored tree) into ONE array with a 64-brick block per sector.
+    shared_dir (e.g. /dev/shm): the writer process creates the arrays there as files and every other process of the node maps them
+    read-only (`wait()` must return once the writer is done) — eight ranks then share one copy of the 13 GB block array."""
+    lib, node = _fastnoise()
+    gen = C.CDLL(str(HERE / "_ref" / "libterrain_gen.so"))
+    gen.terrain_gen_sectors.restype = C.c_uint64
+    gen.terrain_gen_sectors.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int]
+    n = nx * ny * nz
+    tag = f"vrt_terrain_{nx}x{ny}x{nz}_s{y_shift}"
+    if shared_dir is not None:
+        mpath, bpath = Path(shared_dir) / f"{tag}.masks", Path(shared_dir) / f"{tag}.bricks"
+        if is_writer:
+            masks = np.lib.format.open_memmap(mpath, mode="w+", dtype=np.uint64, shape=(n,))
+            bricks = np.lib.format.open_memmap(bpath, mode="w+", dtype=np.uint8, shape=(n * 64, 512))
+        else:
+            wait()
+            masks = np.load(mpath, mmap_mode="r")
+            bricks = np.load(bpath, mmap_mode="r")
+    else:
+        masks = np.zeros(n, np.uint64)
+        bricks = np.empty((n * 64, 512), np.uint8)  # (pages of never-written blocks are never touched)
+    if shared_dir is None or is_writer:
+        fn_ptr = C.cast(lib.fnGenUniformGrid3D, C.c_void_p)
+        gen.terrain_gen_sectors(fn_ptr, node, nx, ny, nz, int(y_shift), masks.ctypes.data, bricks.ctypes.data, 0)
+        if shared_dir is not None:
+            masks.flush()
+            bricks.flush()
+            if wait is not None:
+                wait()
+    sectors = {}
+    nz_idx = np.nonzero(masks)[0]
+    pop = np.array([bin(int(m)).count("1") for m in masks[nz_idx]], np.int64)
+    for i, k in zip(nz_idx.tolist(), pop.tolist()):
+        x, z, y = i % nx, (i // nx) % nz, i // (nx * nz)
+        sectors[(x, y, z)] = (int(masks[i]), bricks[i * 64 : i * 64 + k])
+    return {"sectors": sectors, "palette": reference_palette(), "name": f"FastNoise2 terrain {nx}x{ny}x{nz} sectors raised by {y_shift} voxels"}
+
+
 # ---------------------------------------------------------------------------------------------
 # integer-hash terrain: reproducible bit for bit on any host
 # ---------------------------------------------------------------------------------------------
@@ -259,7 +300,7 @@ def scene_records(scene, dirty_all=True):
 
 def scene_stats(scene):
     nb = sum(bin(m).count("1") for m, _ in scene["sectors"].values())
-    solid = sum(int(np.count_nonzero(b)) for _, b in scene["sectors"].values())
+    solid = sum(int(np.count_nonzero(b)) for _, b in scene["sectors"].values()) if nb <= 4_000_000 else None  # (10 GB scenes: not worth a pass)
     return {"sectors": len(scene["sectors"]), "bricks": nb, "solid_voxels": solid, "voxel_bytes": nb * 512, "cell_mask_bytes": nb * 64}
 
 

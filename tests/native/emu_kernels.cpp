@@ -176,7 +176,7 @@ EMU_API int emu_wave_frame(const EmuScene* e, const VrtFrame* f, const uint8_t* 
         TraceArgs A{B.rays, B.n_rays + level, B.head + level, B.hits, F.max_iters, 24u, B.n_generic + level, B.capacity};
 #pragma omp parallel for schedule(dynamic, 1)
         for (int64_t w = 0; w < (int64_t)trace_warps; w++)
-            run_warp_lockstep((unsigned)(w / wpb), VRT_RENDER_THREADS, (unsigned)(w % wpb) * 32u, [&](int) { k_wave_trace(S, F.W, A); });
+            run_warp_lockstep((unsigned)(w / wpb), VRT_RENDER_THREADS, (unsigned)(w % wpb) * 32u, [&](int) { k_wave_trace<8>(S, F.W, A); });
         {
             gridDim.x = 1, blockDim.x = 128, blockIdx.x = 0;
             for (unsigned t = 0; t < 128; t++) {

@@ -90,6 +90,9 @@ struct VrtContext {
     // run one form each between CUDA events, and the faster one is kept.  0 / 1 force a form.
     int wave_on = 2;
     int trace_refill = VRT_TRACE_REFILL;  // k_wave_trace: lanes in flight below which a warp refills (tuning knob, "trace_refill")
+    int trace_ctas = VRT_TRACE_CTAS;      // k_wave_trace: resident CTAs per SM it is compiled for (8 / 10 / 12, "trace_ctas")
+    cudaStream_t wave_side_stream = nullptr;  // k_wave_trace_generic runs beside k_wave_trace
+    cudaEvent_t ev_wave_fork = nullptr, ev_wave_join = nullptr;
     int wave_choice = -1;         // -1 undecided, 0 per-pixel, 1 wavefront
     int wave_phase = 0;           // 0: time per-pixel next, 1: time wavefront next, 2: waiting for the events
     uint64_t wave_key = 0;        // (bounces, width, height, scene epoch) the decision was taken for
@@ -372,7 +375,8 @@ int launch_render(VrtContext* ctx, const VrtFrame* f, void* d_out, VrtHit* d_aux
         if (rows) k_wave_primary<true><<<blocks, VRT_RENDER_THREADS, 0, s>>>(S, F, B);
         else k_wave_primary<false><<<blocks, VRT_RENDER_THREADS, 0, s>>>(S, F, B);
         ctx->stats.last_launches += 1;
-        const unsigned grid = (unsigned)std::min<size_t>((cap + VRT_RENDER_THREADS - 1) / VRT_RENDER_THREADS, (size_t)ctx->sm_count * VRT_TRACE_CTAS);
+        const int ctas = ctx->trace_ctas >= 12 ? 12 : (ctx->trace_ctas >= 10 ? 10 : 8);
+        const unsigned grid = (unsigned)std::min<size_t>((cap + VRT_RENDER_THREADS - 1) / VRT_RENDER_THREADS, (size_t)ctx->sm_count * ctas);
         for (uint32_t level = 1; level <= F.bounces; level++) {
             TraceArgs A;
             A.rays = B.rays;
@@ -383,8 +387,15 @@ int launch_render(VrtContext* ctx, const VrtFrame* f, void* d_out, VrtHit* d_aux
             A.refill = (uint32_t)ctx->trace_refill;
             A.n_generic = B.n_generic + level;
             A.capacity = B.capacity;
-            k_wave_trace<<<grid, VRT_RENDER_THREADS, 0, s>>>(S, F.W, A);
-            k_wave_trace_generic<<<(unsigned)ctx->sm_count, 128, 0, s>>>(S, F.W, A);
+            // the few generic rays of the level run beside the trace pass on a second stream (long serial chains, few warps)
+            CU(cudaEventRecord(ctx->ev_wave_fork, s));
+            CU(cudaStreamWaitEvent(ctx->wave_side_stream, ctx->ev_wave_fork, 0));
+            k_wave_trace_generic<<<(unsigned)ctx->sm_count * 4u, 32, 0, ctx->wave_side_stream>>>(S, F.W, A);
+            CU(cudaEventRecord(ctx->ev_wave_join, ctx->wave_side_stream));
+            if (ctas == 12) k_wave_trace<12><<<grid, VRT_RENDER_THREADS, 0, s>>>(S, F.W, A);
+            else if (ctas == 10) k_wave_trace<10><<<grid, VRT_RENDER_THREADS, 0, s>>>(S, F.W, A);
+            else k_wave_trace<8><<<grid, VRT_RENDER_THREADS, 0, s>>>(S, F.W, A);
+            CU(cudaStreamWaitEvent(s, ctx->ev_wave_join, 0));
             if (rows) k_wave_shade<true><<<blocks, VRT_RENDER_THREADS, 0, s>>>(S, F, B, level);
             else k_wave_shade<false><<<blocks, VRT_RENDER_THREADS, 0, s>>>(S, F, B, level);
             ctx->stats.last_launches += 3;
@@ -487,6 +498,9 @@ extern "C" int vrt_create(const VrtConfig* cfg, VrtContext** out) {
     CUB(cudaEventCreateWithFlags(&c->ev_sync, cudaEventDisableTiming));
     for (auto& e : c->ev_render) CUB(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     CUB(cudaEventCreateWithFlags(&c->ev_wave, cudaEventDisableTiming));
+    CUB(cudaStreamCreateWithFlags(&c->wave_side_stream, cudaStreamNonBlocking));
+    CUB(cudaEventCreateWithFlags(&c->ev_wave_fork, cudaEventDisableTiming));
+    CUB(cudaEventCreateWithFlags(&c->ev_wave_join, cudaEventDisableTiming));
     for (auto& e : c->ev_tune) CUB(cudaEventCreate(&e));
     for (auto& gs : c->gather_streams) CUB(cudaStreamCreateWithFlags(&gs, cudaStreamNonBlocking));
     for (auto& e : c->ev_gather_src) CUB(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
@@ -529,6 +543,9 @@ extern "C" void vrt_destroy(VrtContext* ctx) {
     for (void* p : ctx->imported) cudaIpcCloseMemHandle(p);
     for (void* p : ctx->exported) cudaFree(p);
     if (ctx->ev_wave) cudaEventDestroy(ctx->ev_wave);
+    if (ctx->ev_wave_fork) cudaEventDestroy(ctx->ev_wave_fork);
+    if (ctx->ev_wave_join) cudaEventDestroy(ctx->ev_wave_join);
+    if (ctx->wave_side_stream) cudaStreamDestroy(ctx->wave_side_stream);
     for (auto& e : ctx->ev_tune) if (e) cudaEventDestroy(e);
     DeviceBuffer* bufs[] = {&ctx->d_wave_rays, &ctx->d_wave_hits, &ctx->d_wave_path, &ctx->d_wave_n, &ctx->d_stage, &ctx->d_rays_o, &ctx->d_rays_d, &ctx->d_hits, &ctx->d_fb,
                             &ctx->d_aux,   &ctx->d_q_o,    &ctx->d_q_d,    &ctx->d_q_out};
@@ -585,6 +602,7 @@ extern "C" int vrt_set_option(VrtContext* ctx, const char* name, int64_t value) 
         if (value != 0) return fail(ctx, VRT_ERR_UNSUPPORTED, "compact_bounces was removed; see the \"wavefront\" option");
     }
     else if (!strcmp(name, "wavefront")) ctx->wave_on = (int)value;
+    else if (!strcmp(name, "trace_ctas")) ctx->trace_ctas = (int)value;
     else if (!strcmp(name, "trace_refill")) ctx->trace_refill = (int)std::min<int64_t>(32, std::max<int64_t>(1, value));
     else return fail(ctx, VRT_ERR_INVALID, std::string("unknown option ") + name);
     return VRT_OK;

@@ -174,8 +174,11 @@ struct TraceArgs {
     const uint32_t* n_generic;  // k_wave_trace_generic: rays queued from the end of `rays`
     uint32_t capacity;
 };
-__global__ void __launch_bounds__(VRT_RENDER_THREADS, VRT_TRACE_CTAS) k_wave_trace(const __grid_constant__ DevScene S, const __grid_constant__ RayFrame W,
-                                                                                   const __grid_constant__ TraceArgs A) {
+// CTAS = resident CTAs per SM the kernel is compiled for (8: <= 64 registers, 10: <= 48, 12: <= 40): the loop is latency-bound (two dependent
+// loads per trip behind ~100 dependent ALU instructions), so warps in flight matter more than a few registers
+template <int CTAS>
+__global__ void __launch_bounds__(VRT_RENDER_THREADS, CTAS) k_wave_trace(const __grid_constant__ DevScene S, const __grid_constant__ RayFrame W,
+                                                                         const __grid_constant__ TraceArgs A) {
     const uint32_t n = *A.n;
     const unsigned lane = threadIdx.x & 31u, lt_mask = (1u << lane) - 1u;
     // loop constants pinned in registers (ptxas otherwise re-loads kernel parameters from the constant bank every trip: see cast_loop_fast)
