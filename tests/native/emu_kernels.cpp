@@ -122,6 +122,10 @@ EMU_API int emu_render_kernel(const EmuScene* e, const VrtFrame* f, const uint8_
     F.out = out;
     if (!fill_frame_partition(F, f, row0, row1)) return -1;
     if (F.n_work <= F.work_offset) return 0;
+    static int order = 0;  // alternate the two grid orders of launch_render ("tile_order"): results must not depend on it
+    order ^= 1;
+    F.work_add = order ? F.n_work - 1u : F.work_offset;
+    F.work_mul = order ? -1 : 1;
     const unsigned wpb = VRT_RENDER_THREADS / 32;
     const int64_t blocks = (F.n_work - F.work_offset + wpb - 1) / wpb;
     const bool rows = (F.flags & VRT_FRAME_PART_ROWS) != 0u, primary = F.bounces == 0;

@@ -90,6 +90,7 @@ struct VrtContext {
     // run one form each between CUDA events, and the faster one is kept.  0 / 1 force a form.
     int wave_on = 2;
     int trace_refill = VRT_TRACE_REFILL;  // k_wave_trace: lanes in flight below which a warp refills (tuning knob, "trace_refill")
+    int tile_order = 1;  // k_render: 0 top-to-bottom, 1 bottom-to-top (see FrameParams::work_add; "tile_order")
     int trace_ctas = VRT_TRACE_CTAS;      // k_wave_trace: resident CTAs per SM it is compiled for (8 / 10 / 12, "trace_ctas")
     cudaStream_t wave_side_stream = nullptr;  // k_wave_trace_generic runs beside k_wave_trace
     cudaEvent_t ev_wave_fork = nullptr, ev_wave_join = nullptr;
@@ -305,6 +306,8 @@ int launch_render(VrtContext* ctx, const VrtFrame* f, void* d_out, VrtHit* d_aux
 
     if (!fill_frame_partition(F, f, row0, row1)) return fail(ctx, VRT_ERR_INVALID, "frame too large");
     if (F.n_work <= F.work_offset) return VRT_OK;
+    F.work_add = ctx->tile_order ? F.n_work - 1u : F.work_offset;
+    F.work_mul = ctx->tile_order ? -1 : 1;
     DevScene S = dev_scene(ctx);
     const unsigned wpb = VRT_RENDER_THREADS / 32;
     unsigned blocks = (F.n_work - F.work_offset + wpb - 1) / wpb;
@@ -603,6 +606,7 @@ extern "C" int vrt_set_option(VrtContext* ctx, const char* name, int64_t value) 
     }
     else if (!strcmp(name, "wavefront")) ctx->wave_on = (int)value;
     else if (!strcmp(name, "trace_ctas")) ctx->trace_ctas = (int)value;
+    else if (!strcmp(name, "tile_order")) ctx->tile_order = value != 0;
     else if (!strcmp(name, "trace_refill")) ctx->trace_refill = (int)std::min<int64_t>(32, std::max<int64_t>(1, value));
     else return fail(ctx, VRT_ERR_INVALID, std::string("unknown option ") + name);
     return VRT_OK;
