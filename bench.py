@@ -598,7 +598,10 @@ def run_b200(args):
         if world > 1:
             i = frame_i[0]
             frame_i[0] += 1
-            ctx.render_gather(frame, local_fbs[i % capi.VRT_GATHER_DEPTH].data_ptr(), owner_ptrs[i % world], streams[i % len(streams)].cuda_stream)
+            owner = {"rotate": i % world, "self": rank, "zero": 0}[os.environ.get("VRT_BENCH_OWNER", "rotate")]
+            # the presenting rank renders its own bands straight into its framebuffer (no local copy)
+            local_ptr = owner_ptrs[owner] if owner == rank else local_fbs[i % capi.VRT_GATHER_DEPTH].data_ptr()
+            ctx.render_gather(frame, local_ptr, owner_ptrs[owner], streams[i % len(streams)].cuda_stream)
         else:
             ctx.render_device(frame, out_ptr, None, stream.cuda_stream)
 
@@ -774,6 +777,12 @@ def run_b200(args):
         dist.broadcast_object_list(names, src=0)
         if rank != 0:
             shm = shared_memory.SharedMemory(name=names[0])
+            try:  # (rank 0 owns and unlinks the segment; keep the other ranks' resource trackers from complaining about it at exit)
+                from multiprocessing import resource_tracker
+
+                resource_tracker.unregister(shm._name, "shared_memory")
+            except Exception:
+                pass
         host_np = np.ndarray((npx * xfer_px // 4,), dtype=np.int32, buffer=shm.buf)
         host_ptr = host_np.ctypes.data
         rc = torch.cuda.cudart().cudaHostRegister(host_ptr, npx * xfer_px, 0)

@@ -206,63 +206,62 @@ __global__ void __launch_bounds__(VRT_RENDER_THREADS, CTAS) k_wave_trace(const _
     const uint32_t refill = A.refill + (uint32_t)opaque0;
     LeanRay r;
     r.ox = r.oy = r.oz = r.dx = r.dy = r.dz = r.ix = r.iy = r.iz = r.tx = r.ty = r.tz = r.cx = r.cy = r.cz = r.sdx = r.sdy = r.sdz = 0.0f;
-    r.nmx = r.nmy = r.nmz = r.qx = r.qy = r.qz = 0;
-    uint32_t left = 0, budget = 0, slot = 0, hit_slot = 0;
+    r.nmx = r.nmy = r.nmz = 0;
+    uint32_t left = 0, budget = 0, slot = 0, hit_at = 0;
     // lane state: 0 idle, 1 a ray is in flight, 2..4 it has ended (2 solid voxel, 3 left the view, 4 out of trips) and its record is not written yet
     uint32_t state = 0;
     uint32_t more = 1;  // the queue may still hold rays (warp-uniform)
+    unsigned act = 0u;  // lanes with a ray in flight
     for (;;) {
-        unsigned act = __ballot_sync(0xFFFFFFFFu, state == 1u);
-        if (act == 0u || (more && (uint32_t)__popc(act) < refill)) {
-            if (state >= 2u) {  // RayCast epilogue (CpuRenderer.cpp:204-223) of the ray that ended in this lane
-                if (budget == 1u && state == 4u) state = 3u;  // the second trip of a NaN ray: currPos = NaN -> voxel INT_MIN -> outside
-                uint32_t flags = HITREC_CAST | normal_code(r.sdx, r.sdy, r.sdz, r.dx, r.dy, r.dz);
-                uint32_t material = 0u;  // (a miss's material is never used at bounce levels >= 1: RenderRow replaces it by the sky, :363-368)
-                if (state == 2u) {
-                    const uint32_t vi = ((uint32_t)r.qx & 7u) | (((uint32_t)r.qz & 7u) << 3) | (((uint32_t)r.qy & 7u) << 6);
-                    material = ldg_u2(S.palette + __ldg(S.voxels + (size_t)hit_slot * 512u + vi)).x;  // :120-132
-                    flags |= HITREC_HIT;
-                } else if (state == 4u) flags |= HITREC_CAPPED;
-                if (left == budget && state != 4u) flags |= HITREC_FIRST;  // no completed step
-                store_hit_rec(A.hits + slot, r.cx, r.cy, r.cz, material, r.dx, r.dy, r.dz, flags);
-                state = 0u;
+        // ---- epilogue of the rays that ended, then refill: entered with fewer than `refill` rays in flight (none, once the queue is empty)
+        if (state >= 2u) {  // RayCast epilogue (CpuRenderer.cpp:204-223) of the ray that ended in this lane
+            if (budget == 1u && state == 4u) state = 3u;  // the second trip of a NaN ray: currPos = NaN -> voxel INT_MIN -> outside
+            uint32_t flags = HITREC_CAST | normal_code(r.sdx, r.sdy, r.sdz, r.dx, r.dy, r.dz);
+            uint32_t material = 0u;  // (a miss's material is never used at bounce levels >= 1: RenderRow replaces it by the sky, :363-368)
+            if (state == 2u) {
+                material = ldg_u2(S.palette + __ldg(S.voxels + hit_at)).x;  // :120-132
+                flags |= HITREC_HIT;
+            } else if (state == 4u) flags |= HITREC_CAPPED;
+            if (left == budget && state != 4u) flags |= HITREC_FIRST;  // no completed step
+            store_hit_rec(A.hits + slot, r.cx, r.cy, r.cz, material, r.dx, r.dy, r.dz, flags);
+            state = 0u;
+        }
+        if (more) {
+            const unsigned want = ~act;
+            const uint32_t cnt = (uint32_t)__popc(want);
+            const int leader = __ffs((int)want) - 1;
+            uint32_t base = 0;
+            if ((int)lane == leader) base = atomicAdd(A.head, cnt);
+            base = __shfl_sync(0xFFFFFFFFu, base, leader);
+            more = base + cnt < n ? 1u : 0u;
+            const uint32_t idx = base + (uint32_t)__popc(want & lt_mask);
+            if (state == 0u && idx < n) {
+                const float4* rp = reinterpret_cast<const float4*>(A.rays + idx);
+                const float4 r0 = __ldg(rp), r1 = __ldg(rp + 1);
+                r.ox = r0.x, r.oy = r0.y, r.oz = r0.z, r.dx = r1.x, r.dy = r1.y, r.dz = r1.z;
+                slot = __float_as_uint(r0.w);
+                r.ix = rcp_rn_normal(r.dx), r.iy = rcp_rn_normal(r.dy), r.iz = rcp_rn_normal(r.dz);  // :173 (== IEEE 1/x for fast rays; NaN stays NaN)
+                r.tx = __fmul_rn(__fsub_rn(r.dx < 0.0f ? 0.0f : 1.0f, r.ox), r.ix);                  // :175-179
+                r.ty = __fmul_rn(__fsub_rn(r.dy < 0.0f ? 0.0f : 1.0f, r.oy), r.iy);
+                r.tz = __fmul_rn(__fsub_rn(r.dz < 0.0f ? 0.0f : 1.0f, r.oz), r.iz);
+                r.nmx = __float_as_int(r.dx) >> 31, r.nmy = __float_as_int(r.dy) >> 31, r.nmz = __float_as_int(r.dz) >> 31;
+                r.cx = r.ox, r.cy = r.oy, r.cz = r.oz;  // :181
+                r.sdx = r.sdy = r.sdz = 0.0f;           // :180
+                budget = left = __float_as_uint(r1.w) == RAY_NAN ? 1u : A.max_iters;
+                state = 1u;
             }
-            if (more) {
-                const unsigned want = ~act;
-                const uint32_t cnt = (uint32_t)__popc(want);
-                const int leader = __ffs((int)want) - 1;
-                uint32_t base = 0;
-                if ((int)lane == leader) base = atomicAdd(A.head, cnt);
-                base = __shfl_sync(0xFFFFFFFFu, base, leader);
-                more = base + cnt < n ? 1u : 0u;
-                const uint32_t idx = base + (uint32_t)__popc(want & lt_mask);
-                if (state == 0u && idx < n) {
-                    const float4* rp = reinterpret_cast<const float4*>(A.rays + idx);
-                    const float4 r0 = __ldg(rp), r1 = __ldg(rp + 1);
-                    r.ox = r0.x, r.oy = r0.y, r.oz = r0.z, r.dx = r1.x, r.dy = r1.y, r.dz = r1.z;
-                    slot = __float_as_uint(r0.w);
-                    r.ix = rcp_rn_normal(r.dx), r.iy = rcp_rn_normal(r.dy), r.iz = rcp_rn_normal(r.dz);  // :173 (== IEEE 1/x for fast rays; NaN stays NaN)
-                    r.tx = __fmul_rn(__fsub_rn(r.dx < 0.0f ? 0.0f : 1.0f, r.ox), r.ix);                  // :175-179
-                    r.ty = __fmul_rn(__fsub_rn(r.dy < 0.0f ? 0.0f : 1.0f, r.oy), r.iy);
-                    r.tz = __fmul_rn(__fsub_rn(r.dz < 0.0f ? 0.0f : 1.0f, r.oz), r.iz);
-                    r.nmx = __float_as_int(r.dx) >> 31, r.nmy = __float_as_int(r.dy) >> 31, r.nmz = __float_as_int(r.dz) >> 31;
-                    r.cx = r.ox, r.cy = r.oy, r.cz = r.oz;  // :181
-                    r.sdx = r.sdy = r.sdz = 0.0f;           // :180
-                    budget = left = __float_as_uint(r1.w) == RAY_NAN ? 1u : A.max_iters;
-                    state = 1u;
-                }
-            }
+        }
+        act = __ballot_sync(0xFFFFFFFFu, state == 1u);
+        if (act == 0u) {
+            if (!more) break;
+            continue;
+        }
+        // ---- the trip loop: every lane with a ray in flight takes one trip per turn, until too few are left
+        const uint32_t need = more ? refill : 1u;
+        do {
+            if (state == 1u) lean_trip(C, r, state, left, hit_at);
             act = __ballot_sync(0xFFFFFFFFu, state == 1u);
-            if (act == 0u) {
-                if (!more) break;
-                continue;
-            }
-        }
-        if (state == 1u) {
-            const int st = lean_trip(C, r, hit_slot);
-            if (st != 0) state = 1u + (uint32_t)st;
-            else if (--left == 0u) state = 4u;
-        }
+        } while ((uint32_t)__popc(act) >= need);
     }
 }
 
