@@ -159,6 +159,10 @@ EMU_API int emu_wave_frame(const EmuScene* e, const VrtFrame* f, const uint8_t* 
     F.aux = aux;
     if (!fill_frame_partition(F, f, 0, 0)) return -1;
     if (F.n_work <= F.work_offset || F.bounces == 0) return 0;
+    static int wave_order = 0;  // both grid orders of the camera pass ("tile_order")
+    wave_order ^= 1;
+    F.work_add = wave_order ? F.n_work - 1u : F.work_offset;
+    F.work_mul = wave_order ? -1 : 1;
     const unsigned wpb = VRT_RENDER_THREADS / 32;
     const int64_t warps = (int64_t)((F.n_work - F.work_offset + wpb - 1) / wpb) * wpb;
     const bool rows = (F.flags & VRT_FRAME_PART_ROWS) != 0u;

@@ -130,8 +130,9 @@ __global__ void __launch_bounds__(VRT_RENDER_THREADS, VRT_RENDER_CTAS(PRIMARY &&
 template <bool ROWS>
 __global__ void __launch_bounds__(VRT_RENDER_THREADS, VRT_RENDER_CTAS(false)) k_wave_primary(const __grid_constant__ DevScene S, const __grid_constant__ FrameParams F,
                                                                                              const __grid_constant__ WaveBuffers B) {
-    const uint32_t work = F.work_offset + blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (work >= F.n_work) return;  // warp-uniform
+    const uint32_t g = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (g >= F.n_work - F.work_offset) return;  // warp-uniform
+    const uint32_t work = F.work_add + (uint32_t)(F.work_mul * (int32_t)g);  // (grid order: see FrameParams::work_add)
     uint32_t x0 = 0, y0 = 0;
     const bool in_frame = warp_tile_origin<ROWS>(F, work, x0, y0);  // warp-uniform; the warp stays for the votes
     const uint32_t lane = threadIdx.x & 31u;
