@@ -256,21 +256,21 @@ VRT_API int vrt_set_sky(VrtContext* ctx, const VrtSkyDesc* desc, const uint32_t*
 VRT_API int vrt_render(VrtContext* ctx, const VrtFrame* frame, void* out, VrtHit* aux_hits);
 VRT_API int vrt_render_device(VrtContext* ctx, const VrtFrame* frame, void* d_out, VrtHit* d_aux_hits, void* stream);
 
-/* ---- multi-GPU tile gather over NVLink (no reference counterpart) ------------------ */
-/* One process per GPU.  The presenting rank exports its framebuffer as a CUDA IPC handle;
- * every other rank opens it and its render kernel stores finished tiles straight into the
- * owner's memory (peer stores over NVLink).  64-byte opaque handle. */
+/* ---- multi-GPU band gather over NVLink (no reference counterpart) ------------------ */
+/* One process per GPU, the brickmap replicated, the screen split into 8-pixel bands (VRT_FRAME_PART_ROWS).  The presenting rank exports
+ * its framebuffer as a CUDA IPC handle (vrt_fb_export) and every other rank opens it (vrt_fb_import).  The exchange is done by the COPY
+ * ENGINES, not by stores of the frame kernel: vrt_render_gather renders this rank's bands into its OWN device buffer d_local_fb on
+ * `stream`, then copies exactly those bands to the same offsets of d_owner_fb (the presenting rank's framebuffer, or a local pointer) on a
+ * copy stream of the context — one strided device-to-device copy over NVLink — while the SMs trace the next frame.  (Why not peer
+ * stores from the kernel's epilogue, as SURVEY 8e sketched: with all ranks in step, every rank would write into ONE GPU during a frame —
+ * 7/8 of the frame through one 770 GB/s ingress, longer than the frame takes to trace — and the stores' back-pressure stalls the tracing
+ * warps; the copy engines decouple the two)  The call returns at once; a d_local_fb may be reused every
+ * VRT_GATHER_DEPTH-th call (the call waits for the copy issued that many calls ago), the owner may change from frame to frame, and when
+ * d_local_fb == d_owner_fb (the presenting rank renders its own bands in place) no copy is issued.  With VRT_FRAME_COMPACT the bands are
+ * 8 B/px.  vrt_gather_wait makes `stream` wait for every gather issued so far.  64-byte opaque handle. */
 VRT_API int vrt_fb_export(VrtContext* ctx, uint64_t bytes, uint8_t handle_out[64], void** d_ptr_out);
 VRT_API int vrt_fb_import(VrtContext* ctx, const uint8_t handle[64], void** d_ptr_out);
 VRT_API int vrt_fb_release(VrtContext* ctx, void* d_ptr);
-/* Pipelined form of the same exchange: renders this rank's bands (frame->flags must carry
- * VRT_FRAME_PART_ROWS, tile layout) into its OWN device buffer d_local_fb on `stream`, then copies
- * exactly those bands to the same offsets of d_owner_fb (the presenting rank's framebuffer opened
- * with vrt_fb_import, or a local pointer) on the context's copy stream, as one strided
- * device-to-device copy over NVLink.  The call returns at once; the next frame can be traced while
- * this one is in flight: a d_local_fb may be reused every VRT_GATHER_DEPTH-th call (the call waits for
- * the copy issued that many calls ago), and the owner may change from frame to frame.
- * vrt_gather_wait makes `stream` wait for every gather issued so far. */
 #define VRT_GATHER_DEPTH 8u
 VRT_API int vrt_render_gather(VrtContext* ctx, const VrtFrame* frame, void* d_local_fb, void* d_owner_fb, void* stream);
 VRT_API int vrt_gather_wait(VrtContext* ctx, void* stream);

@@ -37,3 +37,19 @@ for arr, keep, n in batches[:30]:
     ctx.sync_records(arr, n)
     ctx.render_device(frame, fb.data_ptr(), None, st.cuda_stream)
 torch.cuda.synchronize(); print(f"back-to-back: {1e3*(time.perf_counter()-t0)/30:.3f} ms per edit frame")
+# the same loop when this GPU renders only one eighth of the frame (one rank of 8): what bounds the edit workload at N = 8
+part = bench.bench_frame(w, h, 0, part_index=0, part_count=8, flags=capi.VRT_FRAME_PART_ROWS)
+torch.cuda.synchronize(); t0 = time.perf_counter()
+for arr, keep, n in batches[:30]:
+    ctx.sync_records(arr, n)
+    ctx.render_device(part, fb.data_ptr(), None, st.cuda_stream)
+torch.cuda.synchronize(); print(f"back-to-back, 1/8 of the frame: {1e3*(time.perf_counter()-t0)/30:.3f} ms per edit frame")
+hs = []
+for arr, keep, n in batches[:30]:
+    t0 = time.perf_counter()
+    ctx.sync_records(arr, n)
+    hs.append(time.perf_counter() - t0)
+    ctx.render_device(part, fb.data_ptr(), None, st.cuda_stream)
+torch.cuda.synchronize()
+print(f"host time inside vrt_sync while pipelined: median {1e3*np.median(hs):.3f} ms  min {1e3*np.min(hs):.3f}  max {1e3*np.max(hs):.3f}")
+print("stats", {k: getattr(s, k) for k in ("resident_bricks", "free_ranges", "bricks_uploaded", "bricks_relocated", "last_launches")})
