@@ -210,3 +210,41 @@ def test_config5_edit_frames(bench_scene):
     assert ctx.stats().resident_bricks == fresh.stats().resident_bricks == terrain.scene_stats(fresh_scene)["bricks"]
     ctx.close()
     fresh.close()
+
+
+def test_bricks_beyond_four_gigabytes_of_voxels(hash_scene, hash_oracle, shading_inputs):
+    """64-bit brick addressing: with the first 8.5 M slots of the arena reserved, the scene's bricks live where a 10 GB scene's do (byte offsets
+    beyond 2^32: 8.4 M slots x 512 B) — upload, read-back, explicit rays, frames in both bounce forms must not care.  (Round 2, found at
+    8 GPUs on the 10 GB terrain: the wavefront trace pass computed slot * 512 in 32 bits.)"""
+    from scenes import camera, terrain
+    from voxelrt_b200 import capi
+
+    (bn, _), (desc, tex, _) = shading_inputs
+    ctx = capi.Context(6, 4, device=0, initial_brick_capacity=1 << 17)
+    ctx.set_option("reserve_slots", 8_500_000)
+    ctx.set_palette(hash_scene["palette"])
+    ctx.sync(terrain.scene_records(hash_scene))
+    ctx.set_blue_noise(bn)
+    ctx.set_sky(desc, tex)
+    hash_oracle.set_blue_noise(bn)
+    hash_oracle.set_sky(desc, tex)
+    key = sorted(hash_scene["sectors"])[3]
+    mask, base, bricks, cells = ctx.read_sector(*key)
+    assert base >= 8_500_000 and mask == hash_scene["sectors"][key][0]
+    om, ob, oc = hash_oracle.read_sector(*key)
+    assert np.array_equal(bricks, ob) and np.array_equal(cells, oc)
+    rng = np.random.default_rng(11)
+    from conftest import assert_hits_equal, random_rays
+
+    o, d = random_rays(rng, 50_000, 192, 128, (0, 0, 0))
+    assert_hits_equal(ctx.trace(o, d, (0, 0, 0)), hash_oracle.trace(o, d, (0, 0, 0))[0], "high slots", ignore_iters=True)
+    cam = camera.Camera(pos=(96.3, 90.2, 20.7), yaw=0.2, pitch=-0.45)
+    w, h = 640, 360
+    proj, inv, wo, frac = cam.matrices(w, h)
+    for bounces in (0, 2):
+        want = hash_oracle.render(capi.make_frame(w, h, inv, proj, wo, frac, frame_no=3, bounces=bounces))[0]
+        for wave in (0, 1):
+            ctx.set_option("wavefront", wave)
+            got, _ = ctx.render(capi.make_frame(w, h, inv, proj, wo, frac, frame_no=3, bounces=bounces))
+            assert got.tobytes() == want.tobytes(), (bounces, wave)
+    ctx.close()

@@ -605,6 +605,17 @@ extern "C" int vrt_set_option(VrtContext* ctx, const char* name, int64_t value) 
         if (value != 0) return fail(ctx, VRT_ERR_UNSUPPORTED, "compact_bounces was removed; see the \"wavefront\" option");
     }
     else if (!strcmp(name, "wavefront")) ctx->wave_on = (int)value;
+    else if (!strcmp(name, "reserve_slots")) {
+        // test hook: takes the first `value` brick slots out of the arena, so that a small scene lives at slot numbers a 10 GB scene
+        // reaches (byte offsets beyond 2^32: every kernel must address bricks with 64-bit arithmetic).  Before the first vrt_sync.
+        if (value < 0 || value > 0x7FFFFFFF || ctx->arena.allocated() != 0) return fail(ctx, VRT_ERR_STATE, "reserve_slots: only on an empty arena");
+        DeviceGuard g(ctx->device);
+        const uint64_t want = (uint64_t)value + ctx->arena.capacity();
+        if (want > 0x7FFFFFFFull) return fail(ctx, VRT_ERR_OOM, "Could not allocate brick slots");
+        int st = resize_arena(ctx, (uint32_t)want);
+        if (st) return st;
+        if (ctx->arena.alloc((uint32_t)value) == RangeArena::kNone) return fail(ctx, VRT_ERR_OOM, "Could not allocate brick slots");
+    }
     else if (!strcmp(name, "trace_ctas")) ctx->trace_ctas = (int)value;
     else if (!strcmp(name, "tile_order")) ctx->tile_order = value != 0;
     else if (!strcmp(name, "trace_refill")) ctx->trace_refill = (int)std::min<int64_t>(32, std::max<int64_t>(1, value));

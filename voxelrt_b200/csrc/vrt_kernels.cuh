@@ -208,7 +208,8 @@ __global__ void __launch_bounds__(VRT_RENDER_THREADS, CTAS) k_wave_trace(const _
     LeanRay r;
     r.ox = r.oy = r.oz = r.dx = r.dy = r.dz = r.ix = r.iy = r.iz = r.tx = r.ty = r.tz = r.cx = r.cy = r.cz = r.sdx = r.sdy = r.sdz = 0.0f;
     r.nmx = r.nmy = r.nmz = 0;
-    uint32_t left = 0, budget = 0, slot = 0, hit_at = 0;
+    uint32_t left = 0, budget = 0, slot = 0;
+    unsigned long long hit_at = 0;
     // lane state: 0 idle, 1 a ray is in flight, 2..4 it has ended (2 solid voxel, 3 left the view, 4 out of trips) and its record is not written yet
     uint32_t state = 0;
     uint32_t more = 1;  // the queue may still hold rays (warp-uniform)
