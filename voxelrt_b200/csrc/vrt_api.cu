@@ -92,16 +92,23 @@ struct VrtContext {
     int trace_refill = VRT_TRACE_REFILL;  // k_wave_trace: lanes in flight below which a warp refills (tuning knob, "trace_refill")
     int tile_order = 1;  // k_render: 0 top-to-bottom, 1 bottom-to-top (see FrameParams::work_add; "tile_order")
     int trace_ctas = VRT_TRACE_CTAS;      // k_wave_trace: resident CTAs per SM it is compiled for (8 / 10 / 12, "trace_ctas")
-    cudaStream_t wave_side_stream = nullptr;  // k_wave_trace_generic runs beside k_wave_trace
-    cudaEvent_t ev_wave_fork = nullptr, ev_wave_join = nullptr;
     int wave_choice = -1;         // -1 undecided, 0 per-pixel, 1 wavefront
     int wave_phase = 0;           // 0: time per-pixel next, 1: time wavefront next, 2: waiting for the events
     uint64_t wave_key = 0;        // (bounces, width, height, scene epoch) the decision was taken for
     uint64_t scene_epoch = 0;     // bumped when a sync changes some sector's emptiness
     cudaEvent_t ev_tune[4] = {};
-    DeviceBuffer d_wave_rays, d_wave_hits, d_wave_path, d_wave_n;
-    cudaEvent_t ev_wave = nullptr;  // the queues are shared: a wave frame on another stream waits for the previous one
-    bool wave_used = false;
+    // wavefront frames: a ring of buffer sets, so that consecutive frames issued on different streams (multi-GPU: frames rotate over
+    // streams to overlap one frame's tail with the next frame's start) do not wait for each other's queues
+    struct WaveSet {
+        DeviceBuffer rays, hits, path, n;
+        cudaEvent_t ev = nullptr;          // last frame that used this set has finished
+        cudaStream_t side = nullptr;       // k_wave_trace_generic runs beside k_wave_trace
+        cudaEvent_t fork = nullptr, join = nullptr;
+        bool used = false;
+    };
+    static constexpr uint32_t kWaveSets = 3;
+    WaveSet wave[kWaveSets];
+    uint32_t wave_seq = 0;
     int persist_on = 0;  // measured slower than the grid form on primary frames (tile order loses the L1 locality of 4 adjacent warp tiles per CTA)
     uint32_t* d_tickets = nullptr;
     uint32_t ticket_base[16] = {};
@@ -355,24 +362,27 @@ int launch_render(VrtContext* ctx, const VrtFrame* f, void* d_out, VrtHit* d_aux
         // pass (one thread per pixel in tile order: the packet coupling is two half-warp votes) — vrt_shade.cuh, vrt_kernels.cuh.
         const size_t cap = (size_t)(F.n_work - F.work_offset) * 32u;  // pixel slots of this launch; at most one ray per slot and level
         int st2;
-        if ((st2 = ensure(ctx, ctx->d_wave_rays, cap * sizeof(RayRec)))) return st2;
-        if ((st2 = ensure(ctx, ctx->d_wave_hits, cap * sizeof(HitRec)))) return st2;
-        if (cap > 0x7FFFFFFFull) return fail(ctx, VRT_ERR_INVALID, "frame too large for the wavefront form");
-        if ((st2 = ensure(ctx, ctx->d_wave_path, cap * (sizeof(float4) + sizeof(float2)) + (cap / 16u) * sizeof(uint16_t) + 64u))) return st2;
+        VrtContext::WaveSet& ws = ctx->wave[ctx->wave_seq++ % VrtContext::kWaveSets];
+        const size_t path_bytes = cap * (sizeof(float4) + sizeof(float2)) + (cap / 16u) * sizeof(uint16_t) + 64u;
         const uint32_t n_counters = 3u * 10u;  // per level [0..9]: rays queued, refill cursor, generic rays queued
-        if ((st2 = ensure(ctx, ctx->d_wave_n, n_counters * sizeof(uint32_t)))) return st2;
-        if (ctx->wave_used) CU(cudaStreamWaitEvent(s, ctx->ev_wave, 0));
+        if (ws.used && (ws.rays.bytes < cap * sizeof(RayRec) || ws.path.bytes < path_bytes)) CU(cudaEventSynchronize(ws.ev));  // growing: nobody may still use the set
+        if ((st2 = ensure(ctx, ws.rays, cap * sizeof(RayRec)))) return st2;
+        if ((st2 = ensure(ctx, ws.hits, cap * sizeof(HitRec)))) return st2;
+        if (cap > 0x7FFFFFFFull) return fail(ctx, VRT_ERR_INVALID, "frame too large for the wavefront form");
+        if ((st2 = ensure(ctx, ws.path, path_bytes))) return st2;
+        if ((st2 = ensure(ctx, ws.n, n_counters * sizeof(uint32_t)))) return st2;
+        if (ws.used) CU(cudaStreamWaitEvent(s, ws.ev, 0));
         tune_begin();
-        uint32_t* cnt = static_cast<uint32_t*>(ctx->d_wave_n.p);
+        uint32_t* cnt = static_cast<uint32_t*>(ws.n.p);
         CU(cudaMemsetAsync(cnt, 0, n_counters * sizeof(uint32_t), s));
         WaveBuffers B;
-        B.rays = static_cast<RayRec*>(ctx->d_wave_rays.p);
+        B.rays = static_cast<RayRec*>(ws.rays.p);
         B.capacity = (uint32_t)cap;
         B.n_rays = cnt;
         B.head = cnt + 10;
         B.n_generic = cnt + 20;
-        B.hits = static_cast<HitRec*>(ctx->d_wave_hits.p);
-        B.path_a = static_cast<float4*>(ctx->d_wave_path.p);
+        B.hits = static_cast<HitRec*>(ws.hits.p);
+        B.path_a = static_cast<float4*>(ws.path.p);
         B.path_b = reinterpret_cast<float2*>(B.path_a + cap);
         B.pk_alive = reinterpret_cast<uint16_t*>(B.path_b + cap);
         if (rows) k_wave_primary<true><<<blocks, VRT_RENDER_THREADS, 0, s>>>(S, F, B);
@@ -391,20 +401,20 @@ int launch_render(VrtContext* ctx, const VrtFrame* f, void* d_out, VrtHit* d_aux
             A.n_generic = B.n_generic + level;
             A.capacity = B.capacity;
             // the few generic rays of the level run beside the trace pass on a second stream (long serial chains, few warps)
-            CU(cudaEventRecord(ctx->ev_wave_fork, s));
-            CU(cudaStreamWaitEvent(ctx->wave_side_stream, ctx->ev_wave_fork, 0));
-            k_wave_trace_generic<<<(unsigned)ctx->sm_count * 4u, 32, 0, ctx->wave_side_stream>>>(S, F.W, A);
-            CU(cudaEventRecord(ctx->ev_wave_join, ctx->wave_side_stream));
+            CU(cudaEventRecord(ws.fork, s));
+            CU(cudaStreamWaitEvent(ws.side, ws.fork, 0));
+            k_wave_trace_generic<<<(unsigned)ctx->sm_count * 4u, 32, 0, ws.side>>>(S, F.W, A);
+            CU(cudaEventRecord(ws.join, ws.side));
             if (ctas == 12) k_wave_trace<12><<<grid, VRT_RENDER_THREADS, 0, s>>>(S, F.W, A);
             else if (ctas == 10) k_wave_trace<10><<<grid, VRT_RENDER_THREADS, 0, s>>>(S, F.W, A);
             else k_wave_trace<8><<<grid, VRT_RENDER_THREADS, 0, s>>>(S, F.W, A);
-            CU(cudaStreamWaitEvent(s, ctx->ev_wave_join, 0));
+            CU(cudaStreamWaitEvent(s, ws.join, 0));
             if (rows) k_wave_shade<true><<<blocks, VRT_RENDER_THREADS, 0, s>>>(S, F, B, level);
             else k_wave_shade<false><<<blocks, VRT_RENDER_THREADS, 0, s>>>(S, F, B, level);
             ctx->stats.last_launches += 3;
         }
-        CU(cudaEventRecord(ctx->ev_wave, s));
-        ctx->wave_used = true;
+        CU(cudaEventRecord(ws.ev, s));
+        ws.used = true;
         CU(cudaGetLastError());
         return VRT_OK;
     }
@@ -500,10 +510,12 @@ extern "C" int vrt_create(const VrtConfig* cfg, VrtContext** out) {
     for (auto& e : c->ev_stage) CUB(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     CUB(cudaEventCreateWithFlags(&c->ev_sync, cudaEventDisableTiming));
     for (auto& e : c->ev_render) CUB(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-    CUB(cudaEventCreateWithFlags(&c->ev_wave, cudaEventDisableTiming));
-    CUB(cudaStreamCreateWithFlags(&c->wave_side_stream, cudaStreamNonBlocking));
-    CUB(cudaEventCreateWithFlags(&c->ev_wave_fork, cudaEventDisableTiming));
-    CUB(cudaEventCreateWithFlags(&c->ev_wave_join, cudaEventDisableTiming));
+    for (auto& ws : c->wave) {
+        CUB(cudaEventCreateWithFlags(&ws.ev, cudaEventDisableTiming));
+        CUB(cudaStreamCreateWithFlags(&ws.side, cudaStreamNonBlocking));
+        CUB(cudaEventCreateWithFlags(&ws.fork, cudaEventDisableTiming));
+        CUB(cudaEventCreateWithFlags(&ws.join, cudaEventDisableTiming));
+    }
     for (auto& e : c->ev_tune) CUB(cudaEventCreate(&e));
     for (auto& gs : c->gather_streams) CUB(cudaStreamCreateWithFlags(&gs, cudaStreamNonBlocking));
     for (auto& e : c->ev_gather_src) CUB(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
@@ -545,12 +557,16 @@ extern "C" void vrt_destroy(VrtContext* ctx) {
     cudaDeviceSynchronize();
     for (void* p : ctx->imported) cudaIpcCloseMemHandle(p);
     for (void* p : ctx->exported) cudaFree(p);
-    if (ctx->ev_wave) cudaEventDestroy(ctx->ev_wave);
-    if (ctx->ev_wave_fork) cudaEventDestroy(ctx->ev_wave_fork);
-    if (ctx->ev_wave_join) cudaEventDestroy(ctx->ev_wave_join);
-    if (ctx->wave_side_stream) cudaStreamDestroy(ctx->wave_side_stream);
+    for (auto& ws : ctx->wave) {
+        if (ws.ev) cudaEventDestroy(ws.ev);
+        if (ws.fork) cudaEventDestroy(ws.fork);
+        if (ws.join) cudaEventDestroy(ws.join);
+        if (ws.side) cudaStreamDestroy(ws.side);
+        for (DeviceBuffer* b : {&ws.rays, &ws.hits, &ws.path, &ws.n})
+            if (b->p) cudaFree(b->p);
+    }
     for (auto& e : ctx->ev_tune) if (e) cudaEventDestroy(e);
-    DeviceBuffer* bufs[] = {&ctx->d_wave_rays, &ctx->d_wave_hits, &ctx->d_wave_path, &ctx->d_wave_n, &ctx->d_stage, &ctx->d_rays_o, &ctx->d_rays_d, &ctx->d_hits, &ctx->d_fb,
+    DeviceBuffer* bufs[] = {&ctx->d_stage, &ctx->d_rays_o, &ctx->d_rays_d, &ctx->d_hits, &ctx->d_fb,
                             &ctx->d_aux,   &ctx->d_q_o,    &ctx->d_q_d,    &ctx->d_q_out};
     for (auto* b : bufs)
         if (b->p) cudaFree(b->p);
