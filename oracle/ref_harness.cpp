@@ -26,6 +26,14 @@
 // ---- the reference, verbatim ---------------------------------------------------------------------
 #include "CpuRenderer.cpp"
 #include "VoxelMap.cpp"
+// scene ingest: the reference's surface voxeliser and palette quantiser, VoxelMap::VoxelizeModel
+// (Voxelize.cpp:77-147 + Common/PaletteBuilder.h).  Its model loader (Common/Scene.cpp) sits on assimp + stb_image, which are absent: the
+// glim::Model arrives through ref_voxelize below instead, already decoded.
+#include <cfloat>
+#include <functional>
+#include "Common/Scene.h"
+#include "Voxelize.cpp"
+glim::Model::Model(std::string_view) {}
 
 // ---- externals the two TUs expect from files we do not compile ------------------------------------
 namespace swr {
@@ -44,7 +52,6 @@ HdrTexture2D LoadCubemapFromPanoramaHDR(std::string_view, uint32_t mipLevels) { 
 // The "cvox 0004" (de)serialiser (VoxelMap.cpp:205-274) sits on the reference's Common/BinaryIO.cpp, which oracle/Makefile
 // compiles as a second translation unit straight from /root/reference (its header has no include guard): <zstd.h> resolves to
 // oracle/shim/zstd.h (declarations only) and the system libzstd.so.1 is linked.
-void VoxelMap::VoxelizeModel(const glim::Model&, glm::uvec3, glm::uvec3) {}
 
 // ---- C API -----------------------------------------------------------------------------------------
 #define REF_API extern "C" __attribute__((visibility("default")))
@@ -155,6 +162,57 @@ REF_API int ref_map_read_sector(RefCtx* c, int sx, int sy, int sz, uint64_t* mas
             std::memcpy(bricks, it->second.GetBrick(b)->Data, 512);
             bricks += 512;
         }
+    return 0;
+}
+
+// VoxelMap::VoxelizeModel on a model handed over as plain arrays: triangles (3 x xyz, model space, node transforms already applied),
+// their texture coordinates, a texture id per triangle, and the decoded RGBA8 base-colour images (power-of-two sizes, as swr::Texture2D
+// requires).  Builds the glim::Model the way Common/Scene.cpp does (one texture with 8 mips per image, meshes of <= 65535 16-bit-indexed
+// vertices, bounds per mesh / node) with a single identity node, then runs the reference's own code.  The voxels land in c->map
+// (ref_map_list_sectors / ref_map_read_sector), the palette in c->map.Palette (ref_get_material).
+REF_API int ref_voxelize(RefCtx* c, uint32_t n_tris, const float* pos9, const float* uv6, const int32_t* tri_tex, uint32_t n_tex, const uint8_t* const* tex_rgba,
+                         const uint32_t* tex_w, const uint32_t* tex_h, uint32_t size) {
+    glim::Model model("");
+    model.Materials.reserve(n_tex);
+    for (uint32_t t = 0; t < n_tex; t++) {
+        char name[32];
+        std::snprintf(name, sizeof(name), "tex%04u", t);
+        if (!std::has_single_bit(tex_w[t]) || !std::has_single_bit(tex_h[t])) return -1;
+        swr::RgbaTexture2D tex(tex_w[t], tex_h[t], 8, 1);  // Scene.cpp:105-116
+        tex.SetPixels(tex_rgba[t], tex_w[t], 0);
+        tex.GenerateMips();
+        auto slot = model.Textures.insert({name, std::move(tex)});
+        model.Materials.push_back(glim::Material{.Texture = &slot.first->second});
+    }
+    model.VertexBuffer = std::make_unique<glim::Vertex[]>((size_t)n_tris * 3);
+    model.IndexBuffer = std::make_unique<glim::VertexIndex[]>((size_t)n_tris * 3);
+    glim::ModelNode& root = model.RootNode;
+    root.Transform = glm::mat4(1.0f);
+    root.Bounds[0] = glm::vec3(FLT_MIN), root.Bounds[1] = glm::vec3(-FLT_MAX);  // Scene.cpp:127 (sic: FLT_MIN)
+    const uint32_t kChunk = 65535 / 3;
+    for (uint32_t t0 = 0; t0 < n_tris;) {
+        uint32_t t1 = t0;
+        while (t1 < n_tris && t1 - t0 < kChunk && tri_tex[t1] == tri_tex[t0]) t1++;
+        if (tri_tex[t0] < 0 || (uint32_t)tri_tex[t0] >= n_tex) return -2;
+        glim::Mesh mesh{.VertexOffset = t0 * 3, .IndexOffset = t0 * 3, .IndexCount = (t1 - t0) * 3, .Material = &model.Materials[(size_t)tri_tex[t0]],
+                        .Bounds = {glm::vec3(FLT_MIN), glm::vec3(-FLT_MAX)}};  // Scene.cpp:199
+        for (uint32_t t = t0; t < t1; t++)
+            for (uint32_t j = 0; j < 3; j++) {
+                glim::Vertex& v = model.VertexBuffer[(size_t)t * 3 + j];
+                v = {};
+                v.x = pos9[(size_t)t * 9 + j * 3], v.y = pos9[(size_t)t * 9 + j * 3 + 1], v.z = pos9[(size_t)t * 9 + j * 3 + 2];
+                v.u = uv6[(size_t)t * 6 + j * 2], v.v = uv6[(size_t)t * 6 + j * 2 + 1];
+                model.IndexBuffer[(size_t)t * 3 + j] = (glim::VertexIndex)((t - t0) * 3 + j);
+                glm::vec3 p(v.x, v.y, v.z);
+                mesh.Bounds[0] = glm::min(mesh.Bounds[0], p), mesh.Bounds[1] = glm::max(mesh.Bounds[1], p);  // :216-217
+            }
+        root.Bounds[0] = glm::min(root.Bounds[0], mesh.Bounds[0]), root.Bounds[1] = glm::max(root.Bounds[1], mesh.Bounds[1]);  // :134-135
+        root.Meshes.push_back((uint32_t)model.Meshes.size());
+        model.Meshes.push_back(mesh);
+        t0 = t1;
+    }
+    c->map.Sectors.clear();
+    c->map.VoxelizeModel(model, glm::uvec3(0), glm::uvec3(size));
     return 0;
 }
 

@@ -35,7 +35,7 @@ struct vec<3, T> {
     template <typename U>
     constexpr vec(const vec<3, U>& v) : x((T)v.x), y((T)v.y), z((T)v.z) {}
     template <typename U>
-    constexpr explicit vec(const vec<4, U>& v);
+    constexpr vec(const vec<4, U>& v);  // (GLM's conversion constructors are implicit unless GLM_FORCE_EXPLICIT_CTOR: Voxelize.cpp:104,126 rely on it)
     constexpr T& operator[](int i) { return i == 0 ? x : (i == 1 ? y : z); }
     constexpr const T& operator[](int i) const { return i == 0 ? x : (i == 1 ? y : z); }
 };
@@ -69,6 +69,9 @@ using ivec4 = vec<4, int32_t>;
 using uvec2 = vec<2, uint32_t>;
 using uvec3 = vec<3, uint32_t>;
 using uvec4 = vec<4, uint32_t>;
+using uint32 = uint32_t;
+using int32 = int32_t;
+using uint = unsigned int;
 using bvec2 = vec<2, bool>;
 using bvec3 = vec<3, bool>;
 
@@ -219,6 +222,20 @@ inline T dot(const vec<N, T>& a, const vec<N, T>& b) {
 }
 
 // IEEE binary32 -> binary16, round to nearest even (GLSL packHalf2x16)
+// geometric functions as GLM defines them (func_geometric.inl): cross by components, normalize = v * inversesqrt(dot(v, v))
+template <typename T>
+inline vec<3, T> cross(const vec<3, T>& x, const vec<3, T>& y) {
+    return vec<3, T>(x.y * y.z - y.y * x.z, x.z * y.x - y.z * x.x, x.x * y.y - y.x * x.y);
+}
+template <int N, typename T>
+inline T length(const vec<N, T>& v) { return std::sqrt(dot(v, v)); }
+template <int N, typename T>
+inline vec<N, T> normalize(const vec<N, T>& v) { return v * (T(1) / std::sqrt(dot(v, v))); }
+template <int N, typename T, typename S, typename = std::enable_if_t<std::is_arithmetic_v<S>>>
+constexpr vec<N, T> max(const vec<N, T>& a, S s) { return map1(a, [s](T v) { return max(v, (T)s); }); }
+template <int N, typename T, typename S, typename = std::enable_if_t<std::is_arithmetic_v<S>>>
+constexpr vec<N, T> min(const vec<N, T>& a, S s) { return map1(a, [s](T v) { return min(v, (T)s); }); }
+
 inline uint16_t glms_f32_to_f16(float f) {
     uint32_t x;
     std::memcpy(&x, &f, 4);
