@@ -640,6 +640,20 @@ def run_b200(args):
 
     step()
     torch.cuda.synchronize()
+    # frames with bounces: the context times its two forms (one thread per pixel / wavefront passes) on the first four frames of a new
+    # (size, bounces, scene) combination and keeps the faster one; let that settle before anything is measured
+    for _ in range(8):
+        if not (int(ctx.stats().bounce_form) & 0x100):
+            break
+        step()
+        torch.cuda.synchronize()
+    step()
+    torch.cuda.synchronize()
+    bounce_form = {0: None, 1: "one thread per pixel", 2: "wavefront passes"}[int(ctx.stats().bounce_form) & 0xFF]
+    if world > 1:
+        forms = [None] * world
+        dist.all_gather_object(forms, bounce_form)
+        bounce_form = forms[0] if len(set(forms)) == 1 else forms
     ctx_launches = int(ctx.stats().last_launches)  # kernels one step launches (1 for a primary frame; 1 + 3 per bounce level for a wavefront frame)
     my_primary = partition.pixels_of_rank(w, h, rank, world, rows=world > 1)
     alg_bytes = 8 * m.sector_fetches + 8 * m.cell_fetches + 9 * m.hits + 16 * my_primary
@@ -911,6 +925,7 @@ def run_b200(args):
                 "numa_node_of_rank0": numa if world > 1 else None,
             },
             "gpu_launches": args.steps * ctx_launches + timed_edit_stats["launches"],
+            "bounce_form": bounce_form,
             "residency": residency,
             "edits": None if edit_batches is None else {
                 "mode": args.edit_mode,

@@ -164,6 +164,9 @@ typedef struct VrtStats {
     uint64_t bricks_relocated;  /* bricks moved device-side by the last vrt_sync               */
     uint64_t device_bytes;      /* total device memory owned by the context                    */
     uint64_t last_launches;     /* kernels launched by the last ABI call                       */
+    uint64_t bounce_form;       /* how the last frame with bounces was traced: 0 none yet, 1 one thread per pixel (all levels in one
+                                   kernel), 2 wavefront passes; bit 8 set while the per-context choice between the two is still being
+                                   timed (the first four such frames of a (size, bounces, scene) combination)                     */
 } VrtStats;
 
 /* ---- lifetime ------------------------------------------------------------------------------- */

@@ -165,6 +165,18 @@ REF_API int ref_map_read_sector(RefCtx* c, int sx, int sy, int sz, uint64_t* mas
     return 0;
 }
 
+// glim::PaletteBuilder on its own: AddColor for n packed RGBA8 words, Build(max_colors); -> NumColors, colours in rgb[3 * i ..], and (when
+// `index_of` is given) FindIndex of every input colour.
+REF_API uint32_t ref_palette_build(const uint32_t* colors, uint64_t n, uint32_t max_colors, uint8_t* rgb, uint8_t* index_of) {
+    glim::PaletteBuilder pb;
+    for (uint64_t i = 0; i < n; i++) pb.AddColor(colors[i]);
+    pb.Build(max_colors);
+    for (uint32_t i = 0; i < pb.NumColors; i++) rgb[3 * i] = pb.ColorR[i], rgb[3 * i + 1] = pb.ColorG[i], rgb[3 * i + 2] = pb.ColorB[i];
+    if (index_of)
+        for (uint64_t i = 0; i < n; i++) index_of[i] = (uint8_t)pb.FindIndex(colors[i]);
+    return pb.NumColors;
+}
+
 // VoxelMap::VoxelizeModel on a model handed over as plain arrays: triangles (3 x xyz, model space, node transforms already applied),
 // their texture coordinates, a texture id per triangle, and the decoded RGBA8 base-colour images (power-of-two sizes, as swr::Texture2D
 // requires).  Builds the glim::Model the way Common/Scene.cpp does (one texture with 8 mips per image, meshes of <= 65535 16-bit-indexed

@@ -18,6 +18,9 @@ LIB = HERE / "_ref" / "libref_cpu.so"
 # the same harness built with the flags the reference ships with (-O3 -march=native -ffast-math, src/CMakeLists.txt:36): used for
 # TIMING only (bench.py's reference arm); every parity pin uses the -fno-fast-math build above
 LIB_SHIPPED = HERE / "_ref" / "libref_cpu_fastmath.so"
+# and with FP contraction off (-ffp-contract=off on the unmodified sources): the build the scene-ingest pin (ref_voxelize) compares with,
+# because scenes/voxelizer.c states every fused multiply-add explicitly (none) instead of leaving the choice to the compiler
+LIB_STRICT = HERE / "_ref" / "libref_cpu_strict.so"
 _NEED = ("avx512f", "avx512bw", "avx512dq", "avx512vl", "avx2", "fma", "bmi2")
 _libs = {}
 
@@ -34,16 +37,20 @@ def _cpu_ok() -> bool:
         return False
 
 
-def available(shipped_flags: bool = False) -> bool:
-    return (LIB_SHIPPED if shipped_flags else LIB).exists() and _cpu_ok()
+def _path(shipped_flags):
+    return LIB_STRICT if shipped_flags == "strict" else (LIB_SHIPPED if shipped_flags else LIB)
 
 
-def load(shipped_flags: bool = False):
+def available(shipped_flags=False) -> bool:
+    return _path(shipped_flags).exists() and _cpu_ok()
+
+
+def load(shipped_flags=False):
     if shipped_flags in _libs:
         return _libs[shipped_flags]
     if not available(shipped_flags):
         raise RuntimeError("oracle/_ref/libref_cpu*.so missing or this CPU lacks AVX-512")
-    lib = C.CDLL(str(LIB_SHIPPED if shipped_flags else LIB))
+    lib = C.CDLL(str(_path(shipped_flags)))
     vp, u32, u64 = C.c_void_p, C.c_uint32, C.c_uint64
     lib.ref_create.restype = vp
     lib.ref_destroy.argtypes = [vp]
@@ -93,14 +100,28 @@ def load(shipped_flags: bool = False):
     lib.ref_pack_rg16f.argtypes = [C.c_float] * 2
     lib.ref_pack_rg16f.restype = u32
     lib.ref_num_threads.restype = C.c_int
+    lib.ref_voxelize.argtypes = [vp, u32, vp, vp, vp, u32, vp, vp, vp, u32]
+    lib.ref_voxelize.restype = C.c_int
+    lib.ref_palette_build.argtypes = [vp, u64, u32, vp, vp]
+    lib.ref_palette_build.restype = u32
     _libs[shipped_flags] = lib
     return lib
+
+
+def palette_build(colors, max_colors=240, shipped_flags=False):
+    """glim::PaletteBuilder: (palette uint8[n,3], FindIndex of every input colour)."""
+    lib = load(shipped_flags)
+    c = np.ascontiguousarray(colors, np.uint32).reshape(-1)
+    rgb = np.zeros((256, 3), np.uint8)
+    idx = np.zeros(max(1, c.size), np.uint8)
+    n = lib.ref_palette_build(c.ctypes.data, c.size, int(max_colors), rgb.ctypes.data, idx.ctypes.data)
+    return rgb[:n].copy(), idx[: c.size]
 
 
 class RefMap:
     """The reference's VoxelMap + FlatVoxelStorage (a dense 2048x512x2048 view: ~2.3 GB of host memory)."""
 
-    def __init__(self, shipped_flags: bool = False):
+    def __init__(self, shipped_flags=False):
         self.lib = load(shipped_flags)
         self.h = C.c_void_p(self.lib.ref_create())
 
@@ -157,6 +178,20 @@ class RefMap:
             self.lib.ref_get_material(self.h, i, rgbf, C.byref(em))
             out.append((rgbf[0], rgbf[1], rgbf[2], rgbf[3], em.value))
         return out
+
+    def voxelize(self, tris, uvs, tri_tex, textures, size):
+        """VoxelMap::VoxelizeModel(model, 0, size^3) on a decoded model (see ref_voxelize in ref_harness.cpp); voxels -> map_sectors(),
+        palette -> materials()."""
+        t = np.ascontiguousarray(tris, np.float32)
+        u = np.ascontiguousarray(uvs, np.float32)
+        tt = np.ascontiguousarray(tri_tex, np.int32)
+        imgs = [np.ascontiguousarray(x, np.uint32) for x in textures]
+        ptrs = (C.c_void_p * max(1, len(imgs)))(*[x.ctypes.data for x in imgs])
+        tw = np.array([x.shape[1] for x in imgs] or [1], np.uint32)
+        th = np.array([x.shape[0] for x in imgs] or [1], np.uint32)
+        rc = self.lib.ref_voxelize(self.h, t.shape[0], t.ctypes.data, u.ctypes.data, tt.ctypes.data, len(imgs), ptrs, tw.ctypes.data, th.ctypes.data, int(size))
+        if rc != 0:
+            raise ValueError(f"ref_voxelize: {rc}")
 
     def map_sectors(self):
         """-> {(sx, sy, sz): (alloc_mask, bricks[k, 512])} read from the VoxelMap itself (not the renderer's dense view)."""

@@ -4,18 +4,21 @@ sponza(size): the reference app's start-up model — `assets/models/Sponza/Sponz
 `size` voxels at the origin (VoxelRT/Main.cpp:42-47 uses 2048) by the recipe of VoxelMap::VoxelizeModel
 (VoxelRT/Voxelize.cpp:77-147):
 
-  1. every base-colour texture is reduced to mip 2 (4x4 box filter) and its opaque texels (alpha >= 200) feed an
-     octree colour quantiser that is cut down to <= 240 leaves (Common/PaletteBuilder.h:18-126: 6-level octree,
-     least-populated parents merged first); palette entry i = mean colour of leaf i;
+  1. every base-colour texture gets the sampler's mip chain (2x2 fp32 averages) and the opaque texels (alpha >= 200)
+     of level 2 feed an octree colour quantiser that is cut down to <= 240 leaves (Common/PaletteBuilder.h:18-62:
+     6-level octree, least-populated parents folded first); palette entry i = mean colour of leaf i;
   2. triangles are scaled so the model's longest axis spans `size` voxels, centred in x/z, resting on y = 0;
-  3. conservative surface voxelisation (Schwarz & Seidel), colour = nearest texel of mip 2 at the barycentric
-     projection of the voxel corner, alpha test at 128, voxel id = nearest palette entry (Manhattan distance).
+  3. conservative surface voxelisation (Schwarz & Seidel), colour = the sampler's bilinear LEVEL-0 tap at the
+     barycentric projection of the voxel corner (the `2` handed to Sample() there is overridden by the UV
+     derivatives, which are zero for a broadcast coordinate, Texture.h:504-509), alpha test at 128, voxel id =
+     nearest palette entry (Manhattan distance).
 
-The geometry kernel is scenes/voxelizer.c (built by scenes/Makefile into scenes/_ref/libvoxelizer.so).  The glTF
-is read directly (one buffer, u16 indices, f32 POSITION / TEXCOORD_0, node TRS) instead of through assimp, the
-images through PIL instead of stb_image; neither is pinned against the reference (its loaders are third-party
-libraries absent here), so the result is "the reference's scene by the reference's recipe", not a bit-copy.
-Parity of the TRAVERSAL does not depend on it: oracle and GPU consume the same bricks.
+Steps 1-3 are PINNED: tests/test_ref_pin.py hands the same decoded arrays to the reference's own VoxelizeModel
+(oracle/_ref, compiled from Voxelize.cpp + PaletteBuilder.h where they lie) and demands the same palette and the same
+voxels.  What stays unpinned is DECODING: the glTF is read directly (one buffer, u16 indices, f32 POSITION /
+TEXCOORD_0, node TRS) instead of through assimp, the images through PIL instead of stb_image — third-party loaders
+absent here.  The geometry kernel is scenes/voxelizer.c (built by scenes/Makefile into scenes/_ref/libvoxelizer.so).
+Parity of the TRAVERSAL does not depend on any of it: oracle and GPU consume the same bricks.
 
 The voxelised scene is cached as scenes/_ref/sponza_<size>.dat in the reference's own "cvox 0004" cache format
 (scenes/cvox.py — the file the reference app itself would load as logs/voxels_2k_sponza.dat, Main.cpp:38-49); git-ignored,
@@ -130,97 +133,141 @@ def load_gltf(path: Path):
 # ---------------------------------------------------------------------------------------------
 # textures and palette
 # ---------------------------------------------------------------------------------------------
-def load_mip2(path: Path):
-    """RGBA8 image reduced by a 4x4 box filter (two 2x2 steps with round-to-nearest, like a mip chain)."""
+def load_rgba(path: Path):
+    """Decoded image as packed RGBA8 words (R in the low byte), uint32[h, w] — what stbi_load(..., 4) hands Scene.cpp:102."""
     from PIL import Image
 
-    img = np.asarray(Image.open(path).convert("RGBA"), dtype=np.uint16)
-    for _ in range(2):
-        h, w = img.shape[0] & ~1, img.shape[1] & ~1
-        if h < 2 or w < 2:
-            break
-        img = img[:h, :w]
-        img = (img[0::2, 0::2] + img[1::2, 0::2] + img[0::2, 1::2] + img[1::2, 1::2] + 2) >> 2
-    return img.astype(np.uint8)
+    img = np.ascontiguousarray(np.asarray(Image.open(path).convert("RGBA"), dtype=np.uint8))
+    return img.view(np.uint32).reshape(img.shape[0], img.shape[1])
+
+
+def mip_chain(level0: np.ndarray, max_levels=8):
+    """Texture2D's mip chain (Texture.h:403-419, 683-704): level i exists while both sides >> i are >= 4; 2x2 fp32 average."""
+    h, w = level0.shape
+    if w & (w - 1) or h & (h - 1):
+        raise ValueError(f"texture {w}x{h}: swr::Texture2D takes power-of-two sizes only (Texture.h:404)")
+    lib = _voxlib()
+    levels = [np.ascontiguousarray(level0, dtype=np.uint32)]
+    while len(levels) < max_levels and (w >> len(levels)) >= 4 and (h >> len(levels)) >= 4:
+        src = levels[-1]
+        dst = np.empty((src.shape[0] // 2, src.shape[1] // 2), np.uint32)
+        lib.vox_mip_half(src.ctypes.data, src.shape[1], src.shape[0], dst.ctypes.data)
+        levels.append(dst)
+    return levels
+
+
+def palette_texels(levels):
+    """The texels VoxelizeModel's palette pass reads from one texture (Voxelize.cpp:80-92): IterateTiles over (w/4, h/4) in 4x4
+    lane tiles, u = (x + 0.5) / (w/4), nearest texel of the level the 4-texel UV step selects (2, or the last level of a texture
+    too small to have one), Repeat addressing — lanes past w/4 in a tile wrap around and count again, like they do there."""
+    h, w = levels[0].shape
+    level = min(2, len(levels) - 1)
+
+    def taps(n):
+        cells = n // 4
+        lanes = np.arange(-(-cells // 4) * 4, dtype=np.int32)
+        u = (lanes.astype(np.float32) + np.float32(0.5)) * (np.float32(1.0) / np.float32(cells))
+        ix = np.rint(u * np.float32(n << 8)).astype(np.int64).astype(np.int32) & ((n << 8) - 1)
+        return (ix >> level) >> 8
+
+    tx, ty = taps(w), taps(h)
+    return levels[level][ty[:, None], tx[None, :]].reshape(-1)
 
 
 class OctreePalette:
-    """Octree colour quantiser after Common/PaletteBuilder.h: colours are binned by their top 6 bits per channel;
-    while more than `max_colors` leaves remain, the parent with the smallest population is collapsed into a leaf."""
+    """Octree colour quantiser, PaletteBuilder.h:12-62,150-240 step by step: colours are binned by their top 6 bits per channel; the
+    candidate set holds PARENTS of leaves ordered by (population, larger storage index first); while the running leaf count exceeds
+    `max_colors` the first candidate is folded into a leaf.  The running count drops by (direct children - 1) per fold even when a
+    child was itself an unfolded subtree (Reduce's recursive return value is dropped, :225-231), so the cut goes deeper than 240
+    whenever that happens — kept, the palette is the reference's."""
 
     LEVELS = 6
 
     def __init__(self):
-        self.count = {}  # (level, key) -> population, key = interleaved child indices down to `level`
-        self.rgb = {}    # leaf (level, key) -> [sum r, sum g, sum b]
+        self.count = {}  # storage index -> population (root = 0, children of i at ((i + 1) << 3) + c, PaletteBuilder.h:182-193)
+        self.rgb = {}    # storage index of a leaf -> [sum r, sum g, sum b]
 
     def add_colors(self, rgb: np.ndarray):
         rgb = np.asarray(rgb, np.uint8).reshape(-1, 3)
         if rgb.size == 0:
             return
-        r, g, b = (rgb[:, 0].astype(np.uint32), rgb[:, 1].astype(np.uint32), rgb[:, 2].astype(np.uint32))
-        key = np.zeros(rgb.shape[0], np.uint32)
+        r, g, b = (rgb[:, 0].astype(np.int64), rgb[:, 1].astype(np.int64), rgb[:, 2].astype(np.int64))
+        key = np.zeros(rgb.shape[0], np.int64)
         for level in range(self.LEVELS):  # child index = r bit | g bit << 1 | b bit << 2 (PaletteBuilder.h:176-180)
             child = ((r >> (7 - level)) & 1) | (((g >> (7 - level)) & 1) << 1) | (((b >> (7 - level)) & 1) << 2)
-            key = (key << np.uint32(3)) | child
+            key = (key << 3) | child
         uk, inv, cnt = np.unique(key, return_inverse=True, return_counts=True)
         sr = np.bincount(inv, weights=r, minlength=uk.size)
         sg = np.bincount(inv, weights=g, minlength=uk.size)
         sb = np.bincount(inv, weights=b, minlength=uk.size)
         for k, c, a0, a1, a2 in zip(uk.tolist(), cnt.tolist(), sr.tolist(), sg.tolist(), sb.tolist()):
-            leaf = (self.LEVELS, k)
-            acc = self.rgb.setdefault(leaf, [0, 0, 0])
+            node = 0
+            self.count[0] = self.count.get(0, 0) + c
+            for level in range(self.LEVELS):
+                node = ((node + 1) << 3) + ((k >> (3 * (self.LEVELS - 1 - level))) & 7)
+                self.count[node] = self.count.get(node, 0) + c
+            acc = self.rgb.setdefault(node, [0, 0, 0])
             acc[0] += int(a0)
             acc[1] += int(a1)
             acc[2] += int(a2)
-            for level in range(self.LEVELS + 1):
-                node = (level, k >> (3 * (self.LEVELS - level)))
-                self.count[node] = self.count.get(node, 0) + c
 
     def build(self, max_colors=240):
         import heapq
 
-        leaves = set(self.rgb.keys())
-        children = {}
-        for (level, key) in self.count:
-            if level > 0:
-                children.setdefault((level - 1, key >> 3), []).append((level, key))
-        heap = [(self.count[p], p) for p in {(lv - 1, k >> 3) for (lv, k) in leaves}]
+        count = self.count
+        leaf = set(self.rgb.keys())
+        rgb = {k: list(v) for k, v in self.rgb.items()}
+
+        def parent(i):
+            return (i >> 3) - 1
+
+        def kids(i):
+            base = (i + 1) << 3
+            return [base + c for c in range(8) if count.get(base + c, 0) > 0]
+
+        def reduce(i):  # Octree::Reduce
+            acc = rgb.setdefault(i, [0, 0, 0])
+            n = 0
+            for c in kids(i):
+                if c not in leaf:
+                    reduce(c)
+                for j in range(3):
+                    acc[j] += rgb[c][j]
+                n += 1
+            leaf.add(i)
+            return n - 1
+
+        def find_leafs(i=0, out=None):  # Octree::FindLeafs: depth first, children in index order
+            out = [] if out is None else out
+            if i in leaf:
+                out.append(i)
+                return out
+            for c in kids(i):
+                find_leafs(c, out)
+            return out
+
+        num = len(leaf)
+        members = {parent(i) for i in leaf}
+        heap = [(count[i], -i) for i in members]  # std::set ordered by Count, ties: larger address first (:28)
         heapq.heapify(heap)
-        while len(leaves) > max_colors and heap:
-            _, node = heapq.heappop(heap)
-            if node in leaves:
+        while num > max_colors and heap:
+            _, neg = heapq.heappop(heap)
+            node = -neg
+            members.discard(node)
+            if node in leaf:
                 continue
-            kids = [c for c in children.get(node, []) if self.count.get(c, 0) > 0]
-            if not kids:
-                continue
-            acc = [0, 0, 0]
-            stack = list(kids)
-            removed = 0
-            while stack:  # collapse the whole subtree into `node`
-                c = stack.pop()
-                if c in leaves:
-                    leaves.discard(c)
-                    removed += 1
-                    s = self.rgb.pop(c)
-                    acc[0] += s[0]
-                    acc[1] += s[1]
-                    acc[2] += s[2]
-                else:
-                    stack.extend(k for k in children.get(c, []) if self.count.get(k, 0) > 0)
-            if removed == 0:
-                continue
-            self.rgb[node] = acc
-            leaves.add(node)
-            if node[0] > 0:
-                parent = (node[0] - 1, node[1] >> 3)
-                heapq.heappush(heap, (self.count[parent], parent))
-        # depth-first child order, like Octree::FindLeafs (PaletteBuilder.h:207-221)
-        order = sorted(leaves, key=lambda n: n[1] << (3 * (self.LEVELS - n[0])))
+            num -= reduce(node)
+            if node == 0:
+                break  # the reference would index the root's parent here; 240 leaves are never reached from a single node
+            par = parent(node)
+            if par not in members:
+                members.add(par)
+                heapq.heappush(heap, (count[par], -par))
+        order = find_leafs()
         pal = np.zeros((len(order), 3), np.uint8)
         for i, n in enumerate(order):
-            c = self.count[n]
-            pal[i] = [self.rgb[n][0] // c, self.rgb[n][1] // c, self.rgb[n][2] // c]
+            c = count[n]
+            pal[i] = [rgb[n][0] // c, rgb[n][1] // c, rgb[n][2] // c]
         return pal
 
 
@@ -238,7 +285,13 @@ def nearest_palette_index(pal: np.ndarray, rgb: np.ndarray, chunk=1 << 16):
 # ---------------------------------------------------------------------------------------------
 # voxelisation
 # ---------------------------------------------------------------------------------------------
+_vox = None
+
+
 def _voxlib():
+    global _vox
+    if _vox is not None:
+        return _vox
     lib = C.CDLL(str(VOX_LIB))
     lib.vox_create.argtypes = [C.c_int32] * 3
     lib.vox_create.restype = C.c_void_p
@@ -250,8 +303,11 @@ def _voxlib():
     lib.vox_voxels_set.restype = C.c_int64
     lib.vox_export.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
     lib.vox_export.restype = None
-    lib.vox_triangles.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint8]
+    lib.vox_triangles.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_uint8]
     lib.vox_triangles.restype = C.c_int64
+    lib.vox_mip_half.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]
+    lib.vox_mip_half.restype = None
+    _vox = lib
     return lib
 
 
@@ -276,53 +332,57 @@ def bricks_to_scene(coords: np.ndarray, bricks: np.ndarray, palette: np.ndarray,
     return {"sectors": sectors, "palette": palette, "name": name}
 
 
-def voxelize_model(gltf: Path, size: int):
-    """VoxelMap::VoxelizeModel(model, startPos = 0, size = `size`^3), Voxelize.cpp:77-147."""
-    tris, uvs, mats, images = load_gltf(gltf)
-    # 1. textures -> mip 2, palette from their opaque texels
-    tex_rgba = {}
+FLT_MIN = np.float32(1.17549435e-38)
+
+
+def voxelize_arrays(tris, uvs, tri_tex, textures, size: int, name="model", grid_bricks=None):
+    """VoxelMap::VoxelizeModel(model, startPos = 0, size = `size`^3), Voxelize.cpp:77-147, on a decoded model: triangles float32[T,3,3]
+    (node transforms applied), uvs float32[T,3,2], a texture id per triangle (-1: none) and the level-0 RGBA8 images (uint32[h,w]).
+    -> (scene dict, palette colours uint8[n,3]).  tests/test_ref_pin.py runs the reference's own VoxelizeModel on the same arrays and
+    demands the same palette and the same voxels."""
+    tris = np.ascontiguousarray(tris, np.float32)
+    # 1. palette from the opaque level-2 texels of every texture larger than 4x4 (:80-94)
+    chains = [mip_chain(t) for t in textures]
     quant = OctreePalette()
-    for p in sorted({p for p in images if p is not None}):
-        img = load_mip2(p)
-        tex_rgba[p] = img
-        if img.shape[0] * 4 <= 4 or img.shape[1] * 4 <= 4:  # Voxelize.cpp:81 skips tiny (placeholder) textures
+    for levels in chains:
+        h, w = levels[0].shape
+        if w <= 4 or h <= 4:  # :81 (placeholder textures)
             continue
-        opaque = img[..., 3] >= 200  # :88
-        quant.add_colors(img[..., :3][opaque])
+        tex = palette_texels(levels)
+        tex = tex[(tex >> 24) >= 200]  # :88
+        quant.add_colors(np.stack([tex & 255, (tex >> 8) & 255, (tex >> 16) & 255], axis=1).astype(np.uint8))
     pal_rgb = quant.build(240)  # :94
     palette = terrain.reference_palette()  # debug / emissive entries of Main.cpp:52-60 stay in place
     for i, c in enumerate(pal_rgb):
         palette[i] = terrain.encode_material(int(c[0]), int(c[1]), int(c[2]))  # :96-99 (entry 0 is the empty voxel id)
-    # 2. placement (:101-115): bounds over the (linear-part) transformed vertices
+    # 2. placement (:101-115).  The running minimum starts at +FLT_MIN (sic, :101), so a model that lies wholly on the positive side
+    #    of an axis is measured from ~0 there, not from its own minimum.
     flat = tris.reshape(-1, 3)
-    bmin, bmax = flat.min(axis=0), flat.max(axis=0)
+    bmin = np.minimum(FLT_MIN, flat.min(axis=0)).astype(np.float32)
+    bmax = np.maximum(np.float32(-3.4028235e38), flat.max(axis=0)).astype(np.float32)
     rng = bmax - bmin
     scale = np.float32(size) / np.float32(rng.max())
     center = (np.float32(size) - rng * scale) * np.float32(0.5)
     center[1] = 0
-    vt = ((tris - bmin) * scale + center).astype(np.float32)
-    # 3. quantise every texture once (texel -> palette index, 255 = transparent), then rasterise
-    tex_list = sorted(tex_rgba.keys())
-    tex_index = {p: i for i, p in enumerate(tex_list)}
-    quantised = []
-    for p in tex_list:
-        img = tex_rgba[p]
-        idx = nearest_palette_index(pal_rgb, img[..., :3]).reshape(img.shape[:2])
-        idx = np.where(img[..., 3] >= 128, idx, 255).astype(np.uint8)  # :137 alpha test
-        quantised.append(np.ascontiguousarray(idx))
-    tri_tex = np.array([tex_index[images[m]] if (0 <= m < len(images) and images[m] is not None) else -1 for m in mats.tolist()], np.int32)
+    vt = np.ascontiguousarray(((tris - bmin) * scale + center).astype(np.float32))
+    # 3. rasterise; colour = the sampler's level-0 bilinear tap, alpha test, nearest palette entry (:117-146)
     lib = _voxlib()
-    nb = size // 8
+    nb = size // 8 if grid_bricks is None else grid_bricks
     grid = lib.vox_create(nb, nb, nb)
     if not grid:
         raise MemoryError("voxeliser grid")
     try:
-        ptrs = (C.c_void_p * max(1, len(quantised)))(*[q.ctypes.data for q in quantised])
-        tw = np.array([q.shape[1] for q in quantised] or [1], np.int32)
-        th = np.array([q.shape[0] for q in quantised] or [1], np.int32)
-        vt = np.ascontiguousarray(vt)
+        imgs = [c[0] for c in chains]
+        ptrs = (C.c_void_p * max(1, len(imgs)))(*[q.ctypes.data for q in imgs])
+        tw = np.array([q.shape[1] for q in imgs] or [1], np.int32)
+        th = np.array([q.shape[0] for q in imgs] or [1], np.int32)
         uvc = np.ascontiguousarray(uvs, dtype=np.float32)
-        degenerate = lib.vox_triangles(grid, vt.shape[0], vt.ctypes.data, uvc.ctypes.data, tri_tex.ctypes.data, ptrs, tw.ctypes.data, th.ctypes.data, 1)
+        tri_tex = np.ascontiguousarray(tri_tex, np.int32)
+        palc = np.ascontiguousarray(pal_rgb, np.uint8)
+        degenerate = lib.vox_triangles(grid, vt.shape[0], vt.ctypes.data, uvc.ctypes.data, tri_tex.ctypes.data, ptrs, tw.ctypes.data, th.ctypes.data,
+                                       palc.ctypes.data, palc.shape[0], 1)
+        if degenerate < 0:
+            raise MemoryError("voxeliser colour memo")
         n = lib.vox_brick_count(grid)
         bricks = np.zeros((n, 512), np.uint8)
         coords = np.zeros((n, 3), np.int32)
@@ -330,8 +390,18 @@ def voxelize_model(gltf: Path, size: int):
         written = lib.vox_voxels_set(grid)
     finally:
         lib.vox_destroy(grid)
-    scene = bricks_to_scene(coords, bricks, palette, f"{gltf.parent.name}/{gltf.name} voxelised into {size}^3 ({vt.shape[0]} triangles, {degenerate} degenerate, {written} voxel writes)")
-    return scene
+    scene = bricks_to_scene(coords, bricks, palette, f"{name} voxelised into {size}^3 ({vt.shape[0]} triangles, {degenerate} zero-area, {written} voxel writes)")
+    return scene, pal_rgb
+
+
+def voxelize_model(gltf: Path, size: int):
+    """The bundled glTF through voxelize_arrays."""
+    tris, uvs, mats, images = load_gltf(gltf)
+    tex_list = sorted({p for p in images if p is not None})
+    tex_index = {p: i for i, p in enumerate(tex_list)}
+    textures = [load_rgba(p) for p in tex_list]
+    tri_tex = np.array([tex_index[images[m]] if (0 <= m < len(images) and images[m] is not None) else -1 for m in mats.tolist()], np.int32)
+    return voxelize_arrays(tris, uvs, tri_tex, textures, size, name=f"{gltf.parent.name}/{gltf.name}")[0]
 
 
 def _cache_path(size):

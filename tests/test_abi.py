@@ -35,7 +35,7 @@ def test_struct_sizes_match_header():
     assert C.sizeof(capi.VrtFrame) == 8 + 64 + 64 + 12 + 12 + 16 + 8
     assert C.sizeof(capi.VrtSkyDesc) == 4 * 3 + 64 + 4 + 8  # padded to 8
     assert capi.HIT_DTYPE.itemsize == 48 and capi.HITD_DTYPE.itemsize == 48 and capi.TILE_DTYPE.itemsize == 256
-    assert C.sizeof(capi.VrtStats) == 72 and C.sizeof(capi.VrtTraversalMetrics) == 48
+    assert C.sizeof(capi.VrtStats) == 80 and C.sizeof(capi.VrtTraversalMetrics) == 48
 
 
 def test_no_cpu_fallback_without_a_gpu():

@@ -19,7 +19,8 @@ def _voxelize(tris, size=32):
     tex = np.full(vt.shape[0], -1, np.int32)
     ptrs = (C.c_void_p * 1)()
     one = np.ones(1, np.int32)
-    lib.vox_triangles(g, vt.shape[0], vt.ctypes.data, uv.ctypes.data, tex.ctypes.data, ptrs, one.ctypes.data, one.ctypes.data, 7)
+    pal = np.zeros((1, 3), np.uint8)
+    lib.vox_triangles(g, vt.shape[0], vt.ctypes.data, uv.ctypes.data, tex.ctypes.data, ptrs, one.ctypes.data, one.ctypes.data, pal.ctypes.data, 1, 7)
     n = lib.vox_brick_count(g)
     bricks = np.zeros((n, 512), np.uint8)
     coords = np.zeros((n, 3), np.int32)

@@ -10,6 +10,9 @@ from voxelrt_b200 import capi
 
 scene = terrain.bench_terrain()
 ctx = ctx_for(scene, initial_brick_capacity=1 << 18)
+if len(sys.argv) > 2:
+    ctx.set_option("gather_threads", int(sys.argv[2]))
+    print("gather_threads", sys.argv[2])
 frames, _ = edits.random_edit_frames(scene, 40, int(sys.argv[1]) if len(sys.argv) > 1 else 4096, seed=1)
 batches = [capi.make_records(r) for r in frames]
 w, h = 3840, 2160

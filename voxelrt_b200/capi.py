@@ -95,6 +95,7 @@ class VrtStats(C.Structure):
             "bricks_relocated",
             "device_bytes",
             "last_launches",
+            "bounce_form",
         )
     ]
 

@@ -10,6 +10,9 @@
 #include <cstdio>
 #include <cstring>
 #include <string>
+#include <condition_variable>
+#include <functional>
+#include <mutex>
 #include <thread>
 #include <vector>
 
@@ -30,8 +33,69 @@ struct DeviceBuffer {
 
 }  // namespace
 
+// Host threads that gather dirty bricks from the caller's records into the pinned staging buffer (vrt_sync).  They live as long as the
+// context and sleep between calls: a per-frame edit batch (thousands of 512-byte bricks, a few MB) is too short to pay for starting
+// threads, yet one core's memcpy of it is the longest single piece of a frame's vrt_sync.
+class GatherPool {
+public:
+    ~GatherPool() { stop(); }
+    unsigned workers() const { return (unsigned)th_.size(); }
+    void start(unsigned n) {
+        quit_ = false;  // (no worker exists here)
+        const unsigned g = gen_;
+        for (unsigned i = 0; i < n; i++) th_.emplace_back([this, i, g] { loop(i, g); });
+    }
+    void stop() {
+        {
+            std::lock_guard<std::mutex> l(m_);
+            quit_ = true;
+        }
+        cv_.notify_all();
+        for (auto& t : th_) t.join();
+        th_.clear();
+    }
+    // f(part, parts) on every worker (part 0 .. workers() - 1) and on the caller (part workers()); returns when all are done
+    void run(const std::function<void(unsigned, unsigned)>& f) {
+        const unsigned parts = workers() + 1;
+        {
+            std::lock_guard<std::mutex> l(m_);
+            job_ = &f, pending_ = workers(), gen_++;
+        }
+        cv_.notify_all();
+        f(parts - 1, parts);
+        std::unique_lock<std::mutex> l(m_);
+        done_.wait(l, [this] { return pending_ == 0; });
+        job_ = nullptr;
+    }
+
+private:
+    void loop(unsigned idx, unsigned seen) {
+        for (;;) {
+            const std::function<void(unsigned, unsigned)>* f;
+            {
+                std::unique_lock<std::mutex> l(m_);
+                cv_.wait(l, [&] { return quit_ || gen_ != seen; });
+                if (quit_) return;
+                seen = gen_, f = job_;
+            }
+            (*f)(idx, workers() + 1);
+            {
+                std::lock_guard<std::mutex> l(m_);
+                if (--pending_ == 0) done_.notify_one();
+            }
+        }
+    }
+    std::vector<std::thread> th_;
+    std::mutex m_;
+    std::condition_variable cv_, done_;
+    const std::function<void(unsigned, unsigned)>* job_ = nullptr;
+    unsigned gen_ = 0, pending_ = 0;
+    bool quit_ = false;
+};
+
 struct VrtContext {
     int device = 0;
+    GatherPool gather_pool;  // started by the first vrt_sync that has enough bricks to share out
     cudaStream_t stream = nullptr;
     cudaStream_t copy_stream = nullptr;  // D2H copies of finished bands overlap the next band's kernel
     cudaEvent_t ev_band[16] = {};
@@ -88,15 +152,16 @@ struct VrtContext {
     // Bit-identical, but which is faster depends on the scene (open terrain, 2 bounces: +10..15 %; inside Sponza: -8..12 %), so
     // the default (2) measures: after every change of scene emptiness / bounce count / frame size the next two bounce frames
     // run one form each between CUDA events, and the faster one is kept.  0 / 1 force a form.
+    int gather_threads = 0;
     int wave_on = 2;
     int trace_refill = VRT_TRACE_REFILL;  // k_wave_trace: lanes in flight below which a warp refills (tuning knob, "trace_refill")
     int tile_order = 1;  // k_render: 0 top-to-bottom, 1 bottom-to-top (see FrameParams::work_add; "tile_order")
     int trace_ctas = VRT_TRACE_CTAS;      // k_wave_trace: resident CTAs per SM it is compiled for (8 / 10 / 12, "trace_ctas")
     int wave_choice = -1;         // -1 undecided, 0 per-pixel, 1 wavefront
-    int wave_phase = 0;           // 0: time per-pixel next, 1: time wavefront next, 2: waiting for the events
+    int wave_phase = 0;           // 0..3: the tuning frame to time next (even: per-pixel, odd: wavefront), 4: waiting for the events
     uint64_t wave_key = 0;        // (bounces, width, height, scene epoch) the decision was taken for
     uint64_t scene_epoch = 0;     // bumped when a sync changes some sector's emptiness
-    cudaEvent_t ev_tune[4] = {};
+    cudaEvent_t ev_tune[8] = {};  // (begin, end) of the four tuning frames: per-pixel, wavefront, per-pixel, wavefront
     // wavefront frames: a ring of buffer sets, so that consecutive frames issued on different streams (multi-GPU: frames rotate over
     // streams to overlap one frame's tail with the next frame's start) do not wait for each other's queues
     struct WaveSet {
@@ -322,7 +387,7 @@ int launch_render(VrtContext* ctx, const VrtFrame* f, void* d_out, VrtHit* d_aux
     if (ctx->metrics_on) CU(cudaMemsetAsync(ctx->d_metrics, 0, sizeof(DevMetrics), s));
     // which form traces a frame with bounces (see wave_on)
     bool use_wave = false;
-    int tune_slot = -1;  // >= 0: this frame is one of the two timed ones (events tune_slot, tune_slot + 1)
+    int tune_slot = -1;  // >= 0: this frame is one of the four timed ones (events tune_slot, tune_slot + 1)
     if (!primary && !ctx->metrics_on && !ctx->persist_on && ctx->wave_on) {
         if (ctx->wave_on == 1) use_wave = true;
         else if (row0 != 0 || row1 != 0) use_wave = ctx->wave_choice == 1;  // row-range launches of the band-pipelined host path never tune
@@ -331,18 +396,19 @@ int launch_render(VrtContext* ctx, const VrtFrame* f, void* d_out, VrtHit* d_aux
             const uint64_t key = ((uint64_t)F.bounces << 56) ^ ((uint64_t)F.width << 40) ^ ((uint64_t)F.height << 24) ^ ((uint64_t)part_count << 60) ^
                                  ((uint64_t)(F.flags & VRT_FRAME_PART_ROWS) << 52) ^ (ctx->scene_epoch & 0xFFFFFFu);
             if (key != ctx->wave_key) ctx->wave_key = key, ctx->wave_choice = -1, ctx->wave_phase = 0;
-            if (ctx->wave_choice < 0 && ctx->wave_phase == 2 && cudaEventQuery(ctx->ev_tune[3]) == cudaSuccess) {
-                float t_pixel = 0.0f, t_wave = 0.0f;
-                if (cudaEventElapsedTime(&t_pixel, ctx->ev_tune[0], ctx->ev_tune[1]) == cudaSuccess &&
-                    cudaEventElapsedTime(&t_wave, ctx->ev_tune[2], ctx->ev_tune[3]) == cudaSuccess)
-                    ctx->wave_choice = t_wave < t_pixel ? 1 : 0;
+            if (ctx->wave_choice < 0 && ctx->wave_phase == 4 && cudaEventQuery(ctx->ev_tune[7]) == cudaSuccess) {
+                // two timed frames per form, alternating, the faster one of each counts: the very first frame of a form also pays
+                // for its lazily loaded kernels and cold caches, which is not what the next thousand frames will see
+                float t[4] = {};
+                bool ok = true;
+                for (int i = 0; i < 4; i++) ok = ok && cudaEventElapsedTime(&t[i], ctx->ev_tune[2 * i], ctx->ev_tune[2 * i + 1]) == cudaSuccess;
+                if (ok) ctx->wave_choice = fminf(t[1], t[3]) < fminf(t[0], t[2]) ? 1 : 0;
                 else ctx->wave_phase = 0;
                 cudaGetLastError();
             }
             if (ctx->wave_choice >= 0) use_wave = ctx->wave_choice == 1;
-            else if (ctx->wave_phase == 0) use_wave = false, tune_slot = 0, ctx->wave_phase = 1;
-            else if (ctx->wave_phase == 1) use_wave = true, tune_slot = 2, ctx->wave_phase = 2;
-            else use_wave = true;  // both timed frames are still in flight
+            else if (ctx->wave_phase < 4) use_wave = (ctx->wave_phase & 1) != 0, tune_slot = 2 * ctx->wave_phase, ctx->wave_phase++;
+            else use_wave = true;  // the timed frames are still in flight
         }
     }
     // (the timed region starts right before the first launch — after any one-time buffer allocation of the form)
@@ -357,6 +423,7 @@ int launch_render(VrtContext* ctx, const VrtFrame* f, void* d_out, VrtHit* d_aux
             if (slot >= 0) cudaEventRecord(c->ev_tune[slot + 1], st);
         }
     } tune_end{ctx, tune_slot, s};
+    if (!primary) ctx->stats.bounce_form = (use_wave ? 2u : 1u) | ((ctx->wave_on == 2 && !ctx->metrics_on && !ctx->persist_on && row0 == 0 && row1 == 0 && ctx->wave_choice < 0) ? 0x100u : 0u);
     if (use_wave) {
         // Wavefront: camera pass, then per bounce level a trace pass (persistent, lanes refilled from the level's queue) and a shade
         // pass (one thread per pixel in tile order: the packet coupling is two half-warp votes) — vrt_shade.cuh, vrt_kernels.cuh.
@@ -553,6 +620,7 @@ extern "C" int vrt_create(const VrtConfig* cfg, VrtContext** out) {
 
 extern "C" void vrt_destroy(VrtContext* ctx) {
     if (!ctx) return;
+    ctx->gather_pool.stop();
     DeviceGuard g(ctx->device);
     cudaDeviceSynchronize();
     for (void* p : ctx->imported) cudaIpcCloseMemHandle(p);
@@ -621,6 +689,11 @@ extern "C" int vrt_set_option(VrtContext* ctx, const char* name, int64_t value) 
         if (value != 0) return fail(ctx, VRT_ERR_UNSUPPORTED, "compact_bounces was removed; see the \"wavefront\" option");
     }
     else if (!strcmp(name, "wavefront")) ctx->wave_on = (int)value;
+    else if (!strcmp(name, "gather_threads")) {  // host threads of vrt_sync's staging gather: 0 = min(8, cores), 1 = the calling thread only
+        if (value < 0 || value > 64) return fail(ctx, VRT_ERR_INVALID, "gather_threads: 0..64");
+        if ((int)value != ctx->gather_threads) ctx->gather_pool.stop();
+        ctx->gather_threads = (int)value;
+    }
     else if (!strcmp(name, "reserve_slots")) {
         // test hook: takes the first `value` brick slots out of the arena, so that a small scene lives at slot numbers a 10 GB scene
         // reaches (byte offsets beyond 2^32: every kernel must address bricks with 64-bit arithmetic).  Before the first vrt_sync.
@@ -845,12 +918,15 @@ extern "C" int vrt_sync(VrtContext* ctx, uint32_t n, const VrtDirtySector* recs)
                     slots[i] = uploads[i0 + i].slot;
                 }
             };
-            const unsigned hw = std::max(1u, std::min(8u, std::thread::hardware_concurrency()));
-            if (nb >= 16384 && hw > 1) {
-                std::vector<std::thread> pool;
-                for (unsigned t = 1; t < hw; t++) pool.emplace_back(gather, nb * t / hw, nb * (t + 1) / hw);
-                gather(0, nb / hw);
-                for (auto& th : pool) th.join();
+            if (nb >= 2048 && ctx->gather_threads != 1) {
+                if (ctx->gather_pool.workers() == 0) {
+                    const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
+                    const unsigned want = ctx->gather_threads > 0 ? (unsigned)ctx->gather_threads : std::min(8u, hw);
+                    if (want > 1) ctx->gather_pool.start(want - 1);
+                }
+                if (ctx->gather_pool.workers())
+                    ctx->gather_pool.run([&](unsigned part, unsigned parts) { gather(nb * part / parts, nb * (part + 1) / parts); });
+                else gather(0, nb);
             } else gather(0, nb);
             size_t bytes = off_meta;
             if (c == 0) {
