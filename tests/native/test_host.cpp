@@ -89,6 +89,61 @@ static void test_arena() {
     CHECK(a.allocated() == sum && a.check_invariants());
     for (auto& r : live) a.release(r.first, r.second);
     CHECK(a.allocated() == 0 && a.free_ranges() == 1);  // fully coalesced
+    // ranges beyond a sector's 64 slots (power-of-two size classes: a class member may be too small and must be passed over), growth
+    // in place, and the steady churn of an edit session (sectors re-sized by +-1: the index must not pile up stale entries)
+    live.clear();
+    std::vector<uint8_t> used(a.capacity(), 0);
+    auto mark = [&](uint32_t b, uint32_t n, uint8_t v) {
+        if (used.size() < a.capacity()) used.resize(a.capacity(), 0);
+        for (uint32_t i = b; i < b + n; i++) {
+            CHECK(used[i] != v);
+            used[i] = v;
+        }
+    };
+    std::vector<std::pair<uint32_t, uint32_t>> parked;
+    auto unpark = [&]() {
+        a.flush_quarantine();
+        for (auto& r : parked) mark(r.first, r.second, 0);
+        parked.clear();
+    };
+    for (int i = 0; i < 60000; i++) {
+        const unsigned op = rng() % 8;
+        if (live.empty() || op < 3) {
+            uint32_t n = (rng() % 16 == 0) ? 65 + rng() % 400 : 1 + rng() % 64, base = a.alloc(n);
+            if (base == vrt::RangeArena::kNone) {
+                a.grow(a.capacity() * 2);
+                base = a.alloc(n);
+            }
+            CHECK(base != vrt::RangeArena::kNone && base + n <= a.capacity() && base + n <= a.high_water());
+            mark(base, n, 1);
+            live.push_back({base, n});
+        } else if (op < 5) {
+            auto& r = live[rng() % live.size()];
+            uint32_t want = r.second + 1 + rng() % 3;
+            bool room = r.first + want <= a.capacity();
+            for (uint32_t j = r.first + r.second; room && j < r.first + want; j++) room = used[j] == 0;
+            bool got = a.extend(r.first, r.second, want);
+            CHECK(got == room);  // in place exactly when the slots behind the range are free
+            if (got) mark(r.first + r.second, want - r.second, 1), r.second = want;
+        } else {
+            size_t k = rng() % live.size();
+            mark(live[k].first, live[k].second, 2);  // parked: not yet allocatable
+            parked.push_back(live[k]);
+            a.quarantine(live[k].first, live[k].second);
+            if (rng() % 4 == 0) unpark();
+            live[k] = live.back(), live.pop_back();
+        }
+        if (i % 499 == 0) {
+            unpark();
+            CHECK(a.check_invariants());
+        }
+    }
+    unpark();
+    sum = 0;
+    for (auto& r : live) sum += r.second;
+    CHECK(a.allocated() == sum && a.check_invariants());
+    for (auto& r : live) a.release(r.first, r.second);
+    CHECK(a.allocated() == 0 && a.free_ranges() == 1 && a.largest_free() == a.capacity());
 }
 
 // ---- GPU: adapter vs oracle -----------------------------------------------------------------------

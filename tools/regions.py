@@ -107,26 +107,19 @@ def region_of(regs, frames):
     return names[0] if names else "(no line info)"
 
 
-def main():
-    src_csv = Path(sys.argv[1]) if len(sys.argv) > 1 else ROOT / "gpurun_out" / "prof_render_source.csv"
-    out = Path(sys.argv[2]) if len(sys.argv) > 2 else None
-    rows = list(csv.reader(open(src_csv)))
-    kernel = rows[0][1] if rows and rows[0][0] == "Kernel Name" else "k_render"
-    hdr, data = rows[1], rows[2:]
-    for k, r in enumerate(data):  # a capture of several launches repeats the header block: keep the first launch
-        if r and r[0] == "Kernel Name":
-            data = data[:k]
-            break
+def report(kernel, hdr, data, src_name, regs):
     ia, ie, it, isamp = hdr.index("Address"), hdr.index("Instructions Executed"), hdr.index("Thread Instructions Executed"), hdr.index("# Samples")
-    flags = re.findall(r"\(bool\)([01])", kernel.split("(vrt::")[0])
+    targs = kernel.split("(vrt::")[0]
     mname = re.search(r"vrt::(\w+)", kernel)
     base = mname.group(1) if mname else "k_render"
-    sub = f"{len(base)}{base}I" + "".join(f"Lb{f}E" for f in flags) if flags else base
-    table, regs = line_table(sub), source_regions()
-    base = int(data[0][ia], 16)
+    # mangled template arguments: <(bool)0, (bool)1> -> ILb0ELb1EE, <(int)10> -> ILi10EE
+    margs = "".join(f"L{'b' if t == 'bool' else 'i'}{v}E" for t, v in re.findall(r"\((bool|int)\)(\d+)", targs))
+    sub = f"{len(base)}{base}I{margs}" if margs else f"{len(base)}{base}"
+    table = line_table(sub)
+    base_addr = int(data[0][ia], 16)
     agg, tot_e, tot_s = {}, 0, 0
     for r in data:
-        off = int(r[ia], 16) - base
+        off = int(r[ia], 16) - base_addr
         name = region_of(regs, table.get(off, []))
         a = agg.setdefault(name, [0, 0, 0, 0])
         e, t, s = int(r[ie]), int(r[it]), int(r[isamp])
@@ -136,13 +129,40 @@ def main():
         a[3] += 1
         tot_e += e
         tot_s += s
-    lines = [f"kernel: {kernel}", f"capture: {src_csv.name}; line table: nvdisasm -g of {LIB.name}", f"executed warp instructions: {tot_e}   stall samples: {tot_s}", "",
+    lines = [f"kernel: {kernel}", f"capture: {src_name}; line table: nvdisasm -g of {LIB.name}", f"executed warp instructions: {tot_e}   stall samples: {tot_s}", "",
              f"{'source region':58s} {'SASS':>5s} {'warp inst':>12s} {'%inst':>6s} {'thr/inst':>8s} {'%samples':>8s}"]
     for name, (e, t, s, n) in sorted(agg.items(), key=lambda kv: -kv[1][0]):
         if e == 0 and s == 0:
             continue
         lines.append(f"{name:58s} {n:5d} {e:12d} {100 * e / max(tot_e, 1):6.1f} {t / max(e, 1):8.1f} {100 * s / max(tot_s, 1):8.1f}")
-    text = "\n".join(lines) + "\n"
+    return "\n".join(lines) + "\n"
+
+
+def main():
+    src_csv = Path(sys.argv[1]) if len(sys.argv) > 1 else ROOT / "gpurun_out" / "prof_render_source.csv"
+    out = Path(sys.argv[2]) if len(sys.argv) > 2 else None
+    rows = list(csv.reader(open(src_csv)))
+    # a capture of several launches repeats the ("Kernel Name", name) / header / instruction-rows block: one table per launch
+    blocks, k = [], 0
+    while k < len(rows):
+        if rows[k] and rows[k][0] == "Kernel Name":
+            kernel, hdr = rows[k][1], rows[k + 1]
+            e = k + 2
+            while e < len(rows) and not (rows[e] and rows[e][0] == "Kernel Name"):
+                e += 1
+            blocks.append((kernel, hdr, [r for r in rows[k + 2 : e] if r]))
+            k = e
+        else:  # single-launch export without the name row
+            blocks.append(("k_render", rows[0], [r for r in rows[1:] if r]))
+            break
+    regs = source_regions()
+    uniq, seen = [], set()
+    for kernel, hdr, data in blocks:  # (ncu exports every launch twice: once per view of the source page)
+        key = (kernel, data[0][0] if data else None, len(data), sum(int(r[hdr.index("Instructions Executed")]) for r in data))
+        if data and key not in seen:
+            seen.add(key)
+            uniq.append((kernel, hdr, data))
+    text = "\n".join(report(kernel, hdr, data, src_csv.name.lstrip("."), regs) for kernel, hdr, data in uniq)
     if out:
         out.write_text(text)
     print(text)
