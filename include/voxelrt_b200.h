@@ -121,6 +121,18 @@ typedef struct VrtHitD {
                                     * bands b with b % part_count == r (each band is one contiguous range
                                     * of the tile-layout framebuffer, so a rank's result moves with one
                                     * strided copy); default split is by macro tile, t % part_count       */
+#define VRT_FRAME_GLSL 16u         /* render the frame like the reference's GPU renderer: main() of Shaders/VoxelRender.comp:29-93
+                                    * per pixel (getPrimaryRay :20-25, rayCast, the sun shadow ray, `bounces` = u_MaxBounces
+                                    * diffuse bounces through rayCastCoarse with a sun ray after the first two, sky on a miss),
+                                    * i.e. GpuRenderer::RenderFrame's compute dispatch (GpuRenderer.cpp:257-268) instead of
+                                    * CpuRenderer::RenderFrame's RenderRow.  Same frame constants, same 16 B/px tile output —
+                                    * albedo | packGNormal << 24, depth, irradiance as 3 halfs, and the 4th half = hit.iters
+                                    * (what the shader stores in IrradianceTex.w) — so every way of delivering a frame (host /
+                                    * device buffers, band split, gather, the GBuffer step) applies.  Needs a view of at least
+                                    * 4 sectors per axis (the 128^3 level), vrt_set_blue_noise for bounces > 0.  PARITY
+                                    * UNPINNED (no GL device): bit-equal to its own oracle under the canonical arithmetic and
+                                    * the two stand-ins (sky sampler, unassigned `out` fields) stated in vrt_glsl_frame.cuh  */
+#define VRT_FRAME_GLSL_ANISOTROPIC 32u /* with VRT_FRAME_GLSL: u_UseAnisotropicLods (GpuRenderer.cpp:262)              */
 #define VRT_BAND_ROWS 8u           /* two tile rows: 2.7 % load imbalance at 8 GPUs on the 4K terrain frame
                                     * (32-pixel bands: 14 %)                                              */
 typedef struct VrtFrame {

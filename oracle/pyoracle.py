@@ -76,6 +76,8 @@ def load():
     lib.orc_trace.restype = None
     lib.orc_trace_glsl.argtypes = [vp, u64, vp, vp, C.POINTER(C.c_int32), u32, vp, C.POINTER(OrcStats), C.c_int]
     lib.orc_trace_glsl.restype = None
+    lib.orc_render_glsl.argtypes = [vp, C.POINTER(VrtFrame), vp, C.POINTER(OrcStats), C.c_int]
+    lib.orc_render_glsl.restype = None
     lib.orc_interaction_lut.argtypes = [vp]
     lib.orc_interaction_lut.restype = None
     lib.orc_hit_query.argtypes = [vp, u64, vp, vp, u32, vp, C.c_int]
@@ -186,6 +188,14 @@ class OracleMap:
             frame.height if row1 is None else row1,
         )
         return out, aux, st
+
+    def render_glsl(self, frame: VrtFrame, threads=0):
+        """A VRT_FRAME_GLSL frame (the GPU renderer's VoxelRender.comp per pixel) -> (tiles or 4 planes, stats)."""
+        n = frame.width * frame.height
+        out = np.zeros((4, frame.height, frame.width), np.uint32) if frame.flags & VRT_FRAME_LINEAR_OUTPUT else np.zeros(n // 16, TILE_DTYPE)
+        st = OrcStats()
+        self.lib.orc_render_glsl(self.h, C.byref(frame), out.ctypes.data, C.byref(st), threads)
+        return out, st
 
     def debug_pixel(self, frame: VrtFrame, x, y):
         """-> (rays[n,6], hits[n], out4) of everything pixel (x,y) casts."""

@@ -1180,3 +1180,197 @@ void orc_trace_glsl(const OrcMap* m, uint64_t n, const float* origin3, const flo
     }
     if (stats) *stats = total;
 }
+
+/* ---------------------------------------------------------------------------------------------- */
+/* The GPU renderer's frame shader: main() of VoxelRT/Shaders/VoxelRender.comp:29-93 per pixel, with */
+/* getPrimaryRay :20-25, getSkyColor :15-17, random_dir / blueNoise (RandomGen.glsl:27-48),          */
+/* getMaterialColor / getMaterialEmission (VoxelMap.glsl:78-84), packGNormal (GBuffer.glsl:17-20).   */
+/* PARITY UNPINNED (GLSL needs a GL device).  Canonical arithmetic: fp32, one operation at a time, no */
+/* contraction (this file is compiled with -ffp-contract=off); mat * vec summed column by column;     */
+/* normalize(v) = v * (1 / sqrt(dot(v, v))); sin / cos through the CPU renderer's sincos_2pi on the   */
+/* blue-noise fraction; imageStore: rgba8 = rint(clamp(x, 0, 1) * 255), rgba16f = round to nearest    */
+/* even.  Stand-ins: the sky is the map's cube (the CPU renderer's) at level 0 through ProjectCubemap */
+/* + nearest, not GL's seamless bilinear fetch of the cube PanoramaToCube.comp builds; a HitInfo      */
+/* field the shader leaves unassigned on a path keeps its previous value.                             */
+/* ---------------------------------------------------------------------------------------------- */
+typedef struct {
+    float pos[3], nrm[3];
+    uint32_t mat, iters;
+} GlslHitInfo;
+
+static int glsl_cast_info(const OrcMap* m, const float o[3], const float d[3], const int32_t wo[3], uint32_t flags, const uint64_t* lut, GlslHitInfo* H,
+                          CastCounters* cnt) {
+    VrtHit r;
+    glsl_cast(m, o, d, wo, flags, lut, &r, cnt);
+    if (!(r.flags & VRT_HIT_CAPPED)) H->iters = r.flags >> VRT_HIT_ITERS_SHIFT; /* :189,199 / :223,237; the final `return false` assigns nothing */
+    if (!(r.flags & VRT_HIT_HIT)) return 0;
+    H->mat = r.material;
+    H->pos[0] = r.px, H->pos[1] = r.py, H->pos[2] = r.pz;
+    for (int a = 0; a < 3; a++) H->nrm[a] = (float)((int)((r.flags >> (2 * a)) & 3u) - 1);
+    return 1;
+}
+static void glsl_normalize(float v[3]) {
+    float len2 = (v[0] * v[0] + v[1] * v[1]) + v[2] * v[2];
+    float k = 1.0f / sqrtf(len2);
+    v[0] *= k, v[1] *= k, v[2] *= k;
+}
+static void glsl_material_color(uint32_t md, float c[3]) {
+    c[0] = (float)((md >> 11) & 31u) * (1.0f / 31.0f);
+    c[1] = (float)((md >> 5) & 63u) * (1.0f / 63.0f);
+    c[2] = (float)(md & 31u) * (1.0f / 31.0f);
+    for (int a = 0; a < 3; a++) c[a] = c[a] * c[a];
+}
+static void glsl_sky(const OrcMap* m, const float d[3], float c[3]) {
+    if (!m->sky_texels) {
+        c[0] = c[1] = c[2] = 0.0f;
+        return;
+    }
+    float t[3];
+    orc_sky_sample(m, d, 0, t); /* texel * 3 (exact: 6 + 2 significant bits), so / 3 returns the texel */
+    for (int a = 0; a < 3; a++) c[a] = glsl_min((t[a] / 3.0f) * 5.0f, 50000.0f);
+}
+static void glsl_random_dir(const OrcMap* m, uint32_t x, uint32_t y, uint32_t frame_no, uint32_t i, float r[3]) {
+    float fi = (float)i, ox = fi * 0.75487766624669276005f, oy = fi * 0.56984029099805326591f;
+    float sx = ox + 0.5f, sy0 = oy + 0.5f;
+    sx -= floorf(sx);
+    sy0 -= floorf(sy0);
+    uint32_t px = (x + (uint32_t)(sx * 128.0f)) & 127u, py = ((y + (uint32_t)(sy0 * 128.0f)) & 127u) + (frame_no & 63u) * 128u;
+    const uint8_t* t = m->blue_noise + ((size_t)py * 128 + px) * 2;
+    float nx = ((float)t[0] + 0.5f) * (1.0f / 256.0f), ny = ((float)t[1] + 0.5f) * (1.0f / 256.0f);
+    float yy = nx * 2.0f - 1.0f, s, c;
+    sincos_2pi(ny, &s, &c);
+    float sy = sqrtf(1.0f - yy * yy);
+    r[0] = s * sy, r[1] = yy, r[2] = c * sy;
+}
+static uint32_t glsl_unorm8(float v) { return (uint32_t)(int32_t)nearbyintf(glsl_min(glsl_max(v, 0.0f), 1.0f) * 255.0f); }
+
+static void glsl_frame_pixel(const OrcMap* m, const VrtFrame* f, const uint64_t* lut, uint32_t x, uint32_t y, uint32_t* o_albedo, float* o_depth,
+                             uint32_t* o_rg, uint32_t* o_bx, CastCounters* cnt) {
+    const int32_t* wo = f->world_origin;
+    const float* iv = f->inv_proj;
+    float pos[3], dir[3], nr[4], fr[4];
+    const float fx = (float)(int32_t)x, fy = (float)(int32_t)y;
+    for (int k = 0; k < 4; k++) { /* getPrimaryRay */
+        nr[k] = ((iv[k] * fx + iv[4 + k] * fy) + iv[8 + k] * 0.0f) + iv[12 + k] * 1.0f;
+        fr[k] = nr[k] + iv[8 + k];
+    }
+    const float in = 1.0f / nr[3], iff = 1.0f / fr[3];
+    for (int a = 0; a < 3; a++) {
+        pos[a] = nr[a] * in + f->origin_frac[a];
+        dir[a] = fr[a] * iff;
+    }
+    glsl_normalize(dir);
+    float albedo[3], irr[3], nrm[3] = {0, 0, 0}, depth = -1.0f;
+    GlslHitInfo hit, sun_hit;
+    memset(&hit, 0, sizeof(hit));
+    const uint32_t fine = (f->flags & VRT_FRAME_GLSL_ANISOTROPIC) ? VRT_GLSL_ANISOTROPIC : 0u, coarse = fine | VRT_GLSL_COARSE;
+    if (glsl_cast_info(m, pos, dir, wo, fine, lut, &hit, cnt)) {
+        glsl_material_color(hit.mat, albedo);
+        memcpy(nrm, hit.nrm, sizeof(nrm));
+        {
+            const float hx = hit.pos[0] * 0.0625f, hy = hit.pos[1] * 0.0625f, hz = hit.pos[2] * 0.0625f;
+            const float* q = f->proj;
+            const float pz = ((q[2] * hx + q[6] * hy) + q[10] * hz) + q[14] * 1.0f;
+            const float pw = ((q[3] * hx + q[7] * hy) + q[11] * hz) + q[15] * 1.0f;
+            depth = pz / pw;
+        }
+        const float em0 = f16_to_f32((uint16_t)(hit.mat >> 16));
+        float thr[3] = {1.0f, 1.0f, 1.0f};
+        for (int a = 0; a < 3; a++) irr[a] = f->bounces == 0 ? albedo[a] : albedo[a] * em0;
+        float sun[3] = {0.3f, 0.9f, -0.28f};
+        glsl_normalize(sun);
+        const float sun_intensity = 5.0f;
+        const float sun_col[3] = {1.2f * sun_intensity, 1.1f * sun_intensity, 1.0f * sun_intensity};
+        sun_hit = hit;
+        if (f->bounces != 0) {
+            const float so[3] = {hit.pos[0] + hit.nrm[0] * 0.01f, hit.pos[1] + hit.nrm[1] * 0.01f, hit.pos[2] + hit.nrm[2] * 0.01f};
+            if (!glsl_cast_info(m, so, sun, wo, coarse, lut, &sun_hit, cnt)) {
+                for (int a = 0; a < 3; a++) irr[a] = irr[a] + sun_col[a];
+            } else {
+                for (int a = 0; a < 3; a++) thr[a] = thr[a] * 0.5f;
+            }
+        }
+        for (uint32_t i = 0; i < f->bounces; i++) {
+            float rnd[3];
+            glsl_random_dir(m, x, y, f->frame_no, i, rnd);
+            for (int a = 0; a < 3; a++) {
+                pos[a] = hit.pos[a] + hit.nrm[a] * 0.01f;
+                dir[a] = hit.nrm[a] + rnd[a];
+            }
+            glsl_normalize(dir);
+            if (!glsl_cast_info(m, pos, dir, wo, coarse, lut, &hit, cnt)) {
+                float sky[3];
+                glsl_sky(m, dir, sky);
+                for (int a = 0; a < 3; a++) irr[a] = irr[a] + thr[a] * sky[a];
+                break;
+            }
+            float col[3];
+            glsl_material_color(hit.mat, col);
+            for (int a = 0; a < 3; a++) thr[a] = thr[a] * col[a];
+            float emission = f16_to_f32((uint16_t)(hit.mat >> 16));
+            if (i < 2u) {
+                const float so[3] = {hit.pos[0] + hit.nrm[0] * 0.01f, hit.pos[1] + hit.nrm[1] * 0.01f, hit.pos[2] + hit.nrm[2] * 0.01f};
+                if (!glsl_cast_info(m, so, sun, wo, coarse, lut, &sun_hit, cnt)) {
+                    for (int a = 0; a < 3; a++) thr[a] = thr[a] * sun_col[a];
+                    emission = emission + sun_intensity;
+                }
+            }
+            for (int a = 0; a < 3; a++) irr[a] = irr[a] + thr[a] * emission;
+        }
+    } else {
+        glsl_sky(m, dir, irr);
+        albedo[0] = albedo[1] = albedo[2] = 1.0f;
+    }
+    uint32_t code = 0;
+    for (int a = 0; a < 3; a++) code |= (uint32_t)(int32_t)glsl_min(glsl_max(nrm[a] + 1.0f, 0.0f), 3.0f) << (2 * a);
+    *o_albedo = glsl_unorm8(albedo[0]) | (glsl_unorm8(albedo[1]) << 8) | (glsl_unorm8(albedo[2]) << 16) | (code << 24);
+    *o_depth = depth;
+    *o_rg = (uint32_t)f32_to_f16(irr[0]) | ((uint32_t)f32_to_f16(irr[1]) << 16);
+    *o_bx = (uint32_t)f32_to_f16(irr[2]) | ((uint32_t)f32_to_f16((float)hit.iters) << 16);
+}
+
+/* A frame of the GPU renderer (GpuRenderer::RenderFrame's dispatch, GpuRenderer.cpp:257-268) into the 16 B/px tile framebuffer (or the 4
+ * planes of VRT_FRAME_LINEAR_OUTPUT); honours part_index / part_count like orc_render.  stats->iters = trips of all casts. */
+void orc_render_glsl(const OrcMap* m, const VrtFrame* f, void* out, OrcStats* stats, int threads) {
+    const uint32_t w = f->width, h = f->height;
+    uint64_t lut[512];
+    orc_interaction_lut(lut);
+    const uint32_t part_count = f->part_count ? f->part_count : 1, tiles_x = (w + 31) / 32;
+    uint64_t iters = 0;
+#ifdef _OPENMP
+    if (threads <= 0) threads = omp_get_max_threads();
+#pragma omp parallel for schedule(dynamic, 4) num_threads(threads) reduction(+ : iters)
+#endif
+    for (int64_t y = 0; y < (int64_t)h; y++) {
+        CastCounters c = {0, 0, 0, {0}};
+        for (uint32_t x = 0; x < w; x++) {
+            if (part_count > 1) {
+                uint32_t t = (f->flags & VRT_FRAME_PART_ROWS) ? ((uint32_t)y / VRT_BAND_ROWS) : ((uint32_t)y / 32) * tiles_x + (x / 32);
+                if (t % part_count != f->part_index) continue;
+            }
+            uint32_t alb, rg, bx;
+            float dep;
+            glsl_frame_pixel(m, f, lut, x, (uint32_t)y, &alb, &dep, &rg, &bx, &c);
+            if (f->flags & VRT_FRAME_LINEAR_OUTPUT) {
+                uint32_t* o = (uint32_t*)out;
+                size_t n = (size_t)w * h, p = (size_t)y * w + x;
+                o[p] = alb;
+                memcpy(&o[n + p], &dep, 4);
+                o[2 * n + p] = rg;
+                o[3 * n + p] = bx;
+            } else {
+                VrtTile* t = (VrtTile*)out + ((size_t)(y / 4) * (w / 4) + x / 4);
+                const uint32_t l = (x & 3) | (((uint32_t)y & 3) << 2);
+                t->albedo[l] = alb;
+                t->depth[l] = dep;
+                t->irr_rg[l] = rg;
+                t->irr_bx[l] = bx;
+            }
+        }
+        iters += c.iters;
+    }
+    if (stats) {
+        memset(stats, 0, sizeof(*stats));
+        stats->iters = iters;
+    }
+}

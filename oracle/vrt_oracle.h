@@ -89,6 +89,9 @@ void orc_sincos_2pi(float x, float* s, float* c);
  * Parity unpinned (GLSL needs a GL device); canonical arithmetic in vrt_oracle.c. */
 void orc_trace_glsl(const OrcMap* m, uint64_t n, const float* origin3, const float* dir3, const int32_t world_origin[3], uint32_t flags,
                     VrtHit* out, OrcStats* stats, int threads);
+/* The GPU renderer's frame shader (Shaders/VoxelRender.comp:29-93) per pixel: VRT_FRAME_GLSL frames (include/voxelrt_b200.h).
+ * Parity unpinned as above; canonical arithmetic and stand-ins in vrt_oracle.c. */
+void orc_render_glsl(const OrcMap* m, const VrtFrame* frame, void* out, OrcStats* stats, int threads);
 /* GenerateRayCellInteractionMaskLUT, GpuRenderer.cpp:193-210 */
 void orc_interaction_lut(uint64_t table[512]);
 

@@ -203,7 +203,7 @@ def test_sync_is_transactional_on_bad_records(hash_scene):
 
 @pytest.mark.parametrize("threads", [0, 1, 3])
 def test_staging_gather_threads_deliver_the_same_bricks(threads):
-    """vrt_sync shares the staging gather of a batch of >= 2048 bricks out over a pool of host threads that lives with the context
+    """vrt_sync shares the staging gather of a batch of >= 8192 bricks out over a pool of host threads that lives with the context
     (option gather_threads: 0 = min(8, cores), 1 = calling thread only): every split delivers every brick to its slot, call after call
     (the pool sleeps in between), also after the thread count changes."""
     from voxelrt_b200 import capi
@@ -215,13 +215,13 @@ def test_staging_gather_threads_deliver_the_same_bricks(threads):
     state = {}
     for rnd in range(4):
         recs = []
-        for sx, sz, sy in [(x, z, y) for y in range(2) for z in range(4) for x in range(4)]:
+        for sx, sz, sy in [(x, z, y) for y in range(2) for z in range(8) for x in range(8)]:
             bricks = rng.integers(0, 256, (64, 512), dtype=np.uint8)
             bricks[:, 0] = 1 + (rnd & 1)  # never all-empty
             recs.append((sx, sy, sz, full, full, bricks))
             state[(sx, sy, sz)] = bricks
-        ctx.sync(recs)  # 32 sectors x 64 bricks = 2048 bricks in one batch
-        assert ctx.stats().bricks_uploaded == 2048
+        ctx.sync(recs)  # 128 sectors x 64 bricks = 8192 bricks in one batch
+        assert ctx.stats().bricks_uploaded == 8192
         for (sx, sy, sz), want in state.items():
             gm, base, gb, gc = ctx.read_sector(sx, sy, sz)
             assert gm == full and np.array_equal(gb, want), (rnd, sx, sy, sz)

@@ -23,4 +23,5 @@ timeout 600 $TR bench.py --gpus $N --workload edits --steps 20 --warmup 5 --no-c
 timeout 900 $TR bench.py --gpus $N --workload large --steps 10 --warmup 3 --no-cpu --no-present > $O/bench_large_${N}gpu.json 2> $O/bench_large_${N}gpu.err; summ $O/bench_large_${N}gpu.json; tail -3 $O/bench_large_${N}gpu.err
 if [ "$N" != "1" ]; then timeout 300 $TR bench.py --impl reference --gpus $N --steps 3 --warmup 1 > $O/bench_ref_${N}gpu.json 2> $O/bench_ref_${N}gpu.err; cut -c1-200 $O/bench_ref_${N}gpu.json; fi
 rm -f /dev/shm/vrt_terrain_*
+if [ "$N" != "1" ]; then timeout 300 $TR tools/d2h_ceiling.py > $O/d2h_ceiling_${N}gpu.txt 2> $O/d2h_ceiling_${N}gpu.err; cat $O/d2h_ceiling_${N}gpu.txt; tail -3 $O/d2h_ceiling_${N}gpu.err; fi
 ls -la $O

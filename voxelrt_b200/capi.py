@@ -28,6 +28,8 @@ VRT_FRAME_LINEAR_OUTPUT = 1
 VRT_FRAME_AUX_HITS = 2
 VRT_FRAME_COMPACT = 4
 VRT_FRAME_PART_ROWS = 8
+VRT_FRAME_GLSL = 16
+VRT_FRAME_GLSL_ANISOTROPIC = 32
 VRT_GATHER_DEPTH = 8
 VRT_BLUE_NOISE_BYTES = 128 * 128 * 64 * 2
 

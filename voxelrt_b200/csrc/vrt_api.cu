@@ -19,6 +19,7 @@
 #include "slot_allocator.h"
 #include "vrt_glsl.cuh"
 #include "vrt_kernels.cuh"
+#include "vrt_glsl_frame.cuh"
 
 using namespace vrt;
 
@@ -144,6 +145,7 @@ struct VrtContext {
     uint2* d_groups = nullptr;  // vrt_trace_glsl: SectorMasks of the GLSL renderer (one u64 per 4x4x4 sectors), built on demand
     uint2* d_lut = nullptr;     // vrt_trace_glsl: ray/cell interaction LUT
     bool groups_stale = true;
+    cudaEvent_t ev_groups = nullptr;  // end of the last k_build_groups
     int macro_on = 1;  // 0 off, 1 on, 2 on + "metrics" launches count the macro loop's own trips (diagnostic)
     DevMetrics* d_metrics = nullptr;
     bool metrics_on = false;
@@ -360,6 +362,49 @@ int launch_trace(VrtContext* ctx, uint64_t n, const float* d_o, const float* d_d
 
 // Launches the frame kernel for macro-tile rows [row0, row1) (32-pixel rows; row1 = 0 means "to the end").
 // Bands are only meaningful for an unpartitioned frame (part_count == 1).
+// GenerateRayCellInteractionMaskLUT (GpuRenderer.cpp:193-210): cells of a 4x4x4 mask a ray of a given octant can reach from a cell
+void interaction_lut(uint64_t table[512]) {
+    for (int oct = 0; oct < 8; oct++) {
+        const int sx = (oct & 1) ? 1 : -1, sy = (oct & 2) ? 1 : -1, sz = (oct & 4) ? 1 : -1;
+        for (int origin = 0; origin < 64; origin++) {
+            const int ox = origin & 3, oz = (origin >> 2) & 3, oy = origin >> 4;
+            uint64_t m = 0;
+            for (int jy = 0; jy < 4; jy++)
+                for (int jz = 0; jz < 4; jz++)
+                    for (int jx = 0; jx < 4; jx++) {
+                        const int x = ox + jx * sx, y = oy + jy * sy, z = oz + jz * sz;
+                        if (x >= 0 && x < 4 && y >= 0 && y < 4 && z >= 0 && z < 4) m |= 1ull << (x + 4 * z + 16 * y);
+                    }
+            table[origin + 64 * oct] = m;
+        }
+    }
+}
+
+// SectorMasks (the 128^3 level) and the interaction LUT of the GLSL renderer, built on demand on the context's stream (after the
+// sync that changed the scene, which itself waited for the frames in flight); work on another stream `s` waits for the build
+int glsl_scene(VrtContext* ctx, cudaStream_t s, GlslScene& G, uint64_t& launches) {
+    if (ctx->sxz < 2 || ctx->sy < 2) return fail(ctx, VRT_ERR_UNSUPPORTED, "GLSL casts: the view must span at least 4 sectors per axis (128^3 level)");
+    const uint32_t gxz = ctx->sxz - 2, n_groups = 1u << (2 * gxz + ctx->sy - 2);
+    if (!ctx->d_lut) {
+        uint64_t table[512];
+        interaction_lut(table);
+        CU(cudaMalloc((void**)&ctx->d_lut, sizeof(table)));
+        CU(cudaMemcpy(ctx->d_lut, table, sizeof(table), cudaMemcpyHostToDevice));
+    }
+    if (!ctx->d_groups) CU(cudaMalloc((void**)&ctx->d_groups, (size_t)n_groups * 8));
+    if (ctx->groups_stale) {
+        k_build_groups<<<(n_groups + 127) / 128, 128, 0, ctx->stream>>>(dev_scene(ctx), ctx->d_groups, gxz, n_groups);
+        CU(cudaGetLastError());
+        if (!ctx->ev_groups) CU(cudaEventCreateWithFlags(&ctx->ev_groups, cudaEventDisableTiming));
+        CU(cudaEventRecord(ctx->ev_groups, ctx->stream));
+        ctx->groups_stale = false;
+        launches++;
+    }
+    if (s != ctx->stream && ctx->ev_groups) CU(cudaStreamWaitEvent(s, ctx->ev_groups, 0));
+    G = GlslScene{ctx->d_groups, ctx->d_lut, gxz};
+    return VRT_OK;
+}
+
 int launch_render(VrtContext* ctx, const VrtFrame* f, void* d_out, VrtHit* d_aux, cudaStream_t s, uint32_t row0 = 0, uint32_t row1 = 0) {
     if (f->width == 0 || f->height == 0 || (f->width & 3u) || (f->height & 3u))
         return fail(ctx, VRT_ERR_INVALID, "frame size must be a non-zero multiple of 4 (CpuRenderer.cpp:419)");
@@ -384,6 +429,19 @@ int launch_render(VrtContext* ctx, const VrtFrame* f, void* d_out, VrtHit* d_aux
     const unsigned wpb = VRT_RENDER_THREADS / 32;
     unsigned blocks = (F.n_work - F.work_offset + wpb - 1) / wpb;
     const bool rows = (F.flags & VRT_FRAME_PART_ROWS) != 0u, primary = F.bounces == 0;
+    if (F.flags & VRT_FRAME_GLSL) {  // the GPU renderer's frame shader (vrt_glsl_frame.cuh): one kernel, one thread per pixel
+        if (F.flags & (VRT_FRAME_COMPACT | VRT_FRAME_AUX_HITS)) return fail(ctx, VRT_ERR_INVALID, "VRT_FRAME_GLSL: no compact payload, no aux hits");
+        GlslScene G;
+        uint64_t launches = 0;
+        int st = glsl_scene(ctx, s, G, launches);
+        if (st) return st;
+        const uint32_t cast_flags = (F.flags & VRT_FRAME_GLSL_ANISOTROPIC) ? VRT_GLSL_ANISOTROPIC : 0u;
+        if (rows) k_render_glsl<true><<<blocks, VRT_RENDER_THREADS, 0, s>>>(S, G, F, cast_flags);
+        else k_render_glsl<false><<<blocks, VRT_RENDER_THREADS, 0, s>>>(S, G, F, cast_flags);
+        CU(cudaGetLastError());
+        ctx->stats.last_launches += launches + 1;
+        return VRT_OK;
+    }
     if (ctx->metrics_on) CU(cudaMemsetAsync(ctx->d_metrics, 0, sizeof(DevMetrics), s));
     // which form traces a frame with bounces (see wave_on)
     bool use_wave = false;
@@ -634,6 +692,7 @@ extern "C" void vrt_destroy(VrtContext* ctx) {
             if (b->p) cudaFree(b->p);
     }
     for (auto& e : ctx->ev_tune) if (e) cudaEventDestroy(e);
+    if (ctx->ev_groups) cudaEventDestroy(ctx->ev_groups);
     DeviceBuffer* bufs[] = {&ctx->d_stage, &ctx->d_rays_o, &ctx->d_rays_d, &ctx->d_hits, &ctx->d_fb,
                             &ctx->d_aux,   &ctx->d_q_o,    &ctx->d_q_d,    &ctx->d_q_out};
     for (auto* b : bufs)
@@ -918,7 +977,7 @@ extern "C" int vrt_sync(VrtContext* ctx, uint32_t n, const VrtDirtySector* recs)
                     slots[i] = uploads[i0 + i].slot;
                 }
             };
-            if (nb >= 2048 && ctx->gather_threads != 1) {
+            if (nb >= 8192 && ctx->gather_threads != 1) {  // (a frame's edit batch, ~3 k bricks, is gathered by the caller: with one process per GPU on a shared host, 8 pools waking for 100 us of copying each cost more than they save)
                 if (ctx->gather_pool.workers() == 0) {
                     const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
                     const unsigned want = ctx->gather_threads > 0 ? (unsigned)ctx->gather_threads : std::min(8u, hw);
@@ -1032,54 +1091,23 @@ extern "C" int vrt_trace(VrtContext* ctx, uint64_t n, const float* origin3, cons
     return VRT_OK;
 }
 
-// GenerateRayCellInteractionMaskLUT (GpuRenderer.cpp:193-210): cells of a 4x4x4 mask a ray of a given octant can reach from a cell
-static void interaction_lut(uint64_t table[512]) {
-    for (int oct = 0; oct < 8; oct++) {
-        const int sx = (oct & 1) ? 1 : -1, sy = (oct & 2) ? 1 : -1, sz = (oct & 4) ? 1 : -1;
-        for (int origin = 0; origin < 64; origin++) {
-            const int ox = origin & 3, oz = (origin >> 2) & 3, oy = origin >> 4;
-            uint64_t m = 0;
-            for (int jy = 0; jy < 4; jy++)
-                for (int jz = 0; jz < 4; jz++)
-                    for (int jx = 0; jx < 4; jx++) {
-                        const int x = ox + jx * sx, y = oy + jy * sy, z = oz + jz * sz;
-                        if (x >= 0 && x < 4 && y >= 0 && y < 4 && z >= 0 && z < 4) m |= 1ull << (x + 4 * z + 16 * y);
-                    }
-            table[origin + 64 * oct] = m;
-        }
-    }
-}
-
 extern "C" int vrt_trace_glsl(VrtContext* ctx, uint64_t n, const float* origin3, const float* dir3, const int32_t wo[3], uint32_t flags,
                               VrtHit* out) {
     if (!ctx || !wo || (n && (!origin3 || !dir3 || !out))) return VRT_ERR_INVALID;
     if (flags & ~(VRT_GLSL_COARSE | VRT_GLSL_ANISOTROPIC)) return fail(ctx, VRT_ERR_INVALID, "vrt_trace_glsl: unknown flag");
-    if (ctx->sxz < 2 || ctx->sy < 2) return fail(ctx, VRT_ERR_UNSUPPORTED, "vrt_trace_glsl: the view must span at least 4 sectors per axis (128^3 level)");
     if (n == 0) return VRT_OK;
     if (n > 0x7FFFFFFFull * 128ull) return fail(ctx, VRT_ERR_INVALID, "too many rays for one launch");
     DeviceGuard g(ctx->device);
     int st;
-    const uint32_t gxz = ctx->sxz - 2, n_groups = 1u << (2 * gxz + ctx->sy - 2);
     uint64_t launches = 0;
-    if (!ctx->d_lut) {
-        uint64_t table[512];
-        interaction_lut(table);
-        CU(cudaMalloc((void**)&ctx->d_lut, sizeof(table)));
-        CU(cudaMemcpy(ctx->d_lut, table, sizeof(table), cudaMemcpyHostToDevice));
-    }
-    if (!ctx->d_groups) CU(cudaMalloc((void**)&ctx->d_groups, (size_t)n_groups * 8));
+    GlslScene G;
+    if ((st = glsl_scene(ctx, ctx->stream, G, launches))) return st;
     DevScene S = dev_scene(ctx);
-    if (ctx->groups_stale) {
-        k_build_groups<<<(n_groups + 127) / 128, 128, 0, ctx->stream>>>(S, ctx->d_groups, gxz, n_groups);
-        ctx->groups_stale = false;
-        launches++;
-    }
     if ((st = ensure(ctx, ctx->d_rays_o, n * 12))) return st;
     if ((st = ensure(ctx, ctx->d_rays_d, n * 12))) return st;
     if ((st = ensure(ctx, ctx->d_hits, n * sizeof(VrtHit)))) return st;
     CU(cudaMemcpyAsync(ctx->d_rays_o.p, origin3, n * 12, cudaMemcpyHostToDevice, ctx->stream));
     CU(cudaMemcpyAsync(ctx->d_rays_d.p, dir3, n * 12, cudaMemcpyHostToDevice, ctx->stream));
-    GlslScene G{ctx->d_groups, ctx->d_lut, gxz};
     k_trace_glsl<<<(unsigned)((n + 127) / 128), 128, 0, ctx->stream>>>(S, G, wo[0], wo[1], wo[2], (const float*)ctx->d_rays_o.p,
                                                                       (const float*)ctx->d_rays_d.p, flags, n, (VrtHit*)ctx->d_hits.p);
     launches++;

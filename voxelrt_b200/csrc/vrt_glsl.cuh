@@ -37,15 +37,20 @@ __device__ __forceinline__ int glsl_floor2i(float x) {
     return (f >= -2147483648.0f && f < 2147483648.0f) ? (int)f : (int)0x80000000;
 }
 
-__global__ void __launch_bounds__(128) k_trace_glsl(DevScene S, GlslScene G, int wx, int wy, int wz, const float* __restrict__ o3,
-                                                    const float* __restrict__ d3, uint32_t flags, uint64_t n, VrtHit* __restrict__ out) {
-    const uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (r >= n) return;
+// What rayCast / rayCastCoarse leave behind (VoxelTraversal.glsl:162-243) in raw form: the voxel the walk stopped in, the entry distance
+// and point, the three side distances the normal is taken from.
+struct GlslCast {
+    int p[3];
+    float tmin, cur[3], sd[3], d[3];
+    bool hit, inb, capped;
+    uint32_t iters;  // trips made (the cap when capped)
+};
+
+__device__ inline void glsl_cast(const DevScene& S, const GlslScene& G, const int wo[3], const float o_in[3], const float d_in[3], uint32_t flags, GlslCast& C) {
     const bool coarse_mode = (flags & VRT_GLSL_COARSE) != 0, aniso = (flags & VRT_GLSL_ANISOTROPIC) != 0;
     const uint32_t cap = coarse_mode ? 96u : 256u;
-    float o[3] = {o3[3 * r], o3[3 * r + 1], o3[3 * r + 2]};
-    const float d[3] = {d3[3 * r], d3[3 * r + 1], d3[3 * r + 2]};
-    const int wo[3] = {wx, wy, wz};
+    float o[3] = {o_in[0], o_in[1], o_in[2]};
+    const float d[3] = {d_in[0], d_in[1], d_in[2]};
     float inv[3], ts[3], start[3];
     {  // clipRayToAABB(origin, dir, -wo + 1, grid - wo - 1), VoxelTraversal.glsl:133-145,173,207
         const float grid[3] = {(float)S.lim_xz, (float)S.lim_y, (float)S.lim_xz};
@@ -131,7 +136,31 @@ __global__ void __launch_bounds__(128) k_trace_glsl(DevScene S, GlslScene G, int
 #pragma unroll
         for (int a = 0; a < 3; a++) p[a] = d[a] < 0.0f ? (p[a] & ~cm) : (p[a] | cm);
     }
-    const bool capped = i >= cap;
+    C.p[0] = p[0], C.p[1] = p[1], C.p[2] = p[2];
+    C.tmin = tmin;
+#pragma unroll
+    for (int a = 0; a < 3; a++) C.cur[a] = cur[a], C.sd[a] = sd[a], C.d[a] = d[a];
+    C.hit = hit, C.inb = inb, C.capped = i >= cap;
+    C.iters = C.capped ? cap : i;
+}
+// hit.normal = mix(vec3(0), -sign(dir), greaterThanEqual(vec3(tmin), sideDist)) (VoxelTraversal.glsl:195-197), one axis
+__device__ __forceinline__ int glsl_normal(const GlslCast& C, int a) { return (C.tmin >= C.sd[a]) ? (C.d[a] > 0.0f ? -1 : (C.d[a] < 0.0f ? 1 : 0)) : 0; }
+
+__global__ void __launch_bounds__(128) k_trace_glsl(DevScene S, GlslScene G, int wx, int wy, int wz, const float* __restrict__ o3,
+                                                    const float* __restrict__ d3, uint32_t flags, uint64_t n, VrtHit* __restrict__ out) {
+    const uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n) return;
+    const float o[3] = {o3[3 * r], o3[3 * r + 1], o3[3 * r + 2]};
+    const float d[3] = {d3[3 * r], d3[3 * r + 1], d3[3 * r + 2]};
+    const int wo[3] = {wx, wy, wz};
+    GlslCast C;
+    glsl_cast(S, G, wo, o, d, flags, C);
+    const bool hit = C.hit, inb = C.inb, capped = C.capped;
+    const int* p = C.p;
+    const float tmin = C.tmin;
+    const float* cur = C.cur;
+    const float* sd = C.sd;
+    const uint32_t cap = C.iters, i = C.iters;
     VrtHit H;
     H.vx = p[0], H.vy = p[1], H.vz = p[2];
     H.material = hit ? __ldg(&S.palette[voxel_palette_id(S, p[0], p[1], p[2])]).x : 0u;
@@ -143,7 +172,7 @@ __global__ void __launch_bounds__(128) k_trace_glsl(DevScene S, GlslScene G, int
         code = 0;
 #pragma unroll
         for (int a = 0; a < 3; a++) {
-            const int nrm = (tmin >= sd[a]) ? (d[a] > 0.0f ? -1 : (d[a] < 0.0f ? 1 : 0)) : 0;
+            const int nrm = glsl_normal(C, a);
             code |= (uint32_t)(nrm + 1) << (2 * a);
         }
         const float fu = (tmin >= sd[0]) ? cur[1] : cur[0], fv = (tmin >= sd[2]) ? cur[1] : cur[2];
