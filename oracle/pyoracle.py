@@ -92,6 +92,8 @@ def load():
     lib.orc_blue_noise_sample.restype = None
     lib.orc_sky_sample.argtypes = [vp, vp, u32, vp]
     lib.orc_sky_sample.restype = None
+    lib.orc_sincos_2pi.argtypes = [C.c_float, vp, vp]
+    lib.orc_sincos_2pi.restype = None
     lib.orc_pack_r11g11b10f.argtypes = [C.c_float, C.c_float, C.c_float]
     lib.orc_pack_r11g11b10f.restype = u32
     lib.orc_encode_material.argtypes = [C.c_uint8, C.c_uint8, C.c_uint8, C.c_uint8, C.c_float]
@@ -188,6 +190,19 @@ class OracleMap:
             frame.height if row1 is None else row1,
         )
         return out, aux, st
+
+    def sky_sample(self, dir3, mip):
+        """CpuRenderer's SkyBox.SampleCube at an integer mip, times 3 (CpuRenderer.cpp:348-362): float32[3]."""
+        d = np.ascontiguousarray(dir3, np.float32)
+        out = np.zeros(3, np.float32)
+        self.lib.orc_sky_sample(self.h, d.ctypes.data, int(mip), out.ctypes.data)
+        return out
+
+    def sincos_2pi(self, x):
+        """simd::sincos_2pi (SIMD.h:175-190): (sin, cos) of 2 pi x as float32."""
+        s, c = C.c_float(), C.c_float()
+        self.lib.orc_sincos_2pi(float(x), C.byref(s), C.byref(c))
+        return np.float32(s.value), np.float32(c.value)
 
     def render_glsl(self, frame: VrtFrame, threads=0):
         """A VRT_FRAME_GLSL frame (the GPU renderer's VoxelRender.comp per pixel) -> (tiles or 4 planes, stats)."""

@@ -4,6 +4,7 @@
 #define VRT_HOST_EMULATION 1
 #include "cuda_host_shim.h"
 #include "../../voxelrt_b200/csrc/vrt_kernels.cuh"
+#include "../../voxelrt_b200/csrc/vrt_glsl_frame.cuh"
 
 using namespace vrt;
 
@@ -141,6 +142,38 @@ EMU_API int emu_render_kernel(const EmuScene* e, const VrtFrame* f, const uint8_
             }
         });
     }
+    return (int)blocks;
+}
+
+// k_render_glsl (VRT_FRAME_GLSL frames: the GPU renderer's frame shader per pixel), launched like launch_render does.  groups / lut: the
+// 128^3 level and the interaction LUT as vrt_api.cu's glsl_scene() prepares them (k_build_groups is run here).
+EMU_API int emu_render_glsl(const EmuScene* e, const VrtFrame* f, const uint8_t* bn, const uint32_t* sky, const VrtSkyDesc* sky_desc, const uint2* lut, void* out) {
+    DevScene S = scene_of(e);
+    if (e->sxz < 2 || e->sy < 2) return -2;
+    const uint32_t gxz = e->sxz - 2, n_groups = 1u << (2 * gxz + e->sy - 2);
+    std::vector<uint2> groups(n_groups);
+    gridDim.x = (n_groups + 127) / 128, blockDim.x = 128;
+    for (unsigned b = 0; b < gridDim.x; b++)
+        for (unsigned t = 0; t < 128; t++) {
+            blockIdx.x = b, threadIdx.x = t;
+            k_build_groups(S, groups.data(), gxz, n_groups);
+        }
+    const GlslScene G{groups.data(), lut, gxz};
+    FrameParams F;
+    fill_frame_params(F, f, S.sxp, 0, bn, sky, sky_desc);
+    F.out = out;
+    if (!fill_frame_partition(F, f, 0, 0)) return -1;
+    if (F.n_work <= F.work_offset) return 0;
+    const unsigned wpb = VRT_RENDER_THREADS / 32;
+    const int64_t blocks = (F.n_work - F.work_offset + wpb - 1) / wpb;
+    const bool rows = (F.flags & VRT_FRAME_PART_ROWS) != 0u;
+    const uint32_t cast_flags = (F.flags & VRT_FRAME_GLSL_ANISOTROPIC) ? VRT_GLSL_ANISOTROPIC : 0u;
+#pragma omp parallel for schedule(dynamic, 8)
+    for (int64_t w = 0; w < blocks * (int64_t)wpb; w++)
+        run_warp_lockstep((unsigned)(w / wpb), VRT_RENDER_THREADS, (unsigned)(w % wpb) * 32u, [&](int) {
+            if (rows) k_render_glsl<true>(S, G, F, cast_flags);
+            else k_render_glsl<false>(S, G, F, cast_flags);
+        });
     return (int)blocks;
 }
 

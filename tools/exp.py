@@ -25,12 +25,15 @@ from scenes import terrain
 N = int(os.environ.get("VRT_EXP_N", "40"))
 workload = "terrain"
 bounces = None
+extra_flags = 0
 argv = sys.argv[1:]
 while argv and argv[0].startswith("--"):
     if argv[0] == "--workload":
         workload = argv[1]
     elif argv[0] == "--bounces":
         bounces = int(argv[1])
+    elif argv[0] == "--flags":  # extra VrtFrame.flags, e.g. 16 = VRT_FRAME_GLSL
+        extra_flags = int(argv[1])
     argv = argv[2:]
 scene, recs, sstats = bench.build_scene(workload)
 cap = 1 << 18
@@ -52,6 +55,8 @@ flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
 st = torch.cuda.Stream()
 torch.cuda.set_stream(st)
 frame = bench.bench_frame(w, h, bounces)
+frame.flags |= extra_flags
+rays_per_px = (1 + bounces) if not (extra_flags & 16) else (1 + (1 if bounces else 0) + bounces + min(bounces, 2))
 sets = argv or ["persistent=0"]
 ref = None
 for rep in range(2):
@@ -74,4 +79,4 @@ for rep in range(2):
         if ref is None:
             ref = digest
         ts = np.array(ts)
-        print(f"{workload} b{bounces} {spec:34s} median {np.median(ts):.4f} ms  min {ts.min():.4f} ms  -> {w*h*(1+bounces)/np.median(ts)/1e6:.2f} Grays/s (nominal rays)  same_frame={digest == ref}", flush=True)
+        print(f"{workload} b{bounces} {spec:34s} median {np.median(ts):.4f} ms  min {ts.min():.4f} ms  -> {w*h*rays_per_px/np.median(ts)/1e6:.2f} Grays/s (nominal rays)  same_frame={digest == ref}", flush=True)

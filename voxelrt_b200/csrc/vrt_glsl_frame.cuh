@@ -49,12 +49,7 @@ __device__ __forceinline__ void glsl_material_color(uint32_t md, float c[3]) {
     for (int a = 0; a < 3; a++) c[a] = __fmul_rn(c[a], c[a]);
 }
 __device__ __forceinline__ float glsl_material_emission(uint32_t md) { return __half2float(__ushort_as_half((unsigned short)(md >> 16))); }
-// getSkyColor, VoxelRender.comp:15-17 (stand-in sampler, see the header)
-__device__ __forceinline__ void glsl_sky_color(const FrameParams& F, const float d[3], float c[3]) {
-    float r, g, b;
-    sky_sample(F, d[0], d[1], d[2], 0u, r, g, b);  // (returns the texel x 3, CpuRenderer.cpp:360: undone by the exact / 3 below? no — see note)
-    c[0] = r, c[1] = g, c[2] = b;
-}
+// getSkyColor, VoxelRender.comp:15-17 (stand-in sampler, see the header):
 // the raw R11G11B10F texel of the context's cube at level 0 (ProjectCubemap + nearest), times 5, capped at 50000
 __device__ __forceinline__ void glsl_sky(const FrameParams& F, const float d[3], float c[3]) {
     if (F.sky == nullptr) {
