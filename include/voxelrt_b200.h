@@ -302,7 +302,7 @@ VRT_API int vrt_get_metrics(VrtContext* ctx, VrtTraversalMetrics* out);
  * form of the frame kernel with n x (SMs x CTAs/SM) CTAs, default 0; "compact_bounces" 0/1 — re-deal the live bounce
  * rays of a CTA to full warps between bounces, default 0 (both measured slower than the defaults);
  * "wavefront" 0/1/2 — frames with bounces traced as queued passes with trip budgets: off / on / self-tuning (default 2:
- * the first two bounce frames after a scene change are timed in one form each and the faster is kept).  Every
+ * the first four bounce frames after a scene change alternate between the forms, timed, and the faster is kept).  Every
  * combination produces the same bytes.  Unknown names return VRT_ERR_INVALID. */
 VRT_API int vrt_set_option(VrtContext* ctx, const char* name, int64_t value);
 

@@ -152,8 +152,8 @@ struct VrtContext {
     // persistent frame kernel: ring of ticket counters (one per launch in flight) and the host's view of each
     // frames with bounces: wavefront passes with trip budgets (k_wave_*, vrt_shade.cuh) against the one-thread-per-pixel kernel.
     // Bit-identical, but which is faster depends on the scene (open terrain, 2 bounces: +10..15 %; inside Sponza: -8..12 %), so
-    // the default (2) measures: after every change of scene emptiness / bounce count / frame size the next two bounce frames
-    // run one form each between CUDA events, and the faster one is kept.  0 / 1 force a form.
+    // the default (2) measures: after every change of scene emptiness / bounce count / frame size the next four bounce frames
+    // alternate between the forms between CUDA events, and the form with the faster frame is kept.  0 / 1 force a form.
     int gather_threads = 0;
     int wave_on = 2;
     int trace_refill = VRT_TRACE_REFILL;  // k_wave_trace: lanes in flight below which a warp refills (tuning knob, "trace_refill")
