@@ -212,6 +212,52 @@ def test_config5_edit_frames(bench_scene):
     fresh.close()
 
 
+def test_config5_replicas_stay_identical(bench_scene):
+    """BASELINE configs[4] on N GPUs = N replicas of the brickmap, each applying the same edit records (GpuRenderer.cpp:45-167 run once
+    per process).  Three contexts stand in for three ranks: after every edit frame their resident state is THE SAME — allocation mask, slot
+    base (the arena is deterministic), bricks and cell masks of every edited sector, and equal to the oracle's — and the frame assembled
+    from the three ranks' band shares is the frame one context renders alone."""
+    import ctypes as C
+
+    from scenes import camera, edits, terrain
+    from voxelrt_b200 import capi
+
+    n = 3
+    frames, _ = edits.random_edit_frames(bench_scene, 5, 3000, seed=11)
+    recs0 = terrain.scene_records(bench_scene)
+    ranks = []
+    for _ in range(n):
+        c = capi.Context(6, 4, device=0, initial_brick_capacity=1 << 18)
+        c.set_palette(bench_scene["palette"])
+        c.sync(recs0)
+        ranks.append(c)
+    _, orc = _pair(bench_scene, (6, 4), capacity=1 << 18)
+    cam = camera.Camera()
+    w, h = 1280, 720
+    for i, recs in enumerate(frames):
+        for c in ranks:
+            c.sync(recs)
+        orc.sync(recs)
+        stats = [c.stats() for c in ranks]
+        assert len({(s.resident_bricks, s.free_ranges, s.resident_sectors, s.bricks_uploaded, s.bricks_relocated) for s in stats}) == 1
+        for rec in recs[:: max(1, len(recs) // 60)]:  # a sample of the edited sectors, read back from every replica
+            sx, sy, sz = rec[0], rec[1], rec[2]
+            states = [c.read_sector(sx, sy, sz) for c in ranks]
+            om, ob, oc = orc.read_sector(sx, sy, sz)
+            for gm, base, gb, gc in states:
+                assert gm == om == states[0][0] and base == states[0][1], (i, sx, sy, sz)
+                assert np.array_equal(gb, ob) and np.array_equal(gc, oc), (i, sx, sy, sz)
+        host = np.zeros(w * h // 16, capi.TILE_DTYPE)
+        for r, c in enumerate(ranks):  # every rank delivers its 8-pixel bands into the one host frame
+            f = _frame(cam, w, h, frame_no=i + 1, flags=capi.VRT_FRAME_PART_ROWS, part_index=r, part_count=n)
+            c._chk(c.lib.vrt_render(c.h, C.byref(f), host.ctypes.data, None))
+        alone, _ = ranks[i % n].render(_frame(cam, w, h, frame_no=i + 1))
+        want, _, _ = orc.render(_frame(cam, w, h, frame_no=i + 1))
+        assert host.tobytes() == alone.tobytes() == want.tobytes(), f"edit frame {i}"
+    for c in ranks:
+        c.close()
+
+
 def test_bricks_beyond_four_gigabytes_of_voxels(hash_scene, hash_oracle, shading_inputs):
     """64-bit brick addressing: with the first 8.5 M slots of the arena reserved, the scene's bricks live where a 10 GB scene's do (byte offsets
     beyond 2^32: 8.4 M slots x 512 B) — upload, read-back, explicit rays, frames in both bounce forms must not care.  (Round 2, found at
