@@ -68,7 +68,9 @@ def main():
                 "kernel": r[kn].split("(")[0].replace("void ", ""),
                 "duration_us": round(get(r, "gpu__time_duration.sum", True) * 1e6, 2),
                 "dram_bytes": int(get(r, "dram__bytes_read.sum", True) + get(r, "dram__bytes_write.sum", True)),
-                "l2_bytes": None if get(r, "lts__t_bytes.sum") is None else int(get(r, "lts__t_bytes.sum", True)),
+                # L2 traffic: lts__t_bytes where the set carries it, else 32-byte sectors
+                "l2_bytes": int(get(r, "lts__t_bytes.sum", True)) if get(r, "lts__t_bytes.sum") is not None
+                else (None if get(r, "lts__t_sectors.sum") is None else int(get(r, "lts__t_sectors.sum")) * 32),
                 "warp_instructions": int(get(r, "smsp__inst_executed.sum")),
                 "threads_per_instruction": get(r, "smsp__thread_inst_executed_per_inst_executed.ratio"),
                 "issue_active_pct": get(r, "smsp__issue_active.avg.pct_of_peak_sustained_active"),
