@@ -9,12 +9,18 @@ reference camera, 3840x2160 primary rays + normals/material/depth G-buffer.  One
 
 value   device-resident throughput: CUDA events around each frame's kernel on the launching stream,
         L2 flushed (256 MiB memset) between frames, max over ranks.
-e2e     the same frame through the host-buffer ABI call (vrt_render): frame constants in, 16 B/px
-        G-buffer copied back into pinned host memory, wall clock around the blocking call.
-roofline  algorithmic bytes (8 I_s + 8 I_c + 9 H + 16 P, counted by the kernel's own traversal
-        counters, which tests check against the oracle) / kernel time, vs the measured HBM peak.
+e2e     the same frame through the host-buffer ABI call (vrt_render): frame constants in, the G-buffer
+        copied back into page-locked host memory, wall clock around the blocking call.  Primary-only
+        frames move the compact 8 B/px payload (VRT_FRAME_COMPACT: the other half of the reference's
+        16 B/px tile is the constant 1.0; value_full_16B_per_px times the full tile as well); at N > 1 all
+        ranks deliver their bands into ONE host frame in shared page-locked memory.
+roofline  bound "issue" (the kernels are instruction-issue bound, ncu numbers beside it); achieved / peak /
+        frac = algorithmic bytes (8 I_s + 8 I_c + 9 H + 16 P, counted by the kernel's own traversal
+        counters, which tests check against the oracle) / kernel time vs the measured HBM peak, a
+        work-equivalent figure; traffic = DRAM bytes of the committed ncu capture (profiles/ncu_summary.json).
 cpu_baseline  the CPU path (oracle/_ref = the reference's own CpuRenderer.cpp when it was compiled
-        here, else the oracle port) on all host threads, same frame.
+        here, built with the flags it ships with, else the oracle port) on all host threads, same frame.
+--impl reference  that CPU path alone, as a bench line of its own (rank 0 only under torchrun, all host threads).
 N > 1   screen split of the SAME frame (strong scaling): rank r renders the 8-pixel bands b with
         b % N == r of the replicated brickmap into its own buffer, and vrt_render_gather moves them
         into the presenting GPU's framebuffer with one strided copy over NVLink while the next frame
