@@ -56,3 +56,4 @@ for arr, keep, n in batches[:30]:
 torch.cuda.synchronize()
 print(f"host time inside vrt_sync while pipelined: median {1e3*np.median(hs):.3f} ms  min {1e3*np.min(hs):.3f}  max {1e3*np.max(hs):.3f}")
 print("stats", {k: getattr(s, k) for k in ("resident_bricks", "free_ranges", "bricks_uploaded", "bricks_relocated", "last_launches")})
+ctx.close()

@@ -6,8 +6,10 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <condition_variable>
@@ -94,8 +96,43 @@ private:
     bool quit_ = false;
 };
 
+// VRT_SYNC_PROFILE=1 in the environment: where the HOST time of vrt_sync goes, by phase, printed when the context is destroyed
+// (a diagnostic for the edit workload; costs seven clock reads per call when on, one branch when off)
+struct SyncProfile {
+    bool on = getenv("VRT_SYNC_PROFILE") != nullptr;
+    double t[8] = {};
+    uint64_t calls = 0;
+    std::chrono::steady_clock::time_point last;
+    void start() {
+        if (on) last = std::chrono::steady_clock::now(), calls++;
+    }
+    void mark(int phase) {
+        if (!on) return;
+        const auto now = std::chrono::steady_clock::now();
+        t[phase] += std::chrono::duration<double, std::micro>(now - last).count();
+        last = now;
+    }
+    void report() const {
+        if (!on || !calls) return;
+        static const char* names[8] = {"validate (pass 1)", "arena growth + staging size", "commit (pass 2: arena, work lists)", "wait for staging halves",
+                                       "gather into pinned staging", "H2D + kernel launches", "occupancy / boxes / quarantine", ""};
+        fprintf(stderr, "[vrt_sync profile] %llu calls, host microseconds per call:\n", (unsigned long long)calls);
+        for (int i = 0; i < 7; i++) fprintf(stderr, "  %-40s %8.1f\n", names[i], t[i] / (double)calls);
+    }
+};
+static SyncProfile g_sync_profile;
+
+struct SyncUpload {  // vrt_sync: one brick to stage (payload in the caller's record, or the shared zero brick) and its slot
+    const uint8_t* src;
+    uint32_t slot;
+};
+
 struct VrtContext {
     int device = 0;
+    std::vector<SyncUpload> sync_uploads;  // vrt_sync's work lists, kept between calls
+    std::vector<uint2> sync_moves;
+    std::vector<HeaderUpdate> sync_headers;
+    std::vector<uint32_t> sync_seen;
     GatherPool gather_pool;  // started by the first vrt_sync that has enough bricks to share out
     cudaStream_t stream = nullptr;
     cudaStream_t copy_stream = nullptr;  // D2H copies of finished bands overlap the next band's kernel
@@ -678,6 +715,7 @@ extern "C" int vrt_create(const VrtConfig* cfg, VrtContext** out) {
 
 extern "C" void vrt_destroy(VrtContext* ctx) {
     if (!ctx) return;
+    g_sync_profile.report();
     ctx->gather_pool.stop();
     DeviceGuard g(ctx->device);
     cudaDeviceSynchronize();
@@ -812,14 +850,15 @@ extern "C" int vrt_sync(VrtContext* ctx, uint32_t n, const VrtDirtySector* recs)
     ctx->stats.bytes_uploaded = ctx->stats.bricks_uploaded = ctx->stats.bricks_relocated = 0;
     ctx->stats.last_launches = 0;
     if (n == 0) return VRT_OK;
+    SyncProfile& prof = g_sync_profile;
+    prof.start();
 
-    struct Upload {
-        const uint8_t* src;
-        uint32_t slot;
-    };
-    std::vector<Upload> uploads;
-    std::vector<uint2> moves;
-    std::vector<HeaderUpdate> headers;
+    using Upload = SyncUpload;
+    // (work lists live with the context: a frame of edits lists ~25 k entries, and fresh vectors of that size come from mmap every call)
+    std::vector<Upload>& uploads = ctx->sync_uploads;
+    std::vector<uint2>& moves = ctx->sync_moves;
+    std::vector<HeaderUpdate>& headers = ctx->sync_headers;
+    uploads.clear(), moves.clear(), headers.clear();
     static const uint8_t kZeroBrick[VRT_BRICK_BYTES] = {};
 
     // The call is TRANSACTIONAL: pass 1 looks at every record without touching anything, and everything that can fail for
@@ -829,7 +868,8 @@ extern "C" int vrt_sync(VrtContext* ctx, uint32_t n, const VrtDirtySector* recs)
     // launches below: the second record's moves read what the first one's moves write), and upper bounds for the sizes.
     uint64_t need_slots = 0, max_uploads = 0, max_moves = 0, max_headers = 0;
     {
-        std::vector<uint32_t> seen;
+        std::vector<uint32_t>& seen = ctx->sync_seen;
+        seen.clear();
         seen.reserve(n);
         for (uint32_t r = 0; r < n; r++) {
             const VrtDirtySector& d = recs[r];
@@ -854,6 +894,7 @@ extern "C" int vrt_sync(VrtContext* ctx, uint32_t n, const VrtDirtySector* recs)
         if (std::adjacent_find(seen.begin(), seen.end()) != seen.end())
             return fail(ctx, VRT_ERR_INVALID, "the same sector appears in two records of one vrt_sync call (nothing was changed)");
     }
+    prof.mark(0);
     // Every fresh range of this call fits behind the high-water mark (one coalesced free range): then no alloc() below can
     // fail, whatever the fragmentation.  Grown BEFORE the first mutation; a failure here leaves everything as it was.
     if (need_slots) {
@@ -877,6 +918,7 @@ extern "C" int vrt_sync(VrtContext* ctx, uint32_t n, const VrtDirtySector* recs)
             if (st) return st;
         }
     }
+    prof.mark(1);
     uploads.reserve(max_uploads);
     moves.reserve(max_moves);
     headers.reserve(max_headers);
@@ -940,6 +982,7 @@ extern "C" int vrt_sync(VrtContext* ctx, uint32_t n, const VrtDirtySector* recs)
             uploads.push_back(Upload{kZeroBrick, slot_of(cur, (uint32_t)__builtin_ctzll(m))});
     }
 
+    prof.mark(2);
     // Staging is chunked and double-buffered: a chunk of at most kChunkBricks bricks (64 MiB) is gathered into one half of the
     // pinned buffer (several host threads for big chunks) while the previous chunk's H2D copy and upload kernel run from the
     // other half — a multi-GB scene never needs a multi-GB pinned allocation, and the host gather overlaps the PCIe copy.
@@ -971,6 +1014,7 @@ extern "C" int vrt_sync(VrtContext* ctx, uint32_t n, const VrtDirtySector* recs)
             if (c >= 2) CU(cudaEventSynchronize(ctx->ev_stage[c & 1]));  // the chunk that used this half has been consumed
             const size_t off_slots = nb * 512, off_meta = (off_slots + nb * 4 + 15) & ~(size_t)15;
             uint32_t* slots = reinterpret_cast<uint32_t*>(hs + off_slots);
+            prof.mark(3);
             auto gather = [&](size_t lo, size_t hi) {
                 for (size_t i = lo; i < hi; i++) {
                     memcpy(hs + i * 512, uploads[i0 + i].src, 512);
@@ -987,6 +1031,7 @@ extern "C" int vrt_sync(VrtContext* ctx, uint32_t n, const VrtDirtySector* recs)
                     ctx->gather_pool.run([&](unsigned part, unsigned parts) { gather(nb * part / parts, nb * (part + 1) / parts); });
                 else gather(0, nb);
             } else gather(0, nb);
+            prof.mark(4);
             size_t bytes = off_meta;
             if (c == 0) {
                 if (nm) memcpy(hs + off_meta, moves.data(), nm * 8);
@@ -1017,6 +1062,7 @@ extern "C" int vrt_sync(VrtContext* ctx, uint32_t n, const VrtDirtySector* recs)
             ctx->stage_used[c & 1] = true;
         }
     }
+    prof.mark(5);
     if (ctx->render_pending) { int st_ = wait_renders(ctx, ctx->stream); if (st_) return st_; }  // (box rebuild / callers that sync nothing)
     if (nh) {  // some sector's allocation mask changed: refresh the one-bit view (78 k entries for the 2048x512x2048 view)
         const uint32_t n_all = ctx->n_hdr + 2u * ctx->hdr_guard;
@@ -1032,6 +1078,7 @@ extern "C" int vrt_sync(VrtContext* ctx, uint32_t n, const VrtDirtySector* recs)
     ctx->stats.bytes_uploaded = total;
     ctx->stats.bricks_uploaded = nu;
     ctx->stats.bricks_relocated = nm;
+    prof.mark(6);
     return VRT_OK;
 }
 
