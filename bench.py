@@ -256,6 +256,7 @@ def bench_frame(width, height, bounces, part_index=0, part_count=1, frame_no=1, 
 
     cam = _WL["cam"] or camera.Camera()  # Main.cpp:76-78
     proj, inv, wo, frac = cam.matrices(width, height)
+    flags |= _WL.get("frame_flags", 0)  # --glsl: every frame of the run is a VRT_FRAME_GLSL frame
     return capi.make_frame(width, height, inv, proj, wo, frac, frame_no=frame_no, bounces=bounces, flags=flags, part_index=part_index, part_count=part_count)
 
 
@@ -390,6 +391,9 @@ def workload_config(args, scene, sstats):
         "width": args.width,
         "height": args.height,
         "bounces": args.bounces,
+        "renderer": ("the reference's GPU renderer: Shaders/VoxelRender.comp per pixel (VRT_FRAME_GLSL" + (", anisotropic LODs" if args.glsl_aniso else "") +
+                     "), rays counted like GpuRenderer.cpp:292-296 = pixels * (bounces + 1) * 2; parity with the GLSL unpinned") if getattr(args, "glsl", False)
+        else "the reference's CPU renderer: RenderRow per 4x4 packet (CpuRenderer.cpp:326-402)",
         "bricks": sstats["bricks"],
         "sectors": sstats["sectors"],
         "l2": "flushed between timed frames (256 MiB memset outside the event-timed region)" if args.gpus == 1 else
@@ -408,6 +412,9 @@ def roofline_block(args, world, alg_bytes, ms_per_step, peak, peak_src, m, my_pr
     achieved = alg_bytes / (ms_per_step * 1e-3) / 1e9
     ncu = _ncu_summary(args)
     kernel = ("vrt::k_render<false,true,%s>" % ("true" if world > 1 else "false")) if args.bounces == 0 else "vrt::k_wave_primary + k_wave_trace + k_wave_shade (or k_render<false,false,...>: self-tuned)"
+    if getattr(args, "glsl", False):
+        kernel = "vrt::k_render_glsl (no traversal counters for the GLSL walk: the algorithmic bytes below are the 16 B/px G-buffer only)"
+        ncu = None
     return {
         "bound": "issue",
         "bound_note": "instruction-issue bound (see `ncu`); achieved/peak/frac = algorithmic bytes over the measured HBM copy peak, a work-equivalent figure",
@@ -559,9 +566,14 @@ def run_b200(args):
     w, h = args.width, args.height
     npx = w * h
     rays_frame = npx * (1 + args.bounces)
+    if args.glsl:
+        # the GPU renderer's frame shader (VRT_FRAME_GLSL) and its own ray accounting: (bounces + 1) * 2 rays per pixel, "sun" included
+        # (GpuRenderer.cpp:292-296) — the shader casts 1 + [b > 0] + b + min(b, 2) at most
+        _WL["frame_flags"] = capi.VRT_FRAME_GLSL | (capi.VRT_FRAME_GLSL_ANISOTROPIC if args.glsl_aniso else 0)
+        rays_frame = npx * (1 + args.bounces) * 2
     # primary-only frames: 8 B/px (VRT_FRAME_COMPACT: albedo + normal, depth; the irradiance of such a frame is the constant 1.0 and is
     # not moved) over NVLink and PCIe; the device-resident N = 1 frame keeps the reference's full 16 B/px tiles
-    compact = args.bounces == 0 and args.compact
+    compact = args.bounces == 0 and args.compact and not args.glsl
     xfer_px = 8 if compact else 16
     xflag = capi.VRT_FRAME_COMPACT if compact else 0
     fb = torch.zeros(npx * 4, dtype=torch.int32, device="cuda")  # 16 B/px
@@ -1002,6 +1014,8 @@ def main():
     ap.add_argument("--scene-file", default=None, help="workload 'file': a cvox 0004 voxel-map file written by the reference (or by scenes/cvox.py)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--wavefront", type=int, default=None, choices=[0, 1, 2], help="frames with bounces: 0 one thread per pixel, 1 wavefront passes, 2 self-tuning (library default)")
+    ap.add_argument("--glsl", action="store_true", help="render VRT_FRAME_GLSL frames: the reference's GPU renderer (Shaders/VoxelRender.comp per pixel: sun shadow ray, coarse bounce rays); rays counted like GpuRenderer.cpp:292-296; the traversal counters of the roofline block do not exist for this walk")
+    ap.add_argument("--glsl-aniso", action="store_true", help="with --glsl: u_UseAnisotropicLods")
     ap.add_argument("--no-compact", dest="compact", action="store_false", default=True, help="move the full 16 B/px tiles of primary-only frames over NVLink / PCIe instead of the 8 B/px that carry information")
     ap.add_argument("--large-y", type=int, default=24, help="workload 'large': sectors along y (24 with --large-shift 512 = 10 GB of bricks)")
     ap.add_argument("--large-shift", type=int, default=512, help="workload 'large': voxels the terrain is raised by (solid rock below the surface)")
