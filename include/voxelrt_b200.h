@@ -297,13 +297,21 @@ typedef struct VrtTraversalMetrics {
     uint64_t rays, iters, sector_fetches, cell_fetches, hits, capped;
 } VrtTraversalMetrics;
 VRT_API int vrt_get_metrics(VrtContext* ctx, VrtTraversalMetrics* out);
-/* Settings (the role of Renderer::DrawSettings, Renderer.h:19): "metrics" 0/1 (above); "macro_steps" 0/1 — exact
- * empty-box space skipping for camera rays, default 1 (2 = diagnostic counters); "persistent" 0/n — the resident-grid
- * form of the frame kernel with n x (SMs x CTAs/SM) CTAs, default 0; "compact_bounces" 0/1 — re-deal the live bounce
- * rays of a CTA to full warps between bounces, default 0 (both measured slower than the defaults);
- * "wavefront" 0/1/2 — frames with bounces traced as queued passes with trip budgets: off / on / self-tuning (default 2:
- * the first four bounce frames after a scene change alternate between the forms, timed, and the faster is kept).  Every
- * combination produces the same bytes.  Unknown names return VRT_ERR_INVALID. */
+/* Settings (the role of Renderer::DrawSettings, Renderer.h:19).  Every combination produces the same bytes; they change speed only.
+ *   "metrics" 0/1          traversal counters (above)
+ *   "macro_steps" 0/1      exact empty-box space skipping for camera rays, default 1 (2 = diagnostic counters)
+ *   "wavefront" 0/1/2      frames with bounces: one thread per pixel through all levels / wavefront passes (camera pass, then per level a
+ *                          persistent trace pass with lane refill and a shade pass) / default 2: the first four such frames after a change
+ *                          of scene emptiness, size, bounce count or split alternate between the forms, timed, and the faster is kept
+ *                          (VrtStats.bounce_form reports it)
+ *   "trace_refill" 1..32   trace pass: lanes in flight below which a warp refills from the queue, default 24
+ *   "trace_ctas" 8/10/12   trace pass: resident CTAs per SM it is compiled for, default 10
+ *   "tile_order" 0/1       primary frame kernel: warp tiles top-to-bottom / bottom-to-top (default: the cheap sky rows run last)
+ *   "persistent" 0/n       resident-grid form of the frame kernel with n x (SMs x CTAs/SM) CTAs, default 0 (measured slower)
+ *   "gather_threads" 0..64 host threads of vrt_sync's staging gather for batches of >= 8192 bricks: 0 = min(8, cores), 1 = caller only
+ *   "compact_bounces"      removed (round 1's CTA-level re-dealing of bounce rays): any non-zero value returns VRT_ERR_UNSUPPORTED
+ *   "reserve_slots" n      test hook: take the first n brick slots out of an EMPTY arena (exercises 64-bit brick addressing)
+ * Unknown names return VRT_ERR_INVALID. */
 VRT_API int vrt_set_option(VrtContext* ctx, const char* name, int64_t value);
 
 #ifdef __cplusplus
