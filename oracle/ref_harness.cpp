@@ -34,6 +34,9 @@
 #include "Common/Scene.h"
 #include "Voxelize.cpp"
 glim::Model::Model(std::string_view) {}
+// the editing tool that produces BASELINE configs[4]'s dirty bricks in the app: BrushSession::Dispatch (Brush.cpp:10-37) over
+// VoxelMap::RegionDispatchSIMD (VoxelMap.h:223-263: brick creation, DirtyLocs, garbage collection of emptied bricks / sectors)
+#include "Brush.cpp"
 
 // ---- externals the two TUs expect from files we do not compile ------------------------------------
 namespace swr {
@@ -113,6 +116,29 @@ REF_API int ref_sync(RefCtx* c, uint32_t n, const VrtDirtySector* recs) {
     c->storage->SyncBuffers(c->map);
     std::memcpy(c->storage->Palette, c->palette, sizeof(c->palette));  // SyncBuffers re-encodes map.Palette (unused here)
     return 0;
+}
+
+// One brush stroke on the reference's VoxelMap: capsule from a to b (voxel coordinates), action 0 = Fill / 1 = Replace, material 0 erases.
+REF_API void ref_brush_dispatch(RefCtx* c, const int32_t a[3], const int32_t b[3], float radius, int action, uint8_t material) {
+    BrushSession s;
+    s.Pars.Action = action ? BrushAction::Replace : BrushAction::Fill;
+    s.Pars.Radius = radius;
+    s.Pars.PointA = glm::ivec3(a[0], a[1], a[2]);
+    s.Pars.PointB = glm::ivec3(b[0], b[1], b[2]);
+    s.Pars.Material = Voxel{material};
+    s.Dispatch(c->map);
+}
+// VoxelMap::DirtyLocs as (sector position, dirty-brick mask) pairs; clears it (what SyncBuffers does after consuming it)
+REF_API uint32_t ref_map_take_dirty(RefCtx* c, int32_t* xyz, uint64_t* masks, uint32_t cap) {
+    uint32_t n = 0;
+    for (auto& [idx, mask] : c->map.DirtyLocs) {
+        if (n >= cap) break;
+        glm::ivec3 p = WorldSectorIndexer::GetPos(idx);
+        xyz[3 * n] = p.x, xyz[3 * n + 1] = p.y, xyz[3 * n + 2] = p.z;
+        masks[n++] = mask;
+    }
+    c->map.DirtyLocs.clear();
+    return n;
 }
 
 // ---- cvox files: the reference's own VoxelMap::Serialize / Deserialize (VoxelMap.cpp:205-274) ----

@@ -102,6 +102,10 @@ def load(shipped_flags=False):
     lib.ref_num_threads.restype = C.c_int
     lib.ref_voxelize.argtypes = [vp, u32, vp, vp, vp, u32, vp, vp, vp, u32]
     lib.ref_voxelize.restype = C.c_int
+    lib.ref_brush_dispatch.argtypes = [vp, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.c_float, C.c_int, C.c_uint8]
+    lib.ref_brush_dispatch.restype = None
+    lib.ref_map_take_dirty.argtypes = [vp, vp, vp, u32]
+    lib.ref_map_take_dirty.restype = u32
     lib.ref_palette_build.argtypes = [vp, u64, u32, vp, vp]
     lib.ref_palette_build.restype = u32
     _libs[shipped_flags] = lib
@@ -178,6 +182,21 @@ class RefMap:
             self.lib.ref_get_material(self.h, i, rgbf, C.byref(em))
             out.append((rgbf[0], rgbf[1], rgbf[2], rgbf[3], em.value))
         return out
+
+    def brush(self, point_a, point_b, radius=30.0, action="fill", material=255):
+        """BrushSession::Dispatch (Brush.cpp:10-37) on the VoxelMap; -> {(sx, sy, sz): dirty-brick mask} = VoxelMap::DirtyLocs, cleared."""
+        a = (C.c_int32 * 3)(*[int(v) for v in point_a])
+        b = (C.c_int32 * 3)(*[int(v) for v in point_b])
+        self.take_dirty()
+        self.lib.ref_brush_dispatch(self.h, a, b, float(radius), 1 if action == "replace" else 0, int(material))
+        return self.take_dirty()
+
+    def take_dirty(self):
+        cap = 1 << 16
+        xyz = np.zeros((cap, 3), np.int32)
+        masks = np.zeros(cap, np.uint64)
+        n = self.lib.ref_map_take_dirty(self.h, xyz.ctypes.data, masks.ctypes.data, cap)
+        return {(int(xyz[i, 0]), int(xyz[i, 1]), int(xyz[i, 2])): int(masks[i]) for i in range(n)}
 
     def voxelize(self, tris, uvs, tri_tex, textures, size):
         """VoxelMap::VoxelizeModel(model, 0, size^3) on a decoded model (see ref_voxelize in ref_harness.cpp); voxels -> map_sectors(),

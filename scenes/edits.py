@@ -7,7 +7,7 @@ tests: a seeded stream of single-voxel edits (uniform positions inside a box, ha
 clear one) is applied to a copy of a scene, and every frame's dirty bricks come back as sync records
 `(sx, sy, sz, alloc_mask, dirty_mask, bricks[popcount(dirty & alloc), 512])` — the VrtDirtySector contract.
 Like VoxelMap::Set, writing into a missing brick allocates it, and a brick whose last voxel is cleared stays
-allocated (bricks are only freed by the region GC, VoxelMap.h:254-262).
+allocated; bricks are only freed by the region GC (VoxelMap.h:253-262), which the brush strokes below run like the reference does.
 """
 from __future__ import annotations
 
@@ -89,67 +89,94 @@ def random_edit_frames(scene, n_frames, edits_per_frame, seed=1, box=((0, 768), 
 # ---------------------------------------------------------------------------------------------------------------------
 # the reference's brush (VoxelRT/Brush.cpp:3-37, Brush.h:9-17): a capsule of radius 30 from the previous to the current
 # brush position; Fill writes the material into every voxel whose CENTRE is inside, Replace only into non-empty voxels,
-# material 0 erases.  (VoxelMap::RegionDispatchSIMD creates bricks only when filling, VoxelMap.h:216-264.)
+# material 0 erases.  (VoxelMap::RegionDispatchSIMD creates the bricks of the stroke's box unless it erases and deletes the ones that end
+# up empty, VoxelMap.h:223-263.)
 # ---------------------------------------------------------------------------------------------------------------------
-def _capsule_inside(px, py, pz, a, b, r):
-    """sdCapsule(p, a, b, r) < 0 (Brush.cpp:4-8) for voxel centres p; float32 like the reference."""
-    f = np.float32
-    pa = [px - f(a[0]), py - f(a[1]), pz - f(a[2])]
-    ba = [f(b[0] - a[0]), f(b[1] - a[1]), f(b[2] - a[2])]
-    bb = f(ba[0] * ba[0] + ba[1] * ba[1] + ba[2] * ba[2])
-    if bb > 0:
-        h = np.clip((pa[0] * ba[0] + pa[1] * ba[1] + pa[2] * ba[2]) / bb, f(0), f(1))
-    else:
-        h = np.zeros_like(px)
-    d = [pa[i] - ba[i] * h for i in range(3)]
-    return np.sqrt(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]) - f(r) < 0
+_brush_lib = None
+
+
+def _brushlib():
+    global _brush_lib
+    if _brush_lib is None:
+        import ctypes as C
+        from pathlib import Path
+
+        lib = C.CDLL(str(Path(__file__).resolve().parent / "_ref" / "libbrush.so"))
+        lib.brush_brick_mask.argtypes = [C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.c_float, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]
+        lib.brush_brick_mask.restype = C.c_int
+        _brush_lib = lib
+    return _brush_lib
 
 
 def brush_dispatch(world: EditableWorld, point_a, point_b, radius=30.0, material=255, action="fill"):
-    """BrushSession::Dispatch on an EditableWorld -> sync records of the bricks it changed."""
+    """BrushSession::Dispatch (Brush.cpp:10-37) over VoxelMap::RegionDispatchSIMD (VoxelMap.h:223-263) on an EditableWorld -> the sync
+    records of everything the stroke marked dirty.  Step by step like the reference: every brick of the stroke's bounding box is visited
+    (created on the way: always inside an existing sector — VoxelMap::GetBrick's quirk — and together with their sector unless the stroke
+    erases; a Replace stroke's new bricks stay empty); the capsule test runs in the
+    reference's arithmetic (scenes/brush.cpp); a visited brick is dirty if some voxel was inside the final mask or if it is empty afterwards;
+    and visited bricks that end up empty are deleted again, with their sector if nothing else is left in it (the region's garbage
+    collection).  tests/test_ref_brush_pin.py compares voxels, allocation masks and dirty bricks with the reference's own code."""
+    import ctypes as C
+
+    lib = _brushlib()
     a, b = np.asarray(point_a, np.int64), np.asarray(point_b, np.int64)
+    a3, b3 = (C.c_int32 * 3)(*[int(v) for v in a]), (C.c_int32 * 3)(*[int(v) for v in b])
     pad = int(radius + 0.5)
     lo, hi = np.minimum(a, b) - pad, np.maximum(a, b) + pad  # Brush.cpp:11-12
     erasing = material == 0
-    dirty = {}
-    ax = np.arange(8, dtype=np.float32) + np.float32(0.5)
+    create_empty = not erasing  # :17
+    replace = action == "replace"
+    dirty, emptied = {}, {}
+    inside = np.zeros(512, np.uint8)
     for by in range(int(lo[1]) >> 3, (int(hi[1]) >> 3) + 1):
         for bz in range(int(lo[2]) >> 3, (int(hi[2]) >> 3) + 1):
             for bx in range(int(lo[0]) >> 3, (int(hi[0]) >> 3) + 1):
-                # voxel index x | z << 3 | y << 6  ->  arrays shaped [y, z, x]
-                py, pz, px = np.meshgrid(ax + np.float32(by * 8), ax + np.float32(bz * 8), ax + np.float32(bx * 8), indexing="ij")
-                inside = _capsule_inside(px, py, pz, a, b, radius)
-                ix, iy, iz = px.astype(np.int64), py.astype(np.int64), pz.astype(np.int64)
-                inside &= (ix >= lo[0]) & (ix <= hi[0]) & (iy >= lo[1]) & (iy <= hi[1]) & (iz >= lo[2]) & (iz <= hi[2])
-                if not inside.any():
-                    continue
                 key = (bx >> 2, by >> 2, bz >> 2)
                 if min(key) < 0:
-                    continue
+                    continue  # (the reference's world is signed; nothing below zero is ever in a renderer's view)
                 bi = (bx & 3) | ((bz & 3) << 2) | ((by & 3) << 4)
                 d = world.sectors.get(key)
-                have = d is not None and bi in d
-                if not have and (erasing or action == "replace"):
-                    continue  # nothing to erase / replace in a missing brick (createEmpty = false)
-                if not have:
-                    if d is None:
-                        d = world.sectors[key] = {}
+                if d is None:
+                    if not create_empty:
+                        continue  # GetBrick(pos, false) == nullptr for a missing SECTOR only ...
+                    d = world.sectors[key] = {}
+                if bi not in d:  # ... inside an existing sector the brick is created on lookup whatever `create` says (VoxelMap.cpp:122, quirk Q5)
                     d[bi] = np.zeros(512, np.uint8)
                     world._owned.add((key, bi))
-                elif (key, bi) not in world._owned:
-                    d[bi] = d[bi].copy()
-                    world._owned.add((key, bi))
-                vox = d[bi].reshape(8, 8, 8)
-                m = inside & (vox != 0) if (action == "replace" or erasing) else inside
-                if not m.any():
-                    continue
-                vox[m] = material
-                dirty[key] = dirty.get(key, 0) | (1 << bi)
+                vox = d[bi]
+                m = None
+                if lib.brush_brick_mask(a3, b3, float(radius), bx, by, bz, inside.ctypes.data):
+                    m = inside.astype(bool)
+                    if replace:
+                        m &= vox != 0  # :25-27
+                changed = m is not None and bool(m.any())  # DispatchSIMD's result: simd::any(mask) of some invocation
+                if changed:
+                    if (key, bi) not in world._owned:
+                        vox = d[bi] = vox.copy()
+                        world._owned.add((key, bi))
+                    vox[m] = material
+                is_empty = not vox.any()
+                if changed or is_empty:
+                    dirty[key] = dirty.get(key, 0) | (1 << bi)
+                    if is_empty:
+                        emptied[key] = emptied.get(key, 0) | (1 << bi)
+    for key, emask in emptied.items():  # VoxelMap.h:253-262
+        d = world.sectors[key]
+        if world.alloc_mask(key) & ~emask:
+            for bi in [x for x in d if (emask >> x) & 1]:
+                del d[bi]
+                world._owned.discard((key, bi))
+        else:
+            for bi in list(d):
+                world._owned.discard((key, bi))
+            del world.sectors[key]
     recs = []
     for key in sorted(dirty):
-        d = world.sectors[key]
+        d = world.sectors.get(key)
+        alloc = world.alloc_mask(key)
         dm = dirty[key]
-        recs.append((key[0], key[1], key[2], world.alloc_mask(key), dm, np.stack([d[bb] for bb in sorted(d) if (dm >> bb) & 1])))
+        payload = [d[bb] for bb in sorted(d) if (dm >> bb) & 1] if d else []
+        recs.append((key[0], key[1], key[2], alloc, dm, np.stack(payload) if payload else np.zeros((0, 512), np.uint8), d is None))
     return recs
 
 
