@@ -6,6 +6,7 @@
 #include <random>
 
 #include "../../oracle/vrt_oracle.h"
+#include "../../voxelrt_b200/csrc/gather_pool.h"
 #include "../../voxelrt_b200/csrc/slot_allocator.h"
 #include "../../voxelrt_b200/host/b200_renderer.h"
 
@@ -146,6 +147,31 @@ static void test_arena() {
     CHECK(a.allocated() == 0 && a.free_ranges() == 1 && a.largest_free() == a.capacity());
 }
 
+// vrt_sync's staging pool: every part of every job runs exactly once, on the workers AND the caller, job after job (the workers sleep in
+// between), also after the pool was stopped and started again with another size, and for jobs smaller than the pool.
+static void test_gather_pool() {
+    vrt::GatherPool pool;
+    CHECK(pool.workers() == 0);
+    for (unsigned workers : {3u, 1u, 7u}) {
+        pool.start(workers);
+        CHECK(pool.workers() == workers);
+        for (int job = 0; job < 200; job++) {
+            const size_t n = (size_t)(job % 7 == 0 ? 2 : 1000 + 37 * job);
+            std::vector<int> hits(n, 0);
+            std::vector<unsigned> part_seen(workers + 1, 0);
+            pool.run([&](unsigned part, unsigned parts) {
+                CHECK(parts == workers + 1 && part < parts);
+                part_seen[part]++;
+                for (size_t i = n * part / parts; i < n * (part + 1) / parts; i++) hits[i] += 1 + job;
+            });
+            for (size_t i = 0; i < n; i++) CHECK(hits[i] == 1 + job);
+            for (unsigned k = 0; k <= workers; k++) CHECK(part_seen[k] == 1);
+        }
+        pool.stop();
+        CHECK(pool.workers() == 0);
+    }
+}
+
 // ---- GPU: adapter vs oracle -----------------------------------------------------------------------
 static void fill_scene(VoxelMap& map) {
     for (int z = 0; z < 160; z++)
@@ -276,6 +302,7 @@ int main(int argc, char** argv) {
     test_indexers();
     test_voxel_map();
     test_arena();
+    test_gather_pool();
     if (argc > 1 && !std::strcmp(argv[1], "--gpu-present")) {
         try {
             test_gpu_present();
